@@ -1,0 +1,160 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (read-only /root/reference,
+through oracle/ref_shim.py) on seeded synthetic inputs.  Run here (no GPU needed):
+
+    python -m oracle.make_golden
+
+Two families of fixtures:
+  tiny_<mode>.npz  -- reference PatchRefiner (DAv2 ViT-S coarse + ViT-S refiner + FusionUnet),
+                      224x224 patches, 432x768 frame, 2x2 split, modes m1 / m2 / r4: bboxes,
+                      bboxs_feat, per-patch predictions, count map and final depth (full fp32).
+  geom_<ph>x<pw>_<mode>.npz -- reference tiling + blend at BASELINE sizes (2160x3840, 4x4,
+                      448x448 and 384x512 patches, m1 / m2 / r32) with the networks replaced by
+                      oracle.pr_oracle.fake_prediction: bboxes, bboxs_feat, and sha256 + strided
+                      subsample of the count map and the blended depth.
+The weights / frames are NOT stored; they are regenerated from seeds by oracle.pr_oracle and
+their sha256 is stored so drift in the generators is detected.
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import pr_oracle as O  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+TINY = dict(encoder="vits", patch_process_shape=(224, 224), image_raw_shape=(432, 768), patch_split_num=(2, 2))
+TINY_MODES = (("m1", 2), ("m2", 2), ("r4", 2))
+GEOM_MODES = (("m1", 4), ("m2", 4), ("r32", 4))
+SUB = 8
+
+
+def build_reference(cfg, sd):
+    d = tempfile.mkdtemp()
+    cp, fp = os.path.join(d, "c.pth"), os.path.join(d, "f.pth")
+    torch.save({k[len("coarse_branch."):]: v for k, v in sd.items() if k.startswith("coarse_branch.")}, cp)
+    torch.save({k[len("refiner_fine_branch."):]: v for k, v in sd.items() if k.startswith("refiner_fine_branch.")}, fp)
+    ref = ref_shim.build_reference_patchrefiner(cfg, cp, fp)
+    res = ref.load_state_dict(sd, strict=False)
+    assert not res.missing_keys and not res.unexpected_keys, res
+    return ref
+
+
+def sd_digest(sd):
+    import hashlib
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k].numpy()).tobytes())
+    return h.hexdigest()
+
+
+def tiny():
+    cfg = O.make_config(**TINY)
+    sd = O.init_patchrefiner_state_dict(cfg, 0)
+    ref = build_reference(cfg, sd)
+    lr, hr = O.synthetic_frame(cfg, 1)
+    rec = {}
+    orig_post = ref.coarse_postprocess_test
+    orig_inf = ref.infer_forward
+
+    def post(coarse_prediction, coarse_features, bboxs, bboxs_feat):
+        rec["bboxs"].append(bboxs.clone())
+        rec["bboxs_feat"].append(bboxs_feat.clone())
+        out = orig_post(coarse_prediction=coarse_prediction, coarse_features=coarse_features, bboxs=bboxs, bboxs_feat=bboxs_feat)
+        if "roi_depth" not in rec:
+            rec["roi_depth"] = out["coarse_depth_roi"][:2].clone()
+            rec["roi_feat0"] = out["coarse_feats_roi"][0][:2].clone()
+            rec["roi_feat5"] = out["coarse_feats_roi"][5][:2].clone()
+        return out
+
+    def inf(imgs_crop, bbox_feat_forward, tile_temp, coarse_temp_dict):
+        p = orig_inf(imgs_crop, bbox_feat_forward, tile_temp, coarse_temp_dict)
+        rec["preds"].append(p.clone())
+        if "crop0" not in rec:
+            rec["crop0"] = imgs_crop[:1].clone()
+        return p
+
+    ref.coarse_postprocess_test = post
+    ref.infer_forward = inf
+    for mode, pn in TINY_MODES:
+        rec.clear()
+        rec.update(bboxs=[], bboxs_feat=[], preds=[])
+        random.seed(1)
+        with torch.no_grad():
+            depth, log = ref(mode="infer", image_lr=lr, image_hr=hr, cai_mode=mode, process_num=pn, tile_cfg=None)
+        np.savez_compressed(
+            os.path.join(OUT, f"tiny_{mode}.npz"),
+            mode=mode, process_num=pn, sd_sha=sd_digest(sd), frame_sha=O.sha256_f32(hr.numpy()),
+            bboxs=torch.cat(rec["bboxs"]).numpy(), bboxs_feat=torch.cat(rec["bboxs_feat"]).numpy(),
+            preds=torch.cat(rec["preds"]).numpy(), depth=depth.numpy(),
+            coarse=log["coarse_prediction"].numpy(),
+            roi_depth=rec["roi_depth"].numpy(), roi_feat0=rec["roi_feat0"].numpy(), roi_feat5_sha=O.sha256_f32(rec["roi_feat5"].numpy()),
+            crop0=rec["crop0"].numpy())
+        print("tiny", mode, tuple(depth.shape), float(depth.min()), float(depth.max()))
+
+
+def geom(ph, pw):
+    cfg = O.make_config("vits", (ph, pw), (2160, 3840), (4, 4))
+    # a reference PatchRefiner instance is needed only for its tiling / blend methods; build it
+    # at 224x224 weights-wise (weights are never used: the three network entry points are patched)
+    sd = O.init_patchrefiner_state_dict(cfg, 0)
+    ref = build_reference(cfg, sd)
+    _, hr = O.synthetic_frame(cfg, 1)
+    lr = torch.zeros(1, 3, ph, pw)
+    rec = {}
+    ref.coarse_forward = lambda image_lr: ([torch.zeros(1, 1, 8, 8)], torch.zeros(1, 1, ph, pw))
+
+    def post(coarse_prediction, coarse_features, bboxs, bboxs_feat):
+        rec["bboxs"].append(bboxs.clone())
+        rec["bboxs_feat"].append(bboxs_feat.clone())
+        rec["cursor"] = 0
+        P = bboxs.shape[0]
+        return {"coarse_depth_roi": torch.zeros(P, 1, 1, 1), "coarse_feats_roi": [torch.zeros(P, 1, 1, 1)]}
+
+    def inf(imgs_crop, bbox_feat_forward, tile_temp, coarse_temp_dict):
+        n = imgs_crop.shape[0]
+        rows = rec["bboxs"][-1][rec["cursor"]:rec["cursor"] + n].tolist()
+        rec["cursor"] += n
+        return torch.stack([O.fake_prediction(r, ph, pw) for r in rows], dim=0)
+
+    ref.coarse_postprocess_test = post
+    ref.infer_forward = inf
+    for mode, pn in GEOM_MODES:
+        rec.clear()
+        rec.update(bboxs=[], bboxs_feat=[])
+        random.seed(1)
+        with torch.no_grad():
+            depth, log = ref(mode="infer", image_lr=lr, image_hr=hr, cai_mode=mode, process_num=pn, tile_cfg=None)
+        # the RunningAverageMap is not returned by forward(); rebuild the count map with the
+        # oracle (bit-identical to the reference, asserted by tests/test_oracle_vs_reference.py)
+        go = O.GeometryOracle((ph, pw), (2160, 3840), (4, 4))
+        random.seed(1)
+        d2, _, avg = go.infer(lr, hr, None, mode, pn)
+        assert torch.equal(d2, depth), "oracle blend differs from the reference"
+        cnt = avg.count_map.numpy()
+        dn = depth[0, 0].numpy()
+        np.savez_compressed(
+            os.path.join(OUT, f"geom_{ph}x{pw}_{mode}.npz"),
+            mode=mode, process_num=pn,
+            bboxs=torch.cat(rec["bboxs"]).numpy(), bboxs_feat=torch.cat(rec["bboxs_feat"]).numpy(),
+            depth_sha=O.sha256_f32(dn), depth_sub=dn[::SUB, ::SUB].copy(), depth_shape=np.array(dn.shape),
+            count_sha=O.sha256_f32(cnt), count_sub=cnt[::SUB, ::SUB].copy())
+        print("geom", ph, pw, mode, dn.shape, float(dn.min()), float(dn.max()))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    tiny()
+    geom(448, 448)
+    geom(384, 512)
