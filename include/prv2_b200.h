@@ -1,0 +1,225 @@
+/* prv2_b200.h -- C ABI of the B200-native (sm_100a) PatchRefinerV2 inference hot path.
+ *
+ * The reference (zhyever/PatchRefinerV2) is pure Python: its "FFI" for this path is the set of
+ * PyTorch / torchvision / OpenCV calls made inside the estimator model's infer forward.  Each
+ * entry point below replaces one such call site; the citation is the reference file:line whose
+ * arithmetic the kernel reproduces.  All pointers are DEVICE pointers unless stated; all sizes are
+ * explicit; nothing allocates; every function is asynchronous on `stream` and returns 0 on
+ * success or a negative PRV2_E* code (prv2_last_error() gives the message).  No torch types.
+ *
+ * Activation tensors ("act") are channels-last bf16, optionally as a (hi, lo) pair of bf16 planes
+ * whose sum carries ~16 mantissa bits ("x3" precision mode; lo == NULL selects plain bf16).
+ */
+#ifndef PRV2_B200_H_
+#define PRV2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* prv2_stream_t;           /* cudaStream_t */
+typedef uint16_t prv2_bf16;            /* raw bfloat16 bits */
+
+#define PRV2_OK 0
+#define PRV2_EINVAL (-1)               /* bad argument */
+#define PRV2_ECUDA (-2)                /* CUDA runtime / driver error */
+#define PRV2_EUNSUPPORTED (-3)         /* shape outside what the kernels implement */
+
+int prv2_version(void);
+const char* prv2_last_error(void);
+/* Device properties the host uses for grid sizing: out[0]=SM count, out[1]=cc major, out[2]=cc minor,
+ * out[3]=max dynamic smem per block (opt-in).  Host pointer. */
+int prv2_device_info(int32_t* out4);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) geometry: crop + resize, ROI gather            [HBM-bound gathers]
+ * ------------------------------------------------------------------------------------------ */
+
+/* baseline_pretrain.py:272-280 (regular_tile) / :167-175 (random_tile) + external/depth_anything/
+ * transform.py:127-129: out[p] = bilinear(align_corners=True)(image[:, y0:y1, x0:x1]) -> [ph,pw].
+ * image [3,H,W] fp32; bboxs [P,4] int32 rows (x0,y0,x1,y1); out [P,3,ph,pw] fp32.  Bit-exact with
+ * ATen's CPU kernel (fma(lx0,a,lx1*b) ordering). */
+int prv2_crop_resize(const float* image, int H, int W, const int32_t* bboxs, int P,
+                     float* out, int ph, int pw, prv2_stream_t stream);
+
+/* patchrefiner.py:199-217 -> torchvision.ops.roi_align(feat.repeat(P), rois, (h,w), h/ph,
+ * aligned=True) in the one-sample-per-bin regime.  feat is ONE channels-last map [h,w,C] (no
+ * repeat is materialised); rois [P,4] fp32 rows (x1,y1,x2,y2) = bboxs_feat[:,1:]; out [P,h,w,C].
+ * f32 variant: bit-exact with torchvision's CPU kernel (no FMA contraction). */
+int prv2_roi_gather_f32(const float* feat, int h, int w, int C, const float* rois, int P,
+                        float spatial_scale, float* out, prv2_stream_t stream);
+/* act variant: in/out are bf16 (hi[,lo]) planes with channel pitch in_cs / out_cs (elements). */
+int prv2_roi_gather_act(const prv2_bf16* feat_hi, const prv2_bf16* feat_lo, int h, int w, int C, int in_cs,
+                        const float* rois, int P, float spatial_scale,
+                        prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) consistency-aware-inference blend               [HBM-bound, fused]
+ * ------------------------------------------------------------------------------------------ */
+
+/* One regular-grid stage of the process-resolution canvas (baseline_pretrain.py:249-270). */
+typedef struct {
+  int32_t off_h, off_w;      /* canvas offset of patch (0,0) of this stage           */
+  int32_t n_h, n_w;          /* patches per column / row                              */
+  int32_t first;             /* index of the stage's first patch in `preds`           */
+} prv2_grid_stage;
+
+/* Sequential-exact canvas blend: RunningAverageMap.__init__/update (estimator/models/utils.py:
+ * 24-36) applied in the reference's patch order (baseline_pretrain.py:347-373): stage 0 assigns
+ * (pred, mask); stages 1..n_stages-1 update where mask>0.  preds [n_patches,ph,pw] fp32 in
+ * reference order; mask [ph,pw]; avg,cnt [Hc,Wc] outputs (cnt may be NULL).  Bit-exact. */
+int prv2_blend_canvas(const float* preds, const float* mask, int ph, int pw,
+                      const prv2_grid_stage* stages /*host*/, int n_stages, int Hc, int Wc,
+                      float* avg, float* cnt, prv2_stream_t stream);
+
+/* rN stage (patchrefiner.py:385-392; utils.py:38-43; baseline_pretrain.py:204-229): A0 =
+ * nearest(avg_c), C0 = bilinear_ac(cnt_c) to [H,W], then every random patch k (draw order) with
+ * raw bbox origin (y0,x0) in `starts` [n,2] int32 (device), prediction preds[k] [ph,pw] nearest-
+ * resized to [rh,rw], weight rmask [rh,rw] (already +1e-3): sequential update.  out/out_cnt [H,W]
+ * (out_cnt may be NULL).  n may be 0 (pure resize). */
+int prv2_blend_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc,
+                   const float* preds, const int32_t* starts, int n, int ph, int pw,
+                   const float* rmask, int rh, int rw, int H, int W,
+                   float* out, float* out_cnt, prv2_stream_t stream);
+
+/* Patch-sharded form (multi-GPU): each rank adds ITS patches into packed partial
+ * sums, one NCCL sum-reduce combines them, `finalize` normalises.  own[k]!=0 marks patches this
+ * rank owns (device uint8).  num_c [Hc,Wc] += mask*pred for stages>=1; m1 [Hc,Wc] = pred for
+ * stage 0 (disjoint); num_r [H,W] += rmask*nearest(pred) for random patches. */
+int prv2_blend_partial_canvas(const float* preds, const uint8_t* own, const float* mask, int ph, int pw,
+                              const prv2_grid_stage* stages /*host*/, int n_stages, int Hc, int Wc,
+                              float* num_c, float* m1, prv2_stream_t stream);
+int prv2_blend_partial_raw(const float* preds, const uint8_t* own, const int32_t* starts, int n, int ph, int pw,
+                           const float* rmask, int rh, int rw, int H, int W,
+                           float* num_r, prv2_stream_t stream);
+/* avg = cnt>cnt0 ? (m1*cnt0 + num_c)/cnt : m1, cnt recomputed locally in reference order. */
+int prv2_blend_finalize_canvas(const float* num_c, const float* m1, const float* mask, int ph, int pw,
+                               const prv2_grid_stage* stages /*host*/, int n_stages, int Hc, int Wc,
+                               float* avg, float* cnt, prv2_stream_t stream);
+/* out = (A0*C0 + num_r)/(C0 + cnt_r) with cnt_r recomputed locally in draw order. */
+int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* num_r,
+                            const int32_t* starts, int n, const float* rmask, int rh, int rw, int H, int W,
+                            float* out, float* out_cnt, prv2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) per-patch network: tcgen05 implicit-GEMM (linear layers AND convolutions)
+ * ------------------------------------------------------------------------------------------ */
+
+#define PRV2_MAX_SRC 12
+#define PRV2_MAX_SEG 128
+
+/* One channels-last bf16 source tensor [N,H,W,C] with channel pitch cs (elements, multiple of 8). */
+typedef struct {
+  const prv2_bf16* ptr;
+  int32_t C;                 /* channels used from this source (K extent)             */
+  int32_t cs;                /* channel pitch of the allocation                        */
+} prv2_src;
+
+/* One K-segment: all channels of source `src` seen through spatial offset (dh,dw).  The packed
+ * weight matrix holds the segments back to back, each padded to a multiple of 64 columns. */
+typedef struct {
+  int16_t src, dh, dw, pad_;
+} prv2_seg;
+
+#define PRV2_ACT_NONE 0
+#define PRV2_ACT_RELU 1
+#define PRV2_ACT_GELU 2       /* exact erf GELU (torch.nn.GELU default)                 */
+
+#define PRV2_EPI_STORE 0      /* act(acc+bias) [+ residual act] -> out (and optional relu copy) */
+#define PRV2_EPI_LN_GELU 1    /* channels-first LayerNorm over Cout then GELU (convs.py:21-29,64-75) */
+#define PRV2_EPI_RESID_F32 2  /* x_f32[m,n] += gamma[n]*(acc+bias[n])  (block.py:105-106, layer_scale.py:27) */
+#define PRV2_EPI_F32 3        /* out_f32[m,n] = acc+bias                                 */
+#define PRV2_EPI_SHUFFLE 4    /* ConvTranspose2d k==stride: n=(ky,kx,co) scattered to [N,H*k,W*k,Cout] (dpt.py:62-73) */
+#define PRV2_EPI_HEAD 5       /* relu(acc+bias) . w2 + b2 -> sigmoid * max_depth -> f32 (dpt.py:109-114,190) */
+
+typedef struct {
+  /* problem: D[m, n] = sum_seg sum_c A_src[n_img, h+dh, w+dw, c] * Wt[n, kcol] */
+  int32_t N, H, W;           /* output pixel grid (== input grid; stride-2 convs are fed phase-split sources) */
+  int32_t Cout;              /* real output channels                                   */
+  int32_t tile_w, tile_h;    /* spatial shape of the 128-pixel M tile (tile_w*tile_h==128) */
+  int32_t block_n;           /* UMMA N (multiple of 16, <=256)                          */
+  int32_t n_src, n_seg;
+  prv2_src src[PRV2_MAX_SRC];
+  prv2_seg seg[PRV2_MAX_SEG];
+  const prv2_bf16* weight;   /* [Cout_pad, Ktot] bf16, K-major; Ktot = sum_seg ceil64(C) */
+  int32_t Cout_pad, Ktot;
+  /* epilogue */
+  int32_t epi, act;
+  const float* bias;         /* [Cout] or NULL                                          */
+  const float* gamma;        /* LN weight / LayerScale gamma / head w2                   */
+  const float* beta;         /* LN bias / head b2 (1 element)                            */
+  float eps, head_scale;
+  prv2_bf16* out_hi; prv2_bf16* out_lo; int32_t out_cs;       /* main act output         */
+  prv2_bf16* relu_hi; prv2_bf16* relu_lo; int32_t relu_cs;    /* optional relu(out) copy */
+  const prv2_bf16* res_hi; const prv2_bf16* res_lo; int32_t res_cs;  /* optional residual act */
+  const prv2_bf16* res2_hi; const prv2_bf16* res2_lo; int32_t res2_cs;
+  float* out_f32; int32_t out_f32_ld;                          /* RESID_F32 / F32 / HEAD  */
+  int32_t shuffle_k;         /* EPI_SHUFFLE: kernel==stride                              */
+  int32_t row_map_period, row_map_extra, row_map_offset;       /* out row = m + (m/period)*extra + offset (0 period = identity) */
+} prv2_gemm_desc;
+
+/* attention.py:44-46 / mlp.py:30-32 (nn.Linear), patch_embed.py:69-82, dpt.py:48-80,116-150,
+ * util/blocks.py:57-80,123-148, fusion_model.py:84-122, convs.py:31-75: every dense contraction
+ * on the path, as one persistent TMA + tcgen05.mma (TMEM accumulator) kernel.  Host pointer. */
+int prv2_umma_gemm(const prv2_gemm_desc* desc, prv2_stream_t stream);
+
+/* attention.py:49-62: softmax(q k^T / sqrt(64)) v, all heads; qkv [B, T, 3*D] act (hi[,lo]),
+ * out [B, T, D] act.  head_dim is 64 for every DINOv2 size. */
+int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, int B, int T, int heads,
+                   prv2_bf16* out_hi, prv2_bf16* out_lo, prv2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) per-patch network: hand-written pointwise / normalisation / resampling kernels
+ * ------------------------------------------------------------------------------------------ */
+
+/* nn.LayerNorm(eps) over the last dim of an fp32 matrix x [rows, D] -> act.  If drop_period>0 the
+ * first row of every `drop_period` rows (the class token, dinov2.py:311) is skipped and the output
+ * is compacted (block.py:56,68; dinov2.py:309-312). */
+int prv2_layernorm(const float* x, int rows, int D, const float* w, const float* b, float eps,
+                   int drop_period, prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
+
+/* dpt.py:183 + patch_embed.py:69-82 im2col: crops [B,3,H,W] fp32 in [0,1] -> (x-mean)/std ->
+ * rows (b,ty,tx), cols c*196+ky*14+kx, zero padded to Kp columns. */
+int prv2_patchify(const float* crops, int B, int H, int W, prv2_bf16* out_hi, prv2_bf16* out_lo, int Kp,
+                  prv2_stream_t stream);
+
+/* dinov2.py:218-219: x[b,0]=cls+pos[0]; x[b,1+t]=emb[b,t]+pos[1+t].  pos is the already
+ * interpolated table [T+1, D]. */
+int prv2_assemble_tokens(const float* emb, const float* cls, const float* pos, int B, int T, int D,
+                         float* x, prv2_stream_t stream);
+
+/* F.interpolate(bilinear, align_corners=True) on channels-last act tensors
+ * (util/blocks.py:144, dpt.py:146, fusion_model.py:16). relu!=0 applies ReLU after. */
+int prv2_resize_bilinear_act(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int h, int w, int C, int in_cs,
+                             prv2_bf16* out_hi, prv2_bf16* out_lo, int oh, int ow, int out_cs, int relu,
+                             prv2_stream_t stream);
+
+/* fusion_model.py:94-96,16-17: the two depth maps [N,1,H,W] fp32 resized (bilinear ac) to [oh,ow]
+ * and written into channel slots c0, c0+1 of a channels-last act tensor; the following
+ * `zero_pad` channels are zero-filled. */
+int prv2_depth_slots(const float* pred1, const float* pred2, int N, int H, int W,
+                     prv2_bf16* out_hi, prv2_bf16* out_lo, int oh, int ow, int out_cs, int c0, int zero_pad,
+                     prv2_stream_t stream);
+
+/* fusion_model.py:113-118: offset = conv3x3(feat, w[1,C,3,3], no bias); out = clamp(base+offset, 0)
+ * (base may be NULL -> offset only).  feat act [N,H,W,C]; w fp32 [9,C] (tap-major); out fp32 [N,H,W]. */
+int prv2_final_conv(const prv2_bf16* feat_hi, const prv2_bf16* feat_lo, int N, int H, int W, int C, int cs,
+                    const float* w, const float* base, float* out, prv2_stream_t stream);
+
+/* act <-> fp32 helpers (layout changes at the API edge and for tests). */
+int prv2_nchw_f32_to_act(const float* in, int N, int C, int H, int W,
+                         prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
+int prv2_act_to_nchw_f32(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int C, int H, int W, int in_cs,
+                         float* out, prv2_stream_t stream);
+/* 2x2 space-to-depth phase split for the stride-2 conv (dpt.py:75-80): out[p] [N,H/2,W/2,C], p=(py,px). */
+int prv2_phase_split(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int H, int W, int C, int in_cs,
+                     prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
+/* fp32 [rows, cols] -> bf16 hi[,lo] with pitch (weights packing helper). */
+int prv2_split_f32(const float* in, int64_t n, prv2_bf16* hi, prv2_bf16* lo, prv2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PRV2_B200_H_ */

@@ -1,0 +1,303 @@
+// Fused multi-head attention for the DINOv2 blocks (attention.py:49-62): softmax(q k^T / 8) v with
+// head_dim 64, on tcgen05.  One CTA = 128 query rows of one (image, head).  Per 128-key chunk:
+//   S = Q K^T      tcgen05.mma  (A = Q tile, B = K tile, both K-major SW128 straight from TMA)
+//   online softmax 128 threads, thread t owns query row t = TMEM lane t (no shuffles)
+//   O_c = P V      tcgen05.mma  (A = P written to smem as bf16 in the SW128 K-major layout,
+//                                B = V tile as MN-major operand: rows are keys, as TMA delivers it)
+//   acc = acc * alpha + O_c   in registers (fp32)
+// The 1025-token sequence is 9 chunks; keys >= T are masked.  X3 = (hi,lo) operand splitting for
+// the fp32-class precision mode (3 MMAs per product).
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+using namespace prv2;
+
+namespace {
+
+constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB: 128 rows x 64 bf16
+constexpr uint64_t SPIN_LIMIT_NS = 4000000000ull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 0x3fff) == 0 && globaltimer_ns() - t0 > SPIN_LIMIT_NS) {
+      printf("prv2_attention: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(adesc),
+               "l"(bdesc), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// both operand layouts use 128-byte rows, 8-row groups 1024 B apart, SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+struct alignas(64) AttnParams {
+  CUtensorMap tm_hi, tm_lo;
+  bf16* out_hi; bf16* out_lo;
+  int B, T, heads, D;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  // tiles: Q, K, V, P0, P1 [, Ql, Kl, Vl, Pl0, Pl1]
+  const uint32_t sQ = base, sK = base + TILE_BYTES, sV = base + 2 * TILE_BYTES, sP = base + 3 * TILE_BYTES;
+  const uint32_t sQl = base + 5 * TILE_BYTES, sKl = base + 6 * TILE_BYTES, sVl = base + 7 * TILE_BYTES, sPl = base + 8 * TILE_BYTES;
+  const uint32_t bars = base + (X3 ? 10 : 5) * TILE_BYTES;
+  const uint32_t bar_q = bars, bar_kv = bars + 8, bar_s = bars + 16, bar_o = bars + 24, tmem_slot = bars + 32;
+  uint8_t* pP = base_ptr + 3 * TILE_BYTES;
+  uint8_t* pPl = base_ptr + 8 * TILE_BYTES;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int D = p.D;
+  const int n_chunks = (p.T + 127) / 128;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+
+  const uint32_t kv_bytes = (X3 ? 4 : 2) * TILE_BYTES;
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, (X3 ? 2 : 1) * TILE_BYTES);
+    tma_load_3d(sQ, &p.tm_hi, bar_q, head * 64, q0, b);
+    if (X3) tma_load_3d(sQl, &p.tm_lo, bar_q, head * 64, q0, b);
+    mbar_expect_tx(bar_kv, kv_bytes);
+    tma_load_3d(sK, &p.tm_hi, bar_kv, D + head * 64, 0, b);
+    tma_load_3d(sV, &p.tm_hi, bar_kv, 2 * D + head * 64, 0, b);
+    if (X3) {
+      tma_load_3d(sKl, &p.tm_lo, bar_kv, D + head * 64, 0, b);
+      tma_load_3d(sVl, &p.tm_lo, bar_kv, 2 * D + head * 64, 0, b);
+    }
+  }
+  // instruction descriptors: c=F32, a=b=BF16, M=128; S: N=128 both K-major; PV: N=64, B MN-major (bit 16)
+  const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+  const float c_log2 = 0.125f * 1.4426950408889634f;    // head_dim^-0.5 * log2(e)   (attention.py:41)
+
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  mbar_wait(bar_q, 0);
+  for (int j = 0; j < n_chunks; ++j) {
+    const uint32_t ph = j & 1;
+    mbar_wait(bar_kv, ph);
+    if (tid == 0) {
+      tc_fence_after();
+      uint32_t accum = 0;
+      for (int k = 0; k < 4; ++k) { tc_mma_bf16(tS, umma_desc_sw128(sQ) + 2 * k, umma_desc_sw128(sK) + 2 * k, idesc_s, accum); accum = 1; }
+      if (X3) {
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tS, umma_desc_sw128(sQ) + 2 * k, umma_desc_sw128(sKl) + 2 * k, idesc_s, 1);
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tS, umma_desc_sw128(sQl) + 2 * k, umma_desc_sw128(sK) + 2 * k, idesc_s, 1);
+      }
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    const int key0 = j * 128;
+    const int n_valid = min(128, p.T - key0);
+    float v[32];
+    // pass 1: row max over this chunk
+    float m_new = m_run;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      tc_ld32(tS + lane_off + c * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (c * 32 + i < n_valid) m_new = fmaxf(m_new, v[i]);
+    }
+    const float alpha = exp2f((m_run - m_new) * c_log2);
+    // pass 2: p = exp2((s - m) * c), write P (bf16) to smem in the SW128 K-major layout
+    float l_add = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      tc_ld32(tS + lane_off + c * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float pv = (c * 32 + i < n_valid) ? exp2f((v[i] - m_new) * c_log2) : 0.f;
+        v[i] = pv;
+        l_add += pv;
+      }
+      // keys c*32 .. c*32+31 of row tid: tile (c>>1), 16-byte chunks ((c&1)*4 + g), g = 0..3
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int chunk = (c & 1) * 4 + g;
+        const uint32_t off = (uint32_t)(c >> 1) * TILE_BYTES + tid * 128 + ((chunk ^ (tid & 7)) << 4);
+        bf16x8 hi8, lo8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          hi8.v[e] = f2bf(v[g * 8 + e]);
+          if (X3) lo8.v[e] = f2bf(v[g * 8 + e] - bf2f(hi8.v[e]));
+        }
+        *reinterpret_cast<bf16x8*>(pP + off) = hi8;
+        if (X3) *reinterpret_cast<bf16x8*>(pPl + off) = lo8;
+      }
+    }
+    l_run = l_run * alpha + l_add;
+    m_run = m_new;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      uint32_t accum = 0;
+      for (int k = 0; k < 8; ++k) {      // 8 slices of 16 keys: A advances 32 B inside tile (k>>2), B advances 16 rows (2048 B)
+        const uint64_t ad = umma_desc_sw128(sP + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
+        tc_mma_bf16(tO, ad, umma_desc_sw128(sV + k * 2048), idesc_o, accum);
+        accum = 1;
+        if (X3) {
+          tc_mma_bf16(tO, ad, umma_desc_sw128(sVl + k * 2048), idesc_o, 1);
+          tc_mma_bf16(tO, umma_desc_sw128(sPl + (k >> 2) * TILE_BYTES) + 2 * (k & 3), umma_desc_sw128(sV + k * 2048), idesc_o, 1);
+        }
+      }
+      tc_commit(bar_o);
+    }
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < n_chunks) {       // K/V/P buffers are free again: prefetch the next chunk under the accumulate
+      mbar_expect_tx(bar_kv, kv_bytes);
+      tma_load_3d(sK, &p.tm_hi, bar_kv, D + head * 64, key0 + 128, b);
+      tma_load_3d(sV, &p.tm_hi, bar_kv, 2 * D + head * 64, key0 + 128, b);
+      if (X3) {
+        tma_load_3d(sKl, &p.tm_lo, bar_kv, D + head * 64, key0 + 128, b);
+        tma_load_3d(sVl, &p.tm_lo, bar_kv, 2 * D + head * 64, key0 + 128, b);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tc_ld32(tO + lane_off + c * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * alpha + v[i];
+    }
+  }
+  const int q = q0 + tid;
+  if (q < p.T) {
+    const float inv = 1.0f / l_run;
+    const size_t o = ((size_t)b * p.T + q) * D + head * 64;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float t[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = acc[g * 8 + e] * inv;
+      act_store8(p.out_hi, X3 ? p.out_lo : nullptr, o + g * 8, t);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+  }
+  return fn;
+}
+
+bool g_attr_set = false;
+
+}  // namespace
+
+extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, int B, int T, int heads, prv2_bf16* out_hi, prv2_bf16* out_lo,
+                              prv2_stream_t stream) {
+  PRV2_CHECK_ARG(qkv_hi && out_hi, "prv2_attention: null pointer");
+  PRV2_CHECK_ARG((qkv_lo == nullptr) == (out_lo == nullptr), "prv2_attention: lo planes must both be present or absent");
+  PRV2_CHECK_ARG(B > 0 && T > 0 && heads > 0 && heads <= 65535 && B <= 65535, "prv2_attention: bad shape");
+  auto enc = get_encode();
+  if (!enc) { set_error("prv2_attention: cuTensorMapEncodeTiled unavailable"); return PRV2_ECUDA; }
+  const int D = heads * 64;
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  cuuint64_t dims[3] = {(cuuint64_t)3 * D, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)3 * D * 2, (cuuint64_t)T * 3 * D * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&p.tm_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)qkv_hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("prv2_attention: cuTensorMapEncodeTiled failed (%d)", (int)r); return PRV2_ECUDA; }
+  p.tm_lo = p.tm_hi;
+  if (qkv_lo) {
+    r = enc(&p.tm_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)qkv_lo, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("prv2_attention: cuTensorMapEncodeTiled(lo) failed (%d)", (int)r); return PRV2_ECUDA; }
+  }
+  p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
+  p.B = B; p.T = T; p.heads = heads; p.D = D;
+  const int smem1 = 5 * TILE_BYTES + 1024 + 64, smem3 = 10 * TILE_BYTES + 1024 + 64;
+  if (!g_attr_set) {
+    PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    g_attr_set = true;
+  }
+  dim3 grid(cdiv(T, 128), heads, B);
+  if (qkv_lo) attention_kernel<true><<<grid, 128, smem3, (cudaStream_t)stream>>>(p);
+  else attention_kernel<false><<<grid, 128, smem1, (cudaStream_t)stream>>>(p);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}

@@ -1,0 +1,461 @@
+// Geometry kernels of the tiled-inference path: crop+resize, ROI gather, CAI blend.
+// All HBM-bound gathers: one thread owns an output vector, reads are coalesced along the
+// fastest output dimension, index math is replayed in fp32 exactly as the reference's
+// CPU kernels do it (see oracle/pr_oracle.py np_* for the pinned restatements).
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace prv2 {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace prv2
+
+using namespace prv2;
+
+extern "C" int prv2_version(void) { return 100; }
+extern "C" const char* prv2_last_error(void) { return g_err; }
+extern "C" int prv2_device_info(int32_t* out4) {
+  PRV2_CHECK_ARG(out4 != nullptr, "prv2_device_info: null out");
+  int dev = 0;
+  PRV2_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  PRV2_CUDA(cudaGetDeviceProperties(&p, dev));
+  out4[0] = p.multiProcessorCount;
+  out4[1] = p.major;
+  out4[2] = p.minor;
+  out4[3] = (int32_t)p.sharedMemPerBlockOptin;
+  return PRV2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// crop + bilinear(align_corners=True) resize            baseline_pretrain.py:272-280
+// ---------------------------------------------------------------------------------------------
+// grid: (ceil(pw/4/128), ph, P*3); each thread writes 4 consecutive x (one float4).
+__global__ void __launch_bounds__(128) crop_resize_kernel(const float* __restrict__ image, int H, int W,
+                                                          const int32_t* __restrict__ bboxs, float* __restrict__ out,
+                                                          int ph, int pw) {
+  const int p = blockIdx.z / 3, c = blockIdx.z % 3;
+  const int y = blockIdx.y;
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x4 >= pw) return;
+  const int bx0 = bboxs[p * 4 + 0], by0 = bboxs[p * 4 + 1], bx1 = bboxs[p * 4 + 2], by1 = bboxs[p * 4 + 3];
+  const int rw = bx1 - bx0, rh = by1 - by0;
+  const float sy = ac_scale(rh, ph), sx = ac_scale(rw, pw);
+  const BilinearTap ty = ac_tap(sy, y, rh);
+  const float* r0 = image + ((size_t)c * H + (by0 + ty.i0)) * W + bx0;
+  const float* r1 = image + ((size_t)c * H + (by0 + ty.i1)) * W + bx0;
+  float v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x4 + k;
+    if (x < pw) {
+      const BilinearTap tx = ac_tap(sx, x, rw);
+      v[k] = ac_blend(ty, tx, __ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1));
+    } else {
+      v[k] = 0.f;
+    }
+  }
+  float* o = out + (((size_t)p * 3 + c) * ph + y) * pw + x4;
+  if (x4 + 3 < pw && (pw & 3) == 0) {
+    *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    for (int k = 0; k < 4 && x4 + k < pw; ++k) o[k] = v[k];
+  }
+}
+
+extern "C" int prv2_crop_resize(const float* image, int H, int W, const int32_t* bboxs, int P, float* out, int ph, int pw,
+                                prv2_stream_t stream) {
+  PRV2_CHECK_ARG(image && bboxs && out, "prv2_crop_resize: null pointer");
+  PRV2_CHECK_ARG(H > 0 && W > 0 && ph > 0 && pw > 0 && P >= 0, "prv2_crop_resize: bad shape");
+  if (P == 0) return PRV2_OK;
+  PRV2_CHECK_ARG(P * 3 <= 65535 && ph <= 65535, "prv2_crop_resize: too many patches for one launch (%d)", P);
+  dim3 grid(cdiv(cdiv(pw, 4), 128), ph, P * 3);
+  crop_resize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(image, H, W, bboxs, out, ph, pw);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ROI gather (roi_align, aligned=True, one sample per bin)      patchrefiner.py:199-217
+// ---------------------------------------------------------------------------------------------
+struct RoiAxis { int lo, hi; float l, h; bool valid; };
+
+// torchvision/csrc/ops/cpu/roi_align_common.h pre_calc_for_bilinear_interpolate, fp32, grid==1.
+__device__ __forceinline__ RoiAxis roi_axis(float start, float bin, int p, int n_in) {
+  RoiAxis a;
+  float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)), __fdiv_rn(__fmul_rn(0.5f, bin), 1.0f));
+  a.valid = !(c < -1.0f || c > (float)n_in);
+  c = fmaxf(c, 0.0f);
+  int lo = (int)c;
+  if (lo >= n_in - 1) {
+    lo = n_in - 1;
+    a.hi = lo;
+    c = (float)lo;
+  } else {
+    a.hi = lo + 1;
+  }
+  a.lo = lo;
+  a.l = __fsub_rn(c, (float)lo);
+  a.h = __fsub_rn(1.0f, a.l);
+  return a;
+}
+
+struct RoiGeom { float x1, y1, bw, bh; };
+__device__ __forceinline__ RoiGeom roi_geom(const float* roi, float s, int h, int w) {
+  RoiGeom g;
+  g.x1 = __fsub_rn(__fmul_rn(roi[0], s), 0.5f);
+  g.y1 = __fsub_rn(__fmul_rn(roi[1], s), 0.5f);
+  float x2 = __fsub_rn(__fmul_rn(roi[2], s), 0.5f);
+  float y2 = __fsub_rn(__fmul_rn(roi[3], s), 0.5f);
+  g.bw = __fdiv_rn(__fsub_rn(x2, g.x1), (float)w);
+  g.bh = __fdiv_rn(__fsub_rn(y2, g.y1), (float)h);
+  return g;
+}
+
+__device__ __forceinline__ float roi_mix(const RoiAxis& ay, const RoiAxis& ax, float v1, float v2, float v3, float v4) {
+  // w1*v1 + w2*v2 + w3*v3 + w4*v4, left to right, no contraction (torchvision CPU build)
+  float w1 = __fmul_rn(ay.h, ax.h), w2 = __fmul_rn(ay.h, ax.l), w3 = __fmul_rn(ay.l, ax.h), w4 = __fmul_rn(ay.l, ax.l);
+  float o = __fmul_rn(w1, v1);
+  o = __fadd_rn(o, __fmul_rn(w2, v2));
+  o = __fadd_rn(o, __fmul_rn(w3, v3));
+  o = __fadd_rn(o, __fmul_rn(w4, v4));
+  return o;
+}
+
+// one thread = one output pixel x 4 channels (float4), channels fastest -> coalesced both ways
+__global__ void __launch_bounds__(256) roi_gather_f32_kernel(const float* __restrict__ feat, int h, int w, int C,
+                                                             const float* __restrict__ rois, float s,
+                                                             float* __restrict__ out, long long total) {
+  const int cv = (C + 3) / 4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % cv) * 4;
+    long long pix = idx / cv;
+    const int x = (int)(pix % w);
+    pix /= w;
+    const int y = (int)(pix % h);
+    const int p = (int)(pix / h);
+    const RoiGeom g = roi_geom(rois + p * 4, s, h, w);
+    const RoiAxis ay = roi_axis(g.y1, g.bh, y, h), ax = roi_axis(g.x1, g.bw, x, w);
+    const bool valid = ay.valid && ax.valid;
+    const float* f1 = feat + ((size_t)ay.lo * w + ax.lo) * C + c4;
+    const float* f2 = feat + ((size_t)ay.lo * w + ax.hi) * C + c4;
+    const float* f3 = feat + ((size_t)ay.hi * w + ax.lo) * C + c4;
+    const float* f4 = feat + ((size_t)ay.hi * w + ax.hi) * C + c4;
+    float* o = out + (((size_t)p * h + y) * w + x) * C + c4;
+    for (int k = 0; k < 4 && c4 + k < C; ++k) o[k] = valid ? roi_mix(ay, ax, f1[k], f2[k], f3[k], f4[k]) : 0.f;
+  }
+}
+
+// one thread = one output pixel x 8 channels (16 B of bf16)
+__global__ void __launch_bounds__(256) roi_gather_act_kernel(const bf16* __restrict__ fh, const bf16* __restrict__ fl, int h, int w,
+                                                             int C, int in_cs, const float* __restrict__ rois, float s,
+                                                             bf16* __restrict__ oh, bf16* __restrict__ ol, int out_cs,
+                                                             long long total) {
+  const int cv = C / 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv) * 8;
+    long long pix = idx / cv;
+    const int x = (int)(pix % w);
+    pix /= w;
+    const int y = (int)(pix % h);
+    const int p = (int)(pix / h);
+    const RoiGeom g = roi_geom(rois + p * 4, s, h, w);
+    const RoiAxis ay = roi_axis(g.y1, g.bh, y, h), ax = roi_axis(g.x1, g.bw, x, w);
+    const bool valid = ay.valid && ax.valid;
+    float v1[8], v2[8], v3[8], v4[8], o[8];
+    act_load8(fh, fl, ((size_t)ay.lo * w + ax.lo) * in_cs + c8, v1);
+    act_load8(fh, fl, ((size_t)ay.lo * w + ax.hi) * in_cs + c8, v2);
+    act_load8(fh, fl, ((size_t)ay.hi * w + ax.lo) * in_cs + c8, v3);
+    act_load8(fh, fl, ((size_t)ay.hi * w + ax.hi) * in_cs + c8, v4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = valid ? roi_mix(ay, ax, v1[k], v2[k], v3[k], v4[k]) : 0.f;
+    act_store8(oh, ol, (((size_t)p * h + y) * w + x) * out_cs + c8, o);
+  }
+}
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;          // 16 resident 256-thread CTAs per SM, grid-stride beyond
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+extern "C" int prv2_roi_gather_f32(const float* feat, int h, int w, int C, const float* rois, int P, float spatial_scale, float* out,
+                                   prv2_stream_t stream) {
+  PRV2_CHECK_ARG(feat && rois && out, "prv2_roi_gather_f32: null pointer");
+  PRV2_CHECK_ARG(h > 0 && w > 0 && C > 0 && P >= 0, "prv2_roi_gather_f32: bad shape");
+  if (P == 0) return PRV2_OK;
+  long long total = (long long)P * h * w * ((C + 3) / 4);
+  roi_gather_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(feat, h, w, C, rois, spatial_scale, out, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_roi_gather_act(const prv2_bf16* feat_hi, const prv2_bf16* feat_lo, int h, int w, int C, int in_cs, const float* rois,
+                                   int P, float spatial_scale, prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(feat_hi && rois && out_hi, "prv2_roi_gather_act: null pointer");
+  PRV2_CHECK_ARG(h > 0 && w > 0 && C > 0 && P >= 0, "prv2_roi_gather_act: bad shape");
+  PRV2_CHECK_ARG(C % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0, "prv2_roi_gather_act: C/pitch must be multiples of 8");
+  if (P == 0) return PRV2_OK;
+  long long total = (long long)P * h * w * (C / 8);
+  roi_gather_act_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)feat_hi, (const bf16*)feat_lo, h, w, C, in_cs, rois, spatial_scale, (bf16*)out_hi, (bf16*)out_lo, out_cs, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CAI blend                                   estimator/models/utils.py:22-49
+// ---------------------------------------------------------------------------------------------
+#define PRV2_MAX_STAGES 8
+struct StageTable { int n; prv2_grid_stage s[PRV2_MAX_STAGES]; };
+
+// RunningAverageMap.update for one pixel, exactly as the tensor expression evaluates it:
+// avg = (pred*ct + cnt*avg) / (cnt + ct); cnt = cnt + ct      (all separately rounded)
+__device__ __forceinline__ void ram_update(float& avg, float& cnt, float pred, float ct) {
+  float num = __fadd_rn(__fmul_rn(pred, ct), __fmul_rn(cnt, avg));
+  float den = __fadd_rn(cnt, ct);
+  avg = __fdiv_rn(num, den);
+  cnt = den;
+}
+
+// Thread = 4 consecutive canvas pixels of one row (one float4 store per output plane).
+// MODE 0: sequential-exact; 1: partial sums (own patches only); 2: finalize from reduced sums.
+template <int MODE>
+__global__ void __launch_bounds__(256) blend_canvas_kernel(const float* __restrict__ preds, const uint8_t* __restrict__ own,
+                                                           const float* __restrict__ mask, int ph, int pw, StageTable st, int Hc,
+                                                           int Wc, float* __restrict__ avg_out, float* __restrict__ cnt_out,
+                                                           const float* __restrict__ num_in, const float* __restrict__ m1_in) {
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  if (x0 >= Wc) return;
+  float r_a[4], r_c[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x0 + k;
+    r_a[k] = 0.f; r_c[k] = 0.f;
+    if (x >= Wc) continue;
+    float avg = 0.f, cnt = 0.f, num = 0.f, m1 = 0.f, cnt0 = 0.f;
+    if (MODE == 2) { num = num_in[(size_t)y * Wc + x]; m1 = m1_in[(size_t)y * Wc + x]; }
+    for (int s = 0; s < st.n; ++s) {
+      const prv2_grid_stage g = st.s[s];
+      const int yy = y - g.off_h, xx = x - g.off_w;
+      if (yy < 0 || xx < 0) continue;
+      const int i = yy / ph, j = xx / pw;
+      if (i >= g.n_h || j >= g.n_w) continue;
+      const int ly = yy - i * ph, lx = xx - j * pw;
+      const int pidx = g.first + i * g.n_w + j;
+      const float ct = __ldg(mask + (size_t)ly * pw + lx);
+      if (MODE == 0) {
+        const float p = __ldg(preds + ((size_t)pidx * ph + ly) * pw + lx);
+        if (s == 0) { avg = p; cnt = ct; }                         // baseline_pretrain.py:352-355 (assignment)
+        else if (ct > 0.f) ram_update(avg, cnt, p, ct);            // utils.py:31-36
+      } else if (MODE == 1) {
+        if (own[pidx]) {
+          const float p = __ldg(preds + ((size_t)pidx * ph + ly) * pw + lx);
+          if (s == 0) m1 = p;
+          else if (ct > 0.f) num = __fadd_rn(num, __fmul_rn(p, ct));
+        }
+      } else {
+        if (s == 0) { cnt = ct; cnt0 = ct; }
+        else if (ct > 0.f) cnt = __fadd_rn(cnt, ct);
+      }
+    }
+    if (MODE == 0) { r_a[k] = avg; r_c[k] = cnt; }
+    else if (MODE == 1) { r_a[k] = num; r_c[k] = m1; }
+    else {
+      // sum form of the running mean: (m1*cnt0 + sum w p) / (cnt0 + sum w); untouched pixels keep m1
+      r_a[k] = (cnt > cnt0) ? __fdiv_rn(__fadd_rn(__fmul_rn(m1, cnt0), num), cnt) : m1;
+      r_c[k] = cnt;
+    }
+  }
+  const size_t o = (size_t)y * Wc + x0;
+  const bool vec = ((Wc & 3) == 0);
+  if (MODE == 1) {       // accumulate into num_c (avg_out) and the m1 plane (cnt_out)
+    for (int k = 0; k < 4 && x0 + k < Wc; ++k) { avg_out[o + k] += r_a[k]; cnt_out[o + k] += r_c[k]; }
+  } else if (vec) {
+    *reinterpret_cast<float4*>(avg_out + o) = make_float4(r_a[0], r_a[1], r_a[2], r_a[3]);
+    if (cnt_out) *reinterpret_cast<float4*>(cnt_out + o) = make_float4(r_c[0], r_c[1], r_c[2], r_c[3]);
+  } else {
+    for (int k = 0; k < 4 && x0 + k < Wc; ++k) { avg_out[o + k] = r_a[k]; if (cnt_out) cnt_out[o + k] = r_c[k]; }
+  }
+}
+
+static int fill_stages(StageTable& t, const prv2_grid_stage* stages, int n) {
+  if (!stages || n < 1 || n > PRV2_MAX_STAGES) return -1;
+  t.n = n;
+  for (int i = 0; i < n; ++i) t.s[i] = stages[i];
+  return 0;
+}
+
+extern "C" int prv2_blend_canvas(const float* preds, const float* mask, int ph, int pw, const prv2_grid_stage* stages, int n_stages,
+                                 int Hc, int Wc, float* avg, float* cnt, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(preds && mask && avg, "prv2_blend_canvas: null pointer");
+  StageTable t;
+  PRV2_CHECK_ARG(fill_stages(t, stages, n_stages) == 0, "prv2_blend_canvas: need 1..%d stages", PRV2_MAX_STAGES);
+  PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535, "prv2_blend_canvas: bad shape");
+  dim3 grid(cdiv(cdiv(Wc, 4), 256), Hc);
+  blend_canvas_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(preds, nullptr, mask, ph, pw, t, Hc, Wc, avg, cnt, nullptr, nullptr);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_blend_partial_canvas(const float* preds, const uint8_t* own, const float* mask, int ph, int pw,
+                                         const prv2_grid_stage* stages, int n_stages, int Hc, int Wc, float* num_c, float* m1,
+                                         prv2_stream_t stream) {
+  PRV2_CHECK_ARG(preds && own && mask && num_c && m1, "prv2_blend_partial_canvas: null pointer");
+  StageTable t;
+  PRV2_CHECK_ARG(fill_stages(t, stages, n_stages) == 0, "prv2_blend_partial_canvas: need 1..%d stages", PRV2_MAX_STAGES);
+  PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535, "prv2_blend_partial_canvas: bad shape");
+  dim3 grid(cdiv(cdiv(Wc, 4), 256), Hc);
+  blend_canvas_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(preds, own, mask, ph, pw, t, Hc, Wc, num_c, m1, nullptr, nullptr);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_blend_finalize_canvas(const float* num_c, const float* m1, const float* mask, int ph, int pw,
+                                          const prv2_grid_stage* stages, int n_stages, int Hc, int Wc, float* avg, float* cnt,
+                                          prv2_stream_t stream) {
+  PRV2_CHECK_ARG(num_c && m1 && mask && avg, "prv2_blend_finalize_canvas: null pointer");
+  StageTable t;
+  PRV2_CHECK_ARG(fill_stages(t, stages, n_stages) == 0, "prv2_blend_finalize_canvas: need 1..%d stages", PRV2_MAX_STAGES);
+  PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535, "prv2_blend_finalize_canvas: bad shape");
+  dim3 grid(cdiv(cdiv(Wc, 4), 256), Hc);
+  blend_canvas_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, mask, ph, pw, t, Hc, Wc, avg, cnt, num_c, m1);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+// rN stage.  Block = one raw row segment of 1024 pixels, thread = 4 consecutive pixels.  Warp 0
+// compacts the random-patch list to the patches covering this row (ballot, draw order kept);
+// every pixel then walks that short list in order.
+#define PRV2_MAX_RANDOM 512
+template <int MODE>
+__global__ void __launch_bounds__(256) blend_raw_kernel(const float* __restrict__ avg_c, const float* __restrict__ cnt_c, int Hc, int Wc,
+                                                        const float* __restrict__ preds, const uint8_t* __restrict__ own,
+                                                        const int32_t* __restrict__ starts, int n, int ph, int pw,
+                                                        const float* __restrict__ rmask, int rh, int rw, int H, int W,
+                                                        float* __restrict__ out, float* __restrict__ out_cnt,
+                                                        const float* __restrict__ num_in) {
+  __shared__ int s_k[PRV2_MAX_RANDOM], s_y0[PRV2_MAX_RANDOM], s_x0[PRV2_MAX_RANDOM];
+  __shared__ int s_n;
+  const int y = blockIdx.y;
+  if (threadIdx.x < 32) {
+    int m = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + threadIdx.x;
+      int y0 = 0, x0 = 0;
+      bool hit = false;
+      if (k < n) {
+        y0 = starts[k * 2 + 0]; x0 = starts[k * 2 + 1];
+        hit = (y >= y0 && y < y0 + rh) && (MODE != 1 || own[k]);
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      if (hit) { const int pos = m + __popc(b & ((1u << threadIdx.x) - 1)); s_k[pos] = k; s_y0[pos] = y0; s_x0[pos] = x0; }
+      m += __popc(b);
+    }
+    if (threadIdx.x == 0) s_n = m;
+  }
+  __syncthreads();
+  const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (xb >= W) return;
+  const int m = s_n;
+  const float ps_y = __fdiv_rn((float)ph, (float)rh), ps_x = __fdiv_rn((float)pw, (float)rw);
+  float r_a[4], r_c[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int x = xb + q;
+    r_a[q] = 0.f; r_c[q] = 0.f;
+    if (x >= W) continue;
+    const size_t o = (size_t)y * W + x;
+    float avg = 0.f, cnt = 0.f, num = 0.f, c0 = 0.f;
+    if (MODE != 1) {
+      // utils.py:42: average map -> nearest ; utils.py:43: count map -> bilinear(align_corners=True)
+      const float ns_y = __fdiv_rn((float)Hc, (float)H), ns_x = __fdiv_rn((float)Wc, (float)W);
+      const int sy = nearest_src(y, ns_y, Hc), sx = nearest_src(x, ns_x, Wc);
+      avg = __ldg(avg_c + (size_t)sy * Wc + sx);
+      const BilinearTap ty = ac_tap(ac_scale(Hc, H), y, Hc), tx = ac_tap(ac_scale(Wc, W), x, Wc);
+      cnt = ac_blend(ty, tx, __ldg(cnt_c + (size_t)ty.i0 * Wc + tx.i0), __ldg(cnt_c + (size_t)ty.i0 * Wc + tx.i1),
+                     __ldg(cnt_c + (size_t)ty.i1 * Wc + tx.i0), __ldg(cnt_c + (size_t)ty.i1 * Wc + tx.i1));
+      c0 = cnt;
+      if (MODE == 2) num = num_in[o];
+    }
+    for (int i = 0; i < m; ++i) {
+      const int x0 = s_x0[i];
+      if (x < x0 || x >= x0 + rw) continue;
+      const int ly = y - s_y0[i], lx = x - x0;
+      const float ct = __ldg(rmask + (size_t)ly * rw + lx);
+      if (!(ct > 0.f)) continue;
+      if (MODE == 2) { cnt = __fadd_rn(cnt, ct); continue; }
+      // baseline_pretrain.py:210 F.interpolate(predictions, patch_raw_shape) (nearest)
+      const int py = nearest_src(ly, ps_y, ph), px = nearest_src(lx, ps_x, pw);
+      const float p = __ldg(preds + ((size_t)s_k[i] * ph + py) * pw + px);
+      if (MODE == 0) ram_update(avg, cnt, p, ct);
+      else num = __fadd_rn(num, __fmul_rn(p, ct));
+    }
+    if (MODE == 0) { r_a[q] = avg; r_c[q] = cnt; }
+    else if (MODE == 1) { r_a[q] = num; }
+    else { r_a[q] = (cnt > c0) ? __fdiv_rn(__fadd_rn(__fmul_rn(avg, c0), num), cnt) : avg; r_c[q] = cnt; }
+  }
+  const size_t o = (size_t)y * W + xb;
+  if (MODE == 1) {
+    for (int q = 0; q < 4 && xb + q < W; ++q) out[o + q] += r_a[q];
+  } else if ((W & 3) == 0) {
+    *reinterpret_cast<float4*>(out + o) = make_float4(r_a[0], r_a[1], r_a[2], r_a[3]);
+    if (out_cnt) *reinterpret_cast<float4*>(out_cnt + o) = make_float4(r_c[0], r_c[1], r_c[2], r_c[3]);
+  } else {
+    for (int q = 0; q < 4 && xb + q < W; ++q) { out[o + q] = r_a[q]; if (out_cnt) out_cnt[o + q] = r_c[q]; }
+  }
+}
+
+static int check_raw(const char* fn, int n, int ph, int pw, int rh, int rw, int H, int W) {
+  if (!(n >= 0 && n <= PRV2_MAX_RANDOM)) { set_error("%s: 0 <= n <= %d required (got %d)", fn, PRV2_MAX_RANDOM, n); return PRV2_EINVAL; }
+  if (!(ph > 0 && pw > 0 && rh > 0 && rw > 0 && H > 0 && W > 0 && H <= 65535)) { set_error("%s: bad shape", fn); return PRV2_EINVAL; }
+  return PRV2_OK;
+}
+
+extern "C" int prv2_blend_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* preds, const int32_t* starts, int n,
+                              int ph, int pw, const float* rmask, int rh, int rw, int H, int W, float* out, float* out_cnt,
+                              prv2_stream_t stream) {
+  PRV2_CHECK_ARG(avg_c && cnt_c && out, "prv2_blend_raw: null pointer");
+  PRV2_CHECK_ARG(n == 0 || (preds && starts && rmask), "prv2_blend_raw: null patch inputs");
+  int rc = check_raw("prv2_blend_raw", n, ph, pw, rh, rw, H, W);
+  if (rc) return rc;
+  dim3 grid(cdiv(cdiv(W, 4), 256), H);
+  blend_raw_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(avg_c, cnt_c, Hc, Wc, preds, nullptr, starts, n, ph, pw, rmask, rh, rw, H, W,
+                                                              out, out_cnt, nullptr);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_blend_partial_raw(const float* preds, const uint8_t* own, const int32_t* starts, int n, int ph, int pw,
+                                      const float* rmask, int rh, int rw, int H, int W, float* num_r, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(preds && own && starts && rmask && num_r, "prv2_blend_partial_raw: null pointer");
+  int rc = check_raw("prv2_blend_partial_raw", n, ph, pw, rh, rw, H, W);
+  if (rc) return rc;
+  if (n == 0) return PRV2_OK;
+  dim3 grid(cdiv(cdiv(W, 4), 256), H);
+  blend_raw_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, 1, 1, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W,
+                                                              num_r, nullptr, nullptr);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* num_r, const int32_t* starts,
+                                       int n, const float* rmask, int rh, int rw, int H, int W, float* out, float* out_cnt,
+                                       prv2_stream_t stream) {
+  PRV2_CHECK_ARG(avg_c && cnt_c && num_r && out, "prv2_blend_finalize_raw: null pointer");
+  PRV2_CHECK_ARG(n == 0 || (starts && rmask), "prv2_blend_finalize_raw: null patch inputs");
+  int rc = check_raw("prv2_blend_finalize_raw", n, 1, 1, rh, rw, H, W);
+  if (rc) return rc;
+  dim3 grid(cdiv(cdiv(W, 4), 256), H);
+  blend_raw_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(avg_c, cnt_c, Hc, Wc, nullptr, nullptr, starts, n, 1, 1, rmask, rh, rw, H, W,
+                                                              out, out_cnt, num_r);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}

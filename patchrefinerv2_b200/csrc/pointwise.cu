@@ -1,0 +1,353 @@
+// Hand-written memory-bound kernels around the tcgen05 contractions: LayerNorm, patch-embed
+// im2col, token assembly, bilinear resampling, depth-channel injection, the Cout=1 final conv,
+// layout converters.  Activations are channels-last bf16 (hi[,lo]) so that a warp always touches
+// contiguous channels; every thread moves 16-byte vectors.
+#include "common.cuh"
+
+using namespace prv2;
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct alignas(8) bf16x4 { bf16 v[4]; };
+__device__ __forceinline__ void act_store4(bf16* hi, bf16* lo, size_t i, const float (&in)[4]) {
+  bf16x4 a;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a.v[k] = f2bf(in[k]);
+  *reinterpret_cast<bf16x4*>(hi + i) = a;
+  if (lo) {
+    bf16x4 b;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b.v[k] = f2bf(in[k] - bf2f(a.v[k]));
+    *reinterpret_cast<bf16x4*>(lo + i) = b;
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (block.py:56,68)
+// warp per row, row kept in registers (D <= 1024), two-pass mean / variance.
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int rows, int D, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float eps, int drop_period, bf16* __restrict__ oh,
+                                                        bf16* __restrict__ ol, int out_cs) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long orow = row;
+  if (drop_period > 0) {
+    if (row % drop_period == 0) return;                  // class token dropped (dinov2.py:311)
+    orow = row - row / drop_period - 1;
+  }
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  const int nv = D >> 7;                                 // float4 chunks per lane
+  float4 v[8];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) { v[j] = xr[j * 32 + lane]; sum += v[j].x + v[j].y + v[j].z + v[j].w; }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      const float a = v[j].x - mean, bb = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      sq += a * a + bb * bb + c * c + d * d;
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nv) {
+      const int c0 = (j * 32 + lane) * 4;
+      const float4 ww = *reinterpret_cast<const float4*>(w + c0), bb = *reinterpret_cast<const float4*>(b + c0);
+      float o[4] = {(v[j].x - mean) * rstd * ww.x + bb.x, (v[j].y - mean) * rstd * ww.y + bb.y, (v[j].z - mean) * rstd * ww.z + bb.z,
+                    (v[j].w - mean) * rstd * ww.w + bb.w};
+      act_store4(oh, ol, (size_t)orow * out_cs + c0, o);
+    }
+}
+
+// ------------------------------------------------- patch-embed im2col (patch_embed.py:69-82)
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ crops, int B, int H, int W, bf16* __restrict__ oh,
+                                                       bf16* __restrict__ ol, int Kp, long long total) {
+  const int gw = W / 14, gh = H / 14, groups = Kp / 8;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const long long row = idx / groups;
+    const int tx = (int)(row % gw), ty = (int)((row / gw) % gh), b = (int)(row / ((long long)gw * gh));
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int col = g * 8 + k;
+      if (col < 588) {
+        const int c = col / 196, r = col % 196, ky = r / 14, kx = r % 14;
+        const float px = __ldg(crops + (((size_t)b * 3 + c) * H + (ty * 14 + ky)) * W + tx * 14 + kx);
+        o[k] = (px - mean[c]) / stdv[c];               // dpt.py:183
+      } else {
+        o[k] = 0.f;
+      }
+    }
+    act_store8(oh, ol, (size_t)row * Kp + g * 8, o);
+  }
+}
+
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ emb, const float* __restrict__ cls,
+                                                              const float* __restrict__ pos, int B, int T, int D, float* __restrict__ x,
+                                                              long long total) {
+  const int dv = D / 4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int d4 = (int)(idx % dv) * 4;
+    const long long r = idx / dv;
+    const int t = (int)(r % (T + 1)), b = (int)(r / (T + 1));
+    const float4 a = (t == 0) ? *reinterpret_cast<const float4*>(cls + d4)
+                              : *reinterpret_cast<const float4*>(emb + ((size_t)b * T + (t - 1)) * D + d4);
+    const float4 pp = *reinterpret_cast<const float4*>(pos + (size_t)t * D + d4);
+    *reinterpret_cast<float4*>(x + (size_t)r * D + d4) = make_float4(a.x + pp.x, a.y + pp.y, a.z + pp.z, a.w + pp.w);
+  }
+}
+
+// --------------------------------------- bilinear align_corners=True on channels-last acts
+__global__ void __launch_bounds__(256) resize_act_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il, int h, int w, int C,
+                                                         int in_cs, bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW,
+                                                         int out_cs, int relu, long long total) {
+  const int cv = C / 8;
+  const float sy = ac_scale(h, OH), sx = ac_scale(w, OW);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv) * 8;
+    long long pix = idx / cv;
+    const int x = (int)(pix % OW);
+    pix /= OW;
+    const int y = (int)(pix % OH);
+    const int n = (int)(pix / OH);
+    const BilinearTap ty = ac_tap(sy, y, h), tx = ac_tap(sx, x, w);
+    const size_t base = (size_t)n * h * w;
+    float a[8], b[8], c[8], d[8], o[8];
+    act_load8(ih, il, (base + (size_t)ty.i0 * w + tx.i0) * in_cs + c8, a);
+    act_load8(ih, il, (base + (size_t)ty.i0 * w + tx.i1) * in_cs + c8, b);
+    act_load8(ih, il, (base + (size_t)ty.i1 * w + tx.i0) * in_cs + c8, c);
+    act_load8(ih, il, (base + (size_t)ty.i1 * w + tx.i1) * in_cs + c8, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      o[k] = ac_blend(ty, tx, a[k], b[k], c[k], d[k]);
+      if (relu) o[k] = fmaxf(o[k], 0.f);
+    }
+    act_store8(oh, ol, (((size_t)n * OH + y) * OW + x) * out_cs + c8, o);
+  }
+}
+
+// -------------------------- depth maps into channel slots (fusion_model.py:94-96, 16-17)
+__global__ void __launch_bounds__(256) depth_slots_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int N, int H, int W,
+                                                          bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW, int out_cs,
+                                                          int c0, long long total) {
+  const float sy = ac_scale(H, OH), sx = ac_scale(W, OW);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % OW);
+    const int y = (int)((idx / OW) % OH);
+    const int n = (int)(idx / ((long long)OW * OH));
+    const BilinearTap ty = ac_tap(sy, y, H), tx = ac_tap(sx, x, W);
+    const size_t b = (size_t)n * H * W;
+    const size_t i00 = b + (size_t)ty.i0 * W + tx.i0, i01 = b + (size_t)ty.i0 * W + tx.i1, i10 = b + (size_t)ty.i1 * W + tx.i0,
+                 i11 = b + (size_t)ty.i1 * W + tx.i1;
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    o[0] = ac_blend(ty, tx, __ldg(p1 + i00), __ldg(p1 + i01), __ldg(p1 + i10), __ldg(p1 + i11));
+    o[1] = ac_blend(ty, tx, __ldg(p2 + i00), __ldg(p2 + i01), __ldg(p2 + i10), __ldg(p2 + i11));
+    act_store8(oh, ol, (size_t)idx * out_cs + c0, o);
+  }
+}
+
+// ------------------------------ final 3x3 conv to one channel + base + clamp (fusion_model.py:113-118)
+__global__ void __launch_bounds__(256) final_conv_kernel(const bf16* __restrict__ fh, const bf16* __restrict__ fl, int N, int H, int W,
+                                                         int C, int cs, const float* __restrict__ wgt, const float* __restrict__ base,
+                                                         float* __restrict__ out, long long total) {
+  extern __shared__ float s_w[];                           // [9, C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wgt[i];
+  __syncthreads();
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const int y = (int)((idx / W) % H);
+    const int n = (int)(idx / ((long long)W * H));
+    float acc = 0.f;
+    for (int r = 0; r < 3; ++r) {
+      const int yy = y + r - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int xx = x + s - 1;
+        if (xx < 0 || xx >= W) continue;
+        const size_t p = (((size_t)n * H + yy) * W + xx) * cs;
+        const float* ww = s_w + (r * 3 + s) * C;
+        for (int c = 0; c < C; c += 8) {
+          float v[8];
+          act_load8(fh, fl, p + c, v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc = fmaf(v[k], ww[c + k], acc);
+        }
+      }
+    }
+    if (base) acc = fmaxf(base[idx] + acc, 0.f);
+    out[idx] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ in, int N, int C, int H, int W, bf16* __restrict__ oh,
+                                                          bf16* __restrict__ ol, int out_cs, long long total) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % out_cs);
+    const long long pix = idx / out_cs;
+    const int hw = (int)(pix % ((long long)H * W));
+    const int n = (int)(pix / ((long long)H * W));
+    const float v = c < C ? in[((size_t)n * C + c) * H * W + hw] : 0.f;
+    act_store(oh, ol, (size_t)idx, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) act_to_nchw_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il, int N, int C, int H,
+                                                          int W, int in_cs, float* __restrict__ out, long long total) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int hw = (int)(idx % ((long long)H * W));
+    const int c = (int)((idx / ((long long)H * W)) % C);
+    const int n = (int)(idx / ((long long)H * W * C));
+    out[idx] = act_load(ih, il, ((size_t)n * H * W + hw) * in_cs + c);
+  }
+}
+
+__global__ void __launch_bounds__(256) phase_split_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il, int N, int H, int W,
+                                                          int C, int in_cs, bf16* __restrict__ oh, bf16* __restrict__ ol, int out_cs,
+                                                          long long total) {
+  const int cv = C / 8, H2 = H / 2, W2 = W / 2;
+  const size_t plane = (size_t)N * H2 * W2 * out_cs;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv) * 8;
+    long long pix = idx / cv;
+    const int x = (int)(pix % W);
+    pix /= W;
+    const int y = (int)(pix % H);
+    const int n = (int)(pix / H);
+    const int ph = (y & 1) * 2 + (x & 1);
+    float v[8];
+    act_load8(ih, il, (((size_t)n * H + y) * W + x) * in_cs + c8, v);
+    act_store8(oh, ol ? ol : nullptr, ph * plane + (((size_t)n * H2 + (y >> 1)) * W2 + (x >> 1)) * out_cs + c8, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ in, long long n, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    act_store(hi, lo, (size_t)i, in[i]);
+}
+
+int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int prv2_layernorm(const float* x, int rows, int D, const float* w, const float* b, float eps, int drop_period,
+                              prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(x && w && b && out_hi, "prv2_layernorm: null pointer");
+  PRV2_CHECK_ARG(rows >= 0 && D > 0 && D % 128 == 0 && D <= 1024 && out_cs % 4 == 0 && out_cs >= D, "prv2_layernorm: D must be a multiple of 128, <= 1024 (got %d)", D);
+  if (rows == 0) return PRV2_OK;
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, drop_period, (bf16*)out_hi, (bf16*)out_lo, out_cs);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_patchify(const float* crops, int B, int H, int W, prv2_bf16* out_hi, prv2_bf16* out_lo, int Kp, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(crops && out_hi, "prv2_patchify: null pointer");
+  PRV2_CHECK_ARG(B >= 0 && H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0 && Kp >= 588 && Kp % 8 == 0, "prv2_patchify: H,W must be multiples of 14; Kp>=588, Kp%%8==0");
+  if (B == 0) return PRV2_OK;
+  const long long total = (long long)B * (H / 14) * (W / 14) * (Kp / 8);
+  patchify_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(crops, B, H, W, (bf16*)out_hi, (bf16*)out_lo, Kp, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_assemble_tokens(const float* emb, const float* cls, const float* pos, int B, int T, int D, float* x, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(emb && cls && pos && x, "prv2_assemble_tokens: null pointer");
+  PRV2_CHECK_ARG(B >= 0 && T > 0 && D > 0 && D % 4 == 0, "prv2_assemble_tokens: bad shape");
+  if (B == 0) return PRV2_OK;
+  const long long total = (long long)B * (T + 1) * (D / 4);
+  assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(emb, cls, pos, B, T, D, x, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_resize_bilinear_act(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int h, int w, int C, int in_cs,
+                                        prv2_bf16* out_hi, prv2_bf16* out_lo, int oh, int ow, int out_cs, int relu, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(in_hi && out_hi, "prv2_resize_bilinear_act: null pointer");
+  PRV2_CHECK_ARG(N >= 0 && h > 0 && w > 0 && oh > 0 && ow > 0 && C > 0 && C % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0, "prv2_resize_bilinear_act: bad shape");
+  if (N == 0) return PRV2_OK;
+  const long long total = (long long)N * oh * ow * (C / 8);
+  resize_act_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, h, w, C, in_cs, (bf16*)out_hi,
+                                                                          (bf16*)out_lo, oh, ow, out_cs, relu, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_depth_slots(const float* pred1, const float* pred2, int N, int H, int W, prv2_bf16* out_hi, prv2_bf16* out_lo, int oh,
+                                int ow, int out_cs, int c0, int zero_pad, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(pred1 && pred2 && out_hi, "prv2_depth_slots: null pointer");
+  PRV2_CHECK_ARG(N >= 0 && H > 0 && W > 0 && oh > 0 && ow > 0 && out_cs % 8 == 0 && c0 % 8 == 0 && zero_pad == 6 && c0 + 8 <= out_cs,
+                 "prv2_depth_slots: slot must be an aligned group of 8 channels (2 depth + 6 zero)");
+  if (N == 0) return PRV2_OK;
+  const long long total = (long long)N * oh * ow;
+  depth_slots_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(pred1, pred2, N, H, W, (bf16*)out_hi, (bf16*)out_lo, oh, ow, out_cs,
+                                                                           c0, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_final_conv(const prv2_bf16* feat_hi, const prv2_bf16* feat_lo, int N, int H, int W, int C, int cs, const float* w,
+                               const float* base, float* out, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(feat_hi && w && out, "prv2_final_conv: null pointer");
+  PRV2_CHECK_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && cs % 8 == 0 && C <= 1024, "prv2_final_conv: bad shape");
+  if (N == 0) return PRV2_OK;
+  const long long total = (long long)N * H * W;
+  final_conv_kernel<<<grid_for(total, 256), 256, 9 * C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)feat_hi, (const bf16*)feat_lo, N, H, W,
+                                                                                                  C, cs, w, base, out, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_nchw_f32_to_act(const float* in, int N, int C, int H, int W, prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs,
+                                    prv2_stream_t stream) {
+  PRV2_CHECK_ARG(in && out_hi && out_cs >= C, "prv2_nchw_f32_to_act: bad arguments");
+  const long long total = (long long)N * H * W * out_cs;
+  if (total == 0) return PRV2_OK;
+  nchw_to_act_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, N, C, H, W, (bf16*)out_hi, (bf16*)out_lo, out_cs, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_act_to_nchw_f32(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int C, int H, int W, int in_cs, float* out,
+                                    prv2_stream_t stream) {
+  PRV2_CHECK_ARG(in_hi && out && in_cs >= C, "prv2_act_to_nchw_f32: bad arguments");
+  const long long total = (long long)N * C * H * W;
+  if (total == 0) return PRV2_OK;
+  act_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, N, C, H, W, in_cs, out, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_phase_split(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int H, int W, int C, int in_cs, prv2_bf16* out_hi,
+                                prv2_bf16* out_lo, int out_cs, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(in_hi && out_hi, "prv2_phase_split: null pointer");
+  PRV2_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0, "prv2_phase_split: H,W even; C,pitches multiples of 8");
+  PRV2_CHECK_ARG((in_lo == nullptr) == (out_lo == nullptr), "prv2_phase_split: lo planes must both be present or absent");
+  const long long total = (long long)N * H * W * (C / 8);
+  if (total == 0) return PRV2_OK;
+  phase_split_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, N, H, W, C, in_cs,
+                                                                           (bf16*)out_hi, (bf16*)out_lo, out_cs, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_split_f32(const float* in, int64_t n, prv2_bf16* hi, prv2_bf16* lo, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(in && hi && n >= 0, "prv2_split_f32: bad arguments");
+  if (n == 0) return PRV2_OK;
+  split_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, n, (bf16*)hi, (bf16*)lo);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}

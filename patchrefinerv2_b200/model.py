@@ -1,0 +1,358 @@
+"""Drop-in ``PatchRefiner`` estimator model: the reference's infer forward
+(estimator/models/patchrefiner.py:286-401 with BaselinePretrain.regular_tile / random_tile,
+estimator/models/baseline_pretrain.py:149-375) re-built on the sm_100a kernels.
+
+Kept from the reference API: construction from ``config`` (keys of configs/patchrefiner_dav2/
+pr_u4k.py:10-53), ``forward(mode='infer', image_lr, image_hr, tile_cfg, cai_mode, process_num)``
+returning ``(depth, log_dict)`` with ``depth`` fp32 ``[1,1,ph*Sh,pw*Sw]`` (m1/m2) or ``[1,1,H,W]``
+(rN), ``tile_cfg`` / ``resizer`` attributes, ``load_dict`` / ``get_save_dict`` and state-dict keys
+``coarse_branch.* / refiner_fine_branch.* / refiner_fusion_model.*``.
+
+Changed by design: patches are cropped, gathered, refined and blended on the device in batches
+(no per-patch host round trips), and can be sharded over ranks with one NCCL sum-reduce.
+"""
+from __future__ import annotations
+
+import random as _random
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, masks, ops, tiling
+from .dav2 import VIT_CFG, DepthAnythingV2B200, PATCH
+from .fusion import FusionUnetB200
+from .nn import Act, Workspace
+from .registry import MODELS
+
+
+def _get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def dav2_weight_spec(encoder: str, features: int, out_channels) -> "OrderedDict[str, tuple]":
+    """Names and shapes of a DepthAnythingV2 state dict (external/depth_anything_v2/dpt.py:153-181)."""
+    c = VIT_CFG[encoder]
+    D, depth = c["dim"], c["depth"]
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    p = "pretrained."
+    s[p + "cls_token"] = (1, 1, D)
+    s[p + "pos_embed"] = (1, 37 * 37 + 1, D)
+    s[p + "mask_token"] = (1, D)
+    s[p + "patch_embed.proj.weight"] = (D, 3, PATCH, PATCH)
+    s[p + "patch_embed.proj.bias"] = (D,)
+    for i in range(depth):
+        b = f"{p}blocks.{i}."
+        for n, shp in (("norm1.weight", (D,)), ("norm1.bias", (D,)), ("attn.qkv.weight", (3 * D, D)), ("attn.qkv.bias", (3 * D,)),
+                       ("attn.proj.weight", (D, D)), ("attn.proj.bias", (D,)), ("ls1.gamma", (D,)), ("norm2.weight", (D,)),
+                       ("norm2.bias", (D,)), ("mlp.fc1.weight", (4 * D, D)), ("mlp.fc1.bias", (4 * D,)),
+                       ("mlp.fc2.weight", (D, 4 * D)), ("mlp.fc2.bias", (D,)), ("ls2.gamma", (D,))):
+            s[b + n] = shp
+    s[p + "norm.weight"] = (D,)
+    s[p + "norm.bias"] = (D,)
+    h = "depth_head."
+    oc, Fe = list(out_channels), features
+    for i, o in enumerate(oc):
+        s[f"{h}projects.{i}.weight"] = (o, D, 1, 1)
+        s[f"{h}projects.{i}.bias"] = (o,)
+    s[h + "resize_layers.0.weight"] = (oc[0], oc[0], 4, 4)
+    s[h + "resize_layers.0.bias"] = (oc[0],)
+    s[h + "resize_layers.1.weight"] = (oc[1], oc[1], 2, 2)
+    s[h + "resize_layers.1.bias"] = (oc[1],)
+    s[h + "resize_layers.3.weight"] = (oc[3], oc[3], 3, 3)
+    s[h + "resize_layers.3.bias"] = (oc[3],)
+    for i, o in enumerate(oc):
+        s[f"{h}scratch.layer{i + 1}_rn.weight"] = (Fe, o, 3, 3)
+    for r in (1, 2, 3, 4):
+        q = f"{h}scratch.refinenet{r}."
+        s[q + "out_conv.weight"] = (Fe, Fe, 1, 1)
+        s[q + "out_conv.bias"] = (Fe,)
+        for u in (1, 2):
+            for cv in (1, 2):
+                s[f"{q}resConfUnit{u}.conv{cv}.weight"] = (Fe, Fe, 3, 3)
+                s[f"{q}resConfUnit{u}.conv{cv}.bias"] = (Fe,)
+    s[h + "scratch.output_conv1.weight"] = (Fe // 2, Fe, 3, 3)
+    s[h + "scratch.output_conv1.bias"] = (Fe // 2,)
+    s[h + "scratch.output_conv2.0.weight"] = (32, Fe // 2, 3, 3)
+    s[h + "scratch.output_conv2.0.bias"] = (32,)
+    s[h + "scratch.output_conv2.2.weight"] = (1, 32, 1, 1)
+    s[h + "scratch.output_conv2.2.bias"] = (1,)
+    return s
+
+
+def fusion_weight_spec(input_chl, temp_chl, dec_chl) -> "OrderedDict[str, tuple]":
+    """FusionUnet state dict (estimator/models/blocks/fusion_model.py:52-82)."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    for idx, (ic, tc) in enumerate(zip(input_chl, temp_chl)):
+        s[f"encoder_layers_1.{idx}.single_conv.0.weight"] = (tc, ic, 3, 3)
+        s[f"encoder_layers_1.{idx}.single_conv.1.weight"] = (tc,)
+        s[f"encoder_layers_1.{idx}.single_conv.1.bias"] = (tc,)
+    for idx, (ic, tc) in enumerate(zip(input_chl, temp_chl)):
+        s[f"encoder_layers_2.{idx}.single_conv.0.weight"] = (tc, tc + 2, 3, 3)
+        s[f"encoder_layers_2.{idx}.single_conv.1.weight"] = (tc,)
+        s[f"encoder_layers_2.{idx}.single_conv.1.bias"] = (tc,)
+    rev = list(temp_chl)[::-1]
+    chl = rev[0]
+    for i, (tc, dc) in enumerate(zip(rev[1:], dec_chl)):
+        cin = tc + chl + 2
+        s[f"decoder_layers.{i}.conv.double_conv.0.weight"] = (cin, cin, 3, 3)
+        s[f"decoder_layers.{i}.conv.double_conv.2.weight"] = (dc, cin, 3, 3)
+        chl = dc
+    last = dec_chl[-1] if len(dec_chl) else chl
+    s["final_conv.weight"] = (1, last, 3, 3)
+    return s
+
+
+class _Resizer:
+    """Stand-in for ``model.resizer`` (external/depth_anything/transform.py:127-129): bilinear,
+    align_corners=True, to the process shape rounded to multiples of 14.  Runs the crop kernel."""
+
+    def __init__(self, patch_process_shape):
+        self.size = tiling.resizer_size(patch_process_shape)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        lead = x.shape[:-3]
+        img = x.reshape(-1, *x.shape[-3:])
+        outs = []
+        for im in img:
+            assert im.shape[0] == 3, "resizer expects RGB"
+            H, W = im.shape[-2:]
+            bb = torch.tensor([[0, 0, W, H]], dtype=torch.int32, device=im.device)
+            outs.append(ops.crop_resize(im.contiguous().float(), bb, self.size[0], self.size[1]))
+        return torch.cat(outs, 0).reshape(*lead, 3, *self.size)
+
+
+@MODELS.register_module()
+class PatchRefiner(nn.Module):
+    """B200-native PatchRefiner (DA2 coarse + DA2 refiner + FusionUnet family)."""
+
+    def __init__(self, config, precision: str = "bf16", patch_batch: int = 8, output_device: str = "cpu"):
+        super().__init__()
+        if hasattr(config, "to_dict"):
+            config = config.to_dict()
+        self.config = config
+        self.min_depth = _get(config, "min_depth")
+        self.max_depth = float(_get(config, "max_depth"))
+        self.patch_process_shape = tuple(_get(config, "patch_process_shape"))
+        self.tile_cfg = self.prepare_tile_cfg(_get(config, "image_raw_shape"), _get(config, "patch_split_num"))
+        cb, rf = _get(config, "coarse_branch"), _get(config, "refiner")
+        fb, fu = _get(rf, "fine_branch"), _get(rf, "fusion_model")
+        for name, br in (("coarse_branch", cb), ("refiner.fine_branch", fb)):
+            if _get(br, "type") != "DA2":
+                raise NotImplementedError(f"{name}.type={_get(br, 'type')!r}: only the DA2 (DepthAnythingV2) branch is implemented")
+        if _get(fu, "type") != "FusionUnet":
+            raise NotImplementedError(f"fusion_model.type={_get(fu, 'type')!r}: only FusionUnet is implemented")
+        self._cb_cfg, self._fb_cfg, self._fu_cfg = dict(_get(cb, "model_cfg")), dict(_get(fb, "model_cfg")), fu
+        self.fusion_feat_level = int(_get(config, "fusion_feat_level"))
+        self.strategy_refiner_target = _get(config, "strategy_refiner_target")
+        if self.strategy_refiner_target == "direct":
+            raise NotImplementedError("strategy_refiner_target='direct' is not implemented")
+        self.pre_norm_bbox = _get(config, "pre_norm_bbox", True)
+        self.resizer = _Resizer(self.patch_process_shape)
+        if tuple(self.resizer.size) != tuple(self.patch_process_shape):
+            raise NotImplementedError("patch_process_shape must be a multiple of 14 for the DA2 branches")
+        assert precision in ("bf16", "fp32"), "precision is 'bf16' (one tcgen05 pass) or 'fp32' (3-pass bf16 split, fp32-class)"
+        self.precision, self.patch_batch, self.output_device = precision, int(patch_batch), output_device
+
+        # weights: flat dict with the reference's key names (zeros until load_dict / pretrained files)
+        self._weights: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        spec_of = lambda c: dav2_weight_spec(c["encoder"], c["features"], c["out_channels"])
+        for pre, spec in (("coarse_branch.", spec_of(self._cb_cfg)), ("refiner_fine_branch.", spec_of(self._fb_cfg)),
+                          ("refiner_fusion_model.", fusion_weight_spec(_get(fu, "input_chl"), _get(fu, "temp_chl"), _get(fu, "dec_chl")))):
+            for k, shp in spec.items():
+                self._weights[pre + k] = torch.zeros(shp)
+        for pre, br in (("coarse_branch.", cb), ("refiner_fine_branch.", fb)):
+            path = _get(br, "pretrained")
+            if path:
+                sd = torch.load(path, map_location="cpu")            # patchrefiner.py:94,118
+                self._load({pre + k: v for k, v in sd.items()}, strict=False)
+        for key in ("pretrain_coarse_model", "pretrain_fine_model"):
+            path = _get(config, key)
+            if path:
+                pre = "coarse_branch." if "coarse" in key else "refiner_fine_branch."
+                sd = torch.load(path, map_location="cpu")["model_state_dict"]
+                self._load({pre + k: v for k, v in sd.items()}, strict=False)
+        self._engine = None
+        self._device = torch.device("cpu")
+        self.last_stats: dict = {}
+
+    # -- reference-compatible surface ---------------------------------------------------------
+    def prepare_tile_cfg(self, image_raw_shape, patch_split_num):
+        return tiling.prepare_tile_cfg(self.patch_process_shape, image_raw_shape, patch_split_num)
+
+    def _load(self, sd, strict):
+        missing = [k for k in self._weights if k not in sd]
+        unexpected = [k for k in sd if k not in self._weights]
+        for k, v in sd.items():
+            if k in self._weights:
+                if tuple(v.shape) != tuple(self._weights[k].shape):
+                    raise RuntimeError(f"size mismatch for {k}: {tuple(v.shape)} vs {tuple(self._weights[k].shape)}")
+                self._weights[k] = v.detach().float().cpu().clone()
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"missing keys {missing[:4]}..., unexpected keys {unexpected[:4]}...")
+        self._engine = None
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        return self._load(state_dict, strict)
+
+    def state_dict(self, *args, **kwargs):
+        return OrderedDict((k, v.clone()) for k, v in self._weights.items())
+
+    def load_dict(self, dict):                      # patchrefiner.py:155-156
+        return self.load_state_dict(dict, strict=False)
+
+    def get_save_dict(self):                        # patchrefiner.py:158-166
+        return {k: v for k, v in self.state_dict().items() if "coarse_branch." not in k}
+
+    def _apply(self, fn, recurse=True):
+        probe = fn(torch.zeros(1))
+        if probe.device != self._device:
+            self._device = probe.device
+            self._engine = None
+        return super()._apply(fn, recurse)
+
+    # -- device engine -------------------------------------------------------------------------
+    def _build_engine(self, device):
+        if device.type != "cuda":
+            raise RuntimeError("patchrefinerv2_b200 runs on CUDA (sm_100a) only; there is no CPU path. Call .cuda() first.")
+        _lib.load()
+        x3 = self.precision == "fp32"
+        sd = self._weights
+        fu = self._fu_cfg
+        eng = dict(
+            coarse=DepthAnythingV2B200(sd, "coarse_branch.", self._cb_cfg["encoder"], self._cb_cfg["features"], self._cb_cfg["out_channels"], self.max_depth, x3, device),
+            fine=DepthAnythingV2B200(sd, "refiner_fine_branch.", self._fb_cfg["encoder"], self._fb_cfg["features"], self._fb_cfg["out_channels"], self.max_depth, x3, device),
+            fusion=FusionUnetB200(sd, "refiner_fusion_model.", _get(fu, "input_chl"), _get(fu, "temp_chl"), _get(fu, "dec_chl"), x3, device),
+            ws=Workspace(device, x3), device=device, masks={})
+        return eng
+
+    def _mask_dev(self, eng, kind, size):
+        key = (kind, tuple(size))
+        if key not in eng["masks"]:
+            m = masks.generatemask(size, border=0.15) if kind == "p" else masks.random_patch_mask(size, border=0.15)
+            eng["masks"][key] = torch.from_numpy(np.ascontiguousarray(m)).to(eng["device"])
+        return eng["masks"][key]
+
+    def coarse_forward(self, image_lr):             # patchrefiner.py:168-185
+        eng = self._engine
+        depth, feats = eng["coarse"].forward(image_lr.float().contiguous())
+        return feats, depth
+
+    def refine_patches(self, eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel: np.ndarray, preds: torch.Tensor, trace=None):
+        """crop -> ROI gather -> fine branch -> fusion for the patches ``sel`` (indices into the
+        flattened schedule), ``patch_batch`` at a time; results land in ``preds[sel]``."""
+        dev = eng["device"]
+        ph, pw = self.patch_process_shape
+        level = self.fusion_feat_level
+        for s in range(0, len(sel), self.patch_batch):
+            idx = sel[s:s + self.patch_batch]
+            pb = len(idx)
+            bb = torch.from_numpy(np.ascontiguousarray(bboxs_np[idx])).to(dev)
+            rois = torch.from_numpy(np.ascontiguousarray(rois_np[idx])).to(dev)
+            crops = ops.crop_resize(image_hr, bb, ph, pw)                                    # baseline_pretrain.py:272-280
+            ws = eng["ws"]
+            c_roi = []
+            for li, f in enumerate(coarse_feats):                                           # patchrefiner.py:203-207
+                o = ws.act(f"roi{li}", pb, f.H, f.W, f.C)
+                c_roi.append(ops.roi_gather_act(f, rois, f.H / ph, o))
+            cd = coarse_depth.reshape(ph, pw, 1)
+            d_roi = ops.roi_gather_f32(cd, rois, 1.0).reshape(pb, 1, ph, pw)                # patchrefiner.py:209-210
+            r_depth, r_feats = eng["fine"].forward(crops, trace)                             # patchrefiner.py:219-232
+            if self.strategy_refiner_target == "offset_fine":
+                base = r_depth
+            elif self.strategy_refiner_target == "offset_coarse":
+                base = d_roi
+            else:
+                base = None
+            c_list = c_roi[-level:][::-1]                                                   # patchrefiner.py:245-251
+            f_list = r_feats[-level:][::-1]
+            pred = eng["fusion"].forward(c_list, f_list, d_roi, r_depth, base, trace)        # fusion_model.py:84-122
+            preds[torch.from_numpy(idx).to(dev)] = pred.reshape(pb, ph, pw)
+            if trace is not None:
+                trace.setdefault("crops", crops.clone()); trace.setdefault("roi_depth", d_roi.clone())
+                trace.setdefault("roi_feats", [a.to_nchw() for a in c_roi]); trace.setdefault("fine_depth", r_depth.clone())
+                trace.setdefault("fine_feats", [a.to_nchw() for a in r_feats])
+                trace = None if "fine_depth" in trace else trace
+
+    @torch.no_grad()
+    def forward(self, mode=None, image_lr=None, image_hr=None, crops_image_hr=None, depth_gt=None, crop_depths=None, bboxs=None,
+                tile_cfg=None, cai_mode="m1", process_num=4, shard: bool = False, trace: Optional[dict] = None, **kwargs):
+        if mode == "train":
+            raise NotImplementedError("training is out of scope of patchrefinerv2_b200 (inference hot path only)")
+        if tile_cfg is None:
+            tile_cfg = self.tile_cfg
+        else:
+            tile_cfg = self.prepare_tile_cfg(tile_cfg["image_raw_shape"], tile_cfg["patch_split_num"])
+        assert image_hr.shape[0] == 1                                                        # patchrefiner.py:348
+        dev = image_hr.device
+        if self._engine is None or self._engine["device"] != dev:
+            self._engine = self._build_engine(dev)
+        eng = self._engine
+        ph, pw = self.patch_process_shape
+        rh, rw = tile_cfg["patch_raw_shape"]
+        H, W = tile_cfg["image_raw_shape"]
+        Hc, Wc = tile_cfg["patch_reensemble_shape"]
+        if tuple(image_hr.shape[-2:]) != (H, W):
+            raise ValueError(f"image_hr is {tuple(image_hr.shape[-2:])} but tile_cfg.image_raw_shape is {(H, W)}")
+
+        stages = tiling.schedule(tile_cfg, self.patch_process_shape, cai_mode, process_num)   # consumes `random` like the reference
+        bboxs_np = np.concatenate([s.bboxs for s in stages], axis=0)
+        rois_np = np.concatenate([tiling.bboxs_to_feat(s.bboxs, (H, W), (ph, pw))[:, 1:] for s in stages], axis=0)
+        P = bboxs_np.shape[0]
+        n_regular = sum(s.bboxs.shape[0] for s in stages if s.kind == "regular")
+        n_random = P - n_regular
+
+        coarse_feats, coarse_depth = self.coarse_forward(image_lr)
+        hr = image_hr[0].float().contiguous()
+        preds = eng["ws"].f32("preds", P, ph, pw)
+
+        world, rank = 1, 0
+        if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
+            world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        own_np = tiling.shard_patches(P, rank, world)
+        sel = np.nonzero(own_np)[0]
+        self.refine_patches(eng, hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel, preds, trace)
+
+        grid_stages, first = [], 0
+        for s in stages:
+            if s.kind == "regular":
+                grid_stages.append((s.off_process[0], s.off_process[1], s.grid[0], s.grid[1], first))
+                first += s.bboxs.shape[0]
+        mask = self._mask_dev(eng, "p", (ph, pw))
+        starts = rmask = None
+        if n_random:
+            starts = torch.from_numpy(np.ascontiguousarray(bboxs_np[n_regular:, [1, 0]])).to(dev)     # (y0, x0)
+            rmask = self._mask_dev(eng, "r", (rh, rw))
+        is_r = cai_mode[0] == "r"
+
+        if not shard:
+            avg_c, cnt_c = ops.blend_canvas(preds[:n_regular], mask, grid_stages, Hc, Wc, want_count=True)
+            if is_r:
+                depth, cnt = ops.blend_raw(avg_c, cnt_c, preds[n_regular:] if n_random else None, starts, rmask, ph, pw, rh, rw, H, W)
+            else:
+                depth, cnt = avg_c, cnt_c
+        else:
+            packed = torch.zeros(2 * Hc * Wc + (H * W if is_r else 0), dtype=torch.float32, device=dev)
+            num_c, m1 = packed[:Hc * Wc].view(Hc, Wc), packed[Hc * Wc:2 * Hc * Wc].view(Hc, Wc)
+            own = torch.from_numpy(own_np).to(dev)
+            ops.blend_partial_canvas(preds[:n_regular], own[:n_regular], mask, grid_stages, Hc, Wc, num_c, m1)
+            if is_r and n_random:
+                num_r = packed[2 * Hc * Wc:].view(H, W)
+                ops.blend_partial_raw(preds[n_regular:], own[n_regular:].contiguous(), starts, rmask, ph, pw, H, W, num_r)
+            if world > 1:
+                torch.distributed.all_reduce(packed)                                         # ONE sum-reduce of the packed partial canvases
+            avg_c, cnt_c = ops.blend_finalize_canvas(num_c, m1, mask, grid_stages, Hc, Wc)
+            if is_r:
+                depth, cnt = ops.blend_finalize_raw(avg_c, cnt_c, packed[2 * Hc * Wc:].view(H, W), starts, rmask, rh, rw, H, W)
+            else:
+                depth, cnt = avg_c, cnt_c
+        self.last_stats = dict(patches=P, patches_local=int(len(sel)), count_map=cnt, n_regular=n_regular, n_random=n_random)
+        depth = depth.unsqueeze(0).unsqueeze(0)
+        if self.output_device == "cpu":
+            depth = depth.cpu()
+        return depth, {"rgb": image_lr, "depth_pred": depth, "depth_gt": depth_gt, "coarse_prediction": coarse_depth}

@@ -1,0 +1,218 @@
+"""Host-side plumbing for the per-patch network: channels-last activations, a named workspace,
+packed weights and the descriptor builder for ``prv2_umma_gemm``.  PyTorch is used only for
+device memory and streams; every FLOP runs in the hand-written kernels behind the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc
+
+BF16 = torch.bfloat16
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def ceil_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Act:
+    """Channels-last activation [N,H,W,C] stored with channel pitch ``cs`` as bf16 ``hi`` plus an
+    optional ``lo`` plane (x3 precision mode: value = hi + lo)."""
+
+    __slots__ = ("N", "H", "W", "C", "cs", "hi", "lo")
+
+    def __init__(self, N, H, W, C, cs, hi, lo):
+        self.N, self.H, self.W, self.C, self.cs, self.hi, self.lo = N, H, W, C, cs, hi, lo
+
+    @staticmethod
+    def empty(N, H, W, C, x3: bool, device, cs: Optional[int] = None, zero: bool = False) -> "Act":
+        cs = ceil_to(C, 8) if cs is None else cs
+        assert cs % 8 == 0 and cs >= C
+        mk = torch.zeros if zero else torch.empty
+        hi = mk((N, H, W, cs), dtype=BF16, device=device)
+        lo = mk((N, H, W, cs), dtype=BF16, device=device) if x3 else None
+        return Act(N, H, W, C, cs, hi, lo)
+
+    def view_channels(self, C: int) -> "Act":
+        """Same storage, different logical channel count (e.g. features + depth slots)."""
+        assert C <= self.cs
+        return Act(self.N, self.H, self.W, C, self.cs, self.hi, self.lo)
+
+    def batch_slice(self, s: slice) -> "Act":
+        hi = self.hi[s]
+        return Act(hi.shape[0], self.H, self.W, self.C, self.cs, hi, None if self.lo is None else self.lo[s])
+
+    def to_nchw(self) -> torch.Tensor:
+        """fp32 [N,C,H,W] copy (API edge / tests) through prv2_act_to_nchw_f32."""
+        out = torch.empty((self.N, self.C, self.H, self.W), dtype=torch.float32, device=self.hi.device)
+        _lib.call("prv2_act_to_nchw_f32", ptr(self.hi), ptr(self.lo), self.N, self.C, self.H, self.W, self.cs, ptr(out), stream_ptr())
+        return out
+
+    @staticmethod
+    def from_nchw(x: torch.Tensor, x3: bool, cs: Optional[int] = None) -> "Act":
+        x = x.contiguous().float()
+        N, Cc, H, W = x.shape
+        a = Act.empty(N, H, W, Cc, x3, x.device, cs)
+        _lib.call("prv2_nchw_f32_to_act", ptr(x), N, Cc, H, W, ptr(a.hi), ptr(a.lo), a.cs, stream_ptr())
+        return a
+
+
+class Workspace:
+    """Named persistent device buffers (stable pointers across forwards of the same shape)."""
+
+    def __init__(self, device, x3: bool):
+        self.device, self.x3 = device, x3
+        self._t: Dict[tuple, object] = {}
+
+    def act(self, name: str, N, H, W, Cc, cs: Optional[int] = None, zero: bool = False) -> Act:
+        cs = ceil_to(Cc, 8) if cs is None else cs
+        key = ("act", name, N, H, W, Cc, cs)
+        a = self._t.get(key)
+        if a is None:
+            a = Act.empty(N, H, W, Cc, self.x3, self.device, cs, zero=True)
+            self._t[key] = a
+        return a
+
+    def f32(self, name: str, *shape) -> torch.Tensor:
+        key = ("f32", name, shape)
+        t = self._t.get(key)
+        if t is None:
+            t = torch.zeros(shape, dtype=torch.float32, device=self.device)
+            self._t[key] = t
+        return t
+
+    def nbytes(self) -> int:
+        n = 0
+        for v in self._t.values():
+            if isinstance(v, Act):
+                n += v.hi.numel() * 2 * (2 if v.lo is not None else 1)
+            else:
+                n += v.numel() * v.element_size()
+        return n
+
+
+def pick_block_n(cout: int) -> Tuple[int, int]:
+    """(block_n, Cout_pad): fewest N tiles with block_n <= 256, multiple of 16."""
+    n_tiles = (cout + 255) // 256
+    block_n = ceil_to((cout + n_tiles - 1) // n_tiles, 16)
+    return block_n, block_n * n_tiles
+
+
+def pick_tile(H: int, W: int) -> Tuple[int, int]:
+    """(tile_w, tile_h) with tile_w*tile_h == 128: 16x8 pixel blocks for images, 128x1 for matrices."""
+    th = 1
+    while th < 8 and th < H:
+        th *= 2
+    return 128 // th, th
+
+
+class GemmLayer:
+    """One dense layer (linear / conv / deconv) with its weights packed for ``prv2_umma_gemm``.
+
+    ``segs``: list of (source index, dh, dw, W[Cout, C_src] fp32) in K order.  In x3 mode every
+    segment expands to (A_hi*W_hi, A_hi*W_lo, A_lo*W_hi); the sources passed at call time expand to
+    (hi, lo) pairs accordingly."""
+
+    def __init__(self, segs: Sequence[Tuple[int, int, int, torch.Tensor]], n_src: int, cout: int, x3: bool, device,
+                 epi: int = _lib.EPI_STORE, act: int = _lib.ACT_NONE, bias: Optional[torch.Tensor] = None,
+                 gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, eps: float = 1e-6,
+                 head_scale: float = 1.0, shuffle_k: int = 0):
+        self.x3, self.n_src, self.device = x3, n_src, device
+        cout_real = cout
+        if epi == _lib.EPI_STORE:
+            cout = ceil_to(cout, 8)            # 16-byte channel groups are stored whole; extra rows are zero weights
+        self.cout = cout
+        self.block_n, self.cout_pad = pick_block_n(cout)
+        if bias is not None and cout != cout_real:
+            bias = torch.cat([bias.detach().float().reshape(-1), torch.zeros(cout - cout_real)])
+        blocks, table, src_c = [], [], {}
+        for si, dh, dw, w in segs:
+            w = w.detach().to(torch.float32)
+            assert w.shape[0] == cout_real
+            c = w.shape[1]
+            assert src_c.setdefault(si, c) == c, "a source must present the same channel count in every segment"
+            wp = torch.zeros((self.cout_pad, ceil_to(c, 64)), dtype=torch.float32)
+            wp[:cout_real, :c] = w
+            wh = wp.to(BF16)
+            if x3:
+                wl = (wp - wh.float()).to(BF16)
+                blocks += [wh, wl, wh]
+                table += [(2 * si, dh, dw), (2 * si, dh, dw), (2 * si + 1, dh, dw)]
+            else:
+                blocks.append(wh)
+                table.append((si, dh, dw))
+        assert len(table) <= _lib.MAX_SEG and n_src * (2 if x3 else 1) <= _lib.MAX_SRC
+        self.src_c = [src_c[i] for i in range(n_src)]
+        self.weight = torch.cat(blocks, dim=1).contiguous().to(device)
+        self.ktot = self.weight.shape[1]
+        f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous().to(device)
+        self.bias, self.gamma, self.beta = f32(bias), f32(gamma), f32(beta)
+        d = GemmDesc()
+        d.Cout, d.block_n, d.Cout_pad, d.Ktot = cout, self.block_n, self.cout_pad, self.ktot
+        d.n_src, d.n_seg = n_src * (2 if x3 else 1), len(table)
+        for i, (si, dh, dw) in enumerate(table):
+            d.seg[i].src, d.seg[i].dh, d.seg[i].dw = si, dh, dw
+        d.weight = self.weight.data_ptr()
+        d.epi, d.act = epi, act
+        d.bias = 0 if self.bias is None else self.bias.data_ptr()
+        d.gamma = 0 if self.gamma is None else self.gamma.data_ptr()
+        d.beta = 0 if self.beta is None else self.beta.data_ptr()
+        d.eps, d.head_scale, d.shuffle_k = eps, head_scale, shuffle_k
+        self.desc = d
+        self.flops_per_pixel = 2 * cout * sum(w.shape[1] for _, _, _, w in segs)
+
+    def __call__(self, srcs: Sequence[Act], out: Optional[Act] = None, relu_out: Optional[Act] = None, res: Optional[Act] = None,
+                 res2: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, out_f32_ld: int = 0,
+                 row_map: Tuple[int, int, int] = (0, 0, 0)) -> None:
+        d = self.desc
+        a0 = srcs[0]
+        d.N, d.H, d.W = a0.N, a0.H, a0.W
+        d.tile_w, d.tile_h = pick_tile(a0.H, a0.W)
+        assert len(srcs) == self.n_src
+        for i, a in enumerate(srcs):
+            assert (a.N, a.H, a.W) == (a0.N, a0.H, a0.W) and a.C == self.src_c[i], (i, a.C, self.src_c[i])
+            if self.x3:
+                assert a.lo is not None, "x3 layer needs (hi, lo) sources"
+                d.src[2 * i].ptr, d.src[2 * i].C, d.src[2 * i].cs = a.hi.data_ptr(), a.C, a.cs
+                d.src[2 * i + 1].ptr, d.src[2 * i + 1].C, d.src[2 * i + 1].cs = a.lo.data_ptr(), a.C, a.cs
+            else:
+                d.src[i].ptr, d.src[i].C, d.src[i].cs = a.hi.data_ptr(), a.C, a.cs
+
+        def put(prefix, a):
+            if a is None:
+                setattr(d, prefix + "_hi", 0); setattr(d, prefix + "_lo", 0); setattr(d, prefix + "_cs", 0)
+            else:
+                setattr(d, prefix + "_hi", a.hi.data_ptr())
+                setattr(d, prefix + "_lo", 0 if a.lo is None else a.lo.data_ptr())
+                setattr(d, prefix + "_cs", a.cs)
+        put("out", out); put("relu", relu_out); put("res", res); put("res2", res2)
+        d.out_f32 = 0 if out_f32 is None else out_f32.data_ptr()
+        d.out_f32_ld = out_f32_ld
+        d.row_map_period, d.row_map_extra, d.row_map_offset = row_map
+        _lib.call("prv2_umma_gemm", C.byref(d), stream_ptr())
+
+
+def conv_segments(w: torch.Tensor, splits: Sequence[int], pad: int = 1) -> List[Tuple[int, int, int, torch.Tensor]]:
+    """Segment list of a stride-1 conv with OIHW weight ``w`` whose input channels are the
+    concatenation of sources with ``splits`` channels (virtual concat): taps outer, sources inner."""
+    co, ci, R, S = w.shape
+    assert sum(splits) == ci
+    segs = []
+    for r in range(R):
+        for s in range(S):
+            o = 0
+            for si, c in enumerate(splits):
+                segs.append((si, r - pad, s - pad, w[:, o:o + c, r, s]))
+                o += c
+    return segs

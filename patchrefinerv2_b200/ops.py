@@ -1,0 +1,152 @@
+"""Torch-tensor wrappers over the geometry / blend / pointwise entry points of the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GridStage
+from .nn import Act, ptr, stream_ptr
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.dtype} on {t.device}")
+
+
+def crop_resize(image_hr: torch.Tensor, bboxs: torch.Tensor, ph: int, pw: int) -> torch.Tensor:
+    """image_hr [3,H,W] fp32, bboxs [P,4] int32 (device) -> [P,3,ph,pw] fp32 (baseline_pretrain.py:272-280)."""
+    _chk(image_hr, torch.float32, "image_hr"); _chk(bboxs, torch.int32, "bboxs")
+    _, H, W = image_hr.shape
+    P = bboxs.shape[0]
+    out = torch.empty((P, 3, ph, pw), dtype=torch.float32, device=image_hr.device)
+    _lib.call("prv2_crop_resize", ptr(image_hr), H, W, ptr(bboxs), P, ptr(out), ph, pw, stream_ptr())
+    return out
+
+
+def roi_gather_f32(feat_hwc: torch.Tensor, rois: torch.Tensor, spatial_scale: float) -> torch.Tensor:
+    """feat [h,w,C] fp32, rois [P,4] fp32 -> [P,h,w,C] fp32 (patchrefiner.py:199-217, bit-exact form)."""
+    _chk(feat_hwc, torch.float32, "feat"); _chk(rois, torch.float32, "rois")
+    h, w, Cc = feat_hwc.shape
+    P = rois.shape[0]
+    out = torch.empty((P, h, w, Cc), dtype=torch.float32, device=feat_hwc.device)
+    _lib.call("prv2_roi_gather_f32", ptr(feat_hwc), h, w, Cc, ptr(rois), P, C.c_float(spatial_scale), ptr(out), stream_ptr())
+    return out
+
+
+def roi_gather_act(feat: Act, rois: torch.Tensor, spatial_scale: float, out: Act) -> Act:
+    """feat: ONE image (N==1) channels-last act; out [P,h,w,C] act (pre-allocated)."""
+    assert feat.N == 1 and (out.H, out.W, out.C) == (feat.H, feat.W, feat.C) and out.N == rois.shape[0]
+    _chk(rois, torch.float32, "rois")
+    _lib.call("prv2_roi_gather_act", ptr(feat.hi), ptr(feat.lo), feat.H, feat.W, feat.C, feat.cs, ptr(rois), out.N,
+              C.c_float(spatial_scale), ptr(out.hi), ptr(out.lo), out.cs, stream_ptr())
+    return out
+
+
+def _stages(stages: Sequence[tuple]):
+    arr = (GridStage * len(stages))()
+    for i, (oh, ow, nh, nw, first) in enumerate(stages):
+        arr[i].off_h, arr[i].off_w, arr[i].n_h, arr[i].n_w, arr[i].first = oh, ow, nh, nw, first
+    return arr
+
+
+def blend_canvas(preds: torch.Tensor, mask: torch.Tensor, stages: Sequence[tuple], Hc: int, Wc: int, want_count: bool = True):
+    """Sequential-exact process-canvas blend.  preds [n,ph,pw] fp32; stages = [(off_h, off_w, n_h, n_w, first)]."""
+    _chk(preds, torch.float32, "preds"); _chk(mask, torch.float32, "mask")
+    ph, pw = mask.shape
+    avg = torch.empty((Hc, Wc), dtype=torch.float32, device=preds.device)
+    cnt = torch.empty((Hc, Wc), dtype=torch.float32, device=preds.device) if want_count else None
+    _lib.call("prv2_blend_canvas", ptr(preds), ptr(mask), ph, pw, _stages(stages), len(stages), Hc, Wc, ptr(avg), ptr(cnt), stream_ptr())
+    return avg, cnt
+
+
+def blend_raw(avg_c: torch.Tensor, cnt_c: torch.Tensor, preds: Optional[torch.Tensor], starts: Optional[torch.Tensor],
+              rmask: Optional[torch.Tensor], ph: int, pw: int, rh: int, rw: int, H: int, W: int, want_count: bool = True):
+    """rN stage: resize canvas to raw resolution and fold the random patches in, in draw order."""
+    _chk(avg_c, torch.float32, "avg_c"); _chk(cnt_c, torch.float32, "cnt_c")
+    Hc, Wc = avg_c.shape
+    n = 0 if preds is None else preds.shape[0]
+    if n:
+        _chk(preds, torch.float32, "preds"); _chk(starts, torch.int32, "starts"); _chk(rmask, torch.float32, "rmask")
+    out = torch.empty((H, W), dtype=torch.float32, device=avg_c.device)
+    cnt = torch.empty((H, W), dtype=torch.float32, device=avg_c.device) if want_count else None
+    _lib.call("prv2_blend_raw", ptr(avg_c), ptr(cnt_c), Hc, Wc, ptr(preds), ptr(starts), n, ph, pw, ptr(rmask), rh, rw, H, W,
+              ptr(out), ptr(cnt), stream_ptr())
+    return out, cnt
+
+
+def blend_partial_canvas(preds, own, mask, stages, Hc, Wc, num_c, m1):
+    ph, pw = mask.shape
+    _lib.call("prv2_blend_partial_canvas", ptr(preds), ptr(own), ptr(mask), ph, pw, _stages(stages), len(stages), Hc, Wc,
+              ptr(num_c), ptr(m1), stream_ptr())
+
+
+def blend_partial_raw(preds, own, starts, rmask, ph, pw, H, W, num_r):
+    rh, rw = rmask.shape
+    _lib.call("prv2_blend_partial_raw", ptr(preds), ptr(own), ptr(starts), preds.shape[0], ph, pw, ptr(rmask), rh, rw, H, W,
+              ptr(num_r), stream_ptr())
+
+
+def blend_finalize_canvas(num_c, m1, mask, stages, Hc, Wc):
+    ph, pw = mask.shape
+    avg = torch.empty((Hc, Wc), dtype=torch.float32, device=num_c.device)
+    cnt = torch.empty((Hc, Wc), dtype=torch.float32, device=num_c.device)
+    _lib.call("prv2_blend_finalize_canvas", ptr(num_c), ptr(m1), ptr(mask), ph, pw, _stages(stages), len(stages), Hc, Wc,
+              ptr(avg), ptr(cnt), stream_ptr())
+    return avg, cnt
+
+
+def blend_finalize_raw(avg_c, cnt_c, num_r, starts, rmask, rh, rw, H, W):
+    Hc, Wc = avg_c.shape
+    n = 0 if starts is None else starts.shape[0]
+    out = torch.empty((H, W), dtype=torch.float32, device=avg_c.device)
+    cnt = torch.empty((H, W), dtype=torch.float32, device=avg_c.device)
+    _lib.call("prv2_blend_finalize_raw", ptr(avg_c), ptr(cnt_c), Hc, Wc, ptr(num_r), ptr(starts), n, ptr(rmask), rh, rw, H, W,
+              ptr(out), ptr(cnt), stream_ptr())
+    return out, cnt
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: Act, drop_period: int = 0) -> Act:
+    """x fp32 [rows, D] -> act rows (optionally dropping the class-token rows)."""
+    rows, D = x.shape
+    _lib.call("prv2_layernorm", ptr(x), rows, D, ptr(w), ptr(b), C.c_float(eps), drop_period, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr())
+    return out
+
+
+def patchify(crops: torch.Tensor, out: Act) -> Act:
+    B, _, H, W = crops.shape
+    _lib.call("prv2_patchify", ptr(crops), B, H, W, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr())
+    return out
+
+
+def assemble_tokens(emb: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: int, T: int, D: int, x: torch.Tensor):
+    _lib.call("prv2_assemble_tokens", ptr(emb), ptr(cls), ptr(pos), B, T, D, ptr(x), stream_ptr())
+
+
+def resize_bilinear(a: Act, out: Act, relu: bool = False) -> Act:
+    assert a.C == out.C and a.N == out.N
+    _lib.call("prv2_resize_bilinear_act", ptr(a.hi), ptr(a.lo), a.N, a.H, a.W, a.C, a.cs, ptr(out.hi), ptr(out.lo), out.H, out.W, out.cs,
+              1 if relu else 0, stream_ptr())
+    return out
+
+
+def depth_slots(pred1: torch.Tensor, pred2: torch.Tensor, out: Act, c0: int):
+    """pred1/pred2 [N,1,H,W] fp32 -> channels c0, c0+1 of ``out`` (c0+2..c0+7 zeroed)."""
+    N, _, H, W = pred1.shape
+    _lib.call("prv2_depth_slots", ptr(pred1), ptr(pred2), N, H, W, ptr(out.hi), ptr(out.lo), out.H, out.W, out.cs, c0, 6, stream_ptr())
+
+
+def final_conv(feat: Act, w9c: torch.Tensor, base: Optional[torch.Tensor], out: torch.Tensor):
+    _lib.call("prv2_final_conv", ptr(feat.hi), ptr(feat.lo), feat.N, feat.H, feat.W, feat.C, feat.cs, ptr(w9c), ptr(base), ptr(out), stream_ptr())
+
+
+def phase_split(a: Act, out: Act):
+    """out is [4*N, H/2, W/2, C] (phase-major)."""
+    _lib.call("prv2_phase_split", ptr(a.hi), ptr(a.lo), a.N, a.H, a.W, a.C, a.cs, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr())
+
+
+def attention(qkv: Act, B: int, T: int, heads: int, out: Act):
+    _lib.call("prv2_attention", ptr(qkv.hi), ptr(qkv.lo), B, T, heads, ptr(out.hi), ptr(out.lo), stream_ptr())

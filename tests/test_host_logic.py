@@ -1,0 +1,121 @@
+"""Host-side product logic (tiling, masks, registry, C-ABI surface) on CPU."""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pr_oracle as O
+from patchrefinerv2_b200 import _lib, masks, tiling
+from patchrefinerv2_b200.registry import MODELS, build_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("shape", [(448, 448), (384, 512)])
+@pytest.mark.parametrize("mode", ["m1", "m2", "r32"])
+def test_schedule_matches_reference_golden_bit_exact(golden_dir, shape, mode):
+    g = np.load(os.path.join(golden_dir, f"geom_{shape[0]}x{shape[1]}_{mode}.npz"))
+    tc = tiling.prepare_tile_cfg(shape, (2160, 3840), (4, 4))
+    random.seed(1)
+    stages = tiling.schedule(tc, shape, mode, int(g["process_num"]))
+    bb = np.concatenate([s.bboxs for s in stages])
+    assert bb.dtype == np.int32 and np.array_equal(bb, g["bboxs"])
+    bf = np.concatenate([tiling.bboxs_to_feat(s.bboxs, (2160, 3840), shape) for s in stages])
+    assert bf.dtype == np.float32 and np.array_equal(bf, g["bboxs_feat"])     # inexact float32 factors replayed exactly
+
+
+def test_bbox_factor_is_inexact_like_the_reference():
+    """2160 -> 448 gives y2 = 447.99997, not 448."""
+    bf = tiling.bboxs_to_feat(np.array([[2880, 1620, 3840, 2160]], np.int32), (2160, 3840), (448, 448))
+    assert bf[0, 4] != np.float32(448.0) and abs(float(bf[0, 4]) - 448.0) < 1e-4
+    t = O.bboxs_to_feat(torch.tensor([[2880, 1620, 3840, 2160]]).int(), (2160, 3840), (448, 448)).numpy()
+    assert np.array_equal(bf, t)
+
+
+def test_random_stream_consumption_matches_reference_order():
+    tc = tiling.prepare_tile_cfg((448, 448), (2160, 3840), (4, 4))
+    random.seed(7)
+    st = tiling.random_stage(tc, 4)
+    random.seed(7)
+    hs = [random.randint(0, 2160 - 540 - 1) for _ in range(4)]
+    w0 = random.randint(0, 3840 - 960 - 1)
+    assert st.bboxs[:, 1].tolist() == hs and set(st.bboxs[:, 0].tolist()) == {w0}
+    # r-count is floor(N / process_num) * process_num (patchrefiner.py:389)
+    random.seed(1)
+    n = sum(s.bboxs.shape[0] for s in tiling.schedule(tc, (448, 448), "r10", 4) if s.kind == "random")
+    assert n == 8
+
+
+def test_tile_cfg_and_edge_cases():
+    tc = tiling.prepare_tile_cfg((448, 448), (2160, 3840), (4, 4))
+    ref = O.prepare_tile_cfg((448, 448), (2160, 3840), (4, 4))
+    assert tc == ref
+    assert tiling.resizer_size((448, 448)) == (448, 448) and tiling.resizer_size((384, 512)) == (378, 518)
+    with pytest.raises(NotImplementedError):
+        tiling.parse_cai_mode("p16")
+    with pytest.raises(AssertionError):
+        tiling.regular_stage(tc, (448, 448), (-1, 0), (0, 0), False)
+    one = tiling.prepare_tile_cfg((448, 448), (1080, 1920), (1, 1))
+    random.seed(0)
+    st = tiling.schedule(one, (448, 448), "m2", 4)
+    assert [s.bboxs.shape[0] for s in st] == [1, 0, 0, 0]            # shifted grids are empty for a 1x1 split
+
+
+def test_shard_partition():
+    for P, G in [(81, 8), (49, 4), (16, 2), (5, 8)]:
+        owns = [tiling.shard_patches(P, r, G) for r in range(G)]
+        assert np.array_equal(np.sum(owns, axis=0), np.ones(P, np.uint8))
+        assert max(int(o.sum()) for o in owns) - min(int(o.sum()) for o in owns) <= 1
+
+
+@pytest.mark.parametrize("size,border", [((448, 448), 0.15), ((224, 224), 0.15), ((540, 960), 0.15), ((384, 512), 0.1)])
+def test_masks_bit_identical_to_oracle(size, border):
+    assert np.array_equal(masks.generatemask(size, border), O.generatemask(size, border))
+    assert masks.generatemask(size, border) is masks.generatemask(size, border)        # cached
+    assert np.array_equal(masks.random_patch_mask(size, border), O.generatemask(size, border) + 1e-3)
+
+
+def test_registry_builds_by_type_name():
+    cfg = O.make_config("vits", (224, 224), (432, 768), (2, 2))
+    m = build_model(dict(type="PatchRefiner", config=cfg))
+    assert type(m).__name__ == "PatchRefiner" and MODELS.get("PatchRefiner") is type(m)
+    assert m.tile_cfg["patch_raw_shape"] == (216, 384) and m.tile_cfg["patch_reensemble_shape"] == (448, 448)
+    with pytest.raises(KeyError):
+        build_model(dict(type="Nope"))
+    bad = O.make_config("vits", (224, 224), (432, 768), (2, 2))
+    bad["coarse_branch"]["type"] = "ZoeDepth"
+    with pytest.raises(NotImplementedError):
+        build_model(dict(type="PatchRefiner", config=bad))
+
+
+def test_model_refuses_to_run_without_cuda():
+    cfg = O.make_config("vits", (224, 224), (432, 768), (2, 2))
+    m = build_model(dict(type="PatchRefiner", config=cfg))
+    lr, hr = O.synthetic_frame(cfg, 1)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            m(mode="infer", image_lr=lr, image_hr=hr, cai_mode="m1")
+    with pytest.raises(NotImplementedError):
+        m(mode="train")
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "prv2_b200.h")).read()
+    declared = set(re.findall(r"\b(prv2_[a-z0-9_]+)\s*\(", header))
+    declared -= {"prv2_stream_t"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()                                   # loads; no compute call without a GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.prv2_version() == 100
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "patchrefinerv2_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("the oracle", "").replace("oracle/", ""), fn
