@@ -235,7 +235,7 @@ class PatchRefiner(nn.Module):
         key = (kind, tuple(size))
         if key not in eng["masks"]:
             m = masks.generatemask(size, border=0.15) if kind == "p" else masks.random_patch_mask(size, border=0.15)
-            eng["masks"][key] = torch.from_numpy(np.ascontiguousarray(m)).to(eng["device"])
+            eng["masks"][key] = torch.from_numpy(np.array(m, copy=True)).to(eng["device"])
         return eng["masks"][key]
 
     def coarse_forward(self, image_lr):             # patchrefiner.py:168-185

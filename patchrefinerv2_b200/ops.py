@@ -23,6 +23,8 @@ def crop_resize(image_hr: torch.Tensor, bboxs: torch.Tensor, ph: int, pw: int) -
     _, H, W = image_hr.shape
     P = bboxs.shape[0]
     out = torch.empty((P, 3, ph, pw), dtype=torch.float32, device=image_hr.device)
+    if P == 0:
+        return out
     _lib.call("prv2_crop_resize", ptr(image_hr), H, W, ptr(bboxs), P, ptr(out), ph, pw, stream_ptr())
     return out
 
