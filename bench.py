@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the tiled high-resolution inference hot path (BASELINE.json metric):
+synthetic 2160x3840 frames, CAI r32, PatchRefiner DAv2 ViT-L (coarse + refiner) + FusionUnet,
+frames/s (+ patches/s) on N B200s, with the roofline fraction of the dominant kernel and the
+reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); patches of each frame are sharded over the ranks
+and the packed partial canvases are combined by ONE NCCL sum-reduce ("strong" scaling of a frame).
+A step = one frame through the public model API.  `value` has the frame resident in HBM and the
+result left on the device; `e2e` copies the frame from pinned host memory and the depth map back to
+the host inside the timed region.  Rank 0 prints one JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (encoder, patch_process_shape, image_raw_shape, patch_split_num, cai_mode, process_num)
+    "dav2_vitl_2160x3840_4x4_r32": ("vitl", (448, 448), (2160, 3840), (4, 4), "r32", 4),
+    "dav2_vits_2160x3840_4x4_r32": ("vits", (448, 448), (2160, 3840), (4, 4), "r32", 4),
+    "dav2_vits_1080x1920_2x2_m1": ("vits", (448, 448), (1080, 1920), (2, 2), "m1", 4),
+    "dav2_vits_432x768_2x2_r4": ("vits", (224, 224), (432, 768), (2, 2), "r4", 2),
+}
+METRIC = "frames_per_sec_2160x3840_cai_r32"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]), tf_sustained=float(p["bf16_tflops_sustained"]), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8 and f[0] == str(self.gpu_index):
+                self.rows.append(f)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+def cpu_reference_sample(cfg, sd, cai_mode, process_num, n_patches_frame, steps, warmup, log=lambda *a: None):
+    """Times the oracle port of the reference's CPU path on the host cores: one coarse pass, `steps`
+    single-patch refine passes (crop -> roi_align -> ViT + DPT -> FusionUnet) and the running-average
+    blend update of one patch; extrapolates to a full frame.  Returns (frames/s, description)."""
+    import torch
+    from oracle import pr_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    orc = O.PatchRefinerOracle(cfg, sd)
+    lr, hr = O.synthetic_frame(cfg, 1)
+    tc = orc.tile_cfg
+    ph, pw = orc.patch_process_shape
+    rh, rw = tc["patch_raw_shape"]
+    H, W = tc["image_raw_shape"]
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        feats, coarse = orc.coarse_forward(lr)
+        t_coarse = time.perf_counter() - t0
+        tt = {"coarse_prediction": coarse, "coarse_features": feats}
+        times = []
+        for i in range(warmup + steps):
+            bb = O.make_bboxs([(137 * i) % (H - rh)], [(211 * i) % (W - rw)], rh, rw)
+            t0 = time.perf_counter()
+            orc._predict(hr[0], bb, tc, tt, 1, None)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            log(f"cpu reference patch {i}: {dt:.2f}s")
+        t_patch = statistics.mean(times)
+        # blend: one RunningAverageMap.update at raw resolution (estimator/models/utils.py:31-36)
+        avg = O.RunningAverageMap(torch.rand(H, W), torch.rand(H, W))
+        pred, cnt = torch.zeros(H, W), torch.zeros(H, W)
+        cnt[100:100 + rh, 200:200 + rw] = 1.0
+        t0 = time.perf_counter()
+        for _ in range(3):
+            avg.update(pred, cnt)
+        t_blend = (time.perf_counter() - t0) / 3
+    frame_s = t_coarse + n_patches_frame * (t_patch + t_blend)
+    desc = (f"oracle port of the reference CPU path (torch {torch.__version__}, {cores} threads): 1 coarse pass {t_coarse:.2f}s + "
+            f"{steps} single-patch refine passes (mean {t_patch:.2f}s) + 1 blend update {t_blend * 1e3:.0f}ms, extrapolated to "
+            f"{n_patches_frame} patches/frame")
+    return 1.0 / frame_s, cores, desc
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dav2_vitl_2160x3840_4x4_r32", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--patch-batch", type=int, default=0, help="patches per network launch (0 = balance automatically, <= 12)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    enc, pshape, raw, split, cai_mode, process_num = WORKLOADS[args.workload]
+
+    import torch
+    from oracle import pr_oracle as O          # weight / frame generators + the CPU baseline (never on the measured GPU path)
+    from patchrefinerv2_b200 import tiling
+    cfg = O.make_config(enc, pshape, raw, split)
+    tc = tiling.prepare_tile_cfg(pshape, raw, split)
+    n_patches = sum(s.bboxs.shape[0] for s in tiling.schedule(tc, pshape, cai_mode, process_num, random.Random(0)))
+    config = {"workload": args.workload, "image_raw_shape": list(raw), "patch_process_shape": list(pshape), "patch_split_num": list(split),
+              "cai_mode": cai_mode, "process_num": process_num, "patches_per_frame": n_patches, "precision": args.precision,
+              "parallelism": f"patch-shard x{world} + 1 NCCL sum-reduce" if world > 1 else "single GPU",
+              "weights": "random-init (seeded), reference state-dict layout"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sd = O.init_patchrefiner_state_dict(cfg, 0)
+        fps, cores, desc = cpu_reference_sample(cfg, sd, cai_mode, process_num, n_patches, max(1, args.steps), max(0, args.warmup))
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "patches_per_sec": fps * n_patches,
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    from patchrefinerv2_b200 import _lib, build_model
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sd = O.init_patchrefiner_state_dict(cfg, 0)
+    n_local = -(-n_patches // world)
+    pb = args.patch_batch or -(-n_local // (-(-n_local // 12)))
+    config["patch_batch"] = pb
+    model = build_model(dict(type="PatchRefiner", config=cfg, precision=args.precision, patch_batch=pb, output_device="cuda"))
+    model.load_dict(sd)
+    model = model.cuda().eval()
+    lr, hr = O.synthetic_frame(cfg, 1)
+    lr_pin, hr_pin = lr.pin_memory(), hr.pin_memory()
+    lr_dev, hr_dev = lr.to(dev), hr.to(dev)
+    shard = world > 1
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        random.seed(1)
+        d, _ = model(mode="infer", image_lr=lr_dev, image_hr=hr_dev, cai_mode=cai_mode, process_num=process_num, shard=shard)
+        return d
+
+    host_out = torch.empty((1, 1) + ((raw[0], raw[1]) if cai_mode[0] == "r" else tc["patch_reensemble_shape"]), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        random.seed(1)
+        a = lr_pin.to(dev, non_blocking=True)
+        b = hr_pin.to(dev, non_blocking=True)
+        d, _ = model(mode="infer", image_lr=a, image_hr=b, cai_mode=cai_mode, process_num=process_num, shard=shard)
+        host_out.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller holds the depth map on the host when the step ends
+        return host_out
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if profile:
+            _lib.profile_log = []
+        l0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        log, _lib.profile_log = _lib.profile_log, None
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item()), _lib.launch_count - l0, log
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, log = timed(step_resident, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if sampler else None
+    fps = args.steps / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e, _, _ = timed(step_e2e, args.steps, 1)
+        h2d = lr.numel() * 4 + hr.numel() * 4
+        e2e = {"value": args.steps / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4,
+               "ms_per_step": ms_e / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # per-kernel CUDA-event durations from the timed region (launching stream)
+    peaks = measured_peaks()
+    agg = {}
+    layers = {}
+    for name, unit, amount, a, b, tag in log:
+        dt = a.elapsed_time(b)
+        g = agg.setdefault(name, {"unit": unit, "work": 0.0, "ms": 0.0, "launches": 0})
+        g["work"] += amount
+        g["ms"] += dt
+        g["launches"] += 1
+        if name == "prv2_umma_gemm":
+            grp = tag.split(".")[0] if tag.startswith("vit") or tag.startswith("dpt") else ".".join(tag.split(".")[:2])
+            for key in (grp, tag):
+                l = layers.setdefault(key, {"flop": 0.0, "ms": 0.0, "launches": 0})
+                l["flop"] += amount
+                l["ms"] += dt
+                l["launches"] += 1
+    kern = {}
+    for name, g in agg.items():
+        rate = g["work"] / (g["ms"] * 1e-3) if g["ms"] > 0 else 0.0
+        if g["unit"] == "flop":
+            kern[name] = {"bound": "tensor", "achieved": rate / 1e12, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": rate / 1e12 / peaks["tf_sustained"]}
+        else:
+            kern[name] = {"bound": "hbm", "achieved": rate / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "frac": rate / 1e9 / peaks["hbm"]}
+        kern[name].update(launches_per_step=g["launches"] / args.steps, ms_per_step=g["ms"] / args.steps,
+                          share_of_step=g["ms"] / ms, avg_launch_us=1e3 * g["ms"] / g["launches"])
+    gemm_layers = {k: {"tflops": v["flop"] / (v["ms"] * 1e-3) / 1e12, "frac": v["flop"] / (v["ms"] * 1e-3) / 1e12 / peaks["tf_sustained"],
+                       "ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in sorted(layers.items())}
+    gemm = kern.get("prv2_umma_gemm", {})
+    roofline = {"kernel": "umma_gemm_kernel (prv2_umma_gemm)", "bound": "tensor", "achieved": gemm.get("achieved"), "peak": peaks["tf_sustained"],
+                "unit": "TFLOP/s", "frac": gemm.get("frac"), "traffic": None, "peak_source": f"{peaks['source']} bf16 sustained",
+                "share_of_step": gemm.get("share_of_step"), "launches_per_step": gemm.get("launches_per_step"),
+                "note": "aggregate over all launches of the kernel in the timed region: sum(algorithmic FLOPs) / sum(CUDA-event durations)"}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, desc = cpu_reference_sample(cfg, sd, cai_mode, process_num, n_patches, 2, 1)
+        cpu_baseline = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
+
+    flops_frame = model._engine["coarse"].flops(1, *pshape) + n_patches * (model._engine["fine"].flops(1, *pshape) +
+                  model._engine["fusion"].flops(1, [(f.H, f.W) for f in model._engine["coarse"].forward(lr_dev)[1]][::-1]))
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-class split)", "data": "synthetic", "config": config,
+            "patches_per_sec": fps * n_patches, "algorithmic_tflop_per_frame": flops_frame / 1e12,
+            "model_tflops_per_gpu": flops_frame * fps / 1e12 / world,
+            "l2_policy": "working set per step (activations, several GB) far exceeds the 126 MB L2; no explicit flush",
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kern, "gemm_layers": gemm_layers, "cpu_baseline": cpu_baseline,
+            "workspace_gb": sum(w.nbytes() for eng in (model._engine["coarse"], model._engine["fine"], model._engine["fusion"]) for w in eng.ws.values()) / 1e9}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -203,10 +203,12 @@ int prv2_depth_slots(const float* pred1, const float* pred2, int N, int H, int W
                      prv2_bf16* out_hi, prv2_bf16* out_lo, int oh, int ow, int out_cs, int c0, int zero_pad,
                      prv2_stream_t stream);
 
-/* fusion_model.py:113-118: offset = conv3x3(feat, w[1,C,3,3], no bias); out = clamp(base+offset, 0)
- * (base may be NULL -> offset only).  feat act [N,H,W,C]; w fp32 [9,C] (tap-major); out fp32 [N,H,W]. */
-int prv2_final_conv(const prv2_bf16* feat_hi, const prv2_bf16* feat_lo, int N, int H, int W, int C, int cs,
-                    const float* w, const float* base, float* out, prv2_stream_t stream);
+/* fusion_model.py:113-118: offset = conv3x3(feat, w[1,C,3,3], no bias); out = clamp(base+offset, 0).
+ * The channel contraction runs through prv2_umma_gemm as a 1x1 conv with 9 outputs (one per tap):
+ * taps [N,H,W,ld] fp32, taps[p, r*3+s] = sum_c feat[p,c] * w[0,c,r,s].  This stencil then forms
+ * out[p] = clamp(base[p] + sum_{r,s} taps[p + (r-1, s-1), r*3+s], 0) with zero padding (base may
+ * be NULL -> offset only, no clamp).  out fp32 [N,H,W]. */
+int prv2_tap_stencil(const float* taps, int N, int H, int W, int ld, const float* base, float* out, prv2_stream_t stream);
 
 /* act <-> fp32 helpers (layout changes at the API edge and for tests). */
 int prv2_nchw_f32_to_act(const float* in, int N, int C, int H, int W,

@@ -75,7 +75,7 @@ SIGNATURES = {
     "prv2_assemble_tokens": [_p, _p, _p, _i, _i, _i, _p, _p],
     "prv2_resize_bilinear_act": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p],
     "prv2_depth_slots": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
-    "prv2_final_conv": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "prv2_tap_stencil": [_p, _i, _i, _i, _i, _p, _p, _p],
     "prv2_nchw_f32_to_act": [_p, _i, _i, _i, _i, _p, _p, _i, _p],
     "prv2_act_to_nchw_f32": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
     "prv2_phase_split": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p],
@@ -109,12 +109,25 @@ def load():
     return lib
 
 
-def call(name: str, *args) -> None:
+#: when set to a list, `call(..., work=(unit, amount))` appends (name, unit, amount, start_event, end_event)
+#: so bench.py can time individual kernels with CUDA events on the launching stream
+profile_log = None
+
+
+def call(name: str, *args, work=None) -> None:
     """Call an entry point; raise Prv2Error with the library's message on failure."""
     global launch_count
     lib = load()
+    ev = None
+    if profile_log is not None and work is not None:
+        import torch
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.prv2_last_error()
         raise Prv2Error(f"{name} failed ({rc}): {msg.decode() if msg else ''}")
+    if ev is not None:
+        ev[1].record()
+        profile_log.append((name, work[0], work[1], ev[0], ev[1], work[2] if len(work) > 2 else name))
     launch_count += 1

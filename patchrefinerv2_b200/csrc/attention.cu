@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 using namespace prv2;
 
@@ -69,6 +70,18 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 // both operand layouts use 128-byte rows, 8-row groups 1024 B apart, SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
@@ -249,6 +262,294 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: warp-specialised, software-pipelined kernel for the one-pass bf16 mode.
+//   warp 0        TMA producer: Q tiles once, then a 2-stage ring of K / V chunks
+//   warp 1        MMA issuer (one lane): S_w = Q_w K^T, O_w = P_w V for both warpgroups
+//   warps 2..5    softmax warpgroup 0 (query tile 0), warps 6..9 warpgroup 1 (query tile 1)
+// One CTA owns TWO 128-query tiles of one (image, head) so every K/V chunk is loaded once and used
+// twice, and while one warpgroup runs its softmax the tensor core works for the other.
+// Key chunks are 128 wide except the LAST, which may be up to 144 wide (UMMA N = 16..144), so the
+// 1025-token DINOv2 sequence is 7 x 128 + 129 keys in 8 chunks instead of 9; the leftover query
+// rows (T mod 128 <= 16) go to a small SIMT kernel instead of a whole extra 128-row tile.
+// TMEM: S0 | S1 (160-col slots) | O0 | O1 (64 cols each); O chunks are accumulated in registers.
+// ---------------------------------------------------------------------------------------------
+constexpr int KV_STAGES = 2;
+constexpr int KV_ROWS = 144;
+constexpr int KV_TILE_BYTES = KV_ROWS * 128;       // 18 KB
+constexpr int S_COLS = 160;                         // TMEM columns reserved per S accumulator (32-aligned)
+constexpr int V2_THREADS = 320;
+constexpr int TAIL_MAX = 16;                        // leftover rows / keys folded away from a full extra tile
+
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ float ex2_ftz(float x) {      // one MUFU.EX2; inputs are <= 0, flush-to-zero is what softmax wants
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct alignas(64) AttnParamsV2 {
+  CUtensorMap tm_q, tm_kv;
+  bf16* out_hi;
+  int B, T, heads, D, n_chunks, last_width, tq_main;
+};
+
+__global__ void __launch_bounds__(V2_THREADS, 1) attention_v2_kernel(const __grid_constant__ AttnParamsV2 p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  // tiles: Q0 Q1 | K[2] | V[2] (18 KB each) | P0(3) P1(3)
+  const uint32_t sQ = base, sK = base + 2 * TILE_BYTES, sV = sK + KV_STAGES * KV_TILE_BYTES, sP = sV + KV_STAGES * KV_TILE_BYTES;
+  const uint32_t bars = sP + 6 * TILE_BYTES;
+  const uint32_t bar_q = bars;
+  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (1 + KV_STAGES + s); };
+  auto s_full = [&](int w) { return bars + 8u * (1 + 2 * KV_STAGES + w); };
+  auto p_full = [&](int w) { return bars + 8u * (3 + 2 * KV_STAGES + w); };
+  auto o_full = [&](int w) { return bars + 8u * (5 + 2 * KV_STAGES + w); };
+  const uint32_t tmem_slot = bars + 8u * (7 + 2 * KV_STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
+  const int D = p.D, T = p.T;
+  const int n_chunks = p.n_chunks;
+  const int n_wg = (q0 + 128 < p.tq_main) ? 2 : 1;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full(w), 1); mbar_init(p_full(w), 128); mbar_init(o_full(w), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, n_wg * TILE_BYTES);
+      for (int w = 0; w < n_wg; ++w) tma_load_3d(sQ + w * TILE_BYTES, &p.tm_q, bar_q, head * 64, q0 + w * 128, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_chunks; ++j) {
+        mbar_wait(kv_empty(stage), phase ^ 1);
+        mbar_expect_tx(kv_full(stage), 2 * KV_TILE_BYTES);
+        tma_load_3d(sK + stage * KV_TILE_BYTES, &p.tm_kv, kv_full(stage), D + head * 64, j * 128, b);
+        tma_load_3d(sV + stage * KV_TILE_BYTES, &p.tm_kv, kv_full(stage), 2 * D + head * 64, j * 128, b);
+        if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      auto issue_s = [&](int w, int stage, int width) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(width >> 3) << 17) | ((128u >> 4) << 24);
+        uint32_t accum = 0;
+        for (int k = 0; k < 4; ++k) {
+          tc_mma_bf16(tmem_base + w * S_COLS, umma_desc_sw128(sQ + w * TILE_BYTES) + 2 * k, umma_desc_sw128(sK + stage * KV_TILE_BYTES) + 2 * k, idesc, accum);
+          accum = 1;
+        }
+        tc_commit(s_full(w));
+      };
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      auto issue_o = [&](int w, int stage, int width) {
+        uint32_t accum = 0;
+        for (int k = 0; k < (width >> 4); ++k) {     // 16-key slices: A advances 32 B inside P tile (k>>2), B advances 16 key rows
+          tc_mma_bf16(tmem_base + 2 * S_COLS + w * 64, umma_desc_sw128(sP + (3 * w + (k >> 2)) * TILE_BYTES) + 2 * (k & 3),
+                      umma_desc_sw128(sV + stage * KV_TILE_BYTES + k * 2048), idesc_o, accum);
+          accum = 1;
+        }
+        tc_commit(o_full(w));
+      };
+      auto width_of = [&](int j) { return j == n_chunks - 1 ? p.last_width : 128; };
+      mbar_wait(bar_q, 0);
+      mbar_wait(kv_full(0), 0);
+      tc_fence_after();
+      for (int w = 0; w < n_wg; ++w) issue_s(w, 0, width_of(0));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_chunks; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
+        for (int w = 0; w < n_wg; ++w) {
+          mbar_wait(p_full(w), j & 1);          // P_w(j) is in smem; S_w(j) and O_w(j-1) have been consumed
+          tc_fence_after();
+          issue_o(w, stage, width_of(j));
+          if (j + 1 < n_chunks) {
+            if (w == 0) { mbar_wait(kv_full(nstage), nphase); tc_fence_after(); }
+            issue_s(w, nstage, width_of(j + 1));
+          }
+        }
+        tc_commit(kv_empty(stage));             // K_j / V_j are free once everything issued so far has retired
+        stage = nstage; phase = nphase;
+      }
+    }
+  } else {
+    const int w = (warp - 2) >> 2;
+    if (w < n_wg) {
+      const int row = (warp & 3) * 32 + lane;               // TMEM lane == query row of this tile
+      const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t tS = tmem_base + w * S_COLS + lane_off, tO = tmem_base + 2 * S_COLS + w * 64 + lane_off;
+      uint8_t* pP = base_ptr + (sP - base) + 3 * w * TILE_BYTES;
+      const float c_log2 = 0.125f * 1.4426950408889634f;
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f;
+      // one 16- or 32-column piece of the row: exp, row sum, bf16 pack, swizzled store (SW128 K-major P tile)
+      auto emit = [&](const float* v, int col0, int ncols, float mc, float& l_add, int n_valid, bool masked) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 8 >= ncols) break;
+          float e[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            float pv = ex2_ftz(fmaf(v[g * 8 + t], c_log2, -mc));
+            if (masked && col0 + g * 8 + t >= n_valid) pv = 0.f;
+            e[t] = pv;
+            l_add += pv;
+          }
+          const int key = col0 + g * 8;                  // 8 consecutive keys = one 16-byte chunk of the P row
+          const int tile = key >> 6, chunk = (key & 63) >> 3;
+          __nv_bfloat162 h2[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(e[2 * t], e[2 * t + 1]);
+          *reinterpret_cast<uint4*>(pP + tile * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(h2);
+        }
+      };
+      for (int j = 0; j < n_chunks; ++j) {
+        const uint32_t ph = j & 1;
+        const bool last = j == n_chunks - 1;
+        const int n_valid = T - j * 128;                    // >= width on all but the last chunk
+        const bool masked = last && n_valid < 128;       // stale / padded columns inside the first 128
+        mbar_wait(s_full(w), ph);
+        tc_fence_after();
+        float v[32];
+        float m_new = m_run;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tc_ld32(tS + c * 32, v);
+          if (!masked) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m_new = fmaxf(m_new, v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (c * 32 + i < n_valid) m_new = fmaxf(m_new, v[i]);
+          }
+        }
+        float v16[16];
+        if (last && p.last_width > 128) {                   // keys 128..143 of the wide last chunk
+          tc_ld16(tS + 128, v16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (128 + i < n_valid) m_new = fmaxf(m_new, v16[i]);
+        }
+        const float alpha = ex2_ftz((m_run - m_new) * c_log2);
+        const float mc = m_new * c_log2;
+        float l_add = 0.f;
+        if (last && p.last_width > 128) emit(v16, 128, 16, mc, l_add, n_valid, true);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if (last && c * 32 >= p.last_width) break;
+          tc_ld32(tS + c * 32, v);
+          emit(v, c * 32, 32, mc, l_add, n_valid, masked);
+        }
+        l_run = l_run * alpha + l_add;
+        m_run = m_new;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive_local(p_full(w));
+        mbar_wait(o_full(w), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tc_ld32(tO + c * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha, v[i]);
+        }
+      }
+      const int q = q0 + w * 128 + row;
+      if (q < p.tq_main) {
+        const float inv = 1.0f / l_run;
+        const size_t o = ((size_t)b * T + q) * D + head * 64;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float t[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = acc[g * 8 + e] * inv;
+          act_store8(p.out_hi, nullptr, o + g * 8, t);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// Leftover query rows [tq_main, T): one warp per (image, head, row); plain SIMT online softmax over all keys.
+__global__ void __launch_bounds__(128) attention_tail_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int T, int heads,
+                                                             int tq_main) {
+  const int n_tail = T - tq_main;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= B * heads * n_tail) return;
+  const int r = wid % n_tail, head = (wid / n_tail) % heads, b = wid / (n_tail * heads);
+  const int D = heads * 64;
+  const size_t row_stride = (size_t)3 * D;
+  const bf16* base = qkv + (size_t)b * T * row_stride;
+  const bf16* qp = base + (size_t)(tq_main + r) * row_stride + head * 64;
+  float q[64];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) { float t[8]; act_load8(qp, nullptr, g * 8, t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[g * 8 + e] = t[e]; }
+  float m = -INFINITY, l = 0.f, acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  const float c_log2 = 0.125f * 1.4426950408889634f;
+  for (int k = lane; k < T; k += 32) {
+    const bf16* kp = base + (size_t)k * row_stride + D + head * 64;
+    const bf16* vp = kp + D;
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { float t[8]; act_load8(kp, nullptr, g * 8, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s = fmaf(q[g * 8 + e], t[e], s); }
+    const float m_new = fmaxf(m, s);
+    const float alpha = exp2f((m - m_new) * c_log2), pv = exp2f((s - m_new) * c_log2);
+    l = l * alpha + pv;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { float t[8]; act_load8(vp, nullptr, g * 8, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[g * 8 + e] = fmaf(acc[g * 8 + e], alpha, pv * t[e]); }
+    m = m_new;
+  }
+  // merge the 32 lanes' partial softmax states
+  float m_all = m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, o));
+  const float scale = (m == -INFINITY) ? 0.f : exp2f((m - m_all) * c_log2);
+  l *= scale;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  bf16* op = out + ((size_t)b * T + tq_main + r) * D + head * 64;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    float a = acc[i] * scale;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == (i & 31)) op[i] = f2bf(a / l);
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -290,14 +591,39 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
   p.B = B; p.T = T; p.heads = heads; p.D = D;
   const int smem1 = 5 * TILE_BYTES + 1024 + 64, smem3 = 10 * TILE_BYTES + 1024 + 64;
+  const int smem_v2 = 2 * TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 6 * TILE_BYTES + 1024 + 256;
+  static const bool force_v1 = getenv("PRV2_ATTN_V1") != nullptr;
   if (!g_attr_set) {
+    PRV2_CUDA(cudaFuncSetAttribute(attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v2));
     PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     g_attr_set = true;
   }
   dim3 grid(cdiv(T, 128), heads, B);
-  if (qkv_lo) attention_kernel<true><<<grid, 128, smem3, (cudaStream_t)stream>>>(p);
-  else attention_kernel<false><<<grid, 128, smem1, (cudaStream_t)stream>>>(p);
+  if (qkv_lo) { attention_kernel<true><<<grid, 128, smem3, (cudaStream_t)stream>>>(p); PRV2_LAUNCH_CHECK(); return PRV2_OK; }
+  if (force_v1) { attention_kernel<false><<<grid, 128, smem1, (cudaStream_t)stream>>>(p); PRV2_LAUNCH_CHECK(); return PRV2_OK; }
+
+  AttnParamsV2 p2;
+  memset(&p2, 0, sizeof(p2));
+  p2.tm_q = p.tm_hi;
+  cuuint32_t box_kv[3] = {64, KV_ROWS, 1};
+  r = enc(&p2.tm_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)qkv_hi, dims, strides, box_kv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("prv2_attention: cuTensorMapEncodeTiled(kv) failed (%d)", (int)r); return PRV2_ECUDA; }
+  p2.out_hi = (bf16*)out_hi;
+  p2.B = B; p2.T = T; p2.heads = heads; p2.D = D;
+  // key chunks: 128 wide, the last one 16..144 (multiple of 16) so that T mod 128 <= 16 does not cost a whole chunk
+  p2.n_chunks = T <= KV_ROWS ? 1 : cdiv(T - TAIL_MAX, 128);
+  p2.last_width = ((T - 128 * (p2.n_chunks - 1)) + 15) / 16 * 16;
+  // query rows: leftover rows (<= 16) go to the SIMT tail kernel instead of a mostly empty 128-row tile
+  const int rem = T % 128;
+  p2.tq_main = (rem != 0 && rem <= TAIL_MAX && T > 128) ? T - rem : T;
+  attention_v2_kernel<<<dim3(cdiv(p2.tq_main, 256), heads, B), V2_THREADS, smem_v2, (cudaStream_t)stream>>>(p2);
   PRV2_LAUNCH_CHECK();
+  if (p2.tq_main < T) {
+    const int warps = B * heads * (T - p2.tq_main);
+    attention_tail_kernel<<<cdiv(warps, 4), 128, 0, (cudaStream_t)stream>>>((const bf16*)qkv_hi, (bf16*)out_hi, B, T, heads, p2.tq_main);
+    PRV2_LAUNCH_CHECK();
+  }
   return PRV2_OK;
 }

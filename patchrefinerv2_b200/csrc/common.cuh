@@ -50,25 +50,31 @@ __device__ __forceinline__ void act_store(bf16* hi, bf16* lo, size_t i, float v)
 struct alignas(16) bf16x8 { bf16 v[8]; };
 
 __device__ __forceinline__ void act_load8(const bf16* hi, const bf16* lo, size_t i, float (&out)[8]) {
-  bf16x8 a = *reinterpret_cast<const bf16x8*>(hi + i);
+  const uint4 a = *reinterpret_cast<const uint4*>(hi + i);
+  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) out[k] = bf2f(a.v[k]);
+  for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(a2[k]); out[2 * k] = f.x; out[2 * k + 1] = f.y; }
   if (lo) {
-    bf16x8 b = *reinterpret_cast<const bf16x8*>(lo + i);
+    const uint4 b = *reinterpret_cast<const uint4*>(lo + i);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) out[k] += bf2f(b.v[k]);
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(b2[k]); out[2 * k] += f.x; out[2 * k + 1] += f.y; }
   }
 }
 __device__ __forceinline__ void act_store8(bf16* hi, bf16* lo, size_t i, const float (&in)[8]) {
-  bf16x8 a;
+  // packed conversions (F2FP.BF16.PACK_AB: two values per instruction on the FMA pipe)
+  __nv_bfloat162 h2[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a.v[k] = f2bf(in[k]);
-  *reinterpret_cast<bf16x8*>(hi + i) = a;
+  for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(in[2 * k], in[2 * k + 1]);
+  *reinterpret_cast<uint4*>(hi + i) = *reinterpret_cast<const uint4*>(h2);
   if (lo) {
-    bf16x8 b;
+    __nv_bfloat162 l2[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) b.v[k] = f2bf(in[k] - bf2f(a.v[k]));
-    *reinterpret_cast<bf16x8*>(lo + i) = b;
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h2[k]);
+      l2[k] = __floats2bfloat162_rn(in[2 * k] - f.x, in[2 * k + 1] - f.y);
+    }
+    *reinterpret_cast<uint4*>(lo + i) = *reinterpret_cast<const uint4*>(l2);
   }
 }
 

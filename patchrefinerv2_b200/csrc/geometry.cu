@@ -152,30 +152,33 @@ __global__ void __launch_bounds__(256) roi_gather_f32_kernel(const float* __rest
   }
 }
 
-// one thread = one output pixel x 8 channels (16 B of bf16)
+// one thread = one output pixel x 8 channels (16 B of bf16).  grid (ceil(w*C/8 / 256), h, P): the ROI
+// geometry and the row taps are block-uniform; no 64-bit div/mod per element.
+constexpr int ROI_ITEMS = 8;     // outputs per thread (CTA launch rate, not HBM, limited the one-output-per-thread version)
+
 __global__ void __launch_bounds__(256) roi_gather_act_kernel(const bf16* __restrict__ fh, const bf16* __restrict__ fl, int h, int w,
                                                              int C, int in_cs, const float* __restrict__ rois, float s,
-                                                             bf16* __restrict__ oh, bf16* __restrict__ ol, int out_cs,
-                                                             long long total) {
-  const int cv = C / 8;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % cv) * 8;
-    long long pix = idx / cv;
-    const int x = (int)(pix % w);
-    pix /= w;
-    const int y = (int)(pix % h);
-    const int p = (int)(pix / h);
-    const RoiGeom g = roi_geom(rois + p * 4, s, h, w);
-    const RoiAxis ay = roi_axis(g.y1, g.bh, y, h), ax = roi_axis(g.x1, g.bw, x, w);
+                                                             bf16* __restrict__ oh, bf16* __restrict__ ol, int out_cs) {
+  const unsigned cv = (unsigned)C >> 3, total = (unsigned)w * cv;
+  const int y = blockIdx.y, p = blockIdx.z;
+  const RoiGeom g = roi_geom(rois + p * 4, s, h, w);
+  const RoiAxis ay = roi_axis(g.y1, g.bh, y, h);
+  const size_t r_lo = (size_t)ay.lo * w, r_hi = (size_t)ay.hi * w, orow = ((size_t)p * h + y) * w;
+#pragma unroll 2
+  for (int it = 0; it < ROI_ITEMS; ++it) {
+    const unsigned idx = (blockIdx.x * ROI_ITEMS + it) * 256u + threadIdx.x;
+    if (idx >= total) break;
+    const int x = (int)(idx / cv), c8 = (int)(idx % cv) * 8;
+    const RoiAxis ax = roi_axis(g.x1, g.bw, x, w);
     const bool valid = ay.valid && ax.valid;
     float v1[8], v2[8], v3[8], v4[8], o[8];
-    act_load8(fh, fl, ((size_t)ay.lo * w + ax.lo) * in_cs + c8, v1);
-    act_load8(fh, fl, ((size_t)ay.lo * w + ax.hi) * in_cs + c8, v2);
-    act_load8(fh, fl, ((size_t)ay.hi * w + ax.lo) * in_cs + c8, v3);
-    act_load8(fh, fl, ((size_t)ay.hi * w + ax.hi) * in_cs + c8, v4);
+    act_load8(fh, fl, (r_lo + ax.lo) * in_cs + c8, v1);
+    act_load8(fh, fl, (r_lo + ax.hi) * in_cs + c8, v2);
+    act_load8(fh, fl, (r_hi + ax.lo) * in_cs + c8, v3);
+    act_load8(fh, fl, (r_hi + ax.hi) * in_cs + c8, v4);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = valid ? roi_mix(ay, ax, v1[k], v2[k], v3[k], v4[k]) : 0.f;
-    act_store8(oh, ol, (((size_t)p * h + y) * w + x) * out_cs + c8, o);
+    act_store8(oh, ol, (orow + x) * out_cs + c8, o);
   }
 }
 
@@ -202,9 +205,10 @@ extern "C" int prv2_roi_gather_act(const prv2_bf16* feat_hi, const prv2_bf16* fe
   PRV2_CHECK_ARG(h > 0 && w > 0 && C > 0 && P >= 0, "prv2_roi_gather_act: bad shape");
   PRV2_CHECK_ARG(C % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0, "prv2_roi_gather_act: C/pitch must be multiples of 8");
   if (P == 0) return PRV2_OK;
-  long long total = (long long)P * h * w * (C / 8);
-  roi_gather_act_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)feat_hi, (const bf16*)feat_lo, h, w, C, in_cs, rois, spatial_scale, (bf16*)out_hi, (bf16*)out_lo, out_cs, total);
+  PRV2_CHECK_ARG(h <= 65535 && P <= 65535, "prv2_roi_gather_act: grid too large");
+  dim3 grid(cdiv((long long)w * (C / 8), 256 * ROI_ITEMS), h, P);
+  roi_gather_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)feat_hi, (const bf16*)feat_lo, h, w, C, in_cs, rois, spatial_scale,
+                                                               (bf16*)out_hi, (bf16*)out_lo, out_cs);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -224,7 +228,8 @@ __device__ __forceinline__ void ram_update(float& avg, float& cnt, float pred, f
   cnt = den;
 }
 
-// Thread = 4 consecutive canvas pixels of one row (one float4 store per output plane).
+// Thread = 4 consecutive canvas pixels of one row: one (y / ph, x / pw) per stage per THREAD, float4
+// loads of the mask / prediction rows when the group sits inside one patch, float4 stores.
 // MODE 0: sequential-exact; 1: partial sums (own patches only); 2: finalize from reduced sums.
 template <int MODE>
 __global__ void __launch_bounds__(256) blend_canvas_kernel(const float* __restrict__ preds, const uint8_t* __restrict__ own,
@@ -234,51 +239,86 @@ __global__ void __launch_bounds__(256) blend_canvas_kernel(const float* __restri
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
   if (x0 >= Wc) return;
+  const size_t o = (size_t)y * Wc + x0;
+  const bool vec_out = ((Wc & 3) == 0);
+  float avg[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f}, num[4] = {0.f, 0.f, 0.f, 0.f}, m1[4] = {0.f, 0.f, 0.f, 0.f},
+        cnt0[4] = {0.f, 0.f, 0.f, 0.f};
+  if (MODE == 2) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (x0 + k < Wc) { num[k] = num_in[o + k]; m1[k] = m1_in[o + k]; }
+  }
+  for (int s = 0; s < st.n; ++s) {
+    const prv2_grid_stage g = st.s[s];
+    const int yy = y - g.off_h;
+    if (yy < 0) continue;
+    const int i = yy / ph;
+    if (i >= g.n_h) continue;
+    const int ly = yy - i * ph;
+    const int xx0 = x0 - g.off_w;
+    float ct[4], pv[4];
+    bool ok[4];
+    int j0 = 0, lx0 = 0;
+    if (xx0 >= 0) { j0 = xx0 / pw; lx0 = xx0 - j0 * pw; }
+    const bool fast = xx0 >= 0 && j0 < g.n_w && lx0 + 3 < pw && x0 + 3 < Wc && ((lx0 | pw) & 3) == 0;
+    if (fast) {
+      const int pidx = g.first + i * g.n_w + j0;
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(mask + (size_t)ly * pw + lx0));
+      ct[0] = c4.x; ct[1] = c4.y; ct[2] = c4.z; ct[3] = c4.w;
+      const bool mine = (MODE == 0) || (MODE == 1 && own[pidx]);
+      if (mine) {
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(preds + ((size_t)pidx * ph + ly) * pw + lx0));
+        pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+      } else {
+        pv[0] = pv[1] = pv[2] = pv[3] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ok[k] = (MODE != 1) || mine;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int xx = xx0 + k;
+        ok[k] = false; ct[k] = 0.f; pv[k] = 0.f;
+        if (xx < 0 || x0 + k >= Wc) continue;
+        const int j = xx / pw;
+        if (j >= g.n_w) continue;
+        const int lx = xx - j * pw, pidx = g.first + i * g.n_w + j;
+        ct[k] = __ldg(mask + (size_t)ly * pw + lx);
+        if (MODE == 2) { ok[k] = true; continue; }
+        if (MODE == 1 && !own[pidx]) continue;
+        pv[k] = __ldg(preds + ((size_t)pidx * ph + ly) * pw + lx);
+        ok[k] = true;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      if (MODE == 0) {
+        if (s == 0) { avg[k] = pv[k]; cnt[k] = ct[k]; }                  // baseline_pretrain.py:352-355 (assignment)
+        else if (ct[k] > 0.f) ram_update(avg[k], cnt[k], pv[k], ct[k]);   // utils.py:31-36
+      } else if (MODE == 1) {
+        if (s == 0) m1[k] = pv[k];
+        else if (ct[k] > 0.f) num[k] = __fadd_rn(num[k], __fmul_rn(pv[k], ct[k]));
+      } else {
+        if (s == 0) { cnt[k] = ct[k]; cnt0[k] = ct[k]; }
+        else if (ct[k] > 0.f) cnt[k] = __fadd_rn(cnt[k], ct[k]);
+      }
+    }
+  }
   float r_a[4], r_c[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int x = x0 + k;
-    r_a[k] = 0.f; r_c[k] = 0.f;
-    if (x >= Wc) continue;
-    float avg = 0.f, cnt = 0.f, num = 0.f, m1 = 0.f, cnt0 = 0.f;
-    if (MODE == 2) { num = num_in[(size_t)y * Wc + x]; m1 = m1_in[(size_t)y * Wc + x]; }
-    for (int s = 0; s < st.n; ++s) {
-      const prv2_grid_stage g = st.s[s];
-      const int yy = y - g.off_h, xx = x - g.off_w;
-      if (yy < 0 || xx < 0) continue;
-      const int i = yy / ph, j = xx / pw;
-      if (i >= g.n_h || j >= g.n_w) continue;
-      const int ly = yy - i * ph, lx = xx - j * pw;
-      const int pidx = g.first + i * g.n_w + j;
-      const float ct = __ldg(mask + (size_t)ly * pw + lx);
-      if (MODE == 0) {
-        const float p = __ldg(preds + ((size_t)pidx * ph + ly) * pw + lx);
-        if (s == 0) { avg = p; cnt = ct; }                         // baseline_pretrain.py:352-355 (assignment)
-        else if (ct > 0.f) ram_update(avg, cnt, p, ct);            // utils.py:31-36
-      } else if (MODE == 1) {
-        if (own[pidx]) {
-          const float p = __ldg(preds + ((size_t)pidx * ph + ly) * pw + lx);
-          if (s == 0) m1 = p;
-          else if (ct > 0.f) num = __fadd_rn(num, __fmul_rn(p, ct));
-        }
-      } else {
-        if (s == 0) { cnt = ct; cnt0 = ct; }
-        else if (ct > 0.f) cnt = __fadd_rn(cnt, ct);
-      }
-    }
-    if (MODE == 0) { r_a[k] = avg; r_c[k] = cnt; }
-    else if (MODE == 1) { r_a[k] = num; r_c[k] = m1; }
+    if (MODE == 0) { r_a[k] = avg[k]; r_c[k] = cnt[k]; }
+    else if (MODE == 1) { r_a[k] = num[k]; r_c[k] = m1[k]; }
     else {
       // sum form of the running mean: (m1*cnt0 + sum w p) / (cnt0 + sum w); untouched pixels keep m1
-      r_a[k] = (cnt > cnt0) ? __fdiv_rn(__fadd_rn(__fmul_rn(m1, cnt0), num), cnt) : m1;
-      r_c[k] = cnt;
+      r_a[k] = (cnt[k] > cnt0[k]) ? __fdiv_rn(__fadd_rn(__fmul_rn(m1[k], cnt0[k]), num[k]), cnt[k]) : m1[k];
+      r_c[k] = cnt[k];
     }
   }
-  const size_t o = (size_t)y * Wc + x0;
-  const bool vec = ((Wc & 3) == 0);
   if (MODE == 1) {       // accumulate into num_c (avg_out) and the m1 plane (cnt_out)
     for (int k = 0; k < 4 && x0 + k < Wc; ++k) { avg_out[o + k] += r_a[k]; cnt_out[o + k] += r_c[k]; }
-  } else if (vec) {
+  } else if (vec_out) {
     *reinterpret_cast<float4*>(avg_out + o) = make_float4(r_a[0], r_a[1], r_a[2], r_a[3]);
     if (cnt_out) *reinterpret_cast<float4*>(cnt_out + o) = make_float4(r_c[0], r_c[1], r_c[2], r_c[3]);
   } else {
@@ -332,17 +372,20 @@ extern "C" int prv2_blend_finalize_canvas(const float* num_c, const float* m1, c
 }
 
 // rN stage.  Block = one raw row segment of 1024 pixels, thread = 4 consecutive pixels.  Warp 0
-// compacts the random-patch list to the patches covering this row (ballot, draw order kept);
-// every pixel then walks that short list in order.
+// compacts the random-patch list to the patches covering this row (ballot, draw order kept) and
+// precomputes their row offsets; every pixel then walks that short list in order.  All resampling
+// scales are fp32 quotients formed once on the host (same IEEE division the device would do).
 #define PRV2_MAX_RANDOM 512
+struct RawScales { float ns_y, ns_x, bs_y, bs_x, ps_y, ps_x; };
+
 template <int MODE>
 __global__ void __launch_bounds__(256) blend_raw_kernel(const float* __restrict__ avg_c, const float* __restrict__ cnt_c, int Hc, int Wc,
                                                         const float* __restrict__ preds, const uint8_t* __restrict__ own,
                                                         const int32_t* __restrict__ starts, int n, int ph, int pw,
                                                         const float* __restrict__ rmask, int rh, int rw, int H, int W,
                                                         float* __restrict__ out, float* __restrict__ out_cnt,
-                                                        const float* __restrict__ num_in) {
-  __shared__ int s_k[PRV2_MAX_RANDOM], s_y0[PRV2_MAX_RANDOM], s_x0[PRV2_MAX_RANDOM];
+                                                        const float* __restrict__ num_in, RawScales sc) {
+  __shared__ int s_x0[PRV2_MAX_RANDOM], s_prow[PRV2_MAX_RANDOM], s_mrow[PRV2_MAX_RANDOM];
   __shared__ int s_n;
   const int y = blockIdx.y;
   if (threadIdx.x < 32) {
@@ -356,7 +399,14 @@ __global__ void __launch_bounds__(256) blend_raw_kernel(const float* __restrict_
         hit = (y >= y0 && y < y0 + rh) && (MODE != 1 || own[k]);
       }
       const unsigned b = __ballot_sync(0xffffffffu, hit);
-      if (hit) { const int pos = m + __popc(b & ((1u << threadIdx.x) - 1)); s_k[pos] = k; s_y0[pos] = y0; s_x0[pos] = x0; }
+      if (hit) {
+        const int pos = m + __popc(b & ((1u << threadIdx.x) - 1));
+        const int ly = y - y0;
+        s_x0[pos] = x0;
+        s_mrow[pos] = ly * rw;
+        // baseline_pretrain.py:210 F.interpolate(predictions, patch_raw_shape) (nearest), row part
+        s_prow[pos] = (k * ph + nearest_src(ly, sc.ps_y, ph)) * pw;
+      }
       m += __popc(b);
     }
     if (threadIdx.x == 0) s_n = m;
@@ -365,44 +415,52 @@ __global__ void __launch_bounds__(256) blend_raw_kernel(const float* __restrict_
   const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (xb >= W) return;
   const int m = s_n;
-  const float ps_y = __fdiv_rn((float)ph, (float)rh), ps_x = __fdiv_rn((float)pw, (float)rw);
+  const size_t o = (size_t)y * W + xb;
+  float avg[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f}, num[4] = {0.f, 0.f, 0.f, 0.f}, c0[4] = {0.f, 0.f, 0.f, 0.f};
+  if (MODE != 1) {
+    // utils.py:42: average map -> nearest ; utils.py:43: count map -> bilinear(align_corners=True)
+    const float* arow = avg_c + (size_t)nearest_src(y, sc.ns_y, Hc) * Wc;
+    const BilinearTap ty = ac_tap(sc.bs_y, y, Hc);
+    const float* c_r0 = cnt_c + (size_t)ty.i0 * Wc;
+    const float* c_r1 = cnt_c + (size_t)ty.i1 * Wc;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int x = xb + q;
+      if (x >= W) continue;
+      avg[q] = __ldg(arow + nearest_src(x, sc.ns_x, Wc));
+      const BilinearTap tx = ac_tap(sc.bs_x, x, Wc);
+      cnt[q] = ac_blend(ty, tx, __ldg(c_r0 + tx.i0), __ldg(c_r0 + tx.i1), __ldg(c_r1 + tx.i0), __ldg(c_r1 + tx.i1));
+      c0[q] = cnt[q];
+    }
+    if (MODE == 2) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (xb + q < W) num[q] = num_in[o + q];
+    }
+  }
+  for (int i = 0; i < m; ++i) {
+    const int x0 = s_x0[i];
+    if (xb + 3 < x0 || xb >= x0 + rw) continue;            // group entirely outside this patch
+    const float* mrow = rmask + s_mrow[i];
+    const float* prow = preds + s_prow[i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int lx = xb + q - x0;
+      if (lx < 0 || lx >= rw || xb + q >= W) continue;
+      const float ct = __ldg(mrow + lx);
+      if (!(ct > 0.f)) continue;
+      if (MODE == 2) { cnt[q] = __fadd_rn(cnt[q], ct); continue; }
+      const float p = __ldg(prow + nearest_src(lx, sc.ps_x, pw));
+      if (MODE == 0) ram_update(avg[q], cnt[q], p, ct);
+      else num[q] = __fadd_rn(num[q], __fmul_rn(p, ct));
+    }
+  }
   float r_a[4], r_c[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const int x = xb + q;
-    r_a[q] = 0.f; r_c[q] = 0.f;
-    if (x >= W) continue;
-    const size_t o = (size_t)y * W + x;
-    float avg = 0.f, cnt = 0.f, num = 0.f, c0 = 0.f;
-    if (MODE != 1) {
-      // utils.py:42: average map -> nearest ; utils.py:43: count map -> bilinear(align_corners=True)
-      const float ns_y = __fdiv_rn((float)Hc, (float)H), ns_x = __fdiv_rn((float)Wc, (float)W);
-      const int sy = nearest_src(y, ns_y, Hc), sx = nearest_src(x, ns_x, Wc);
-      avg = __ldg(avg_c + (size_t)sy * Wc + sx);
-      const BilinearTap ty = ac_tap(ac_scale(Hc, H), y, Hc), tx = ac_tap(ac_scale(Wc, W), x, Wc);
-      cnt = ac_blend(ty, tx, __ldg(cnt_c + (size_t)ty.i0 * Wc + tx.i0), __ldg(cnt_c + (size_t)ty.i0 * Wc + tx.i1),
-                     __ldg(cnt_c + (size_t)ty.i1 * Wc + tx.i0), __ldg(cnt_c + (size_t)ty.i1 * Wc + tx.i1));
-      c0 = cnt;
-      if (MODE == 2) num = num_in[o];
-    }
-    for (int i = 0; i < m; ++i) {
-      const int x0 = s_x0[i];
-      if (x < x0 || x >= x0 + rw) continue;
-      const int ly = y - s_y0[i], lx = x - x0;
-      const float ct = __ldg(rmask + (size_t)ly * rw + lx);
-      if (!(ct > 0.f)) continue;
-      if (MODE == 2) { cnt = __fadd_rn(cnt, ct); continue; }
-      // baseline_pretrain.py:210 F.interpolate(predictions, patch_raw_shape) (nearest)
-      const int py = nearest_src(ly, ps_y, ph), px = nearest_src(lx, ps_x, pw);
-      const float p = __ldg(preds + ((size_t)s_k[i] * ph + py) * pw + px);
-      if (MODE == 0) ram_update(avg, cnt, p, ct);
-      else num = __fadd_rn(num, __fmul_rn(p, ct));
-    }
-    if (MODE == 0) { r_a[q] = avg; r_c[q] = cnt; }
-    else if (MODE == 1) { r_a[q] = num; }
-    else { r_a[q] = (cnt > c0) ? __fdiv_rn(__fadd_rn(__fmul_rn(avg, c0), num), cnt) : avg; r_c[q] = cnt; }
+    if (MODE == 0) { r_a[q] = avg[q]; r_c[q] = cnt[q]; }
+    else if (MODE == 1) { r_a[q] = num[q]; r_c[q] = 0.f; }
+    else { r_a[q] = (cnt[q] > c0[q]) ? __fdiv_rn(__fadd_rn(__fmul_rn(avg[q], c0[q]), num[q]), cnt[q]) : avg[q]; r_c[q] = cnt[q]; }
   }
-  const size_t o = (size_t)y * W + xb;
   if (MODE == 1) {
     for (int q = 0; q < 4 && xb + q < W; ++q) out[o + q] += r_a[q];
   } else if ((W & 3) == 0) {
@@ -411,6 +469,15 @@ __global__ void __launch_bounds__(256) blend_raw_kernel(const float* __restrict_
   } else {
     for (int q = 0; q < 4 && xb + q < W; ++q) { out[o + q] = r_a[q]; if (out_cnt) out_cnt[o + q] = r_c[q]; }
   }
+}
+
+static RawScales raw_scales(int Hc, int Wc, int H, int W, int ph, int pw, int rh, int rw) {
+  RawScales s;
+  s.ns_y = (float)Hc / (float)H; s.ns_x = (float)Wc / (float)W;                  // ATen nearest: (float)in / out
+  s.bs_y = H > 1 ? (float)(Hc - 1) / (float)(H - 1) : 0.f;                       // ATen bilinear align_corners
+  s.bs_x = W > 1 ? (float)(Wc - 1) / (float)(W - 1) : 0.f;
+  s.ps_y = (float)ph / (float)rh; s.ps_x = (float)pw / (float)rw;
+  return s;
 }
 
 static int check_raw(const char* fn, int n, int ph, int pw, int rh, int rw, int H, int W) {
@@ -428,7 +495,7 @@ extern "C" int prv2_blend_raw(const float* avg_c, const float* cnt_c, int Hc, in
   if (rc) return rc;
   dim3 grid(cdiv(cdiv(W, 4), 256), H);
   blend_raw_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(avg_c, cnt_c, Hc, Wc, preds, nullptr, starts, n, ph, pw, rmask, rh, rw, H, W,
-                                                              out, out_cnt, nullptr);
+                                                              out, out_cnt, nullptr, raw_scales(Hc, Wc, H, W, ph, pw, rh, rw));
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -441,7 +508,7 @@ extern "C" int prv2_blend_partial_raw(const float* preds, const uint8_t* own, co
   if (n == 0) return PRV2_OK;
   dim3 grid(cdiv(cdiv(W, 4), 256), H);
   blend_raw_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, 1, 1, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W,
-                                                              num_r, nullptr, nullptr);
+                                                              num_r, nullptr, nullptr, raw_scales(1, 1, H, W, ph, pw, rh, rw));
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -455,7 +522,7 @@ extern "C" int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, i
   if (rc) return rc;
   dim3 grid(cdiv(cdiv(W, 4), 256), H);
   blend_raw_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(avg_c, cnt_c, Hc, Wc, nullptr, nullptr, starts, n, 1, 1, rmask, rh, rw, H, W,
-                                                              out, out_cnt, num_r);
+                                                              out, out_cnt, num_r, raw_scales(Hc, Wc, H, W, 1, 1, rh, rw));
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

@@ -109,85 +109,79 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
 }
 
 // --------------------------------------- bilinear align_corners=True on channels-last acts
+// grid (ceil(OW*C/8 / 256), OH, N): row taps are block-uniform, no 64-bit div/mod per element.
+constexpr int PW_ITEMS = 8;      // outputs per thread: few fat CTAs instead of ~1e5 tiny ones (CTA launch rate was the limit)
+
 __global__ void __launch_bounds__(256) resize_act_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il, int h, int w, int C,
                                                          int in_cs, bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW,
-                                                         int out_cs, int relu, long long total) {
-  const int cv = C / 8;
-  const float sy = ac_scale(h, OH), sx = ac_scale(w, OW);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(idx % cv) * 8;
-    long long pix = idx / cv;
-    const int x = (int)(pix % OW);
-    pix /= OW;
-    const int y = (int)(pix % OH);
-    const int n = (int)(pix / OH);
-    const BilinearTap ty = ac_tap(sy, y, h), tx = ac_tap(sx, x, w);
-    const size_t base = (size_t)n * h * w;
+                                                         int out_cs, int relu, float sy, float sx) {
+  const unsigned cv = (unsigned)C >> 3, total = (unsigned)OW * cv;
+  const int y = blockIdx.y, n = blockIdx.z;
+  const BilinearTap ty = ac_tap(sy, y, h);
+  const size_t r0 = ((size_t)n * h + ty.i0) * w, r1 = ((size_t)n * h + ty.i1) * w;
+  const size_t orow = ((size_t)n * OH + y) * OW;
+#pragma unroll 2
+  for (int it = 0; it < PW_ITEMS; ++it) {
+    const unsigned idx = (blockIdx.x * PW_ITEMS + it) * 256u + threadIdx.x;
+    if (idx >= total) break;
+    const int x = (int)(idx / cv), c8 = (int)(idx % cv) * 8;
+    const BilinearTap tx = ac_tap(sx, x, w);
     float a[8], b[8], c[8], d[8], o[8];
-    act_load8(ih, il, (base + (size_t)ty.i0 * w + tx.i0) * in_cs + c8, a);
-    act_load8(ih, il, (base + (size_t)ty.i0 * w + tx.i1) * in_cs + c8, b);
-    act_load8(ih, il, (base + (size_t)ty.i1 * w + tx.i0) * in_cs + c8, c);
-    act_load8(ih, il, (base + (size_t)ty.i1 * w + tx.i1) * in_cs + c8, d);
+    act_load8(ih, il, (r0 + tx.i0) * in_cs + c8, a);
+    act_load8(ih, il, (r0 + tx.i1) * in_cs + c8, b);
+    act_load8(ih, il, (r1 + tx.i0) * in_cs + c8, c);
+    act_load8(ih, il, (r1 + tx.i1) * in_cs + c8, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       o[k] = ac_blend(ty, tx, a[k], b[k], c[k], d[k]);
       if (relu) o[k] = fmaxf(o[k], 0.f);
     }
-    act_store8(oh, ol, (((size_t)n * OH + y) * OW + x) * out_cs + c8, o);
+    act_store8(oh, ol, (orow + x) * out_cs + c8, o);
   }
 }
 
 // -------------------------- depth maps into channel slots (fusion_model.py:94-96, 16-17)
-__global__ void __launch_bounds__(256) depth_slots_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int N, int H, int W,
+// grid (ceil(OW/256), OH, N)
+__global__ void __launch_bounds__(256) depth_slots_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int H, int W,
                                                           bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW, int out_cs,
-                                                          int c0, long long total) {
-  const float sy = ac_scale(H, OH), sx = ac_scale(W, OW);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % OW);
-    const int y = (int)((idx / OW) % OH);
-    const int n = (int)(idx / ((long long)OW * OH));
-    const BilinearTap ty = ac_tap(sy, y, H), tx = ac_tap(sx, x, W);
-    const size_t b = (size_t)n * H * W;
-    const size_t i00 = b + (size_t)ty.i0 * W + tx.i0, i01 = b + (size_t)ty.i0 * W + tx.i1, i10 = b + (size_t)ty.i1 * W + tx.i0,
-                 i11 = b + (size_t)ty.i1 * W + tx.i1;
-    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    o[0] = ac_blend(ty, tx, __ldg(p1 + i00), __ldg(p1 + i01), __ldg(p1 + i10), __ldg(p1 + i11));
-    o[1] = ac_blend(ty, tx, __ldg(p2 + i00), __ldg(p2 + i01), __ldg(p2 + i10), __ldg(p2 + i11));
-    act_store8(oh, ol, (size_t)idx * out_cs + c0, o);
-  }
+                                                          int c0, float sy, float sx) {
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  if (x >= OW) return;
+  const int y = blockIdx.y, n = blockIdx.z;
+  const BilinearTap ty = ac_tap(sy, y, H), tx = ac_tap(sx, x, W);
+  const size_t b = (size_t)n * H * W;
+  const size_t i00 = b + (size_t)ty.i0 * W + tx.i0, i01 = b + (size_t)ty.i0 * W + tx.i1, i10 = b + (size_t)ty.i1 * W + tx.i0,
+               i11 = b + (size_t)ty.i1 * W + tx.i1;
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  o[0] = ac_blend(ty, tx, __ldg(p1 + i00), __ldg(p1 + i01), __ldg(p1 + i10), __ldg(p1 + i11));
+  o[1] = ac_blend(ty, tx, __ldg(p2 + i00), __ldg(p2 + i01), __ldg(p2 + i10), __ldg(p2 + i11));
+  act_store8(oh, ol, (((size_t)n * OH + y) * OW + x) * out_cs + c0, o);
 }
 
 // ------------------------------ final 3x3 conv to one channel + base + clamp (fusion_model.py:113-118)
-__global__ void __launch_bounds__(256) final_conv_kernel(const bf16* __restrict__ fh, const bf16* __restrict__ fl, int N, int H, int W,
-                                                         int C, int cs, const float* __restrict__ wgt, const float* __restrict__ base,
-                                                         float* __restrict__ out, long long total) {
-  extern __shared__ float s_w[];                           // [9, C]
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wgt[i];
-  __syncthreads();
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % W);
-    const int y = (int)((idx / W) % H);
-    const int n = (int)(idx / ((long long)W * H));
-    float acc = 0.f;
-    for (int r = 0; r < 3; ++r) {
-      const int yy = y + r - 1;
-      if (yy < 0 || yy >= H) continue;
-      for (int s = 0; s < 3; ++s) {
-        const int xx = x + s - 1;
-        if (xx < 0 || xx >= W) continue;
-        const size_t p = (((size_t)n * H + yy) * W + xx) * cs;
-        const float* ww = s_w + (r * 3 + s) * C;
-        for (int c = 0; c < C; c += 8) {
-          float v[8];
-          act_load8(fh, fl, p + c, v);
+// The channel contraction runs on the tensor cores as a 1x1 conv producing the 9 tap responses
+// Y[p, t] = sum_c feat[p, c] * w[t, c] (fp32, 16 floats per pixel); this stencil gathers
+// out[p] = clamp(base[p] + sum_t Y[p + off_t, t], 0) with zero padding.  grid (ceil(W/256), H, N).
+__global__ void __launch_bounds__(256) tap_stencil_kernel(const float* __restrict__ Y, int H, int W, int ld,
+                                                          const float* __restrict__ base, float* __restrict__ out) {
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  if (x >= W) return;
+  const int y = blockIdx.y, n = blockIdx.z;
+  float acc = 0.f;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc = fmaf(v[k], ww[c + k], acc);
-        }
-      }
+  for (int r = 0; r < 3; ++r) {
+    const int yy = y + r - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int xx = x + s - 1;
+      if (xx < 0 || xx >= W) continue;
+      acc += __ldg(Y + (((size_t)n * H + yy) * W + xx) * ld + r * 3 + s);
     }
-    if (base) acc = fmaxf(base[idx] + acc, 0.f);
-    out[idx] = acc;
   }
+  const size_t o = ((size_t)n * H + y) * W + x;
+  if (base) acc = fmaxf(base[o] + acc, 0.f);
+  out[o] = acc;
 }
 
 __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ in, int N, int C, int H, int W, bf16* __restrict__ oh,
@@ -278,10 +272,12 @@ extern "C" int prv2_resize_bilinear_act(const prv2_bf16* in_hi, const prv2_bf16*
                                         prv2_bf16* out_hi, prv2_bf16* out_lo, int oh, int ow, int out_cs, int relu, prv2_stream_t stream) {
   PRV2_CHECK_ARG(in_hi && out_hi, "prv2_resize_bilinear_act: null pointer");
   PRV2_CHECK_ARG(N >= 0 && h > 0 && w > 0 && oh > 0 && ow > 0 && C > 0 && C % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0, "prv2_resize_bilinear_act: bad shape");
+  PRV2_CHECK_ARG(oh <= 65535 && N <= 65535, "prv2_resize_bilinear_act: grid too large");
   if (N == 0) return PRV2_OK;
-  const long long total = (long long)N * oh * ow * (C / 8);
-  resize_act_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, h, w, C, in_cs, (bf16*)out_hi,
-                                                                          (bf16*)out_lo, oh, ow, out_cs, relu, total);
+  const float sy = oh > 1 ? (float)(h - 1) / (float)(oh - 1) : 0.f, sx = ow > 1 ? (float)(w - 1) / (float)(ow - 1) : 0.f;
+  dim3 grid(cdiv((long long)ow * (C / 8), 256 * PW_ITEMS), oh, N);
+  resize_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, h, w, C, in_cs, (bf16*)out_hi, (bf16*)out_lo,
+                                                          oh, ow, out_cs, relu, sy, sx);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -291,22 +287,21 @@ extern "C" int prv2_depth_slots(const float* pred1, const float* pred2, int N, i
   PRV2_CHECK_ARG(pred1 && pred2 && out_hi, "prv2_depth_slots: null pointer");
   PRV2_CHECK_ARG(N >= 0 && H > 0 && W > 0 && oh > 0 && ow > 0 && out_cs % 8 == 0 && c0 % 8 == 0 && zero_pad == 6 && c0 + 8 <= out_cs,
                  "prv2_depth_slots: slot must be an aligned group of 8 channels (2 depth + 6 zero)");
+  PRV2_CHECK_ARG(oh <= 65535 && N <= 65535, "prv2_depth_slots: grid too large");
   if (N == 0) return PRV2_OK;
-  const long long total = (long long)N * oh * ow;
-  depth_slots_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(pred1, pred2, N, H, W, (bf16*)out_hi, (bf16*)out_lo, oh, ow, out_cs,
-                                                                           c0, total);
+  const float sy = oh > 1 ? (float)(H - 1) / (float)(oh - 1) : 0.f, sx = ow > 1 ? (float)(W - 1) / (float)(ow - 1) : 0.f;
+  dim3 grid(cdiv(ow, 256), oh, N);
+  depth_slots_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred1, pred2, H, W, (bf16*)out_hi, (bf16*)out_lo, oh, ow, out_cs, c0, sy, sx);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
 
-extern "C" int prv2_final_conv(const prv2_bf16* feat_hi, const prv2_bf16* feat_lo, int N, int H, int W, int C, int cs, const float* w,
-                               const float* base, float* out, prv2_stream_t stream) {
-  PRV2_CHECK_ARG(feat_hi && w && out, "prv2_final_conv: null pointer");
-  PRV2_CHECK_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && cs % 8 == 0 && C <= 1024, "prv2_final_conv: bad shape");
+extern "C" int prv2_tap_stencil(const float* taps, int N, int H, int W, int ld, const float* base, float* out, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(taps && out, "prv2_tap_stencil: null pointer");
+  PRV2_CHECK_ARG(N >= 0 && H > 0 && W > 0 && ld >= 9 && H <= 65535 && N <= 65535, "prv2_tap_stencil: bad shape");
   if (N == 0) return PRV2_OK;
-  const long long total = (long long)N * H * W;
-  final_conv_kernel<<<grid_for(total, 256), 256, 9 * C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)feat_hi, (const bf16*)feat_lo, N, H, W,
-                                                                                                  C, cs, w, base, out, total);
+  dim3 grid(cdiv(W, 256), H, N);
+  tap_stencil_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(taps, H, W, ld, base, out);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

@@ -13,7 +13,9 @@
 //   descriptor; weights [Cout_pad, Ktot] (K-major) are fetched with a 2-D box {64, block_n}.
 // * Accumulators live in TMEM (2 x block_n fp32 columns, double buffered) so the epilogue of tile
 //   i overlaps the MMAs of tile i+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer
-//   (one elected lane each), warps 2..5 = epilogue (one TMEM lane quadrant each).
+//   (one elected lane each), warps 2..9 = epilogue (two per TMEM lane quadrant); the epilogue
+//   transposes 32x16 fp32 tiles through shared memory so that global traffic is 16-byte vectors
+//   over whole 32-byte sectors.
 // * Epilogues fuse bias, ReLU / erf-GELU, channels-first LayerNorm+GELU, residual adds,
 //   LayerScale*gamma + fp32 residual stream, the ConvTranspose pixel shuffle and the DPT
 //   sigmoid head.
@@ -28,10 +30,15 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                        // bf16 per K chunk (128 B rows)
 constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_EPI_WARPS = 8;              // two per TMEM lane quadrant, each takes every other 16-column chunk
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int EPI_THREADS = 32 * NUM_EPI_WARPS;
 constexpr int MAX_STAGES = 8;
-constexpr int SMEM_BUDGET = 220 * 1024;       // data stages; barriers sit behind
+constexpr int STG_LD = 20;                    // floats per staged row (16 + 4 pad: conflict-free float4 access both ways)
+constexpr int STG_BYTES_PER_WARP = 32 * STG_LD * 4 + 768;   // 32x16 fp32 transpose tile + LN partial/final statistics
+constexpr int PAR_BYTES = 2 * 3 * 256 * 4;    // per-tile bias / gamma / beta, double buffered by accumulator parity
+constexpr int SMEM_BUDGET = 192 * 1024;       // operand stages; epilogue staging, parameters and barriers sit behind
+constexpr int SMEM_TOTAL = SMEM_BUDGET + NUM_EPI_WARPS * STG_BYTES_PER_WARP + PAR_BYTES + 1024 + 256;
 constexpr uint64_t SPIN_LIMIT_NS = 4000000000ull;   // a wedged pipeline traps instead of hanging the box
 
 struct alignas(64) KParams {
@@ -44,7 +51,7 @@ struct alignas(64) KParams {
   uint8_t seg_last[PRV2_MAX_SEG];             // 16-wide MMA slices in the last chunk (1..4)
   int32_t n_seg;
   int32_t N, H, W, Cout;
-  int32_t tile_w, tile_h, tiles_w, tiles_h, tiles_n, total_tiles;
+  int32_t tile_w, tile_h, tile_w_log2, tiles_w, tiles_h, tiles_n, total_tiles;
   int32_t block_n, stages, b_stage_bytes, tmem_cols;
   int32_t epi, act;
   const float* bias;
@@ -143,26 +150,27 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
          ((uint64_t)2 << 61);
 }
 
-// 16 consecutive channels of an act tensor
-__device__ __forceinline__ void load16(const bf16* hi, const bf16* lo, size_t i, float (&v)[16]) {
-  float a[8], b[8];
-  act_load8(hi, lo, i, a);
-  act_load8(hi, lo, i + 8, b);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { v[k] = a[k]; v[8 + k] = b[k]; }
-}
-__device__ __forceinline__ void store_n(bf16* hi, bf16* lo, size_t i, const float (&v)[16], int n_valid, bool relu) {
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    if (g * 8 + 8 <= n_valid) {
-      float t[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) t[k] = relu ? fmaxf(v[g * 8 + k], 0.f) : v[g * 8 + k];
-      act_store8(hi, lo, i + g * 8, t);
-    }
-  }
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 6 FMA instead of
+// erff's ~25-instruction branchy path; exact-GELU error stays at fp32 rounding level.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * exp2f(-z * z * 1.4426950408889634f);
+  return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
+struct Row {              // one output pixel handled by this lane in the coalesced phase
+  size_t m, orow;
+  int h, w, img;
+  bool valid;
+};
+
+// EPI / ACT are compile-time: each instantiation carries only its own epilogue (small, branch-free SASS)
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -175,6 +183,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  uint8_t* const stage_area = smem_raw + (bar_base - smem_u32(smem_raw)) + 256;     // epilogue transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -263,120 +272,243 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     }
   } else {
     // ================================ epilogue =============================================
+    // Phase A: the lane that owns TMEM lane (= output pixel) r pulls 16 fp32 columns and parks them in a
+    // padded shared tile.  Phase B: lanes re-read the tile so that a lane owns 8 CONSECUTIVE channels of
+    // rows (lane&15) and (lane&15)+16 -> every global access is a 16-byte vector and a warp instruction
+    // covers whole 32-byte sectors.  Two warps share a lane quadrant and alternate 16-column chunks.
+    const int ew = warp - 2;
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;
-    const int n_chunks = p.block_n >> 4;
+    const int Cout = p.Cout, block_n = p.block_n, out_cs = p.out_cs, relu_cs = p.relu_cs, res_cs = p.res_cs, res2_cs = p.res2_cs;
+    const int out_f32_ld = p.out_f32_ld, tile_w_log2 = p.tile_w_log2, tile_w_mask = p.tile_w - 1, pH = p.H, pW = p.W;
+    bf16* const out_hi = p.out_hi; bf16* const out_lo = p.out_lo;
+    bf16* const relu_hi = p.relu_hi; bf16* const relu_lo = p.relu_lo;
+    const bf16* const res_hi = p.res_hi; const bf16* const res_lo = p.res_lo;
+    const bf16* const res2_hi = p.res2_hi; const bf16* const res2_lo = p.res2_lo;
+    float* const out_f32 = p.out_f32;
+    const int csel = ew >> 2;                     // which of the two warps of this quadrant
+    const int te = threadIdx.x - 64;              // 0..255 over the epilogue warps
+    const int n_chunks = block_n >> 4;
+    float* const stg = reinterpret_cast<float*>(stage_area + ew * STG_BYTES_PER_WARP);
+    float* const stg_peer = reinterpret_cast<float*>(stage_area + (ew ^ 4) * STG_BYTES_PER_WARP);
+    float* const s_par = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * STG_BYTES_PER_WARP);
+    const int rB = lane & 15, cB = (lane >> 4) * 8;
+    constexpr bool is_ln = EPI == PRV2_EPI_LN_GELU;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
       const int img = mt / tiles_per_img, r = mt % tiles_per_img;
-      const int h = (r / p.tiles_w) * p.tile_h + row / p.tile_w;
-      const int w = (r % p.tiles_w) * p.tile_w + row % p.tile_w;
-      const bool valid = (h < p.H) && (w < p.W);
-      const int n0 = nt * p.block_n;
-      const size_t m = ((size_t)img * p.H + h) * p.W + w;
-      size_t orow = m;
-      if (p.row_map_period > 0) orow = m + (m / p.row_map_period) * p.row_map_extra + p.row_map_offset;
+      const int h0 = (r / p.tiles_w) * p.tile_h, w0 = (r % p.tiles_w) * p.tile_w;
+      const int n0 = nt * block_n;
+      Row rows[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int tr = quad * 32 + rB + 16 * i;
+        Row& q = rows[i];
+        q.img = img;
+        q.h = h0 + (tr >> tile_w_log2);
+        q.w = w0 + (tr & tile_w_mask);
+        q.valid = (q.h < pH) && (q.w < pW);
+        q.m = ((size_t)img * pH + q.h) * pW + q.w;
+        q.orow = q.m;
+        if (p.row_map_period > 0) q.orow = q.m + (q.m / p.row_map_period) * p.row_map_extra + p.row_map_offset;
+      }
+      // (1) per-tile parameters -> shared memory (one coalesced load instead of 8..24 scalar loads per chunk)
+      float* const par = s_par + acc * 768;
+      if (te < block_n) {
+        const int n = min(n0 + te, Cout - 1);
+        int nb = n;
+        if (EPI == PRV2_EPI_SHUFFLE) nb = n % (Cout / (p.shuffle_k * p.shuffle_k));
+        par[te] = p.bias ? __ldg(p.bias + nb) : 0.f;
+        par[256 + te] = p.gamma ? __ldg(p.gamma + n) : 0.f;
+        par[512 + te] = (p.beta && is_ln) ? __ldg(p.beta + n) : 0.f;
+      }
+      // (2) pull the rows this tile will read-modify-write (fp32 residual stream / residual acts) towards L2
+      //     while the MMAs of this tile are still running
+      {
+        const Row& q = csel ? rows[1] : rows[0];
+        if (q.valid) {
+          if (EPI == PRV2_EPI_RESID_F32) {
+            const char* x = reinterpret_cast<const char*>(out_f32 + q.orow * out_f32_ld + n0);
+            for (int off = (lane >> 4) * 128; off < block_n * 4; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + off));
+          } else if (EPI == PRV2_EPI_STORE && res_hi) {
+            const char* x = reinterpret_cast<const char*>(res_hi + q.m * res_cs + n0);
+            for (int off = (lane >> 4) * 128; off < block_n * 2; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + off));
+            if (res2_hi) {
+              const char* y = reinterpret_cast<const char*>(res2_hi + q.m * res2_cs + n0);
+              for (int off = (lane >> 4) * 128; off < block_n * 2; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + off));
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 5, 256;" ::: "memory");          // parameters visible to all epilogue warps
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * p.block_n;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * block_n;
       float v[16];
 
-      if (p.epi == PRV2_EPI_LN_GELU) {
-        // channels-first LayerNorm over the Cout channels of this pixel (two-pass, as convs.py:24-27)
-        float sum = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-          tc_ld16(taddr + c * 16, v);
+      if (EPI == PRV2_EPI_HEAD) {
+        if (csel == 0) {                           // one float per pixel: lane-per-row stores are already coalesced
+          const int tr = quad * 32 + lane;
+          const int h = h0 + (tr >> tile_w_log2), w = w0 + (tr & tile_w_mask);
+          float dot = 0.f;
+          for (int c = 0; c < n_chunks; ++c) {
+            tc_ld16(taddr + c * 16, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < p.Cout) sum += v[j];
-        }
-        const float mean = sum / (float)p.Cout;
-        float sq = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-          tc_ld16(taddr + c * 16, v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < p.Cout) { const float d = v[j] - mean; sq += d * d; }
-        }
-        const float rstd = 1.0f / sqrtf(sq / (float)p.Cout + p.eps);
-        for (int c = 0; c < n_chunks; ++c) {
-          const int n = n0 + c * 16;
-          tc_ld16(taddr + c * 16, v);
-          if (valid && n < p.Cout) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int nn = min(n + j, p.Cout - 1);
-              v[j] = gelu_erf(__ldg(p.gamma + nn) * ((v[j] - mean) * rstd) + __ldg(p.beta + nn));
-            }
-            store_n(p.out_hi, p.out_lo, orow * p.out_cs + n, v, min(16, p.Cout - n), false);
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c * 16 + j < Cout) dot += fmaxf(v[j] + par[c * 16 + j], 0.f) * par[256 + c * 16 + j];
           }
+          if (h < pH && w < pW) out_f32[((size_t)img * pH + h) * pW + w] = p.head_scale / (1.0f + expf(-(dot + __ldg(p.beta))));
         }
-      } else if (p.epi == PRV2_EPI_HEAD) {
-        float dot = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-          const int n = n0 + c * 16;
-          tc_ld16(taddr + c * 16, v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n + j < p.Cout) dot += fmaxf(v[j] + __ldg(p.bias + n + j), 0.f) * __ldg(p.gamma + n + j);
-        }
-        if (valid) p.out_f32[orow] = p.head_scale / (1.0f + expf(-(dot + __ldg(p.beta))));
       } else {
-        for (int c = 0; c < n_chunks; ++c) {
-          const int n = n0 + c * 16;
-          tc_ld16(taddr + c * 16, v);
-          if (!valid || n >= p.Cout) continue;
-          const int nv = min(16, p.Cout - n);
-          if (p.epi == PRV2_EPI_SHUFFLE) {
-            // n = (ky*k + kx)*Cout_real + co ; Cout here counts k*k*Cout_real columns
-            const int k = p.shuffle_k, co_n = p.Cout / (k * k);
-            const int tap = n / co_n, co = n % co_n, ky = tap / k, kx = tap % k;
+        float* const s_fin = stg + 32 * STG_LD + 128;          // [mean(32) | rstd(32)]
+        if (is_ln) {
+          // channels-first LayerNorm statistics of this lane's pixel (convs.py:24-27).  The two warps of the
+          // quadrant each reduce their own chunks two-pass (mean, then centred squares) and merge with
+          // Chan's parallel update; partials are double buffered by accumulator parity.
+          float* const s_mine = stg + 32 * STG_LD + acc * 64;
+          float* const s_theirs = stg_peer + 32 * STG_LD + acc * 64;
+          float sum = 0.f;
+          int cnt = 0;
+          for (int c = csel; c < n_chunks; c += 2) {
+            tc_ld16(taddr + c * 16, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += p.bias ? __ldg(p.bias + co + j) : 0.f;
-            const size_t opix = ((size_t)img * (p.H * k) + (h * k + ky)) * (p.W * k) + (w * k + kx);
-            store_n(p.out_hi, p.out_lo, opix * p.out_cs + co, v, 16, false);
-            continue;
+            for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < Cout) { sum += v[j]; ++cnt; }
           }
-          if (p.bias) {
+          const float mean_a = cnt ? sum / (float)cnt : 0.f;
+          float m2 = 0.f;
+          for (int c = csel; c < n_chunks; c += 2) {
+            tc_ld16(taddr + c * 16, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + min(n + j, p.Cout - 1));
+            for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < Cout) { const float d = v[j] - mean_a; m2 += d * d; }
           }
-          if (p.epi == PRV2_EPI_RESID_F32) {
-            float* x = p.out_f32 + orow * p.out_f32_ld + n;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (j < nv) x[j] = x[j] + __ldg(p.gamma + n + j) * v[j];
-            continue;
+          s_mine[lane] = mean_a;
+          s_mine[32 + lane] = m2;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+          const float mean_b = s_theirs[lane], m2_b = s_theirs[32 + lane];
+          const float na = (float)cnt, nb = (float)(Cout - cnt), nn = (float)Cout;
+          const float delta = mean_b - mean_a;
+          const float mean = mean_a + delta * (nb / nn);
+          const float var = (m2 + m2_b + delta * delta * (na * nb / nn)) / nn;
+          s_fin[lane] = mean;
+          s_fin[32 + lane] = 1.0f / sqrtf(var + p.eps);
+        }
+        // (3) chunk loop, software pipelined: the TMEM load of chunk c+2 is in flight while chunk c goes
+        //     through its coalesced phase.
+        int c = csel;
+        if (c < n_chunks) tc_ld16(taddr + c * 16, v);
+        for (; c < n_chunks; c += 2) {
+          float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+          dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+          __syncwarp();                                      // tile visible; warp converged for the .aligned load below
+          const bool more = c + 2 < n_chunks;
+          uint32_t rr[16];
+          if (more) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+                  "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+                : "r"(taddr + (c + 2) * 16)
+                : "memory");
           }
-          if (p.epi == PRV2_EPI_F32) {
-            float* x = p.out_f32 + orow * p.out_f32_ld + n;
+          const int nl = c * 16 + cB;                        // first of this lane's 8 channels, tile-local
+          const int n = n0 + nl;
+          if (n < Cout) {
+            const float4 b0 = *reinterpret_cast<const float4*>(par + nl), b1 = *reinterpret_cast<const float4*>(par + nl + 4);
+            const float4 g0 = *reinterpret_cast<const float4*>(par + 256 + nl), g1 = *reinterpret_cast<const float4*>(par + 256 + nl + 4);
+            const float bias8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float g8[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            int sh_co = 0, sh_ky = 0, sh_kx = 0;
+            if (EPI == PRV2_EPI_SHUFFLE) {
+              // n = (ky*k + kx)*C + co ; Cout counts k*k*C columns
+              const int k = p.shuffle_k, co_n = Cout / (k * k), tap = n / co_n;
+              sh_co = n % co_n; sh_ky = tap / k; sh_kx = tap % k;
+            }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (j < nv) x[j] = v[j];
-            continue;
+            for (int i = 0; i < 2; ++i) {
+              const Row& q = rows[i];
+              if (!q.valid) continue;
+              const int rl = rB + 16 * i;
+              const float4 lo4 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cB);
+              const float4 hi4 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cB + 4);
+              float t[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+              if (is_ln) {
+                const float4 e0 = *reinterpret_cast<const float4*>(par + 512 + nl), e1 = *reinterpret_cast<const float4*>(par + 512 + nl + 4);
+                const float b8[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                const float mean = s_fin[rl], rstd = s_fin[32 + rl];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = gelu_fast(g8[j] * ((t[j] - mean) * rstd) + b8[j]);
+                act_store8(out_hi, out_lo, q.orow * out_cs + n, t);
+                continue;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) t[j] += bias8[j];
+              if (EPI == PRV2_EPI_SHUFFLE) {
+                const int k = p.shuffle_k;
+                const size_t opix = ((size_t)q.img * (pH * k) + (q.h * k + sh_ky)) * (pW * k) + (q.w * k + sh_kx);
+                act_store8(out_hi, out_lo, opix * out_cs + sh_co, t);
+                continue;
+              }
+              if (EPI == PRV2_EPI_RESID_F32) {
+                float* x = out_f32 + q.orow * out_f32_ld + n;
+                if (n + 8 <= Cout && (out_f32_ld & 3) == 0) {
+                  float4 x0 = *reinterpret_cast<float4*>(x), x1 = *reinterpret_cast<float4*>(x + 4);
+                  x0.x += g8[0] * t[0]; x0.y += g8[1] * t[1]; x0.z += g8[2] * t[2]; x0.w += g8[3] * t[3];
+                  x1.x += g8[4] * t[4]; x1.y += g8[5] * t[5]; x1.z += g8[6] * t[6]; x1.w += g8[7] * t[7];
+                  *reinterpret_cast<float4*>(x) = x0;
+                  *reinterpret_cast<float4*>(x + 4) = x1;
+                } else {
+                  for (int j = 0; j < 8 && n + j < Cout; ++j) x[j] += g8[j] * t[j];
+                }
+                continue;
+              }
+              if (EPI == PRV2_EPI_F32) {
+                float* x = out_f32 + q.orow * out_f32_ld + n;
+                if (n + 8 <= Cout && (out_f32_ld & 3) == 0) {
+                  *reinterpret_cast<float4*>(x) = make_float4(t[0], t[1], t[2], t[3]);
+                  *reinterpret_cast<float4*>(x + 4) = make_float4(t[4], t[5], t[6], t[7]);
+                } else {
+                  for (int j = 0; j < 8 && n + j < Cout; ++j) x[j] = t[j];
+                }
+                continue;
+              }
+              if (ACT == PRV2_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = fmaxf(t[j], 0.f);
+              } else if (ACT == PRV2_ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = gelu_fast(t[j]);
+              }
+              if (res_hi) {
+                float r8[8];
+                act_load8(res_hi, res_lo, q.m * res_cs + n, r8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] += r8[j];
+              }
+              if (res2_hi) {
+                float r8[8];
+                act_load8(res2_hi, res2_lo, q.m * res2_cs + n, r8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] += r8[j];
+              }
+              if (out_hi) act_store8(out_hi, out_lo, q.orow * out_cs + n, t);
+              if (relu_hi) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = fmaxf(t[j], 0.f);
+                act_store8(relu_hi, relu_lo, q.orow * relu_cs + n, t);
+              }
+            }
           }
-          if (p.act == PRV2_ACT_RELU) {
+          __syncwarp();                                      // coalesced phase done (tile reusable), lanes reconverged
+          if (more) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act == PRV2_ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
           }
-          if (p.res_hi) {
-            float rr[16];
-            if (nv == 16) load16(p.res_hi, p.res_lo, m * p.res_cs + n, rr);
-            else { for (int j = 0; j < 16; ++j) rr[j] = j < nv ? act_load(p.res_hi, p.res_lo, m * p.res_cs + n + j) : 0.f; }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += rr[j];
-          }
-          if (p.res2_hi) {
-            float rr[16];
-            if (nv == 16) load16(p.res2_hi, p.res2_lo, m * p.res2_cs + n, rr);
-            else { for (int j = 0; j < 16; ++j) rr[j] = j < nv ? act_load(p.res2_hi, p.res2_lo, m * p.res2_cs + n + j) : 0.f; }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += rr[j];
-          }
-          if (p.out_hi) store_n(p.out_hi, p.out_lo, orow * p.out_cs + n, v, nv, false);
-          if (p.relu_hi) store_n(p.relu_hi, p.relu_lo, orow * p.relu_cs + n, v, nv, true);
         }
       }
       tc_fence_before();
@@ -462,6 +594,9 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   p.n_seg = d->n_seg;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
   p.tile_w = d->tile_w; p.tile_h = d->tile_h;
+  PRV2_CHECK_ARG((d->tile_w & (d->tile_w - 1)) == 0, "prv2_umma_gemm: tile_w must be a power of two");
+  p.tile_w_log2 = 0;
+  while ((1 << p.tile_w_log2) < d->tile_w) ++p.tile_w_log2;
   p.tiles_w = cdiv(d->W, d->tile_w); p.tiles_h = cdiv(d->H, d->tile_h);
   p.tiles_n = d->Cout_pad / d->block_n;
   const long long total = (long long)d->N * p.tiles_h * p.tiles_w * p.tiles_n;
@@ -518,12 +653,32 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
     int dev = 0;
     PRV2_CUDA(cudaGetDevice(&dev));
     PRV2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024 + 256));
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_LN_GELU, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_RESID_F32, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_F32, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_SHUFFLE, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_HEAD, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   }
   // always request the full budget: guarantees one CTA per SM, so a 512-column TMEM allocation can never deadlock
-  const int smem = SMEM_BUDGET + 1024 + 256;
+  const int smem = SMEM_TOTAL;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  umma_gemm_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->epi) {
+    case PRV2_EPI_STORE:
+      PRV2_CHECK_ARG(d->act >= PRV2_ACT_NONE && d->act <= PRV2_ACT_GELU, "prv2_umma_gemm: unknown activation %d", d->act);
+      if (d->act == PRV2_ACT_RELU) umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_RELU><<<grid, NUM_THREADS, smem, st>>>(p);
+      else if (d->act == PRV2_ACT_GELU) umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_GELU><<<grid, NUM_THREADS, smem, st>>>(p);
+      else umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p);
+      break;
+    case PRV2_EPI_LN_GELU: umma_gemm_kernel<PRV2_EPI_LN_GELU, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
+    case PRV2_EPI_RESID_F32: umma_gemm_kernel<PRV2_EPI_RESID_F32, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
+    case PRV2_EPI_F32: umma_gemm_kernel<PRV2_EPI_F32, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
+    case PRV2_EPI_SHUFFLE: umma_gemm_kernel<PRV2_EPI_SHUFFLE, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
+    default: umma_gemm_kernel<PRV2_EPI_HEAD, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
+  }
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

@@ -60,28 +60,28 @@ class DepthAnythingV2B200:
         self.cls = dv(g(p + "cls_token").reshape(D))
         mk = lambda segs, n_src, cout, **kw: GemmLayer(segs, n_src, cout, x3, device, **kw)
         self.patch_embed = mk([(0, 0, 0, g(p + "patch_embed.proj.weight").reshape(D, 588))], 1, D, epi=_lib.EPI_F32,
-                              bias=g(p + "patch_embed.proj.bias"))
+                              bias=g(p + "patch_embed.proj.bias"), name="vit.patch_embed")
         self.blocks = []
         for i in range(self.depth):
             b = f"{p}blocks.{i}."
             self.blocks.append(dict(
                 n1w=dv(g(b + "norm1.weight")), n1b=dv(g(b + "norm1.bias")),
                 n2w=dv(g(b + "norm2.weight")), n2b=dv(g(b + "norm2.bias")),
-                qkv=mk([(0, 0, 0, g(b + "attn.qkv.weight"))], 1, 3 * D, bias=g(b + "attn.qkv.bias")),
-                proj=mk([(0, 0, 0, g(b + "attn.proj.weight"))], 1, D, epi=_lib.EPI_RESID_F32, bias=g(b + "attn.proj.bias"), gamma=g(b + "ls1.gamma")),
-                fc1=mk([(0, 0, 0, g(b + "mlp.fc1.weight"))], 1, 4 * D, act=_lib.ACT_GELU, bias=g(b + "mlp.fc1.bias")),
-                fc2=mk([(0, 0, 0, g(b + "mlp.fc2.weight"))], 1, D, epi=_lib.EPI_RESID_F32, bias=g(b + "mlp.fc2.bias"), gamma=g(b + "ls2.gamma")),
+                qkv=mk([(0, 0, 0, g(b + "attn.qkv.weight"))], 1, 3 * D, bias=g(b + "attn.qkv.bias"), name="vit.qkv"),
+                proj=mk([(0, 0, 0, g(b + "attn.proj.weight"))], 1, D, epi=_lib.EPI_RESID_F32, bias=g(b + "attn.proj.bias"), gamma=g(b + "ls1.gamma"), name="vit.proj"),
+                fc1=mk([(0, 0, 0, g(b + "mlp.fc1.weight"))], 1, 4 * D, act=_lib.ACT_GELU, bias=g(b + "mlp.fc1.bias"), name="vit.fc1"),
+                fc2=mk([(0, 0, 0, g(b + "mlp.fc2.weight"))], 1, D, epi=_lib.EPI_RESID_F32, bias=g(b + "mlp.fc2.bias"), gamma=g(b + "ls2.gamma"), name="vit.fc2"),
             ))
         self.norm_w, self.norm_b = dv(g(p + "norm.weight")), dv(g(p + "norm.bias"))
 
         h = "depth_head."
         oc, Fe = self.oc, features
-        self.projects = [mk([(0, 0, 0, g(f"{h}projects.{i}.weight").reshape(oc[i], D))], 1, oc[i], bias=g(f"{h}projects.{i}.bias")) for i in range(4)]
+        self.projects = [mk([(0, 0, 0, g(f"{h}projects.{i}.weight").reshape(oc[i], D))], 1, oc[i], bias=g(f"{h}projects.{i}.bias"), name="dpt.projects") for i in range(4)]
 
         def deconv(name, cch, k):
             w = g(h + name + ".weight")                      # [Cin, Cout, k, k]  (dpt.py:62-73)
             wg = w.permute(2, 3, 1, 0).reshape(k * k * cch, cch)   # rows n = (ky*k+kx)*Cout + co
-            return mk([(0, 0, 0, wg)], 1, k * k * cch, epi=_lib.EPI_SHUFFLE, bias=g(h + name + ".bias"), shuffle_k=k)
+            return mk([(0, 0, 0, wg)], 1, k * k * cch, epi=_lib.EPI_SHUFFLE, bias=g(h + name + ".bias"), shuffle_k=k, name="dpt.deconv")
         self.resize0 = deconv("resize_layers.0", oc[0], 4)
         self.resize1 = deconv("resize_layers.1", oc[1], 2)
         # 3x3 stride-2 pad-1 conv on 2x2 phase-split sources: in(2y+r-1, 2x+s-1) = phase[(r-1)&1][(s-1)&1] at offset (r==0 ? -1 : 0)
@@ -91,20 +91,20 @@ class DepthAnythingV2B200:
             for s in range(3):
                 py, px = (r - 1) & 1, (s - 1) & 1
                 segs.append((py * 2 + px, -1 if r == 0 else 0, -1 if s == 0 else 0, w3[:, :, r, s]))
-        self.resize3 = mk(segs, 4, oc[3], bias=g(h + "resize_layers.3.bias"))
-        self.layer_rn = [mk(conv_segments(g(f"{h}scratch.layer{i + 1}_rn.weight"), [oc[i]]), 1, Fe) for i in range(4)]
+        self.resize3 = mk(segs, 4, oc[3], bias=g(h + "resize_layers.3.bias"), name="dpt.conv_s2")
+        self.layer_rn = [mk(conv_segments(g(f"{h}scratch.layer{i + 1}_rn.weight"), [oc[i]]), 1, Fe, name=f"dpt.layer{i + 1}_rn") for i in range(4)]
         self.refine = {}
         for r in (1, 2, 3, 4):
             q = f"{h}scratch.refinenet{r}."
-            d = {"out_conv": mk([(0, 0, 0, g(q + "out_conv.weight").reshape(Fe, Fe))], 1, Fe, bias=g(q + "out_conv.bias"))}
+            d = {"out_conv": mk([(0, 0, 0, g(q + "out_conv.weight").reshape(Fe, Fe))], 1, Fe, bias=g(q + "out_conv.bias"), name=f"dpt.refine{r}.out_conv")}
             for u in (1, 2):
-                d[f"u{u}c1"] = mk(conv_segments(g(f"{q}resConfUnit{u}.conv1.weight"), [Fe]), 1, Fe, act=_lib.ACT_RELU, bias=g(f"{q}resConfUnit{u}.conv1.bias"))
-                d[f"u{u}c2"] = mk(conv_segments(g(f"{q}resConfUnit{u}.conv2.weight"), [Fe]), 1, Fe, bias=g(f"{q}resConfUnit{u}.conv2.bias"))
+                d[f"u{u}c1"] = mk(conv_segments(g(f"{q}resConfUnit{u}.conv1.weight"), [Fe]), 1, Fe, act=_lib.ACT_RELU, bias=g(f"{q}resConfUnit{u}.conv1.bias"), name=f"dpt.refine{r}.rcu")
+                d[f"u{u}c2"] = mk(conv_segments(g(f"{q}resConfUnit{u}.conv2.weight"), [Fe]), 1, Fe, bias=g(f"{q}resConfUnit{u}.conv2.bias"), name=f"dpt.refine{r}.rcu")
             self.refine[r] = d
         s = h + "scratch."
-        self.out1 = mk(conv_segments(g(s + "output_conv1.weight"), [Fe]), 1, Fe // 2, bias=g(s + "output_conv1.bias"))
+        self.out1 = mk(conv_segments(g(s + "output_conv1.weight"), [Fe]), 1, Fe // 2, bias=g(s + "output_conv1.bias"), name="dpt.output_conv1")
         self.out2 = mk(conv_segments(g(s + "output_conv2.0.weight"), [Fe // 2]), 1, 32, epi=_lib.EPI_HEAD, bias=g(s + "output_conv2.0.bias"),
-                       gamma=g(s + "output_conv2.2.weight").reshape(32), beta=g(s + "output_conv2.2.bias").reshape(1), head_scale=self.max_depth)
+                       gamma=g(s + "output_conv2.2.weight").reshape(32), beta=g(s + "output_conv2.2.bias").reshape(1), head_scale=self.max_depth, name="dpt.output_conv2")
 
     # ------------------------------------------------------------------------------------------
     def _pos_for(self, H, W):

@@ -27,23 +27,23 @@ class FusionUnetB200:
             assert ic % 2 == 0
             q = f"encoder_layers_1.{idx}.single_conv."
             self.enc1.append(mk(conv_segments(g(q + "0.weight"), [ic // 2, ic // 2]), 2, tc, epi=_lib.EPI_LN_GELU,
-                                gamma=g(q + "1.weight"), beta=g(q + "1.bias"), eps=LN_EPS))
+                                gamma=g(q + "1.weight"), beta=g(q + "1.bias"), eps=LN_EPS, name=f"fusion.enc1.L{idx}"))
             q = f"encoder_layers_2.{idx}.single_conv."
             self.enc2.append(mk(conv_segments(g(q + "0.weight"), [tc + 2]), 1, tc, epi=_lib.EPI_LN_GELU,
-                                gamma=g(q + "1.weight"), beta=g(q + "1.bias"), eps=LN_EPS))
+                                gamma=g(q + "1.weight"), beta=g(q + "1.bias"), eps=LN_EPS, name=f"fusion.enc2.L{idx}"))
         self.dec = []
         rev = self.temp_chl[::-1]
         chl = rev[0]
         for i, (tc, dc) in enumerate(zip(rev[1:], self.dec_chl)):
             cin = tc + chl + 2
             q = f"decoder_layers.{i}.conv.double_conv."
-            c1 = mk(conv_segments(g(q + "0.weight"), [chl, tc + 2]), 2, cin, act=_lib.ACT_GELU)
-            c2 = mk(conv_segments(g(q + "2.weight"), [cin]), 1, dc, act=_lib.ACT_GELU)
+            c1 = mk(conv_segments(g(q + "0.weight"), [chl, tc + 2]), 2, cin, act=_lib.ACT_GELU, name=f"fusion.dec{i}.conv1")
+            c2 = mk(conv_segments(g(q + "2.weight"), [cin]), 1, dc, act=_lib.ACT_GELU, name=f"fusion.dec{i}.conv2")
             self.dec.append((c1, c2, cin, dc))
             chl = dc
-        wf = g("final_conv.weight")                       # [1, C, 3, 3] -> [9, C] tap-major
-        self.final_w = wf[0].permute(1, 2, 0).reshape(9, wf.shape[1]).contiguous().to(device)
+        wf = g("final_conv.weight")                       # [1, C, 3, 3] -> 1x1 conv with one output per tap: [9, C]
         self.final_c = wf.shape[1]
+        self.final_taps = mk([(0, 0, 0, wf[0].permute(1, 2, 0).reshape(9, self.final_c))], 1, 9, epi=_lib.EPI_F32, name="fusion.final_taps")
 
     def flops(self, B: int, sizes) -> float:
         """sizes: list of (h, w) per level, finest first."""
@@ -90,6 +90,8 @@ class FusionUnetB200:
             feat = o
         if trace is not None:
             trace["fusion_dec"] = feat.to_nchw()
+        taps = ws.f32("final_taps", B, feat.H, feat.W, 16)
+        self.final_taps([feat], out_f32=taps, out_f32_ld=16)
         out = ws.f32("pred", B, 1, feat.H, feat.W)
-        ops.final_conv(feat, self.final_w, update_base, out)
+        ops.tap_stencil(taps, update_base, out)
         return out

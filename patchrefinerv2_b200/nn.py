@@ -127,8 +127,8 @@ class GemmLayer:
     def __init__(self, segs: Sequence[Tuple[int, int, int, torch.Tensor]], n_src: int, cout: int, x3: bool, device,
                  epi: int = _lib.EPI_STORE, act: int = _lib.ACT_NONE, bias: Optional[torch.Tensor] = None,
                  gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, eps: float = 1e-6,
-                 head_scale: float = 1.0, shuffle_k: int = 0):
-        self.x3, self.n_src, self.device = x3, n_src, device
+                 head_scale: float = 1.0, shuffle_k: int = 0, name: str = "gemm"):
+        self.x3, self.n_src, self.device, self.name = x3, n_src, device, name
         cout_real = cout
         if epi == _lib.EPI_STORE:
             cout = ceil_to(cout, 8)            # 16-byte channel groups are stored whole; extra rows are zero weights
@@ -138,11 +138,11 @@ class GemmLayer:
             bias = torch.cat([bias.detach().float().reshape(-1), torch.zeros(cout - cout_real)])
         blocks, table, src_c = [], [], {}
         for si, dh, dw, w in segs:
-            w = w.detach().to(torch.float32)
+            w = w.detach().to(device=device, dtype=torch.float32)      # packing runs on the device (setup, not hot path)
             assert w.shape[0] == cout_real
             c = w.shape[1]
             assert src_c.setdefault(si, c) == c, "a source must present the same channel count in every segment"
-            wp = torch.zeros((self.cout_pad, ceil_to(c, 64)), dtype=torch.float32)
+            wp = torch.zeros((self.cout_pad, ceil_to(c, 64)), dtype=torch.float32, device=device)
             wp[:cout_real, :c] = w
             wh = wp.to(BF16)
             if x3:
@@ -154,7 +154,7 @@ class GemmLayer:
                 table.append((si, dh, dw))
         assert len(table) <= _lib.MAX_SEG and n_src * (2 if x3 else 1) <= _lib.MAX_SRC
         self.src_c = [src_c[i] for i in range(n_src)]
-        self.weight = torch.cat(blocks, dim=1).contiguous().to(device)
+        self.weight = torch.cat(blocks, dim=1).contiguous()
         self.ktot = self.weight.shape[1]
         f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous().to(device)
         self.bias, self.gamma, self.beta = f32(bias), f32(gamma), f32(beta)
@@ -200,7 +200,7 @@ class GemmLayer:
         d.out_f32 = 0 if out_f32 is None else out_f32.data_ptr()
         d.out_f32_ld = out_f32_ld
         d.row_map_period, d.row_map_extra, d.row_map_offset = row_map
-        _lib.call("prv2_umma_gemm", C.byref(d), stream_ptr())
+        _lib.call("prv2_umma_gemm", C.byref(d), stream_ptr(), work=("flop", float(self.flops_per_pixel) * a0.N * a0.H * a0.W, self.name))
 
 
 def conv_segments(w: torch.Tensor, splits: Sequence[int], pad: int = 1) -> List[Tuple[int, int, int, torch.Tensor]]:

@@ -25,7 +25,8 @@ def crop_resize(image_hr: torch.Tensor, bboxs: torch.Tensor, ph: int, pw: int) -
     out = torch.empty((P, 3, ph, pw), dtype=torch.float32, device=image_hr.device)
     if P == 0:
         return out
-    _lib.call("prv2_crop_resize", ptr(image_hr), H, W, ptr(bboxs), P, ptr(out), ph, pw, stream_ptr())
+    bb = bboxs.shape[0]
+    _lib.call("prv2_crop_resize", ptr(image_hr), H, W, ptr(bboxs), P, ptr(out), ph, pw, stream_ptr(), work=("byte", 12.0 * P * ph * pw))
     return out
 
 
@@ -35,7 +36,8 @@ def roi_gather_f32(feat_hwc: torch.Tensor, rois: torch.Tensor, spatial_scale: fl
     h, w, Cc = feat_hwc.shape
     P = rois.shape[0]
     out = torch.empty((P, h, w, Cc), dtype=torch.float32, device=feat_hwc.device)
-    _lib.call("prv2_roi_gather_f32", ptr(feat_hwc), h, w, Cc, ptr(rois), P, C.c_float(spatial_scale), ptr(out), stream_ptr())
+    _lib.call("prv2_roi_gather_f32", ptr(feat_hwc), h, w, Cc, ptr(rois), P, C.c_float(spatial_scale), ptr(out), stream_ptr(),
+              work=("byte", 4.0 * P * h * w * Cc))
     return out
 
 
@@ -43,8 +45,10 @@ def roi_gather_act(feat: Act, rois: torch.Tensor, spatial_scale: float, out: Act
     """feat: ONE image (N==1) channels-last act; out [P,h,w,C] act (pre-allocated)."""
     assert feat.N == 1 and (out.H, out.W, out.C) == (feat.H, feat.W, feat.C) and out.N == rois.shape[0]
     _chk(rois, torch.float32, "rois")
+    planes = 2 if out.lo is not None else 1
     _lib.call("prv2_roi_gather_act", ptr(feat.hi), ptr(feat.lo), feat.H, feat.W, feat.C, feat.cs, ptr(rois), out.N,
-              C.c_float(spatial_scale), ptr(out.hi), ptr(out.lo), out.cs, stream_ptr())
+              C.c_float(spatial_scale), ptr(out.hi), ptr(out.lo), out.cs, stream_ptr(),
+              work=("byte", 2.0 * planes * out.N * out.H * out.W * out.C))
     return out
 
 
@@ -61,7 +65,9 @@ def blend_canvas(preds: torch.Tensor, mask: torch.Tensor, stages: Sequence[tuple
     ph, pw = mask.shape
     avg = torch.empty((Hc, Wc), dtype=torch.float32, device=preds.device)
     cnt = torch.empty((Hc, Wc), dtype=torch.float32, device=preds.device) if want_count else None
-    _lib.call("prv2_blend_canvas", ptr(preds), ptr(mask), ph, pw, _stages(stages), len(stages), Hc, Wc, ptr(avg), ptr(cnt), stream_ptr())
+    nbytes = 4.0 * (preds.numel() + mask.numel() + (2 if want_count else 1) * Hc * Wc)      # algorithmic bytes
+    _lib.call("prv2_blend_canvas", ptr(preds), ptr(mask), ph, pw, _stages(stages), len(stages), Hc, Wc, ptr(avg), ptr(cnt), stream_ptr(),
+              work=("byte", nbytes))
     return avg, cnt
 
 
@@ -75,8 +81,9 @@ def blend_raw(avg_c: torch.Tensor, cnt_c: torch.Tensor, preds: Optional[torch.Te
         _chk(preds, torch.float32, "preds"); _chk(starts, torch.int32, "starts"); _chk(rmask, torch.float32, "rmask")
     out = torch.empty((H, W), dtype=torch.float32, device=avg_c.device)
     cnt = torch.empty((H, W), dtype=torch.float32, device=avg_c.device) if want_count else None
+    nbytes = 4.0 * (2 * Hc * Wc + n * ph * pw + (rh * rw if n else 0) + (2 if want_count else 1) * H * W)
     _lib.call("prv2_blend_raw", ptr(avg_c), ptr(cnt_c), Hc, Wc, ptr(preds), ptr(starts), n, ph, pw, ptr(rmask), rh, rw, H, W,
-              ptr(out), ptr(cnt), stream_ptr())
+              ptr(out), ptr(cnt), stream_ptr(), work=("byte", nbytes))
     return out, cnt
 
 
@@ -114,41 +121,50 @@ def blend_finalize_raw(avg_c, cnt_c, num_r, starts, rmask, rh, rw, H, W):
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: Act, drop_period: int = 0) -> Act:
     """x fp32 [rows, D] -> act rows (optionally dropping the class-token rows)."""
     rows, D = x.shape
-    _lib.call("prv2_layernorm", ptr(x), rows, D, ptr(w), ptr(b), C.c_float(eps), drop_period, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr())
+    planes = 2 if out.lo is not None else 1
+    _lib.call("prv2_layernorm", ptr(x), rows, D, ptr(w), ptr(b), C.c_float(eps), drop_period, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr(),
+              work=("byte", rows * D * (4.0 + 2.0 * planes)))
     return out
 
 
 def patchify(crops: torch.Tensor, out: Act) -> Act:
     B, _, H, W = crops.shape
-    _lib.call("prv2_patchify", ptr(crops), B, H, W, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr())
+    _lib.call("prv2_patchify", ptr(crops), B, H, W, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr(),
+              work=("byte", B * 3.0 * H * W * 4 + B * (H // 14) * (W // 14) * out.cs * 2.0 * (2 if out.lo is not None else 1)))
     return out
 
 
 def assemble_tokens(emb: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: int, T: int, D: int, x: torch.Tensor):
-    _lib.call("prv2_assemble_tokens", ptr(emb), ptr(cls), ptr(pos), B, T, D, ptr(x), stream_ptr())
+    _lib.call("prv2_assemble_tokens", ptr(emb), ptr(cls), ptr(pos), B, T, D, ptr(x), stream_ptr(), work=("byte", 8.0 * B * (T + 1) * D))
 
 
 def resize_bilinear(a: Act, out: Act, relu: bool = False) -> Act:
     assert a.C == out.C and a.N == out.N
+    planes = 2 if out.lo is not None else 1
     _lib.call("prv2_resize_bilinear_act", ptr(a.hi), ptr(a.lo), a.N, a.H, a.W, a.C, a.cs, ptr(out.hi), ptr(out.lo), out.H, out.W, out.cs,
-              1 if relu else 0, stream_ptr())
+              1 if relu else 0, stream_ptr(), work=("byte", 2.0 * planes * a.N * a.C * (a.H * a.W + out.H * out.W)))
     return out
 
 
 def depth_slots(pred1: torch.Tensor, pred2: torch.Tensor, out: Act, c0: int):
     """pred1/pred2 [N,1,H,W] fp32 -> channels c0, c0+1 of ``out`` (c0+2..c0+7 zeroed)."""
     N, _, H, W = pred1.shape
-    _lib.call("prv2_depth_slots", ptr(pred1), ptr(pred2), N, H, W, ptr(out.hi), ptr(out.lo), out.H, out.W, out.cs, c0, 6, stream_ptr())
+    _lib.call("prv2_depth_slots", ptr(pred1), ptr(pred2), N, H, W, ptr(out.hi), ptr(out.lo), out.H, out.W, out.cs, c0, 6, stream_ptr(),
+              work=("byte", N * (8.0 * H * W + 16.0 * out.H * out.W * (2 if out.lo is not None else 1))))
 
 
-def final_conv(feat: Act, w9c: torch.Tensor, base: Optional[torch.Tensor], out: torch.Tensor):
-    _lib.call("prv2_final_conv", ptr(feat.hi), ptr(feat.lo), feat.N, feat.H, feat.W, feat.C, feat.cs, ptr(w9c), ptr(base), ptr(out), stream_ptr())
+def tap_stencil(taps: torch.Tensor, base: Optional[torch.Tensor], out: torch.Tensor):
+    """taps fp32 [N,H,W,ld] (9 tap responses per pixel) -> out[N,1,H,W] = clamp(base + 3x3 gather, 0)."""
+    N, H, W, ld = taps.shape
+    _lib.call("prv2_tap_stencil", ptr(taps), N, H, W, ld, ptr(base), ptr(out), stream_ptr(), work=("byte", N * H * W * (4.0 * 9 + 8.0)))
 
 
 def phase_split(a: Act, out: Act):
     """out is [4*N, H/2, W/2, C] (phase-major)."""
-    _lib.call("prv2_phase_split", ptr(a.hi), ptr(a.lo), a.N, a.H, a.W, a.C, a.cs, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr())
+    _lib.call("prv2_phase_split", ptr(a.hi), ptr(a.lo), a.N, a.H, a.W, a.C, a.cs, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr(),
+              work=("byte", 4.0 * a.N * a.H * a.W * a.C * (2 if a.lo is not None else 1)))
 
 
 def attention(qkv: Act, B: int, T: int, heads: int, out: Act):
-    _lib.call("prv2_attention", ptr(qkv.hi), ptr(qkv.lo), B, T, heads, ptr(out.hi), ptr(out.lo), stream_ptr())
+    _lib.call("prv2_attention", ptr(qkv.hi), ptr(qkv.lo), B, T, heads, ptr(out.hi), ptr(out.lo), stream_ptr(),
+              work=("flop", 4.0 * B * heads * T * T * 64))

@@ -1,0 +1,57 @@
+"""Single launches of the hot kernels at ViT-L / 12-patch shapes, for ncu captures."""
+import math
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from patchrefinerv2_b200 import _lib, ops
+from patchrefinerv2_b200.nn import Act, GemmLayer, conv_segments
+
+DEV = "cuda:0"
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+torch.manual_seed(0)
+B, T, D, heads = 12, 1025, 1024, 16
+M = B * T
+reps = 3
+
+
+def run(fn):
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+
+
+if which in ("all", "qkv"):
+    y = Act.empty(1, 1, M, D, False, DEV); y.hi.normal_()
+    lay = GemmLayer([(0, 0, 0, torch.randn(3 * D, D) / 32)], 1, 3 * D, False, DEV, bias=torch.randn(3 * D), name="qkv")
+    out = Act.empty(1, 1, M, 3 * D, False, DEV)
+    run(lambda: lay([y], out=out))
+if which in ("all", "proj"):
+    y = Act.empty(1, 1, M, D, False, DEV); y.hi.normal_()
+    lay = GemmLayer([(0, 0, 0, torch.randn(D, D) / 32)], 1, D, False, DEV, epi=_lib.EPI_RESID_F32, bias=torch.randn(D), gamma=torch.rand(D), name="proj")
+    x = torch.zeros(M, D, device=DEV)
+    run(lambda: lay([y], out_f32=x, out_f32_ld=D))
+if which in ("all", "attn"):
+    qkv = Act.empty(1, 1, M, 3 * D, False, DEV); qkv.hi.normal_()
+    out = Act.empty(1, 1, M, D, False, DEV)
+    run(lambda: ops.attention(qkv, B, T, heads, out))
+if which in ("all", "conv"):
+    # fusion.dec3.conv1-like: 2 sources (256, 264->258) at 256x256, Cout 514
+    a = Act.empty(4, 256, 256, 256, False, DEV); a.hi.normal_()
+    b = Act.empty(4, 256, 256, 258, False, DEV, cs=264); b.hi.normal_()
+    w = torch.randn(514, 514, 3, 3) / math.sqrt(514 * 9)
+    lay = GemmLayer(conv_segments(w, [256, 258]), 2, 514, False, DEV, act=_lib.ACT_GELU, name="dec3.conv1")
+    out = Act.empty(4, 256, 256, 514, False, DEV)
+    run(lambda: lay([a, b], out=out))
+if which in ("all", "blend"):
+    preds = torch.rand(81, 448, 448, device=DEV)
+    mask = torch.rand(448, 448, device=DEV)
+    stages = [(0, 0, 4, 4, 0), (0, 224, 4, 3, 16), (224, 0, 3, 4, 28), (224, 224, 3, 3, 40)]
+    starts = torch.randint(0, 1600, (32, 2), dtype=torch.int32, device=DEV)
+    rmask = torch.rand(540, 960, device=DEV) + 1e-3
+
+    def f():
+        avg, cnt = ops.blend_canvas(preds[:49], mask, stages, 1792, 1792)
+        ops.blend_raw(avg, cnt, preds[49:], starts, rmask, 448, 448, 540, 960, 2160, 3840)
+    run(f)
+print("done", _lib.launch_count)

@@ -231,6 +231,10 @@ def test_resize_depth_slots_final_conv(x3, tol):
     w = torch.randn(1, 32, 3, 3, generator=g) / 17
     base = torch.rand(2, 1, 56, 56, generator=g) - 0.3
     want = torch.clamp(base + F.conv2d(f, w, padding=1), min=0)
+    from patchrefinerv2_b200 import _lib
+    from patchrefinerv2_b200.nn import GemmLayer
+    taps = torch.zeros(2, 56, 56, 16, device=DEV)
+    GemmLayer([(0, 0, 0, w[0].permute(1, 2, 0).reshape(9, 32))], 1, 9, x3, DEV, epi=_lib.EPI_F32)([_act(f, x3)], out_f32=taps, out_f32_ld=16)
     out = torch.zeros(2, 1, 56, 56, device=DEV)
-    ops.final_conv(_act(f, x3), w[0].permute(1, 2, 0).reshape(9, 32).contiguous().to(DEV), base.to(DEV), out)
+    ops.tap_stencil(taps, base.to(DEV), out)
     assert rel_err(out.cpu(), want) < tol
