@@ -495,58 +495,79 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v2_kernel(const __gri
   }
 }
 
-// Leftover query rows [tq_main, T): one warp per (image, head, row); plain SIMT online softmax over all keys.
-__global__ void __launch_bounds__(128) attention_tail_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int T, int heads,
-                                                             int tq_main) {
+// Leftover query rows [tq_main, T) (1 row for the 1025-token DINOv2 sequence): one 256-thread CTA per
+// (image, head, row).  Phase 1: thread-per-key scores into shared memory + block softmax statistics;
+// phase 2: thread (kgroup, 4 dims) accumulates p*V over its keys, 16 key groups reduced through smem.
+constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_MAX_T = 2048;
+__global__ void __launch_bounds__(TAIL_THREADS) attention_tail_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int T, int heads,
+                                                                      int tq_main) {
+  __shared__ float s_p[TAIL_MAX_T];
+  __shared__ float s_q[64];
+  __shared__ float s_red[TAIL_THREADS / 32];
+  __shared__ float s_acc[16][64];
   const int n_tail = T - tq_main;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (wid >= B * heads * n_tail) return;
-  const int r = wid % n_tail, head = (wid / n_tail) % heads, b = wid / (n_tail * heads);
+  const int r = blockIdx.x % n_tail, head = (blockIdx.x / n_tail) % heads, b = blockIdx.x / (n_tail * heads);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = heads * 64;
   const size_t row_stride = (size_t)3 * D;
   const bf16* base = qkv + (size_t)b * T * row_stride;
-  const bf16* qp = base + (size_t)(tq_main + r) * row_stride + head * 64;
-  float q[64];
-#pragma unroll
-  for (int g = 0; g < 8; ++g) { float t[8]; act_load8(qp, nullptr, g * 8, t);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) q[g * 8 + e] = t[e]; }
-  float m = -INFINITY, l = 0.f, acc[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  if (tid < 64) s_q[tid] = bf2f(base[(size_t)(tq_main + r) * row_stride + head * 64 + tid]);
+  __syncthreads();
   const float c_log2 = 0.125f * 1.4426950408889634f;
-  for (int k = lane; k < T; k += 32) {
+  // phase 1: scores
+  float m = -INFINITY;
+  for (int k = tid; k < T; k += TAIL_THREADS) {
     const bf16* kp = base + (size_t)k * row_stride + D + head * 64;
-    const bf16* vp = kp + D;
-    float s = 0.f;
+    float sc = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) { float t[8]; act_load8(kp, nullptr, g * 8, t);
+    for (int g = 0; g < 8; ++g) {
+      float t[8];
+      act_load8(kp, nullptr, g * 8, t);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s = fmaf(q[g * 8 + e], t[e], s); }
-    const float m_new = fmaxf(m, s);
-    const float alpha = exp2f((m - m_new) * c_log2), pv = exp2f((s - m_new) * c_log2);
-    l = l * alpha + pv;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) { float t[8]; act_load8(vp, nullptr, g * 8, t);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[g * 8 + e] = fmaf(acc[g * 8 + e], alpha, pv * t[e]); }
-    m = m_new;
+      for (int e = 0; e < 8; ++e) sc = fmaf(s_q[g * 8 + e], t[e], sc);
+    }
+    s_p[k] = sc;
+    m = fmaxf(m, sc);
   }
-  // merge the 32 lanes' partial softmax states
-  float m_all = m;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, o));
-  const float scale = (m == -INFINITY) ? 0.f : exp2f((m - m_all) * c_log2);
-  l *= scale;
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < TAIL_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+  __syncthreads();
+  float l = 0.f;
+  for (int k = tid; k < T; k += TAIL_THREADS) {
+    const float pv = exp2f((s_p[k] - m) * c_log2);
+    s_p[k] = pv;
+    l += pv;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-  bf16* op = out + ((size_t)b * T + tq_main + r) * D + head * 64;
+  if (lane == 0) s_red[warp] = l;
+  __syncthreads();
+  l = 0.f;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) {
-    float a = acc[i] * scale;
+  for (int w = 0; w < TAIL_THREADS / 32; ++w) l += s_red[w];
+  // phase 2: out[d] = sum_k p_k V[k, d]
+  const int kg = tid >> 4, d4 = (tid & 15) * 4;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int k = kg; k < T; k += 16) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(base + (size_t)k * row_stride + 2 * D + head * 64 + d4);
+    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const float2 f0 = __bfloat1622float2(v2[0]), f1 = __bfloat1622float2(v2[1]);
+    const float pv = s_p[k];
+    a0 = fmaf(pv, f0.x, a0); a1 = fmaf(pv, f0.y, a1); a2 = fmaf(pv, f1.x, a2); a3 = fmaf(pv, f1.y, a3);
+  }
+  s_acc[kg][d4] = a0; s_acc[kg][d4 + 1] = a1; s_acc[kg][d4 + 2] = a2; s_acc[kg][d4 + 3] = a3;
+  __syncthreads();
+  if (tid < 64) {
+    float a = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == (i & 31)) op[i] = f2bf(a / l);
+    for (int g = 0; g < 16; ++g) a += s_acc[g][tid];
+    out[((size_t)b * T + tq_main + r) * D + head * 64 + tid] = f2bf(a / l);
   }
 }
 
@@ -617,12 +638,11 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
   p2.last_width = ((T - 128 * (p2.n_chunks - 1)) + 15) / 16 * 16;
   // query rows: leftover rows (<= 16) go to the SIMT tail kernel instead of a mostly empty 128-row tile
   const int rem = T % 128;
-  p2.tq_main = (rem != 0 && rem <= TAIL_MAX && T > 128) ? T - rem : T;
+  p2.tq_main = (rem != 0 && rem <= TAIL_MAX && T > 128 && T <= TAIL_MAX_T) ? T - rem : T;
   attention_v2_kernel<<<dim3(cdiv(p2.tq_main, 256), heads, B), V2_THREADS, smem_v2, (cudaStream_t)stream>>>(p2);
   PRV2_LAUNCH_CHECK();
   if (p2.tq_main < T) {
-    const int warps = B * heads * (T - p2.tq_main);
-    attention_tail_kernel<<<cdiv(warps, 4), 128, 0, (cudaStream_t)stream>>>((const bf16*)qkv_hi, (bf16*)out_hi, B, T, heads, p2.tq_main);
+    attention_tail_kernel<<<B * heads * (T - p2.tq_main), TAIL_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)qkv_hi, (bf16*)out_hi, B, T, heads, p2.tq_main);
     PRV2_LAUNCH_CHECK();
   }
   return PRV2_OK;

@@ -19,9 +19,16 @@
 // * Epilogues fuse bias, ReLU / erf-GELU, channels-first LayerNorm+GELU, residual adds,
 //   LayerScale*gamma + fp32 residual stream, the ConvTranspose pixel shuffle and the DPT
 //   sigmoid head.
+// * CG = 2 (large problems): two CTAs of a cluster (one SM pair) run ONE tcgen05.mma.cta_group::2 of
+//   256 x N: each CTA stages its own 128-pixel A tile and HALF of the weight tile, so shared-memory
+//   fill traffic per FLOP drops by a third (48 KB -> 32 KB per 128x256x64 MACs) -- the kernel is
+//   bound by L2 -> SM bandwidth, not by the tensor pipe.  The leader CTA issues the MMAs and
+//   multicasts its commits to both CTAs' barriers; each CTA drains its own 128 TMEM lanes.
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <string.h>
 
 using namespace prv2;
 
@@ -51,7 +58,7 @@ struct alignas(64) KParams {
   uint8_t seg_last[PRV2_MAX_SEG];             // 16-wide MMA slices in the last chunk (1..4)
   int32_t n_seg;
   int32_t N, H, W, Cout;
-  int32_t tile_w, tile_h, tile_w_log2, tiles_w, tiles_h, tiles_n, total_tiles;
+  int32_t tile_w, tile_h, tile_w_log2, tiles_w, tiles_h, tiles_n, total_tiles;   // total_tiles counts tile PAIRS when CG == 2
   int32_t block_n, stages, b_stage_bytes, tmem_cols;
   int32_t epi, act;
   const float* bias;
@@ -65,6 +72,7 @@ struct alignas(64) KParams {
   float* out_f32; int32_t out_f32_ld;
   int32_t shuffle_k;
   int32_t row_map_period, row_map_extra, row_map_offset;
+  int32_t debug;      // diagnostics (PRV2_GEMM_DEBUG): bit0 = no TMA after the first ring pass, bit1 = epilogue drains TMEM only
 };
 static_assert(sizeof(KParams) <= 4096, "kernel parameter block too large");
 
@@ -119,6 +127,53 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {      // same offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {          // arrives on `bar` at the same offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One lane of a CONVERGED warp.  The single-thread roles run their loops with the whole warp converged and elect the
+// issuing lane per step: under `if (lane == 0)` ptxas cannot prove uniformity and wraps every UTCHMMA / UTMALDG /
+// UTCBAR in an ELECT + BRA.U.ANY loop, which made MMA issue (not the tensor pipe) the bottleneck.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -169,13 +224,31 @@ struct Row {              // one output pixel handled by this lane in the coales
   bool valid;
 };
 
+struct Pre { uint4 a[4]; };   // one chunk's worth of prefetched epilogue operands of this lane (2 rows)
+
+// bf16x8 already in registers (hi plane) [+ lo plane read from memory in the 3-pass precision mode]
+__device__ __forceinline__ void act_unpack8(const uint4& hi, const bf16* lo, size_t i, float (&out)[8]) {
+  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(a2[k]); out[2 * k] = f.x; out[2 * k + 1] = f.y; }
+  if (lo) {
+    const uint4 b = *reinterpret_cast<const uint4*>(lo + i);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(b2[k]); out[2 * k] += f.x; out[2 * k + 1] += f.y; }
+  }
+}
+
 // EPI / ACT are compile-time: each instantiation carries only its own epilogue (small, branch-free SASS)
-template <int EPI, int ACT>
+template <int EPI, int ACT, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int stages = p.stages;
-  const uint32_t stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+  const uint32_t stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;        // b_stage_bytes: this CTA's share (half the N tile when CG == 2)
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const uint32_t n_workers = CG == 2 ? gridDim.x >> 1 : gridDim.x;      // CTAs (CG 1) or CTA pairs (CG 2) walking the tile list
+  const uint32_t worker = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
   const uint32_t bar_base = smem_base + stages * stage_bytes;
   // barrier map: full[s] | empty[s] | tmem_full[2] | tmem_empty[2] | tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -189,7 +262,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_THREADS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -197,11 +270,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     prefetch_tmap(&p.tmB);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();     // the peer's barriers are initialised before any remote arrive / complete_tx
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -210,14 +289,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 
   if (warp == 0) {
     // ================================ TMA producer =========================================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
-        const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+      for (int tile = worker; tile < p.total_tiles; tile += n_workers) {
+        const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)cta_rank;
+        const int img = mt / tiles_per_img, r = mt % tiles_per_img;       // img >= N (odd tile count): the box is out of bounds -> zeros
         const int h0 = (r / p.tiles_w) * p.tile_h, w0 = (r % p.tiles_w) * p.tile_w;
-        const int n0 = nt * p.block_n;
+        const int n0 = nt * p.block_n + (int)cta_rank * (p.block_n >> 1) * (CG - 1);
         int kcol = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const CUtensorMap* map = &p.tmA[p.seg_src[s]];
@@ -226,9 +305,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           for (int c = 0; c < chunks; ++c) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t a_dst = smem_base + stage * stage_bytes;
-            mbar_expect_tx(full_bar(stage), stage_bytes);
-            tma_load_4d(a_dst, map, full_bar(stage), c * BK, w0 + dw, h0 + dh, img);
-            tma_load_2d(a_dst + A_STAGE_BYTES, &p.tmB, full_bar(stage), kcol, n0);
+            if (elect_one()) {
+              if ((p.debug & 1) && (phase != 0 || tile != (int)worker)) {      // diagnostics: operands stay whatever the first ring pass loaded
+                if (cta_rank == 0) mbar_arrive(full_bar(stage));
+              } else if (CG == 2) {
+                // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of the pair
+                const uint32_t lbar = mapa_shared(full_bar(stage), 0);
+                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * stage_bytes);
+                tma_load_4d_pair(a_dst, map, lbar, c * BK, w0 + dw, h0 + dh, img);
+                tma_load_2d_pair(a_dst + A_STAGE_BYTES, &p.tmB, lbar, kcol, n0);
+              } else {
+                mbar_expect_tx(full_bar(stage), stage_bytes);
+                tma_load_4d(a_dst, map, full_bar(stage), c * BK, w0 + dw, h0 + dh, img);
+                tma_load_2d(a_dst + A_STAGE_BYTES, &p.tmB, full_bar(stage), kcol, n0);
+              }
+            }
+            __syncwarp();
             kcol += BK;
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
@@ -237,13 +329,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===========================================
-    if (lane == 0) {
+    if (cta_rank == 0) {
       // cute::UMMA::InstrDescriptor: c=F32(1)<<4 | a=BF16(1)<<7 | b=BF16(1)<<10 | N>>3 <<17 | M>>4 <<24, both K-major
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // (CG == 2: M = 256 = 128 rows in each CTA of the pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accum) {
+        if (CG == 2) tc_mma_bf16_pair(d, a, b, idesc, accum); else tc_mma_bf16(d, a, b, idesc, accum);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -252,22 +348,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         uint32_t accumulate = 0;
         for (int s = 0; s < p.n_seg; ++s) {
           const int chunks = p.seg_chunks[s];
+          const int last = p.seg_last[s];
           for (int c = 0; c < chunks; ++c) {
-            const int slices = (c == chunks - 1) ? p.seg_last[s] : 4;
+            const int slices = (c == chunks - 1) ? last : 4;
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_addr = smem_base + stage * stage_bytes;
             const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
-            for (int k = 0; k < slices; ++k) {
+            if (elect_one()) {
               // +32 bytes per 16-element K slice inside the 128-byte swizzle row (encoded >>4)
-              tc_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-              accumulate = 1;
+              if (slices == 4) {
+                mma(tmem_d, adesc, bdesc, accumulate);
+                mma(tmem_d, adesc + 2, bdesc + 2, 1);
+                mma(tmem_d, adesc + 4, bdesc + 4, 1);
+                mma(tmem_d, adesc + 6, bdesc + 6, 1);
+              } else {
+                for (int k = 0; k < slices; ++k) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, k ? 1u : accumulate);
+              }
+              if (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
             }
-            tc_commit(empty_bar(stage));
+            __syncwarp();
+            accumulate = 1;
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
-        tc_commit(tfull_bar(acc));
+        if (elect_one()) { if (CG == 2) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc)); }
+        __syncwarp();
       }
     }
   } else {
@@ -293,11 +399,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     float* const s_par = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * STG_BYTES_PER_WARP);
     const int rB = lane & 15, cB = (lane >> 4) * 8;
     constexpr bool is_ln = EPI == PRV2_EPI_LN_GELU;
+    const uint32_t tempty_leader0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+      const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)cta_rank;
       const int img = mt / tiles_per_img, r = mt % tiles_per_img;
       const int h0 = (r / p.tiles_w) * p.tile_h, w0 = (r % p.tiles_w) * p.tile_w;
       const int n0 = nt * block_n;
@@ -309,7 +416,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         q.img = img;
         q.h = h0 + (tr >> tile_w_log2);
         q.w = w0 + (tr & tile_w_mask);
-        q.valid = (q.h < pH) && (q.w < pW);
+        q.valid = (q.h < pH) && (q.w < pW) && (img < p.N);
         q.m = ((size_t)img * pH + q.h) * pW + q.w;
         q.orow = q.m;
         if (p.row_map_period > 0) q.orow = q.m + (q.m / p.row_map_period) * p.row_map_extra + p.row_map_offset;
@@ -324,31 +431,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         par[256 + te] = p.gamma ? __ldg(p.gamma + n) : 0.f;
         par[512 + te] = (p.beta && is_ln) ? __ldg(p.beta + n) : 0.f;
       }
-      // (2) pull the rows this tile will read-modify-write (fp32 residual stream / residual acts) towards L2
-      //     while the MMAs of this tile are still running
-      {
-        const Row& q = csel ? rows[1] : rows[0];
-        if (q.valid) {
+      // (2) operands the epilogue READS from global memory (fp32 residual stream / residual activations) do not
+      //     depend on the accumulator: fetch them into registers three chunks ahead, starting NOW, while the MMAs
+      //     of this tile are still running.  (A load issued only when its chunk is processed costs a full
+      //     DRAM/L2 latency per row and made the read-modify-write epilogues latency-bound.)
+      constexpr bool kPre = (EPI == PRV2_EPI_RESID_F32) || (EPI == PRV2_EPI_STORE);
+      const bool x_vec = (out_f32_ld & 3) == 0 && (Cout & 7) == 0;
+      auto prefetch = [&](int cc, Pre& pre) {
+        if (!kPre || cc >= n_chunks) return;
+        const int n = n0 + cc * 16 + cB;
+        if (n >= Cout) return;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const Row& q = rows[i];
+          if (!q.valid) continue;
           if (EPI == PRV2_EPI_RESID_F32) {
-            const char* x = reinterpret_cast<const char*>(out_f32 + q.orow * out_f32_ld + n0);
-            for (int off = (lane >> 4) * 128; off < block_n * 4; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + off));
-          } else if (EPI == PRV2_EPI_STORE && res_hi) {
-            const char* x = reinterpret_cast<const char*>(res_hi + q.m * res_cs + n0);
-            for (int off = (lane >> 4) * 128; off < block_n * 2; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + off));
-            if (res2_hi) {
-              const char* y = reinterpret_cast<const char*>(res2_hi + q.m * res2_cs + n0);
-              for (int off = (lane >> 4) * 128; off < block_n * 2; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + off));
+            if (x_vec) {
+              const uint4* x = reinterpret_cast<const uint4*>(out_f32 + q.orow * out_f32_ld + n);
+              pre.a[2 * i] = x[0]; pre.a[2 * i + 1] = x[1];
             }
+          } else {
+            if (res_hi) pre.a[i] = *reinterpret_cast<const uint4*>(res_hi + q.m * res_cs + n);
+            if (res2_hi) pre.a[2 + i] = *reinterpret_cast<const uint4*>(res2_hi + q.m * res2_cs + n);
           }
         }
-      }
+      };
+      Pre pre0, pre1, pre2;
+      prefetch(csel, pre0);
+      if (EPI == PRV2_EPI_RESID_F32) { prefetch(csel + 2, pre1); prefetch(csel + 4, pre2); }
       asm volatile("bar.sync 5, 256;" ::: "memory");          // parameters visible to all epilogue warps
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * block_n;
       float v[16];
 
-      if (EPI == PRV2_EPI_HEAD) {
+      if (p.debug & 2) {
+        tc_ld16(taddr + csel * 16, v);
+        if (v[0] == 123.456f && out_f32) out_f32[0] = v[1];             // keep the load alive
+      } else if (EPI == PRV2_EPI_HEAD) {
         if (csel == 0) {                           // one float per pixel: lane-per-row stores are already coalesced
           const int tr = quad * 32 + lane;
           const int h = h0 + (tr >> tile_w_log2), w = w0 + (tr & tile_w_mask);
@@ -359,7 +479,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             for (int j = 0; j < 16; ++j)
               if (n0 + c * 16 + j < Cout) dot += fmaxf(v[j] + par[c * 16 + j], 0.f) * par[256 + c * 16 + j];
           }
-          if (h < pH && w < pW) out_f32[((size_t)img * pH + h) * pW + w] = p.head_scale / (1.0f + expf(-(dot + __ldg(p.beta))));
+          if (h < pH && w < pW && img < p.N) out_f32[((size_t)img * pH + h) * pW + w] = p.head_scale / (1.0f + expf(-(dot + __ldg(p.beta))));
         }
       } else {
         float* const s_fin = stg + 32 * STG_LD + 128;          // [mean(32) | rstd(32)]
@@ -396,9 +516,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         }
         // (3) chunk loop, software pipelined: the TMEM load of chunk c+2 is in flight while chunk c goes
         //     through its coalesced phase.
-        int c = csel;
-        if (c < n_chunks) tc_ld16(taddr + c * 16, v);
-        for (; c < n_chunks; c += 2) {
+        if (csel < n_chunks) tc_ld16(taddr + csel * 16, v);
+        auto chunk = [&](const int c, const Pre& pre) {
           float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD);
           dst[0] = make_float4(v[0], v[1], v[2], v[3]);
           dst[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -455,8 +574,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
               }
               if (EPI == PRV2_EPI_RESID_F32) {
                 float* x = out_f32 + q.orow * out_f32_ld + n;
-                if (n + 8 <= Cout && (out_f32_ld & 3) == 0) {
-                  float4 x0 = *reinterpret_cast<float4*>(x), x1 = *reinterpret_cast<float4*>(x + 4);
+                if (x_vec) {
+                  float4 x0 = *reinterpret_cast<const float4*>(&pre.a[2 * i]), x1 = *reinterpret_cast<const float4*>(&pre.a[2 * i + 1]);
                   x0.x += g8[0] * t[0]; x0.y += g8[1] * t[1]; x0.z += g8[2] * t[2]; x0.w += g8[3] * t[3];
                   x1.x += g8[4] * t[4]; x1.y += g8[5] * t[5]; x1.z += g8[6] * t[6]; x1.w += g8[7] * t[7];
                   *reinterpret_cast<float4*>(x) = x0;
@@ -485,13 +604,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
               }
               if (res_hi) {
                 float r8[8];
-                act_load8(res_hi, res_lo, q.m * res_cs + n, r8);
+                act_unpack8(pre.a[i], res_lo, q.m * res_cs + n, r8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) t[j] += r8[j];
               }
               if (res2_hi) {
                 float r8[8];
-                act_load8(res2_hi, res2_lo, q.m * res2_cs + n, r8);
+                act_unpack8(pre.a[2 + i], res2_lo, q.m * res2_cs + n, r8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) t[j] += r8[j];
               }
@@ -509,18 +628,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
           }
+        };
+        if (EPI == PRV2_EPI_RESID_F32) {
+          // three-deep register ring: the global reads of chunk c+6 are issued right after chunk c retires
+          for (int c = csel; c < n_chunks; c += 6) {
+            chunk(c, pre0); prefetch(c + 6, pre0);
+            if (c + 2 < n_chunks) { chunk(c + 2, pre1); prefetch(c + 8, pre1); }
+            if (c + 4 < n_chunks) { chunk(c + 4, pre2); prefetch(c + 10, pre2); }
+          }
+        } else if (EPI == PRV2_EPI_STORE) {
+          // residual activations (16 B per row): issue the reads of the NEXT chunk before working on this one.
+          // (A code-doubling two-buffer ring measurably slowed the residual-free GELU epilogue of fc1.)
+          for (int c = csel; c < n_chunks; c += 2) {
+            if (res_hi) { pre1 = pre0; prefetch(c + 2, pre0); }
+            chunk(c, pre1);
+          }
+        } else {
+          for (int c = csel; c < n_chunks; c += 2) chunk(c, pre0);
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      __syncwarp();                                          // every lane's TMEM reads of this accumulator have completed
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc);
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -568,10 +710,19 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("prv2_umma_gemm: cuTensorMapEncodeTiled(A%d) failed (%d) C=%d cs=%d N=%d H=%d W=%d", s, (int)r, src.C, src.cs, d->N, d->H, d->W); return PRV2_ECUDA; }
   }
   for (int s = d->n_src; s < PRV2_MAX_SRC; ++s) p.tmA[s] = p.tmA[0];
+  // CTA pairs (cta_group::2) whenever there is enough work to fill the chip with pairs: each CTA of a pair stages its own
+  // A tile and half of the weight tile.  PRV2_GEMM_CG=1|2 forces the choice (diagnostics).
+  const int tiles_w = cdiv(d->W, d->tile_w), tiles_h = cdiv(d->H, d->tile_h);
+  const long long m_tiles = (long long)d->N * tiles_h * tiles_w;
+  const int tiles_n = d->Cout_pad / d->block_n;
+  static const char* cg_env = getenv("PRV2_GEMM_CG");
+  int cg = (m_tiles >= 2 && m_tiles * tiles_n >= 2 * 148) ? 2 : 1;
+  if (cg_env && (cg_env[0] == '1' || cg_env[0] == '2')) cg = cg_env[0] - '0';
+  if (m_tiles < 2 || d->block_n % 16 != 0) cg = 1;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->Ktot, (cuuint64_t)d->Cout_pad};
     cuuint64_t strides[1] = {(cuuint64_t)d->Ktot * 2};
-    cuuint32_t box[2] = {BK, (cuuint32_t)d->block_n};
+    cuuint32_t box[2] = {BK, (cuuint32_t)(d->block_n / cg)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -597,15 +748,19 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   PRV2_CHECK_ARG((d->tile_w & (d->tile_w - 1)) == 0, "prv2_umma_gemm: tile_w must be a power of two");
   p.tile_w_log2 = 0;
   while ((1 << p.tile_w_log2) < d->tile_w) ++p.tile_w_log2;
-  p.tiles_w = cdiv(d->W, d->tile_w); p.tiles_h = cdiv(d->H, d->tile_h);
-  p.tiles_n = d->Cout_pad / d->block_n;
-  const long long total = (long long)d->N * p.tiles_h * p.tiles_w * p.tiles_n;
+  p.tiles_w = tiles_w; p.tiles_h = tiles_h;
+  p.tiles_n = tiles_n;
+  const long long total = ((m_tiles + cg - 1) / cg) * p.tiles_n;         // tiles (CG 1) or tile pairs (CG 2)
   PRV2_CHECK_ARG(total < (1LL << 31), "prv2_umma_gemm: too many tiles");
   p.total_tiles = (int)total;
   p.block_n = d->block_n;
-  p.b_stage_bytes = d->block_n * BK * 2;
+  p.b_stage_bytes = (d->block_n / cg) * BK * 2;
   p.stages = SMEM_BUDGET / (A_STAGE_BYTES + p.b_stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  static const char* dbg_env = getenv("PRV2_GEMM_DEBUG");
+  p.debug = dbg_env ? atoi(dbg_env) : 0;
+  static const char* st_env = getenv("PRV2_GEMM_STAGES");          // diagnostics: cap the pipeline depth
+  if (st_env && atoi(st_env) >= 2 && atoi(st_env) < p.stages) p.stages = atoi(st_env);
   int cols = 32;
   while (cols < 2 * d->block_n) cols <<= 1;
   p.tmem_cols = cols;
@@ -653,32 +808,45 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
     int dev = 0;
     PRV2_CUDA(cudaGetDevice(&dev));
     PRV2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_LN_GELU, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_RESID_F32, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_F32, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_SHUFFLE, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<PRV2_EPI_HEAD, PRV2_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+#define PRV2_SET_SMEM(E, A)                                                                                                        \
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<E, A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));           \
+    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<E, A, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PRV2_SET_SMEM(PRV2_EPI_STORE, PRV2_ACT_NONE)
+    PRV2_SET_SMEM(PRV2_EPI_STORE, PRV2_ACT_RELU)
+    PRV2_SET_SMEM(PRV2_EPI_STORE, PRV2_ACT_GELU)
+    PRV2_SET_SMEM(PRV2_EPI_LN_GELU, PRV2_ACT_NONE)
+    PRV2_SET_SMEM(PRV2_EPI_RESID_F32, PRV2_ACT_NONE)
+    PRV2_SET_SMEM(PRV2_EPI_F32, PRV2_ACT_NONE)
+    PRV2_SET_SMEM(PRV2_EPI_SHUFFLE, PRV2_ACT_NONE)
+    PRV2_SET_SMEM(PRV2_EPI_HEAD, PRV2_ACT_NONE)
+#undef PRV2_SET_SMEM
   }
   // always request the full budget: guarantees one CTA per SM, so a 512-column TMEM allocation can never deadlock
-  const int smem = SMEM_TOTAL;
-  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  cudaStream_t st = (cudaStream_t)stream;
+  int grid = p.total_tiles * cg < g_num_sms ? p.total_tiles * cg : g_num_sms;
+  if (cg == 2) grid &= ~1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_TOTAL; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+#define PRV2_LAUNCH(E, A)                                                                     \
+  PRV2_CUDA(cg == 2 ? cudaLaunchKernelEx(&cfg, umma_gemm_kernel<E, A, 2>, p) : cudaLaunchKernelEx(&cfg, umma_gemm_kernel<E, A, 1>, p))
   switch (d->epi) {
     case PRV2_EPI_STORE:
       PRV2_CHECK_ARG(d->act >= PRV2_ACT_NONE && d->act <= PRV2_ACT_GELU, "prv2_umma_gemm: unknown activation %d", d->act);
-      if (d->act == PRV2_ACT_RELU) umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_RELU><<<grid, NUM_THREADS, smem, st>>>(p);
-      else if (d->act == PRV2_ACT_GELU) umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_GELU><<<grid, NUM_THREADS, smem, st>>>(p);
-      else umma_gemm_kernel<PRV2_EPI_STORE, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p);
+      if (d->act == PRV2_ACT_RELU) { PRV2_LAUNCH(PRV2_EPI_STORE, PRV2_ACT_RELU); }
+      else if (d->act == PRV2_ACT_GELU) { PRV2_LAUNCH(PRV2_EPI_STORE, PRV2_ACT_GELU); }
+      else { PRV2_LAUNCH(PRV2_EPI_STORE, PRV2_ACT_NONE); }
       break;
-    case PRV2_EPI_LN_GELU: umma_gemm_kernel<PRV2_EPI_LN_GELU, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
-    case PRV2_EPI_RESID_F32: umma_gemm_kernel<PRV2_EPI_RESID_F32, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
-    case PRV2_EPI_F32: umma_gemm_kernel<PRV2_EPI_F32, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
-    case PRV2_EPI_SHUFFLE: umma_gemm_kernel<PRV2_EPI_SHUFFLE, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
-    default: umma_gemm_kernel<PRV2_EPI_HEAD, PRV2_ACT_NONE><<<grid, NUM_THREADS, smem, st>>>(p); break;
+    case PRV2_EPI_LN_GELU: PRV2_LAUNCH(PRV2_EPI_LN_GELU, PRV2_ACT_NONE); break;
+    case PRV2_EPI_RESID_F32: PRV2_LAUNCH(PRV2_EPI_RESID_F32, PRV2_ACT_NONE); break;
+    case PRV2_EPI_F32: PRV2_LAUNCH(PRV2_EPI_F32, PRV2_ACT_NONE); break;
+    case PRV2_EPI_SHUFFLE: PRV2_LAUNCH(PRV2_EPI_SHUFFLE, PRV2_ACT_NONE); break;
+    default: PRV2_LAUNCH(PRV2_EPI_HEAD, PRV2_ACT_NONE); break;
   }
+#undef PRV2_LAUNCH
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
