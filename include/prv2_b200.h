@@ -126,9 +126,10 @@ typedef struct {
 #define PRV2_ACT_NONE 0
 #define PRV2_ACT_RELU 1
 #define PRV2_ACT_GELU 2       /* exact erf GELU (torch.nn.GELU default)                 */
+#define PRV2_ACT_GELU_TANH 3  /* tanh-form GELU (|diff| <= 1e-3 abs vs erf); one-pass bf16 mode only */
 
 #define PRV2_EPI_STORE 0      /* act(acc+bias) [+ residual act] -> out (and optional relu copy) */
-#define PRV2_EPI_LN_GELU 1    /* channels-first LayerNorm over Cout then GELU (convs.py:21-29,64-75) */
+#define PRV2_EPI_LN_GELU 1    /* channels-first LayerNorm over Cout then GELU (convs.py:21-29,64-75); act = GELU or GELU_TANH */
 #define PRV2_EPI_RESID_F32 2  /* x_f32[m,n] += gamma[n]*(acc+bias[n])  (block.py:105-106, layer_scale.py:27) */
 #define PRV2_EPI_F32 3        /* out_f32[m,n] = acc+bias                                 */
 #define PRV2_EPI_SHUFFLE 4    /* ConvTranspose2d k==stride: n=(ky,kx,co) scattered to [N,H*k,W*k,Cout] (dpt.py:62-73) */

@@ -13,7 +13,7 @@ MAX_SRC = 12
 MAX_SEG = 128
 
 EPI_STORE, EPI_LN_GELU, EPI_RESID_F32, EPI_F32, EPI_SHUFFLE, EPI_HEAD = range(6)
-ACT_NONE, ACT_RELU, ACT_GELU = range(3)
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_TANH = range(4)
 
 
 class Prv2Error(RuntimeError):

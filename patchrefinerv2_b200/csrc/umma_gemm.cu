@@ -42,10 +42,13 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int EPI_THREADS = 32 * NUM_EPI_WARPS;
 constexpr int MAX_STAGES = 8;
 constexpr int STG_LD = 20;                    // floats per staged row (16 + 4 pad: conflict-free float4 access both ways)
-constexpr int STG_BYTES_PER_WARP = 32 * STG_LD * 4 + 768;   // 32x16 fp32 transpose tile + LN partial/final statistics
+constexpr int ROW_PITCH = 144;                // row epilogue: 64 bf16 (128 B) + 16 B pad per staged row (conflict-free 16-byte stores)
+constexpr int STG_BYTES_PER_WARP = 32 * ROW_PITCH;          // >= 32x16 fp32 transpose tile + LN statistics of the generic epilogue (3328 B)
 constexpr int PAR_BYTES = 2 * 3 * 256 * 4;    // per-tile bias / gamma / beta, double buffered by accumulator parity
-constexpr int SMEM_BUDGET = 192 * 1024;       // operand stages; epilogue staging, parameters and barriers sit behind
-constexpr int SMEM_TOTAL = SMEM_BUDGET + NUM_EPI_WARPS * STG_BYTES_PER_WARP + PAR_BYTES + 1024 + 256;
+constexpr int LN_BYTES = NUM_EPI_WARPS * 2 * 64 * 4;        // row epilogue: LayerNorm partials exchanged between the two warps of a quadrant
+constexpr int SMEM_BUDGET = 179 * 1024;       // operand stages; epilogue staging, parameters and barriers sit behind
+constexpr int SMEM_TOTAL = SMEM_BUDGET + NUM_EPI_WARPS * STG_BYTES_PER_WARP + PAR_BYTES + LN_BYTES + 1024 + 256;
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 constexpr uint64_t SPIN_LIMIT_NS = 4000000000ull;   // a wedged pipeline traps instead of hanging the box
 
 struct alignas(64) KParams {
@@ -218,6 +221,42 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
+// tanh-form GELU on MUFU.TANH (5 FP32 ops + 1 MUFU): |gelu_tanh - gelu_erf| <= ~1e-3 abs, below the bf16 rounding of
+// the stored activation; used by the one-pass bf16 mode only.  The erf form above costs ~17 FP32 ops + 2 MUFU per
+// element and made the fc1 / FusionUnet GELU epilogues FMA-pipe bound.
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float x2 = x * x;
+  const float inner = x * fmaf(0.0356774081f, x2, 0.7978845608f);      // sqrt(2/pi) * (x + 0.044715 x^3)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) {
+  if (ACT == PRV2_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == PRV2_ACT_GELU) return gelu_fast(x);
+  if (ACT == PRV2_ACT_GELU_TANH) return gelu_tanh(x);
+  return x;
+}
+
+// bulk async copy shared -> global of one staged row segment (row epilogue)
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 struct Row {              // one output pixel handled by this lane in the coalesced phase
   size_t m, orow;
   int h, w, img;
@@ -240,7 +279,10 @@ __device__ __forceinline__ void act_unpack8(const uint4& hi, const bf16* lo, siz
 }
 
 // EPI / ACT are compile-time: each instantiation carries only its own epilogue (small, branch-free SASS)
-template <int EPI, int ACT, int CG>
+// FAST selects the row epilogue (plain bf16 output, no residual / ReLU copy / lo plane): lane == TMEM lane == output
+// pixel; the lane converts its own row segment, parks it in a padded shared row and ships it with ONE bulk async copy
+// (cp.async.bulk shared -> global).  No transposes, no per-chunk global-store instructions, ragged edges by predicate.
+template <int EPI, int ACT, int CG, bool FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -376,6 +418,125 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         __syncwarp();
       }
     }
+  } else if (FAST) {
+    // ================================ row epilogue ==========================================
+    const int ew = warp - 2;
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+    const int csel = ew >> 2;                     // the two warps of a quadrant alternate 64-column panels
+    const int te = threadIdx.x - 64;
+    const int Cout = p.Cout, block_n = p.block_n, out_cs = p.out_cs;
+    const int tile_w_log2 = p.tile_w_log2, tile_w_mask = p.tile_w - 1, pH = p.H, pW = p.W;
+    bf16* const out_hi = p.out_hi;
+    uint8_t* const srow = stage_area + ew * STG_BYTES_PER_WARP + lane * ROW_PITCH;
+    const uint32_t srow_s = smem_u32(srow);
+    float* const s_par = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * STG_BYTES_PER_WARP);
+    float* const s_ln = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * STG_BYTES_PER_WARP + PAR_BYTES);
+    constexpr bool is_ln = EPI == PRV2_EPI_LN_GELU;
+    const int n_panels = (block_n + 63) >> 6;
+    const uint32_t tempty_leader0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+    int it = 0;
+    for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)cta_rank;
+      const int img = mt / tiles_per_img, r = mt % tiles_per_img;
+      const int h0 = (r / p.tiles_w) * p.tile_h, w0 = (r % p.tiles_w) * p.tile_w;
+      const int n0 = nt * block_n;
+      const int tr = quad * 32 + lane;
+      const int h = h0 + (tr >> tile_w_log2), w = w0 + (tr & tile_w_mask);
+      const bool valid = (h < pH) && (w < pW) && (img < p.N);
+      bf16* const grow = out_hi + (((size_t)img * pH + h) * pW + w) * out_cs + n0;
+      float* const par = s_par + acc * 768;
+      if (te < block_n) {
+        const int n = min(n0 + te, Cout - 1);
+        par[te] = p.bias ? __ldg(p.bias + n) : 0.f;
+        if (is_ln) { par[256 + te] = __ldg(p.gamma + n); par[512 + te] = __ldg(p.beta + n); }
+      }
+      asm volatile("bar.sync 5, 256;" ::: "memory");          // parameters visible to all epilogue warps
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * block_n;
+      float mean = 0.f, rstd = 1.f;
+      if (is_ln) {
+        // channels-first LayerNorm statistics of this lane's pixel (convs.py:24-27): each warp of the quadrant reduces
+        // its own panels two-pass (mean, then centred squares); the halves merge with Chan's parallel update.
+        float v[16];
+        float sum = 0.f;
+        int cnt = 0;
+        for (int pn = csel; pn < n_panels; pn += 2)
+          for (int c0 = pn * 64; c0 < min(pn * 64 + 64, block_n); c0 += 16) {
+            tc_ld16(taddr + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { sum += v[j]; ++cnt; }
+          }
+        const float mean_a = cnt ? sum / (float)cnt : 0.f;
+        float m2 = 0.f;
+        for (int pn = csel; pn < n_panels; pn += 2)
+          for (int c0 = pn * 64; c0 < min(pn * 64 + 64, block_n); c0 += 16) {
+            tc_ld16(taddr + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { const float d = v[j] - mean_a; m2 += d * d; }
+          }
+        float* const mine = s_ln + (ew * 2 + acc) * 64;
+        const float* const theirs = s_ln + ((ew ^ 4) * 2 + acc) * 64;
+        mine[lane] = mean_a;
+        mine[32 + lane] = m2;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        const float mean_b = theirs[lane], m2_b = theirs[32 + lane];
+        const float na = (float)cnt, nb = (float)(Cout - cnt), nn = (float)Cout;
+        const float delta = mean_b - mean_a;
+        mean = mean_a + delta * (nb / nn);
+        rstd = 1.0f / sqrtf((m2 + m2_b + delta * delta * (na * nb / nn)) / nn + p.eps);
+      }
+      for (int pn = csel; pn < n_panels; pn += 2) {
+        const int c0 = pn * 64;
+        const int cols = min(64, block_n - c0);
+        const int nq = cols >> 4;
+        bulk_wait_read0();                                    // this lane's previous copy has left its staging row
+        uint32_t rr[16], rn[16];
+        tc_ld16_issue(taddr + c0, rr);
+        tc_ld_wait();
+        for (int q = 0; q < nq; ++q) {
+          if (q + 1 < nq) tc_ld16_issue(taddr + c0 + (q + 1) * 16, rn);
+          const int nl = c0 + q * 16;
+          float t[16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b4 = *reinterpret_cast<const float4*>(par + nl + g * 4);
+            t[g * 4 + 0] = __uint_as_float(rr[g * 4 + 0]); t[g * 4 + 1] = __uint_as_float(rr[g * 4 + 1]);
+            t[g * 4 + 2] = __uint_as_float(rr[g * 4 + 2]); t[g * 4 + 3] = __uint_as_float(rr[g * 4 + 3]);
+            if (is_ln) {
+              const float4 g4 = *reinterpret_cast<const float4*>(par + 256 + nl + g * 4), e4 = *reinterpret_cast<const float4*>(par + 512 + nl + g * 4);
+              t[g * 4 + 0] = g4.x * ((t[g * 4 + 0] - mean) * rstd) + e4.x; t[g * 4 + 1] = g4.y * ((t[g * 4 + 1] - mean) * rstd) + e4.y;
+              t[g * 4 + 2] = g4.z * ((t[g * 4 + 2] - mean) * rstd) + e4.z; t[g * 4 + 3] = g4.w * ((t[g * 4 + 3] - mean) * rstd) + e4.w;
+            } else {
+              t[g * 4 + 0] += b4.x; t[g * 4 + 1] += b4.y; t[g * 4 + 2] += b4.z; t[g * 4 + 3] += b4.w;
+            }
+          }
+          __nv_bfloat162 h2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h2[j] = __floats2bfloat162_rn(act_fn<ACT>(t[2 * j]), act_fn<ACT>(t[2 * j + 1]));
+          *reinterpret_cast<uint4*>(srow + q * 32) = *reinterpret_cast<const uint4*>(&h2[0]);
+          *reinterpret_cast<uint4*>(srow + q * 32 + 16) = *reinterpret_cast<const uint4*>(&h2[4]);
+          if (q + 1 < nq) {
+            tc_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = rn[j];
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // staged row -> visible to the bulk copy engine
+        const int nvalid = min(cols, Cout - (n0 + c0));
+        if (valid && nvalid > 0 && !(p.debug & 4)) bulk_store(grow + c0, srow_s, (uint32_t)nvalid * 2u);
+        bulk_commit();
+      }
+      tc_fence_before();
+      __syncwarp();                                          // every lane's TMEM reads of this accumulator have completed
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc);
+        else mbar_arrive(tempty_bar(acc));
+      }
+    }
+    bulk_wait_all();
   } else {
     // ================================ epilogue =============================================
     // Phase A: the lane that owns TMEM lane (= output pixel) r pulls 16 fp32 columns and parks them in a
@@ -536,7 +697,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           }
           const int nl = c * 16 + cB;                        // first of this lane's 8 channels, tile-local
           const int n = n0 + nl;
-          if (n < Cout) {
+          if (n < Cout && !(p.debug & 8)) {
             const float4 b0 = *reinterpret_cast<const float4*>(par + nl), b1 = *reinterpret_cast<const float4*>(par + nl + 4);
             const float4 g0 = *reinterpret_cast<const float4*>(par + 256 + nl), g1 = *reinterpret_cast<const float4*>(par + 256 + nl + 4);
             const float bias8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -560,7 +721,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
                 const float b8[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
                 const float mean = s_fin[rl], rstd = s_fin[32 + rl];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = gelu_fast(g8[j] * ((t[j] - mean) * rstd) + b8[j]);
+                for (int j = 0; j < 8; ++j) t[j] = act_fn<ACT>(g8[j] * ((t[j] - mean) * rstd) + b8[j]);
                 act_store8(out_hi, out_lo, q.orow * out_cs + n, t);
                 continue;
               }
@@ -595,12 +756,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
                 }
                 continue;
               }
-              if (ACT == PRV2_ACT_RELU) {
+              if (ACT != PRV2_ACT_NONE) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = fmaxf(t[j], 0.f);
-              } else if (ACT == PRV2_ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = gelu_fast(t[j]);
+                for (int j = 0; j < 8; ++j) t[j] = act_fn<ACT>(t[j]);
               }
               if (res_hi) {
                 float r8[8];
@@ -614,7 +772,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) t[j] += r8[j];
               }
-              if (out_hi) act_store8(out_hi, out_lo, q.orow * out_cs + n, t);
+              if (out_hi && !(p.debug & 4)) act_store8(out_hi, out_lo, q.orow * out_cs + n, t);
               if (relu_hi) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) t[j] = fmaxf(t[j], 0.f);
@@ -679,6 +837,17 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 int g_num_sms = 0;
+
+template <int EPI, int ACT, int CG, bool FAST>
+cudaError_t launch(const cudaLaunchConfig_t& cfg, const KParams& p) {
+  static bool attr_done = false;                   // per instantiation (one device per process)
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<EPI, ACT, CG, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  return cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, ACT, CG, FAST>, p);
+}
 
 }  // namespace
 
@@ -808,19 +977,11 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
     int dev = 0;
     PRV2_CUDA(cudaGetDevice(&dev));
     PRV2_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-#define PRV2_SET_SMEM(E, A)                                                                                                        \
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<E, A, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));           \
-    PRV2_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<E, A, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PRV2_SET_SMEM(PRV2_EPI_STORE, PRV2_ACT_NONE)
-    PRV2_SET_SMEM(PRV2_EPI_STORE, PRV2_ACT_RELU)
-    PRV2_SET_SMEM(PRV2_EPI_STORE, PRV2_ACT_GELU)
-    PRV2_SET_SMEM(PRV2_EPI_LN_GELU, PRV2_ACT_NONE)
-    PRV2_SET_SMEM(PRV2_EPI_RESID_F32, PRV2_ACT_NONE)
-    PRV2_SET_SMEM(PRV2_EPI_F32, PRV2_ACT_NONE)
-    PRV2_SET_SMEM(PRV2_EPI_SHUFFLE, PRV2_ACT_NONE)
-    PRV2_SET_SMEM(PRV2_EPI_HEAD, PRV2_ACT_NONE)
-#undef PRV2_SET_SMEM
   }
+  // row epilogue (bulk-copy stores) whenever the layer writes one plain bf16 tensor
+  static const char* fast_env = getenv("PRV2_GEMM_FAST");
+  bool fast = !(fast_env && fast_env[0] == '0') && d->out_hi && !d->out_lo && d->row_map_period == 0 && d->out_cs % 8 == 0 && d->Cout % 8 == 0 &&
+              ((d->epi == PRV2_EPI_STORE && !d->relu_hi && !d->res_hi && !d->res2_hi) || d->epi == PRV2_EPI_LN_GELU);
   // always request the full budget: guarantees one CTA per SM, so a 512-column TMEM allocation can never deadlock
   int grid = p.total_tiles * cg < g_num_sms ? p.total_tiles * cg : g_num_sms;
   if (cg == 2) grid &= ~1;
@@ -831,22 +992,29 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-#define PRV2_LAUNCH(E, A)                                                                     \
-  PRV2_CUDA(cg == 2 ? cudaLaunchKernelEx(&cfg, umma_gemm_kernel<E, A, 2>, p) : cudaLaunchKernelEx(&cfg, umma_gemm_kernel<E, A, 1>, p))
+  const int act = d->act;
+  PRV2_CHECK_ARG(act >= PRV2_ACT_NONE && act <= PRV2_ACT_GELU_TANH, "prv2_umma_gemm: unknown activation %d", act);
+  cudaError_t err = cudaSuccess;
+#define PRV2_L2(E, A, F) (cg == 2 ? launch<E, A, 2, F>(cfg, p) : launch<E, A, 1, F>(cfg, p))
+#define PRV2_L(E, A) (fast ? PRV2_L2(E, A, true) : PRV2_L2(E, A, false))
   switch (d->epi) {
     case PRV2_EPI_STORE:
-      PRV2_CHECK_ARG(d->act >= PRV2_ACT_NONE && d->act <= PRV2_ACT_GELU, "prv2_umma_gemm: unknown activation %d", d->act);
-      if (d->act == PRV2_ACT_RELU) { PRV2_LAUNCH(PRV2_EPI_STORE, PRV2_ACT_RELU); }
-      else if (d->act == PRV2_ACT_GELU) { PRV2_LAUNCH(PRV2_EPI_STORE, PRV2_ACT_GELU); }
-      else { PRV2_LAUNCH(PRV2_EPI_STORE, PRV2_ACT_NONE); }
+      err = act == PRV2_ACT_RELU ? PRV2_L(PRV2_EPI_STORE, PRV2_ACT_RELU)
+            : act == PRV2_ACT_GELU ? PRV2_L(PRV2_EPI_STORE, PRV2_ACT_GELU)
+            : act == PRV2_ACT_GELU_TANH ? PRV2_L(PRV2_EPI_STORE, PRV2_ACT_GELU_TANH)
+                                        : PRV2_L(PRV2_EPI_STORE, PRV2_ACT_NONE);
       break;
-    case PRV2_EPI_LN_GELU: PRV2_LAUNCH(PRV2_EPI_LN_GELU, PRV2_ACT_NONE); break;
-    case PRV2_EPI_RESID_F32: PRV2_LAUNCH(PRV2_EPI_RESID_F32, PRV2_ACT_NONE); break;
-    case PRV2_EPI_F32: PRV2_LAUNCH(PRV2_EPI_F32, PRV2_ACT_NONE); break;
-    case PRV2_EPI_SHUFFLE: PRV2_LAUNCH(PRV2_EPI_SHUFFLE, PRV2_ACT_NONE); break;
-    default: PRV2_LAUNCH(PRV2_EPI_HEAD, PRV2_ACT_NONE); break;
+    case PRV2_EPI_LN_GELU:
+      err = act == PRV2_ACT_GELU_TANH ? PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU_TANH) : PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU);
+      break;
+    case PRV2_EPI_RESID_F32: err = PRV2_L2(PRV2_EPI_RESID_F32, PRV2_ACT_NONE, false); break;
+    case PRV2_EPI_F32: err = PRV2_L2(PRV2_EPI_F32, PRV2_ACT_NONE, false); break;
+    case PRV2_EPI_SHUFFLE: err = PRV2_L2(PRV2_EPI_SHUFFLE, PRV2_ACT_NONE, false); break;
+    default: err = PRV2_L2(PRV2_EPI_HEAD, PRV2_ACT_NONE, false); break;
   }
-#undef PRV2_LAUNCH
+#undef PRV2_L
+#undef PRV2_L2
+  PRV2_CUDA(err);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

@@ -61,6 +61,8 @@ def conv(name, Bc, H, W, splits, pitches, Cout, **kw):
     timed(name, lambda: lay(srcs, out=out), 2.0 * Bc * H * W * 9 * sum(splits) * Cout, iters=3)
 
 
+for kk in (512, 1024, 2048, 4096, 8192):        # K sweep at the qkv shape: separates per-tile overhead from per-chunk cost
+    linear(f"k{kk}", kk, 3 * D)
 linear("qkv", D, 3 * D)
 linear("fc1", D, 4 * D, act=_lib.ACT_GELU)
 linear("fc2", 4 * D, D, epi=_lib.EPI_RESID_F32, gamma=torch.rand(D))
