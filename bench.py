@@ -176,7 +176,18 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at the first collective; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     sd = O.init_patchrefiner_state_dict(cfg, 0)
     n_local = -(-n_patches // world)
     pb = args.patch_batch or -(-n_local // (-(-n_local // 12)))
@@ -244,6 +255,15 @@ def main():
         e2e = {"value": args.steps / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": host_out.numel() * 4,
                "ms_per_step": ms_e / args.steps}
 
+    # multi-GPU parity evidence (untimed): the sharded frame against the same frame refined by this rank alone
+    shard_check = None
+    if world > 1:
+        d_sh = step_resident().clone()
+        random.seed(1)
+        d_one, _ = model(mode="infer", image_lr=lr_dev, image_hr=hr_dev, cai_mode=cai_mode, process_num=process_num, shard=False)
+        shard_check = {"max_rel_diff_vs_unsharded": float(((d_sh - d_one).abs() / d_one.abs().clamp_min(1e-3)).max().item())}
+        torch.distributed.barrier()
+
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -296,7 +316,7 @@ def main():
             "patches_per_sec": fps * n_patches, "algorithmic_tflop_per_frame": flops_frame / 1e12,
             "model_tflops_per_gpu": flops_frame * fps / 1e12 / world,
             "l2_policy": "working set per step (activations, several GB) far exceeds the 126 MB L2; no explicit flush",
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kern, "gemm_layers": gemm_layers, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "shard_check": shard_check, "roofline": roofline, "kernels": kern, "gemm_layers": gemm_layers, "cpu_baseline": cpu_baseline,
             "workspace_gb": sum(w.nbytes() for eng in (model._engine["coarse"], model._engine["fine"], model._engine["fusion"]) for w in eng.ws.values()) / 1e9}
     print(json.dumps(line))
     if world > 1:

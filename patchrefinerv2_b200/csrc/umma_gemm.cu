@@ -44,6 +44,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int STG_LD = 20;                    // floats per staged row (16 + 4 pad: conflict-free float4 access both ways)
 constexpr int ROW_PITCH = 144;                // row epilogue: 64 bf16 (128 B) + 16 B pad per staged row (conflict-free 16-byte stores)
 constexpr int STG_BYTES_PER_WARP = 32 * ROW_PITCH;          // >= 32x16 fp32 transpose tile + LN statistics of the generic epilogue (3328 B)
+constexpr int STG_BYTES_PER_WARP_RESID = 2 * STG_BYTES_PER_WARP;   // two staged rows per lane
 constexpr int PAR_BYTES = 2 * 3 * 256 * 4;    // per-tile bias / gamma / beta, double buffered by accumulator parity
 constexpr int LN_BYTES = NUM_EPI_WARPS * 2 * 64 * 4;        // row epilogue: LayerNorm partials exchanged between the two warps of a quadrant
 constexpr int SMEM_BUDGET = 179 * 1024;       // operand stages; epilogue staging, parameters and barriers sit behind
@@ -75,6 +76,7 @@ struct alignas(64) KParams {
   float* out_f32; int32_t out_f32_ld;
   int32_t shuffle_k;
   int32_t row_map_period, row_map_extra, row_map_offset;
+  int32_t stg_warp_bytes;   // epilogue staging per warp (row epilogue of the fp32 residual stream double-buffers its row)
   int32_t debug;      // diagnostics (PRV2_GEMM_DEBUG): bit0 = no TMA after the first ring pass, bit1 = epilogue drains TMEM only
 };
 static_assert(sizeof(KParams) <= 4096, "kernel parameter block too large");
@@ -244,6 +246,10 @@ __device__ __forceinline__ float act_fn(float x) {
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -427,10 +433,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     const int Cout = p.Cout, block_n = p.block_n, out_cs = p.out_cs;
     const int tile_w_log2 = p.tile_w_log2, tile_w_mask = p.tile_w - 1, pH = p.H, pW = p.W;
     bf16* const out_hi = p.out_hi;
-    uint8_t* const srow = stage_area + ew * STG_BYTES_PER_WARP + lane * ROW_PITCH;
+    uint8_t* const srow = stage_area + ew * p.stg_warp_bytes + lane * ROW_PITCH;      // (+ 32 * ROW_PITCH: second buffer, RESID only)
     const uint32_t srow_s = smem_u32(srow);
-    float* const s_par = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * STG_BYTES_PER_WARP);
-    float* const s_ln = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * STG_BYTES_PER_WARP + PAR_BYTES);
+    float* const s_par = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * p.stg_warp_bytes);
+    float* const s_ln = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * p.stg_warp_bytes + PAR_BYTES);
+    int n_sub_done = 0;
     constexpr bool is_ln = EPI == PRV2_EPI_LN_GELU;
     const int n_panels = (block_n + 63) >> 6;
     const uint32_t tempty_leader0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
@@ -451,6 +458,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         const int n = min(n0 + te, Cout - 1);
         par[te] = p.bias ? __ldg(p.bias + n) : 0.f;
         if (is_ln) { par[256 + te] = __ldg(p.gamma + n); par[512 + te] = __ldg(p.beta + n); }
+        if (EPI == PRV2_EPI_RESID_F32) par[256 + te] = __ldg(p.gamma + n);
       }
       asm volatile("bar.sync 5, 256;" ::: "memory");          // parameters visible to all epilogue warps
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -488,6 +496,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         mean = mean_a + delta * (nb / nn);
         rstd = 1.0f / sqrtf((m2 + m2_b + delta * delta * (na * nb / nn)) / nn + p.eps);
       }
+      if (EPI == PRV2_EPI_RESID_F32) {
+        // x[row, n] += gamma[n] * (acc + bias[n])  (block.py:105-106, layer_scale.py:27): the lane stages 32 fp32 columns
+        // of its row and hands them to the L2 as ONE bulk reduce-add -- the SM never reads the residual stream, so the
+        // read-modify-write latency that bound this epilogue is gone.  Two staged rows per lane alternate.
+        float* const grow32 = p.out_f32 + (((size_t)img * pH + h) * pW + w) * p.out_f32_ld + n0;
+        const int n_sub = (block_n + 31) >> 5;
+        for (int sp = csel; sp < n_sub; sp += 2, ++n_sub_done) {
+          const int c0 = sp * 32;
+          const int cols = min(32, block_n - c0);
+          const int buf = n_sub_done & 1;
+          bulk_wait_read1();                                  // the copy issued two steps ago has left this buffer
+          uint32_t ra[16], rb[16];
+          tc_ld16_issue(taddr + c0, ra);
+          if (cols > 16) tc_ld16_issue(taddr + c0 + 16, rb);
+          tc_ld_wait();
+          uint8_t* const dst = srow + buf * (32 * ROW_PITCH);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g * 4 >= cols) break;
+            const float4 b4 = *reinterpret_cast<const float4*>(par + c0 + g * 4), g4 = *reinterpret_cast<const float4*>(par + 256 + c0 + g * 4);
+            const uint32_t* rsrc = g < 4 ? &ra[g * 4] : &rb[(g - 4) * 4];
+            float4 o;
+            o.x = g4.x * (__uint_as_float(rsrc[0]) + b4.x); o.y = g4.y * (__uint_as_float(rsrc[1]) + b4.y);
+            o.z = g4.z * (__uint_as_float(rsrc[2]) + b4.z); o.w = g4.w * (__uint_as_float(rsrc[3]) + b4.w);
+            *reinterpret_cast<float4*>(dst + g * 16) = o;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          const int nvalid = min(cols, Cout - (n0 + c0));
+          if (valid && nvalid > 0 && !(p.debug & 4)) bulk_reduce_add_f32(grow32 + c0, srow_s + buf * (32 * ROW_PITCH), (uint32_t)nvalid * 4u);
+          bulk_commit();
+        }
+      } else
       for (int pn = csel; pn < n_panels; pn += 2) {
         const int c0 = pn * 64;
         const int cols = min(64, block_n - c0);
@@ -555,9 +595,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     const int csel = ew >> 2;                     // which of the two warps of this quadrant
     const int te = threadIdx.x - 64;              // 0..255 over the epilogue warps
     const int n_chunks = block_n >> 4;
-    float* const stg = reinterpret_cast<float*>(stage_area + ew * STG_BYTES_PER_WARP);
-    float* const stg_peer = reinterpret_cast<float*>(stage_area + (ew ^ 4) * STG_BYTES_PER_WARP);
-    float* const s_par = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * STG_BYTES_PER_WARP);
+    float* const stg = reinterpret_cast<float*>(stage_area + ew * p.stg_warp_bytes);
+    float* const stg_peer = reinterpret_cast<float*>(stage_area + (ew ^ 4) * p.stg_warp_bytes);
+    float* const s_par = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * p.stg_warp_bytes);
     const int rB = lane & 15, cB = (lane >> 4) * 8;
     constexpr bool is_ln = EPI == PRV2_EPI_LN_GELU;
     const uint32_t tempty_leader0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
@@ -928,6 +968,7 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   static const char* dbg_env = getenv("PRV2_GEMM_DEBUG");
   p.debug = dbg_env ? atoi(dbg_env) : 0;
+  p.stg_warp_bytes = STG_BYTES_PER_WARP;
   static const char* st_env = getenv("PRV2_GEMM_STAGES");          // diagnostics: cap the pipeline depth
   if (st_env && atoi(st_env) >= 2 && atoi(st_env) < p.stages) p.stages = atoi(st_env);
   int cols = 32;
@@ -982,6 +1023,15 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   static const char* fast_env = getenv("PRV2_GEMM_FAST");
   bool fast = !(fast_env && fast_env[0] == '0') && d->out_hi && !d->out_lo && d->row_map_period == 0 && d->out_cs % 8 == 0 && d->Cout % 8 == 0 &&
               ((d->epi == PRV2_EPI_STORE && !d->relu_hi && !d->res_hi && !d->res2_hi) || d->epi == PRV2_EPI_LN_GELU);
+  static const char* red_env = getenv("PRV2_GEMM_REDUCE");          // diagnostics: 0 keeps the register read-modify-write epilogue
+  const bool fast_resid = d->epi == PRV2_EPI_RESID_F32 && !(fast_env && fast_env[0] == '0') && !(red_env && red_env[0] == '0') &&
+                          d->row_map_period == 0 && d->out_f32_ld % 4 == 0 && d->Cout % 4 == 0 && ((uintptr_t)d->out_f32 & 15) == 0;
+  const int resid_stages = (SMEM_BUDGET - NUM_EPI_WARPS * (STG_BYTES_PER_WARP_RESID - STG_BYTES_PER_WARP)) / (A_STAGE_BYTES + p.b_stage_bytes);
+  const bool use_fast_resid = fast_resid && resid_stages >= 3;        // a two-stage operand ring costs more than the epilogue gains
+  if (use_fast_resid) {
+    p.stg_warp_bytes = STG_BYTES_PER_WARP_RESID;
+    if (resid_stages < p.stages) p.stages = resid_stages;
+  }
   // always request the full budget: guarantees one CTA per SM, so a 512-column TMEM allocation can never deadlock
   int grid = p.total_tiles * cg < g_num_sms ? p.total_tiles * cg : g_num_sms;
   if (cg == 2) grid &= ~1;
@@ -1007,7 +1057,7 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
     case PRV2_EPI_LN_GELU:
       err = act == PRV2_ACT_GELU_TANH ? PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU_TANH) : PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU);
       break;
-    case PRV2_EPI_RESID_F32: err = PRV2_L2(PRV2_EPI_RESID_F32, PRV2_ACT_NONE, false); break;
+    case PRV2_EPI_RESID_F32: err = use_fast_resid ? PRV2_L2(PRV2_EPI_RESID_F32, PRV2_ACT_NONE, true) : PRV2_L2(PRV2_EPI_RESID_F32, PRV2_ACT_NONE, false); break;
     case PRV2_EPI_F32: err = PRV2_L2(PRV2_EPI_F32, PRV2_ACT_NONE, false); break;
     case PRV2_EPI_SHUFFLE: err = PRV2_L2(PRV2_EPI_SHUFFLE, PRV2_ACT_NONE, false); break;
     default: err = PRV2_L2(PRV2_EPI_HEAD, PRV2_ACT_NONE, false); break;
