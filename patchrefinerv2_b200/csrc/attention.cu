@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+#include <type_traits>
 
 using namespace prv2;
 
@@ -263,16 +264,22 @@ __global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// v2: warp-specialised, software-pipelined kernel for the one-pass bf16 mode.
+// v3: warp-specialised, software-pipelined kernel for the one-pass bf16 mode.
 //   warp 0        TMA producer: Q tiles once, then a 2-stage ring of K / V chunks
-//   warp 1        MMA issuer (one lane): S_w = Q_w K^T, O_w = P_w V for both warpgroups
+//   warp 1        MMA issuer (converged warp, one elected lane): S_w = Q_w K^T, O_w += P_w V
 //   warps 2..5    softmax warpgroup 0 (query tile 0), warps 6..9 warpgroup 1 (query tile 1)
-// One CTA owns TWO 128-query tiles of one (image, head) so every K/V chunk is loaded once and used
-// twice, and while one warpgroup runs its softmax the tensor core works for the other.
-// Key chunks are 128 wide except the LAST, which may be up to 144 wide (UMMA N = 16..144), so the
-// 1025-token DINOv2 sequence is 7 x 128 + 129 keys in 8 chunks instead of 9; the leftover query
-// rows (T mod 128 <= 16) go to a small SIMT kernel instead of a whole extra 128-row tile.
-// TMEM: S0 | S1 (160-col slots) | O0 | O1 (64 cols each); O chunks are accumulated in registers.
+// One CTA owns TWO 128-query tiles of one (image, head): every K/V chunk is loaded once and used twice, and
+// while one warpgroup runs its softmax the tensor core works for the other.
+// * O_w accumulates in TMEM over all key chunks (tcgen05.mma accumulate); the row owner rescales it in
+//   place (tcgen05.ld / st) only when its running maximum grows by more than 2^8 ("lazy rescale": the
+//   exponentials are taken against a stale maximum otherwise, which is exact after the final 1/l).
+// * TMEM reads of S are double-buffered in registers so the load of the next 32 columns overlaps the
+//   exponentials of the current ones.
+// * Key chunks are 128 wide except the LAST, which may be up to 144 wide (UMMA N = 16..144), so the 1025-token
+//   DINOv2 sequence is 7 x 128 + 129 keys in 8 chunks instead of 9; the leftover query rows (T mod 128 <= 16)
+//   go to a small SIMT kernel instead of a whole extra 128-row tile.
+// * Output rows are staged in shared memory and leave with one bulk async copy per row.
+// TMEM: S0 | S1 (160-col slots) | O0 | O1 (64 cols each).
 // ---------------------------------------------------------------------------------------------
 constexpr int KV_STAGES = 2;
 constexpr int KV_ROWS = 144;
@@ -280,13 +287,42 @@ constexpr int KV_TILE_BYTES = KV_ROWS * 128;       // 18 KB
 constexpr int S_COLS = 160;                         // TMEM columns reserved per S accumulator (32-aligned)
 constexpr int V2_THREADS = 320;
 constexpr int TAIL_MAX = 16;                        // leftover rows / keys folded away from a full extra tile
+constexpr int OUT_PITCH = 144;                      // staged output row: 64 bf16 + 16 B pad
+constexpr float RESCALE_LOG2 = 8.0f;                // lazy rescale threshold (log2 units)
 
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ float ex2_ftz(float x) {      // one MUFU.EX2; inputs are <= 0, flush-to-zero is what softmax wants
+__device__ __forceinline__ float ex2_ftz(float x) {      // one MUFU.EX2; inputs are <= 8, flush-to-zero is what softmax wants
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+      "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+      "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+      "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct alignas(64) AttnParamsV2 {
   CUtensorMap tm_q, tm_kv;
@@ -294,7 +330,7 @@ struct alignas(64) AttnParamsV2 {
   int B, T, heads, D, n_chunks, last_width, tq_main;
 };
 
-__global__ void __launch_bounds__(V2_THREADS, 1) attention_v2_kernel(const __grid_constant__ AttnParamsV2 p) {
+__global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __grid_constant__ AttnParamsV2 p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -306,7 +342,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v2_kernel(const __gri
   auto kv_empty = [&](int s) { return bars + 8u * (1 + KV_STAGES + s); };
   auto s_full = [&](int w) { return bars + 8u * (1 + 2 * KV_STAGES + w); };
   auto p_full = [&](int w) { return bars + 8u * (3 + 2 * KV_STAGES + w); };
-  auto o_full = [&](int w) { return bars + 8u * (5 + 2 * KV_STAGES + w); };
+  auto o_done = [&](int w) { return bars + 8u * (5 + 2 * KV_STAGES + w); };
   const uint32_t tmem_slot = bars + 8u * (7 + 2 * KV_STAGES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -318,7 +354,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v2_kernel(const __gri
   if (tid == 0) {
     mbar_init(bar_q, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full(w), 1); mbar_init(p_full(w), 128); mbar_init(o_full(w), 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full(w), 1); mbar_init(p_full(w), 128); mbar_init(o_done(w), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -330,161 +366,244 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v2_kernel(const __gri
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  auto width_of = [&](int j) { return j == n_chunks - 1 ? p.last_width : 128; };
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ------------------------------------------------ TMA producer (converged warp, elected lane issues)
+    if (elect_one()) {
       mbar_expect_tx(bar_q, n_wg * TILE_BYTES);
       for (int w = 0; w < n_wg; ++w) tma_load_3d(sQ + w * TILE_BYTES, &p.tm_q, bar_q, head * 64, q0 + w * 128, b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_chunks; ++j) {
-        mbar_wait(kv_empty(stage), phase ^ 1);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_chunks; ++j) {
+      mbar_wait(kv_empty(stage), phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(kv_full(stage), 2 * KV_TILE_BYTES);
         tma_load_3d(sK + stage * KV_TILE_BYTES, &p.tm_kv, kv_full(stage), D + head * 64, j * 128, b);
         tma_load_3d(sV + stage * KV_TILE_BYTES, &p.tm_kv, kv_full(stage), 2 * D + head * 64, j * 128, b);
-        if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      auto issue_s = [&](int w, int stage, int width) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(width >> 3) << 17) | ((128u >> 4) << 24);
-        uint32_t accum = 0;
-        for (int k = 0; k < 4; ++k) {
-          tc_mma_bf16(tmem_base + w * S_COLS, umma_desc_sw128(sQ + w * TILE_BYTES) + 2 * k, umma_desc_sw128(sK + stage * KV_TILE_BYTES) + 2 * k, idesc, accum);
-          accum = 1;
-        }
-        tc_commit(s_full(w));
-      };
-      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      auto issue_o = [&](int w, int stage, int width) {
-        uint32_t accum = 0;
-        for (int k = 0; k < (width >> 4); ++k) {     // 16-key slices: A advances 32 B inside P tile (k>>2), B advances 16 key rows
-          tc_mma_bf16(tmem_base + 2 * S_COLS + w * 64, umma_desc_sw128(sP + (3 * w + (k >> 2)) * TILE_BYTES) + 2 * (k & 3),
-                      umma_desc_sw128(sV + stage * KV_TILE_BYTES + k * 2048), idesc_o, accum);
-          accum = 1;
-        }
-        tc_commit(o_full(w));
-      };
-      auto width_of = [&](int j) { return j == n_chunks - 1 ? p.last_width : 128; };
-      mbar_wait(bar_q, 0);
-      mbar_wait(kv_full(0), 0);
-      tc_fence_after();
-      for (int w = 0; w < n_wg; ++w) issue_s(w, 0, width_of(0));
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_chunks; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
-        for (int w = 0; w < n_wg; ++w) {
-          mbar_wait(p_full(w), j & 1);          // P_w(j) is in smem; S_w(j) and O_w(j-1) have been consumed
-          tc_fence_after();
-          issue_o(w, stage, width_of(j));
-          if (j + 1 < n_chunks) {
-            if (w == 0) { mbar_wait(kv_full(nstage), nphase); tc_fence_after(); }
-            issue_s(w, nstage, width_of(j + 1));
-          }
-        }
-        tc_commit(kv_empty(stage));             // K_j / V_j are free once everything issued so far has retired
-        stage = nstage; phase = nphase;
+    // ------------------------------------------------ MMA issuer
+    auto issue_s = [&](int w, int stage, int width) {          // S_w = Q_w K^T
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(width >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t qd = umma_desc_sw128(sQ + w * TILE_BYTES), kd = umma_desc_sw128(sK + stage * KV_TILE_BYTES);
+      tc_mma_bf16(tmem_base + w * S_COLS, qd, kd, idesc, 0);
+      tc_mma_bf16(tmem_base + w * S_COLS, qd + 2, kd + 2, idesc, 1);
+      tc_mma_bf16(tmem_base + w * S_COLS, qd + 4, kd + 4, idesc, 1);
+      tc_mma_bf16(tmem_base + w * S_COLS, qd + 6, kd + 6, idesc, 1);
+      tc_commit(s_full(w));
+    };
+    const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    auto issue_o = [&](int w, int stage, int width, uint32_t accum) {     // O_w (+)= P_w V
+      for (int k = 0; k < (width >> 4); ++k) {     // 16-key slices: A advances 32 B inside P tile (k>>2), B advances 16 key rows
+        tc_mma_bf16(tmem_base + 2 * S_COLS + w * 64, umma_desc_sw128(sP + (3 * w + (k >> 2)) * TILE_BYTES) + 2 * (k & 3),
+                    umma_desc_sw128(sV + stage * KV_TILE_BYTES + k * 2048), idesc_o, accum);
+        accum = 1;
       }
+      tc_commit(o_done(w));
+    };
+    mbar_wait(bar_q, 0);
+    mbar_wait(kv_full(0), 0);
+    tc_fence_after();
+    if (elect_one()) for (int w = 0; w < n_wg; ++w) issue_s(w, 0, width_of(0));
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_chunks; ++j) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
+      const bool more = j + 1 < n_chunks;
+      for (int w = 0; w < n_wg; ++w) {
+        mbar_wait(p_full(w), j & 1);          // P_w(j) is in smem (and O_w rescaled); S_w(j) has been consumed
+        if (more && w == 0) mbar_wait(kv_full(nstage), nphase);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_o(w, stage, width_of(j), j > 0 ? 1u : 0u);
+          if (more) issue_s(w, nstage, width_of(j + 1));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(kv_empty(stage));   // K_j / V_j are free once everything issued so far has retired
+      __syncwarp();
+      stage = nstage; phase = nphase;
     }
   } else {
+    // ------------------------------------------------ softmax warpgroups
     const int w = (warp - 2) >> 2;
     if (w < n_wg) {
       const int row = (warp & 3) * 32 + lane;               // TMEM lane == query row of this tile
       const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
       const uint32_t tS = tmem_base + w * S_COLS + lane_off, tO = tmem_base + 2 * S_COLS + w * 64 + lane_off;
-      uint8_t* pP = base_ptr + (sP - base) + 3 * w * TILE_BYTES;
-      const float c_log2 = 0.125f * 1.4426950408889634f;
-      float acc[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      uint8_t* const pP = base_ptr + (sP - base) + 3 * w * TILE_BYTES;
+      const float c_log2 = 0.125f * 1.4426950408889634f;    // head_dim^-0.5 * log2(e)   (attention.py:41)
+      const float tau = RESCALE_LOG2 / c_log2;
       float m_run = -INFINITY, l_run = 0.f;
-      // one 16- or 32-column piece of the row: exp, row sum, bf16 pack, swizzled store (SW128 K-major P tile)
-      auto emit = [&](const float* v, int col0, int ncols, float mc, float& l_add, int n_valid, bool masked) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g * 8 >= ncols) break;
-          float e[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            float pv = ex2_ftz(fmaf(v[g * 8 + t], c_log2, -mc));
-            if (masked && col0 + g * 8 + t >= n_valid) pv = 0.f;
-            e[t] = pv;
-            l_add += pv;
-          }
-          const int key = col0 + g * 8;                  // 8 consecutive keys = one 16-byte chunk of the P row
-          const int tile = key >> 6, chunk = (key & 63) >> 3;
-          __nv_bfloat162 h2[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(e[2 * t], e[2 * t + 1]);
-          *reinterpret_cast<uint4*>(pP + tile * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(h2);
-        }
-      };
-      for (int j = 0; j < n_chunks; ++j) {
-        const uint32_t ph = j & 1;
-        const bool last = j == n_chunks - 1;
-        const int n_valid = T - j * 128;                    // >= width on all but the last chunk
-        const bool masked = last && n_valid < 128;       // stale / padded columns inside the first 128
-        mbar_wait(s_full(w), ph);
+      uint32_t ra[32], rb[32];
+      // (Forcing the two warpgroups to alternate in the MUFU-heavy section with named barriers was measured 16 % SLOWER:
+      // one warpgroup alone is latency-bound, not MUFU-bound, so letting both run concurrently overlaps better.)
+      // One key chunk of this warpgroup's softmax.  GENERAL = the last chunk (ragged: masked keys, 16..144 wide); every other
+      // chunk runs the specialisation with compile-time width 128 and no per-element predicates (the generic code spent
+      // ~320 of its ~1350 instructions per chunk on ISETP / FSEL masking).
+      auto chunk_body = [&](auto general_tag, const int j) {
+        constexpr bool GENERAL = decltype(general_tag)::value;
+        const int n_valid = GENERAL ? T - j * 128 : 128;
+        const int width = GENERAL ? p.last_width : 128;
+        const int n_pieces = GENERAL ? min(4, (width + 31) >> 5) : 4;     // 32-column pieces inside the first 128 columns
+        const bool wide = GENERAL && width > 128;                          // keys 128..143 of the wide last chunk
+        mbar_wait(s_full(w), j & 1);
         tc_fence_after();
-        float v[32];
-        float m_new = m_run;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          tc_ld32(tS + c * 32, v);
-          if (!masked) {
+        // ---- pass 1: row maximum (TMEM loads double-buffered in registers)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // independent chains: 2 warps per SMSP hide little latency
+        auto pmax = [&](const uint32_t (&r)[32], int col0) {
+          if (!GENERAL || col0 + 32 <= n_valid) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m_new = fmaxf(m_new, v[i]);
+            for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (c * 32 + i < n_valid) m_new = fmaxf(m_new, v[i]);
+            for (int i = 0; i < 32; ++i) if (col0 + i < n_valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
+          }
+        };
+        tc_ld32_issue(tS, ra);
+        tc_ld_wait();
+        if (n_pieces > 1) tc_ld32_issue(tS + 32, rb);
+        pmax(ra, 0);
+        if (n_pieces > 1) {
+          tc_ld_wait();
+          if (n_pieces > 2) tc_ld32_issue(tS + 64, ra);
+          pmax(rb, 32);
+          if (n_pieces > 2) {
+            tc_ld_wait();
+            if (n_pieces > 3) tc_ld32_issue(tS + 96, rb);
+            pmax(ra, 64);
+            if (n_pieces > 3) { tc_ld_wait(); pmax(rb, 96); }
           }
         }
-        float v16[16];
-        if (last && p.last_width > 128) {                   // keys 128..143 of the wide last chunk
-          tc_ld16(tS + 128, v16);
+        uint32_t rw[16];
+        if (wide) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]), "=r"(rw[8]), "=r"(rw[9]),
+                "=r"(rw[10]), "=r"(rw[11]), "=r"(rw[12]), "=r"(rw[13]), "=r"(rw[14]), "=r"(rw[15])
+              : "r"(tS + 128)
+              : "memory");
+          tc_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) if (128 + i < n_valid) m_new = fmaxf(m_new, v16[i]);
+          for (int i = 0; i < 16; ++i) if (128 + i < n_valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(rw[i]));
         }
-        const float alpha = ex2_ftz((m_run - m_new) * c_log2);
-        const float mc = m_new * c_log2;
-        float l_add = 0.f;
-        if (last && p.last_width > 128) emit(v16, 128, 16, mc, l_add, n_valid, true);
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (last && c * 32 >= p.last_width) break;
-          tc_ld32(tS + c * 32, v);
-          emit(v, c * 32, 32, mc, l_add, n_valid, masked);
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // ---- lazy rescale decision: keep the stale maximum unless the new one is > 2^8 larger
+        const bool need = mx > m_run + tau;
+        float alpha = 1.f;
+        if (need) {
+          alpha = ex2_ftz((m_run - mx) * c_log2);             // 0 on the first chunk (m_run = -inf)
+          m_run = mx;
+          l_run *= alpha;
         }
-        l_run = l_run * alpha + l_add;
-        m_run = m_new;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const float mc = m_run * c_log2;
+        // first piece of pass 2 can be fetched while we wait for the previous P V product
+        tc_ld32_issue(tS, ra);
+        if (j > 0) {
+          mbar_wait(o_done(w), (j - 1) & 1);                // P_w(j-1) V(j-1) has retired: P buffer and O_w are ours
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {              // warp-uniform: tcgen05.ld / st are warp collectives
+            tc_ld_wait();                                     // (drains the prefetched S piece too)
+            uint32_t ro[32];
+            tc_ld32_issue(tO, ro);
+            tc_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tc_st32(tO, ro);
+            tc_ld32_issue(tO + 32, ro);
+            tc_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tc_st32(tO + 32, ro);
+            tc_st_wait();
+          }
+        }
+        // ---- pass 2: p = 2^(s*c - m*c) -> bf16 -> P tile (SW128 K-major), row sum
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        auto emit = [&](const uint32_t* r, int col0, int n) {
+          const bool masked = GENERAL && col0 + n > n_valid;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g * 8 >= n) break;
+            float e[8];
+            if (!masked) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) e[t] = ex2_ftz(fmaf(__uint_as_float(r[g * 8 + t]), c_log2, -mc));
+            } else {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                const float pv = ex2_ftz(fmaf(__uint_as_float(r[g * 8 + t]), c_log2, -mc));
+                e[t] = (col0 + g * 8 + t < n_valid) ? pv : 0.f;
+              }
+            }
+            l4[0] += e[0] + e[4]; l4[1] += e[1] + e[5]; l4[2] += e[2] + e[6]; l4[3] += e[3] + e[7];
+            const int key = col0 + g * 8;                  // 8 consecutive keys = one 16-byte chunk of the P row
+            const int tile = key >> 6, chunk = (key & 63) >> 3;
+            __nv_bfloat162 h2[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(e[2 * t], e[2 * t + 1]);
+            *reinterpret_cast<uint4*>(pP + tile * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(h2);
+          }
+        };
+        if (wide) emit(rw, 128, 16);
+        tc_ld_wait();
+        if (n_pieces > 1) tc_ld32_issue(tS + 32, rb);
+        emit(ra, 0, 32);
+        if (n_pieces > 1) {
+          tc_ld_wait();
+          if (n_pieces > 2) tc_ld32_issue(tS + 64, ra);
+          emit(rb, 32, 32);
+          if (n_pieces > 2) {
+            tc_ld_wait();
+            if (n_pieces > 3) tc_ld32_issue(tS + 96, rb);
+            emit(ra, 64, 32);
+            if (n_pieces > 3) { tc_ld_wait(); emit(rb, 96, 32); }
+          }
+        }
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // P rows -> visible to the tensor core
         tc_fence_before();
         mbar_arrive_local(p_full(w));
-        mbar_wait(o_full(w), ph);
-        tc_fence_after();
+      };
+      const bool last_general = p.last_width != 128 || T - (n_chunks - 1) * 128 < 128;
+      for (int j = 0; j < n_chunks - 1; ++j) chunk_body(std::false_type{}, j);
+      if (last_general) chunk_body(std::true_type{}, n_chunks - 1);
+      else chunk_body(std::false_type{}, n_chunks - 1);
+      // ---- epilogue: O / l -> bf16 -> staged row -> one bulk copy
+      mbar_wait(o_done(w), (n_chunks - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      uint8_t* const srow = pP + row * OUT_PITCH;             // the P tiles are free now
+      tc_ld32_issue(tO, ra);
+      tc_ld32_issue(tO + 32, rb);
+      tc_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tc_ld32(tO + c * 32, v);
+      for (int g = 0; g < 4; ++g) {
+        __nv_bfloat162 h2[4];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha, v[i]);
-        }
+        for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(__uint_as_float(ra[g * 8 + 2 * t]) * inv, __uint_as_float(ra[g * 8 + 2 * t + 1]) * inv);
+        *reinterpret_cast<uint4*>(srow + g * 16) = *reinterpret_cast<const uint4*>(h2);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(__uint_as_float(rb[g * 8 + 2 * t]) * inv, __uint_as_float(rb[g * 8 + 2 * t + 1]) * inv);
+        *reinterpret_cast<uint4*>(srow + 64 + g * 16) = *reinterpret_cast<const uint4*>(h2);
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       const int q = q0 + w * 128 + row;
       if (q < p.tq_main) {
-        const float inv = 1.0f / l_run;
-        const size_t o = ((size_t)b * T + q) * D + head * 64;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float t[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) t[e] = acc[g * 8 + e] * inv;
-          act_store8(p.out_hi, nullptr, o + g * 8, t);
-        }
+        bf16* const gdst = p.out_hi + ((size_t)b * T + q) * D + head * 64;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(gdst), "r"(smem_u32(srow)) : "memory");
       }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
   tc_fence_before();
@@ -515,7 +634,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) attention_tail_kernel(const bf16
   if (tid < 64) s_q[tid] = bf2f(base[(size_t)(tq_main + r) * row_stride + head * 64 + tid]);
   __syncthreads();
   const float c_log2 = 0.125f * 1.4426950408889634f;
-  // phase 1: scores
+  // phase 1: scores, thread per key (an 8-lanes-per-key "coalesced" variant with shuffle reduction measured 2x slower:
+  // the K rows are L2 hits and the extra passes cost more than the uncoalesced lines)
   float m = -INFINITY;
   for (int k = tid; k < T; k += TAIL_THREADS) {
     const bf16* kp = base + (size_t)k * row_stride + D + head * 64;
@@ -554,8 +674,22 @@ __global__ void __launch_bounds__(TAIL_THREADS) attention_tail_kernel(const bf16
   // phase 2: out[d] = sum_k p_k V[k, d]
   const int kg = tid >> 4, d4 = (tid & 15) * 4;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int k = kg; k < T; k += 16) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(base + (size_t)k * row_stride + 2 * D + head * 64 + d4);
+  const bf16* vbase = base + 2 * D + head * 64 + d4;
+  int k = kg;
+  for (; k + 7 * 16 < T; k += 8 * 16) {                      // eight independent 8-byte loads in flight per thread
+    uint2 raw[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) raw[u] = *reinterpret_cast<const uint2*>(vbase + (size_t)(k + u * 16) * row_stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+      const float2 f0 = __bfloat1622float2(v2[0]), f1 = __bfloat1622float2(v2[1]);
+      const float pv = s_p[k + u * 16];
+      a0 = fmaf(pv, f0.x, a0); a1 = fmaf(pv, f0.y, a1); a2 = fmaf(pv, f1.x, a2); a3 = fmaf(pv, f1.y, a3);
+    }
+  }
+  for (; k < T; k += 16) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(vbase + (size_t)k * row_stride);
     const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
     const float2 f0 = __bfloat1622float2(v2[0]), f1 = __bfloat1622float2(v2[1]);
     const float pv = s_p[k];
@@ -615,7 +749,7 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
   const int smem_v2 = 2 * TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 6 * TILE_BYTES + 1024 + 256;
   static const bool force_v1 = getenv("PRV2_ATTN_V1") != nullptr;
   if (!g_attr_set) {
-    PRV2_CUDA(cudaFuncSetAttribute(attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v2));
+    PRV2_CUDA(cudaFuncSetAttribute(attention_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v2));
     PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     g_attr_set = true;
@@ -639,7 +773,7 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
   // query rows: leftover rows (<= 16) go to the SIMT tail kernel instead of a mostly empty 128-row tile
   const int rem = T % 128;
   p2.tq_main = (rem != 0 && rem <= TAIL_MAX && T > 128 && T <= TAIL_MAX_T) ? T - rem : T;
-  attention_v2_kernel<<<dim3(cdiv(p2.tq_main, 256), heads, B), V2_THREADS, smem_v2, (cudaStream_t)stream>>>(p2);
+  attention_v3_kernel<<<dim3(cdiv(p2.tq_main, 256), heads, B), V2_THREADS, smem_v2, (cudaStream_t)stream>>>(p2);
   PRV2_LAUNCH_CHECK();
   if (p2.tq_main < T) {
     attention_tail_kernel<<<B * heads * (T - p2.tq_main), TAIL_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)qkv_hi, (bf16*)out_hi, B, T, heads, p2.tq_main);

@@ -74,5 +74,12 @@ conv("dec3.conv2", 4, 256, 256, [514], [520], 256, act=_lib.ACT_GELU)
 conv("enc1.L0", 4, 448, 448, [128, 128], [128, 128], 128, epi=_lib.EPI_LN_GELU, gamma=torch.rand(128), beta=torch.rand(128))
 conv("enc2.L0", 4, 448, 448, [130], [136], 128, epi=_lib.EPI_LN_GELU, gamma=torch.rand(128), beta=torch.rand(128))
 conv("enc1.L1", 4, 256, 256, [256, 256], [256, 256], 256, epi=_lib.EPI_LN_GELU, gamma=torch.rand(256), beta=torch.rand(256))
+
+if not which or "attn" in which:
+    from patchrefinerv2_b200 import ops
+    heads = 16
+    qkv = Act.empty(1, 1, M, 3 * D, False, DEV); qkv.hi.normal_()
+    ao = Act.empty(1, 1, M, D, False, DEV)
+    timed("attn", lambda: ops.attention(qkv, B, T, heads, ao), 4.0 * B * heads * T * T * 64)
 print("SUMMARY", os.environ.get("PRV2_GEMM_CG", "auto"), os.environ.get("PRV2_GEMM_STAGES", "-"),
       " ".join(f"{n}={t:.0f}" for n, _, t in results))
