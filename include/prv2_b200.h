@@ -197,12 +197,12 @@ int prv2_resize_bilinear_act(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int
                              prv2_bf16* out_hi, prv2_bf16* out_lo, int oh, int ow, int out_cs, int relu,
                              prv2_stream_t stream);
 
-/* fusion_model.py:94-96,16-17: the two depth maps [N,1,H,W] fp32 resized (bilinear ac) to [oh,ow]
- * and written into channel slots c0, c0+1 of a channels-last act tensor; the following
- * `zero_pad` channels are zero-filled. */
-int prv2_depth_slots(const float* pred1, const float* pred2, int N, int H, int W,
-                     prv2_bf16* out_hi, prv2_bf16* out_lo, int oh, int ow, int out_cs, int c0, int zero_pad,
-                     prv2_stream_t stream);
+/* fusion_model.py:94-96,16-17: the reference concatenates the two depth maps [N,1,H,W] fp32, resized (bilinear ac) to the
+ * level [oh,ow], to a feature tensor that feeds a 3x3 conv.  Here their 3x3 neighbourhoods are laid out once per level as
+ * an 18-channel im2col tensor: out[n,y,x,(r*3+s)*2+d] = resized(pred_d)[y+r-1, x+s-1] (0 outside = the conv's zero
+ * padding), channels 18..23 zero; the conv consumes it as one 1x1 K segment. */
+int prv2_depth_taps(const float* pred1, const float* pred2, int N, int H, int W,
+                    prv2_bf16* out_hi, prv2_bf16* out_lo, int oh, int ow, int out_cs, prv2_stream_t stream);
 
 /* fusion_model.py:113-118: offset = conv3x3(feat, w[1,C,3,3], no bias); out = clamp(base+offset, 0).
  * The channel contraction runs through prv2_umma_gemm as a 1x1 conv with 9 outputs (one per tap):

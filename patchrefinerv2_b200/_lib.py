@@ -74,7 +74,7 @@ SIGNATURES = {
     "prv2_patchify": [_p, _i, _i, _i, _p, _p, _i, _p],
     "prv2_assemble_tokens": [_p, _p, _p, _i, _i, _i, _p, _p],
     "prv2_resize_bilinear_act": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p],
-    "prv2_depth_slots": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p],
+    "prv2_depth_taps": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p],
     "prv2_tap_stencil": [_p, _i, _i, _i, _i, _p, _p, _p],
     "prv2_nchw_f32_to_act": [_p, _i, _i, _i, _i, _p, _p, _i, _p],
     "prv2_act_to_nchw_f32": [_p, _p, _i, _i, _i, _i, _i, _p, _p],

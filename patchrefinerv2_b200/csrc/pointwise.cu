@@ -140,22 +140,46 @@ __global__ void __launch_bounds__(256) resize_act_kernel(const bf16* __restrict_
   }
 }
 
-// -------------------------- depth maps into channel slots (fusion_model.py:94-96, 16-17)
-// grid (ceil(OW/256), OH, N)
-__global__ void __launch_bounds__(256) depth_slots_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int H, int W,
-                                                          bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW, int out_cs,
-                                                          int c0, float sy, float sx) {
+// -------------------------- depth maps as an im2col source (fusion_model.py:94-96, 16-17)
+// The reference concatenates the two depth maps (bilinear-resized to the level) to a feature tensor that then goes
+// through a 3x3 conv.  Two extra channels per tap would cost one mostly empty 64-wide K chunk per tap (9 per conv);
+// instead the 3x3 neighbourhood of both maps is laid out ONCE per level as 18 channels
+//   out[n, y, x, (r*3+s)*2 + d] = resized(pred_d)[y+r-1, x+s-1]   (0 outside the map = the conv's zero padding)
+// and enters every conv of the level as a single 1x1 K segment.  Channels 18..23 are zero.  grid (ceil(OW/256), OH, N)
+__global__ void __launch_bounds__(256) depth_taps_kernel(const float* __restrict__ p1, const float* __restrict__ p2, int H, int W,
+                                                         bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW, int out_cs,
+                                                         float sy, float sx) {
   const int x = blockIdx.x * 256 + threadIdx.x;
   if (x >= OW) return;
   const int y = blockIdx.y, n = blockIdx.z;
-  const BilinearTap ty = ac_tap(sy, y, H), tx = ac_tap(sx, x, W);
   const size_t b = (size_t)n * H * W;
-  const size_t i00 = b + (size_t)ty.i0 * W + tx.i0, i01 = b + (size_t)ty.i0 * W + tx.i1, i10 = b + (size_t)ty.i1 * W + tx.i0,
-               i11 = b + (size_t)ty.i1 * W + tx.i1;
-  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  o[0] = ac_blend(ty, tx, __ldg(p1 + i00), __ldg(p1 + i01), __ldg(p1 + i10), __ldg(p1 + i11));
-  o[1] = ac_blend(ty, tx, __ldg(p2 + i00), __ldg(p2 + i01), __ldg(p2 + i10), __ldg(p2 + i11));
-  act_store8(oh, ol, (((size_t)n * OH + y) * OW + x) * out_cs + c0, o);
+  float o[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int yy = y + r - 1;
+    if (yy < 0 || yy >= OH) continue;
+    const BilinearTap ty = ac_tap(sy, yy, H);
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int xx = x + s - 1;
+      if (xx < 0 || xx >= OW) continue;
+      const BilinearTap tx = ac_tap(sx, xx, W);
+      const size_t i00 = b + (size_t)ty.i0 * W + tx.i0, i01 = b + (size_t)ty.i0 * W + tx.i1, i10 = b + (size_t)ty.i1 * W + tx.i0,
+                   i11 = b + (size_t)ty.i1 * W + tx.i1;
+      o[(r * 3 + s) * 2 + 0] = ac_blend(ty, tx, __ldg(p1 + i00), __ldg(p1 + i01), __ldg(p1 + i10), __ldg(p1 + i11));
+      o[(r * 3 + s) * 2 + 1] = ac_blend(ty, tx, __ldg(p2 + i00), __ldg(p2 + i01), __ldg(p2 + i10), __ldg(p2 + i11));
+    }
+  }
+  const size_t ob = (((size_t)n * OH + y) * OW + x) * out_cs;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = o[g * 8 + k];
+    act_store8(oh, ol, ob + g * 8, t);
+  }
 }
 
 // ------------------------------ final 3x3 conv to one channel + base + clamp (fusion_model.py:113-118)
@@ -282,16 +306,15 @@ extern "C" int prv2_resize_bilinear_act(const prv2_bf16* in_hi, const prv2_bf16*
   return PRV2_OK;
 }
 
-extern "C" int prv2_depth_slots(const float* pred1, const float* pred2, int N, int H, int W, prv2_bf16* out_hi, prv2_bf16* out_lo, int oh,
-                                int ow, int out_cs, int c0, int zero_pad, prv2_stream_t stream) {
-  PRV2_CHECK_ARG(pred1 && pred2 && out_hi, "prv2_depth_slots: null pointer");
-  PRV2_CHECK_ARG(N >= 0 && H > 0 && W > 0 && oh > 0 && ow > 0 && out_cs % 8 == 0 && c0 % 8 == 0 && zero_pad == 6 && c0 + 8 <= out_cs,
-                 "prv2_depth_slots: slot must be an aligned group of 8 channels (2 depth + 6 zero)");
-  PRV2_CHECK_ARG(oh <= 65535 && N <= 65535, "prv2_depth_slots: grid too large");
+extern "C" int prv2_depth_taps(const float* pred1, const float* pred2, int N, int H, int W, prv2_bf16* out_hi, prv2_bf16* out_lo, int oh,
+                               int ow, int out_cs, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(pred1 && pred2 && out_hi, "prv2_depth_taps: null pointer");
+  PRV2_CHECK_ARG(N >= 0 && H > 0 && W > 0 && oh > 0 && ow > 0 && out_cs % 8 == 0 && out_cs >= 24, "prv2_depth_taps: pitch must be a multiple of 8, >= 24");
+  PRV2_CHECK_ARG(oh <= 65535 && N <= 65535, "prv2_depth_taps: grid too large");
   if (N == 0) return PRV2_OK;
   const float sy = oh > 1 ? (float)(H - 1) / (float)(oh - 1) : 0.f, sx = ow > 1 ? (float)(W - 1) / (float)(ow - 1) : 0.f;
   dim3 grid(cdiv(ow, 256), oh, N);
-  depth_slots_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred1, pred2, H, W, (bf16*)out_hi, (bf16*)out_lo, oh, ow, out_cs, c0, sy, sx);
+  depth_taps_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred1, pred2, H, W, (bf16*)out_hi, (bf16*)out_lo, oh, ow, out_cs, sy, sx);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

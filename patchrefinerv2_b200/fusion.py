@@ -1,8 +1,9 @@
 """FusionUnet on the B200 kernels (estimator/models/blocks/fusion_model.py:52-122, convs.py).
 
-Every concatenation is virtual: the conv kernel walks several source tensors in its K loop, and
-the two injected depth maps live in an 8-channel slot appended to the feature tensor they are
-concatenated with (2 real channels + 6 zeros)."""
+Every concatenation is virtual: the conv kernel walks several source tensors in its K loop.  The
+two depth maps the reference concatenates at every level enter as ONE extra 1x1 K segment over an
+18-channel im2col tensor of their 3x3 neighbourhoods (``ops.depth_taps``), instead of two extra
+channels per tap (which would cost a mostly empty 64-wide K chunk per tap)."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
@@ -13,6 +14,12 @@ from . import _lib, ops
 from .nn import Act, GemmLayer, Workspace, conv_segments
 
 LN_EPS = 1e-6   # convs.py:11
+
+
+def depth_tap_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, 2, 3, 3] slice of a conv weight (the two concatenated depth channels) -> [Cout, 18] matching the
+    channel order of ``ops.depth_taps``: (r*3+s)*2 + d."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], 18)
 
 
 class FusionUnetB200:
@@ -29,7 +36,8 @@ class FusionUnetB200:
             self.enc1.append(mk(conv_segments(g(q + "0.weight"), [ic // 2, ic // 2]), 2, tc, epi=_lib.EPI_LN_GELU,
                                 gamma=g(q + "1.weight"), beta=g(q + "1.bias"), eps=LN_EPS, name=f"fusion.enc1.L{idx}"))
             q = f"encoder_layers_2.{idx}.single_conv."
-            self.enc2.append(mk(conv_segments(g(q + "0.weight"), [tc + 2]), 1, tc, epi=_lib.EPI_LN_GELU,
+            w2 = g(q + "0.weight")                     # [tc, tc + 2, 3, 3]: cat[f, pred1, pred2]
+            self.enc2.append(mk(conv_segments(w2[:, :tc], [tc]) + [(1, 0, 0, depth_tap_weight(w2[:, tc:tc + 2]))], 2, tc, epi=_lib.EPI_LN_GELU,
                                 gamma=g(q + "1.weight"), beta=g(q + "1.bias"), eps=LN_EPS, name=f"fusion.enc2.L{idx}"))
         self.dec = []
         rev = self.temp_chl[::-1]
@@ -37,7 +45,9 @@ class FusionUnetB200:
         for i, (tc, dc) in enumerate(zip(rev[1:], self.dec_chl)):
             cin = tc + chl + 2
             q = f"decoder_layers.{i}.conv.double_conv."
-            c1 = mk(conv_segments(g(q + "0.weight"), [chl, tc + 2]), 2, cin, act=_lib.ACT_GELU, name=f"fusion.dec{i}.conv1")
+            w1 = g(q + "0.weight")                     # [cin, cin, 3, 3]: cat[up(chl), skip(tc), pred1, pred2]
+            c1 = mk(conv_segments(w1[:, :chl + tc], [chl, tc]) + [(2, 0, 0, depth_tap_weight(w1[:, chl + tc:chl + tc + 2]))], 3, cin,
+                    act=_lib.ACT_GELU, name=f"fusion.dec{i}.conv1")
             c2 = mk(conv_segments(g(q + "2.weight"), [cin]), 1, dc, act=_lib.ACT_GELU, name=f"fusion.dec{i}.conv2")
             self.dec.append((c1, c2, cin, dc))
             chl = dc
@@ -66,25 +76,26 @@ class FusionUnetB200:
         ws = self.ws.setdefault(key, Workspace(self.device, self.x3))
         A = ws.act
         temp: List[Act] = []
+        dtaps: List[Act] = []
         for idx, (c, f) in enumerate(zip(c_feat, f_feat)):
             tc = self.temp_chl[idx]
-            e1 = A(f"e1_{idx}", B, c.H, c.W, tc, cs=tc + 8)
+            e1 = A(f"e1_{idx}", B, c.H, c.W, tc)
             self.enc1[idx]([c, f], out=e1)
-            ops.depth_slots(pred1, pred2, e1, tc)
-            t = A(f"t_{idx}", B, c.H, c.W, tc, cs=tc + 8)
-            self.enc2[idx]([e1.view_channels(tc + 2)], out=t)
-            if idx < len(c_feat) - 1:
-                ops.depth_slots(pred1, pred2, t, tc)          # this level is a decoder skip: [feat | pred1 | pred2]
+            d18 = A(f"dtaps_{idx}", B, c.H, c.W, 18, cs=24)
+            ops.depth_taps(pred1, pred2, d18)                 # shared by enc2 of this level and the decoder conv that takes it as skip
+            t = A(f"t_{idx}", B, c.H, c.W, tc)
+            self.enc2[idx]([e1, d18], out=t)
             temp.append(t)
+            dtaps.append(d18)
         if trace is not None:
             trace["fusion_enc"] = [t.to_nchw() for t in temp]
-        rev = temp[::-1]
+        rev, rev_d = temp[::-1], dtaps[::-1]
         feat = rev[0]
         for i, skip in enumerate(rev[1:]):
             c1, c2, cin, dc = self.dec[i]
             up = ops.resize_bilinear(feat, A(f"d{i}_up", B, skip.H, skip.W, feat.C))
             mid = A(f"d{i}_mid", B, skip.H, skip.W, cin)
-            c1([up, skip.view_channels(skip.C + 2)], out=mid)
+            c1([up, skip, rev_d[i + 1]], out=mid)
             o = A(f"d{i}_out", B, skip.H, skip.W, dc)
             c2([mid], out=o)
             feat = o

@@ -146,11 +146,13 @@ def resize_bilinear(a: Act, out: Act, relu: bool = False) -> Act:
     return out
 
 
-def depth_slots(pred1: torch.Tensor, pred2: torch.Tensor, out: Act, c0: int):
-    """pred1/pred2 [N,1,H,W] fp32 -> channels c0, c0+1 of ``out`` (c0+2..c0+7 zeroed)."""
+def depth_taps(pred1: torch.Tensor, pred2: torch.Tensor, out: Act):
+    """pred1/pred2 [N,1,H,W] fp32 -> ``out`` [N,oh,ow,24]: 3x3 neighbourhoods of both maps resized to (oh, ow) as
+    18 im2col channels ((r*3+s)*2+d), zero outside the map, channels 18..23 zero."""
     N, _, H, W = pred1.shape
-    _lib.call("prv2_depth_slots", ptr(pred1), ptr(pred2), N, H, W, ptr(out.hi), ptr(out.lo), out.H, out.W, out.cs, c0, 6, stream_ptr(),
-              work=("byte", N * (8.0 * H * W + 16.0 * out.H * out.W * (2 if out.lo is not None else 1))))
+    assert out.N == N and out.cs >= 24
+    _lib.call("prv2_depth_taps", ptr(pred1), ptr(pred2), N, H, W, ptr(out.hi), ptr(out.lo), out.H, out.W, out.cs, stream_ptr(),
+              work=("byte", N * (8.0 * H * W + 48.0 * out.H * out.W * (2 if out.lo is not None else 1))))
 
 
 def tap_stencil(taps: torch.Tensor, base: Optional[torch.Tensor], out: torch.Tensor):

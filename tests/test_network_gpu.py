@@ -209,7 +209,7 @@ def test_layernorm_and_token_kernels(x3, tol):
 
 
 @pytest.mark.parametrize("x3,tol", [(False, 1e-2), (True, 1e-4)])
-def test_resize_depth_slots_final_conv(x3, tol):
+def test_resize_depth_taps_final_conv(x3, tol):
     from patchrefinerv2_b200 import ops
     from patchrefinerv2_b200.nn import Act
     g = torch.Generator().manual_seed(71)
@@ -220,13 +220,15 @@ def test_resize_depth_slots_final_conv(x3, tol):
         assert rel_err(out.to_nchw().cpu(), F.interpolate(x, size, mode="bilinear", align_corners=True)) < tol
     p1, p2 = torch.rand(2, 1, 224, 224, generator=g) * 80, torch.rand(2, 1, 224, 224, generator=g) * 80
     for size in [(224, 224), (64, 64), (8, 8)]:
-        t = Act.empty(2, size[0], size[1], 66, x3, DEV, cs=72)
+        # depth maps as an im2col source: channel (r*3+s)*2+d = resized(pred_d) shifted by tap (r,s), zero padded
+        t = Act.empty(2, size[0], size[1], 18, x3, DEV, cs=24)
         t.hi.fill_(1.0)
-        ops.depth_slots(p1.to(DEV), p2.to(DEV), t, 64)
+        ops.depth_taps(p1.to(DEV), p2.to(DEV), t)
         got = t.to_nchw().cpu()
-        want = torch.cat([F.interpolate(p1, size, mode="bilinear", align_corners=True), F.interpolate(p2, size, mode="bilinear", align_corners=True)], 1)
-        assert rel_err(got[:, 64:66], want) < tol
-        assert torch.all(t.hi[..., 66:72] == 0) and torch.all(t.hi[..., :64] == 1)
+        rs = torch.cat([F.interpolate(p1, size, mode="bilinear", align_corners=True), F.interpolate(p2, size, mode="bilinear", align_corners=True)], 1)
+        want = F.unfold(rs, 3, padding=1).reshape(2, 2, 9, size[0], size[1]).permute(0, 2, 1, 3, 4).reshape(2, 18, size[0], size[1])
+        assert rel_err(got, want) < tol
+        assert torch.all(t.hi[..., 18:24] == 0)
     f = torch.randn(2, 32, 56, 56, generator=g)
     w = torch.randn(1, 32, 3, 3, generator=g) / 17
     base = torch.rand(2, 1, 56, 56, generator=g) - 0.3
