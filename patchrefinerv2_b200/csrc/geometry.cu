@@ -152,33 +152,59 @@ __global__ void __launch_bounds__(256) roi_gather_f32_kernel(const float* __rest
   }
 }
 
-// one thread = one output pixel x 8 channels (16 B of bf16).  grid (ceil(w*C/8 / 256), h, P): the ROI
-// geometry and the row taps are block-uniform; no 64-bit div/mod per element.
-constexpr int ROI_ITEMS = 8;     // outputs per thread (CTA launch rate, not HBM, limited the one-output-per-thread version)
+// grid (ceil(w*C/8 / 256), ceil(h / ROI_ROWS), P).  A thread owns 8 channels (16 B of bf16) of one output column and walks
+// ROI_ROWS consecutive output rows; the horizontal mix of a source row is computed once and reused by every output row
+// that samples it (the ROI is up-sampled ~Sh x, so each source row serves several output rows).  The bf16 variant uses
+// the separable form hy*(hx*v1 + lx*v2) + ly*(hx*v3 + lx*v4); only the f32 variant replays torchvision's rounding order.
+constexpr int ROI_ROWS = 8;
 
 __global__ void __launch_bounds__(256) roi_gather_act_kernel(const bf16* __restrict__ fh, const bf16* __restrict__ fl, int h, int w,
                                                              int C, int in_cs, const float* __restrict__ rois, float s,
                                                              bf16* __restrict__ oh, bf16* __restrict__ ol, int out_cs) {
   const unsigned cv = (unsigned)C >> 3, total = (unsigned)w * cv;
-  const int y = blockIdx.y, p = blockIdx.z;
+  const unsigned idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx / cv), c8 = (int)(idx % cv) * 8;
+  const int y0 = blockIdx.y * ROI_ROWS, p = blockIdx.z;
   const RoiGeom g = roi_geom(rois + p * 4, s, h, w);
-  const RoiAxis ay = roi_axis(g.y1, g.bh, y, h);
-  const size_t r_lo = (size_t)ay.lo * w, r_hi = (size_t)ay.hi * w, orow = ((size_t)p * h + y) * w;
-#pragma unroll 2
-  for (int it = 0; it < ROI_ITEMS; ++it) {
-    const unsigned idx = (blockIdx.x * ROI_ITEMS + it) * 256u + threadIdx.x;
-    if (idx >= total) break;
-    const int x = (int)(idx / cv), c8 = (int)(idx % cv) * 8;
-    const RoiAxis ax = roi_axis(g.x1, g.bw, x, w);
-    const bool valid = ay.valid && ax.valid;
-    float v1[8], v2[8], v3[8], v4[8], o[8];
-    act_load8(fh, fl, (r_lo + ax.lo) * in_cs + c8, v1);
-    act_load8(fh, fl, (r_lo + ax.hi) * in_cs + c8, v2);
-    act_load8(fh, fl, (r_hi + ax.lo) * in_cs + c8, v3);
-    act_load8(fh, fl, (r_hi + ax.hi) * in_cs + c8, v4);
+  const RoiAxis ax = roi_axis(g.x1, g.bw, x, w);
+  auto hmix = [&](int row, float (&o)[8]) {
+    float a[8], b[8];
+    act_load8(fh, fl, ((size_t)row * w + ax.lo) * in_cs + c8, a);
+    act_load8(fh, fl, ((size_t)row * w + ax.hi) * in_cs + c8, b);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = valid ? roi_mix(ay, ax, v1[k], v2[k], v3[k], v4[k]) : 0.f;
-    act_store8(oh, ol, (orow + x) * out_cs + c8, o);
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(ax.h, a[k], ax.l * b[k]);
+  };
+  int r_lo = -1, r_hi = -1;
+  float hb_lo[8], hb_hi[8];
+#pragma unroll
+  for (int yy = 0; yy < ROI_ROWS; ++yy) {
+    const int y = y0 + yy;
+    if (y >= h) break;
+    const RoiAxis ay = roi_axis(g.y1, g.bh, y, h);
+    if (ay.lo != r_lo) {
+      if (ay.lo == r_hi) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hb_lo[k] = hb_hi[k];
+      } else {
+        hmix(ay.lo, hb_lo);
+      }
+      r_lo = ay.lo;
+    }
+    if (ay.hi != r_hi) {
+      if (ay.hi == r_lo) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hb_hi[k] = hb_lo[k];
+      } else {
+        hmix(ay.hi, hb_hi);
+      }
+      r_hi = ay.hi;
+    }
+    const bool valid = ay.valid && ax.valid;
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = valid ? fmaf(ay.h, hb_lo[k], ay.l * hb_hi[k]) : 0.f;
+    act_store8(oh, ol, (((size_t)p * h + y) * w + x) * out_cs + c8, o);
   }
 }
 
@@ -206,7 +232,7 @@ extern "C" int prv2_roi_gather_act(const prv2_bf16* feat_hi, const prv2_bf16* fe
   PRV2_CHECK_ARG(C % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0, "prv2_roi_gather_act: C/pitch must be multiples of 8");
   if (P == 0) return PRV2_OK;
   PRV2_CHECK_ARG(h <= 65535 && P <= 65535, "prv2_roi_gather_act: grid too large");
-  dim3 grid(cdiv((long long)w * (C / 8), 256 * ROI_ITEMS), h, P);
+  dim3 grid(cdiv((long long)w * (C / 8), 256), cdiv(h, ROI_ROWS), P);
   roi_gather_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)feat_hi, (const bf16*)feat_lo, h, w, C, in_cs, rois, spatial_scale,
                                                                (bf16*)out_hi, (bf16*)out_lo, out_cs);
   PRV2_LAUNCH_CHECK();

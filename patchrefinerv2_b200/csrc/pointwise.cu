@@ -109,34 +109,61 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
 }
 
 // --------------------------------------- bilinear align_corners=True on channels-last acts
-// grid (ceil(OW*C/8 / 256), OH, N): row taps are block-uniform, no 64-bit div/mod per element.
-constexpr int PW_ITEMS = 8;      // outputs per thread: few fat CTAs instead of ~1e5 tiny ones (CTA launch rate was the limit)
+// grid (ceil(OW*C/8 / 256), ceil(OH / RS_ROWS), N).  A thread owns 8 channels of one output column and walks RS_ROWS
+// consecutive output rows: the horizontal blend of a source row (2 x 16-byte loads, bf16 unpack, 8 FMAs) is computed once
+// and reused by every output row that needs it (an up-sampling ratio r reuses each source row ~r times).  The first
+// version recomputed all four taps per output and was ALU-pipe bound (77 % ALU, 2.0 TB/s) on the unpack / index work.
+constexpr int RS_ROWS = 4;
 
 __global__ void __launch_bounds__(256) resize_act_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il, int h, int w, int C,
                                                          int in_cs, bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW,
                                                          int out_cs, int relu, float sy, float sx) {
   const unsigned cv = (unsigned)C >> 3, total = (unsigned)OW * cv;
-  const int y = blockIdx.y, n = blockIdx.z;
-  const BilinearTap ty = ac_tap(sy, y, h);
-  const size_t r0 = ((size_t)n * h + ty.i0) * w, r1 = ((size_t)n * h + ty.i1) * w;
-  const size_t orow = ((size_t)n * OH + y) * OW;
-#pragma unroll 2
-  for (int it = 0; it < PW_ITEMS; ++it) {
-    const unsigned idx = (blockIdx.x * PW_ITEMS + it) * 256u + threadIdx.x;
-    if (idx >= total) break;
-    const int x = (int)(idx / cv), c8 = (int)(idx % cv) * 8;
-    const BilinearTap tx = ac_tap(sx, x, w);
-    float a[8], b[8], c[8], d[8], o[8];
-    act_load8(ih, il, (r0 + tx.i0) * in_cs + c8, a);
-    act_load8(ih, il, (r0 + tx.i1) * in_cs + c8, b);
-    act_load8(ih, il, (r1 + tx.i0) * in_cs + c8, c);
-    act_load8(ih, il, (r1 + tx.i1) * in_cs + c8, d);
+  const unsigned idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= total) return;
+  const int x = (int)(idx / cv), c8 = (int)(idx % cv) * 8;
+  const int y0 = blockIdx.y * RS_ROWS, n = blockIdx.z;
+  const BilinearTap tx = ac_tap(sx, x, w);
+  const size_t ibase = (size_t)n * h * w;
+  auto hblend = [&](int row, float (&o)[8]) {
+    float a[8], b[8];
+    act_load8(ih, il, (ibase + (size_t)row * w + tx.i0) * in_cs + c8, a);
+    act_load8(ih, il, (ibase + (size_t)row * w + tx.i1) * in_cs + c8, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = __fmaf_rn(tx.l0, a[k], __fmul_rn(tx.l1, b[k]));
+  };
+  int r_lo = -1, r_hi = -1;
+  float hb_lo[8], hb_hi[8];
+#pragma unroll
+  for (int yy = 0; yy < RS_ROWS; ++yy) {
+    const int y = y0 + yy;
+    if (y >= OH) break;
+    const BilinearTap ty = ac_tap(sy, y, h);
+    if (ty.i0 != r_lo) {
+      if (ty.i0 == r_hi) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hb_lo[k] = hb_hi[k];
+      } else {
+        hblend(ty.i0, hb_lo);
+      }
+      r_lo = ty.i0;
+    }
+    if (ty.i1 != r_hi) {
+      if (ty.i1 == r_lo) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hb_hi[k] = hb_lo[k];
+      } else {
+        hblend(ty.i1, hb_hi);
+      }
+      r_hi = ty.i1;
+    }
+    float o[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      o[k] = ac_blend(ty, tx, a[k], b[k], c[k], d[k]);
+      o[k] = __fmaf_rn(ty.l0, hb_lo[k], __fmul_rn(ty.l1, hb_hi[k]));
       if (relu) o[k] = fmaxf(o[k], 0.f);
     }
-    act_store8(oh, ol, (orow + x) * out_cs + c8, o);
+    act_store8(oh, ol, (((size_t)n * OH + y) * OW + x) * out_cs + c8, o);
   }
 }
 
@@ -299,7 +326,8 @@ extern "C" int prv2_resize_bilinear_act(const prv2_bf16* in_hi, const prv2_bf16*
   PRV2_CHECK_ARG(oh <= 65535 && N <= 65535, "prv2_resize_bilinear_act: grid too large");
   if (N == 0) return PRV2_OK;
   const float sy = oh > 1 ? (float)(h - 1) / (float)(oh - 1) : 0.f, sx = ow > 1 ? (float)(w - 1) / (float)(ow - 1) : 0.f;
-  dim3 grid(cdiv((long long)ow * (C / 8), 256 * PW_ITEMS), oh, N);
+  PRV2_CHECK_ARG((long long)ow * (C / 8) < (1LL << 31), "prv2_resize_bilinear_act: row too long");
+  dim3 grid(cdiv((long long)ow * (C / 8), 256), cdiv(oh, RS_ROWS), N);
   resize_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, h, w, C, in_cs, (bf16*)out_hi, (bf16*)out_lo,
                                                           oh, ow, out_cs, relu, sy, sx);
   PRV2_LAUNCH_CHECK();

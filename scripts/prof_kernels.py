@@ -54,4 +54,18 @@ if which in ("all", "blend"):
         avg, cnt = ops.blend_canvas(preds[:49], mask, stages, 1792, 1792)
         ops.blend_raw(avg, cnt, preds[49:], starts, rmask, 448, 448, 540, 960, 2160, 3840)
     run(f)
+if which in ("all", "resize"):
+    a = Act.empty(12, 256, 256, 256, False, DEV); a.hi.normal_()
+    out = Act.empty(12, 448, 448, 256, False, DEV)
+    run(lambda: ops.resize_bilinear(a, out))
+if which in ("all", "ln"):
+    x = torch.randn(M, D, device=DEV)
+    w, b = torch.rand(D, device=DEV), torch.rand(D, device=DEV)
+    y = Act.empty(1, 1, M, D, False, DEV)
+    run(lambda: ops.layernorm(x, w, b, 1e-6, y))
+if which in ("all", "roi"):
+    f = Act.empty(1, 256, 256, 256, False, DEV); f.hi.normal_()
+    rois = torch.tensor([[0.0, 0.0, 112.0, 112.0]] * 12, device=DEV) + torch.arange(12, device=DEV)[:, None] * 20.0
+    out = Act.empty(12, 256, 256, 256, False, DEV)
+    run(lambda: ops.roi_gather_act(f, rois.contiguous(), 256 / 448, out))
 print("done", _lib.launch_count)
