@@ -136,7 +136,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dav2_vitl_2160x3840_4x4_r32", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--patch-batch", type=int, default=0, help="patches per network launch (0 = balance automatically, <= 12)")
+    ap.add_argument("--patch-batch", type=int, default=0, help="patches per network launch (0 = balance automatically, <= 27)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -190,7 +190,7 @@ def main():
             os.close(saved_fd)
     sd = O.init_patchrefiner_state_dict(cfg, 0)
     n_local = -(-n_patches // world)
-    pb = args.patch_batch or -(-n_local // (-(-n_local // 12)))
+    pb = args.patch_batch or -(-n_local // (-(-n_local // 27)))
     config["patch_batch"] = pb
     model = build_model(dict(type="PatchRefiner", config=cfg, precision=args.precision, patch_batch=pb, output_device="cuda"))
     model.load_dict(sd)

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
 // consecutive output rows: the horizontal blend of a source row (2 x 16-byte loads, bf16 unpack, 8 FMAs) is computed once
 // and reused by every output row that needs it (an up-sampling ratio r reuses each source row ~r times).  The first
 // version recomputed all four taps per output and was ALU-pipe bound (77 % ALU, 2.0 TB/s) on the unpack / index work.
-constexpr int RS_ROWS = 4;
+constexpr int RS_ROWS = 8;
 
 __global__ void __launch_bounds__(256) resize_act_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il, int h, int w, int C,
                                                          int in_cs, bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW,

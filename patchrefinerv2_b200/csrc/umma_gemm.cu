@@ -44,7 +44,9 @@ constexpr int MAX_STAGES = 8;
 constexpr int STG_LD = 20;                    // floats per staged row (16 + 4 pad: conflict-free float4 access both ways)
 constexpr int ROW_PITCH = 144;                // row epilogue: 64 bf16 (128 B) + 16 B pad per staged row (conflict-free 16-byte stores)
 constexpr int STG_BYTES_PER_WARP = 32 * ROW_PITCH;          // >= 32x16 fp32 transpose tile + LN statistics of the generic epilogue (3328 B)
-constexpr int STG_BYTES_PER_WARP_RESID = 2 * STG_BYTES_PER_WARP;   // two staged rows per lane
+constexpr int STG_BYTES_PER_WARP_RESID = 2 * STG_BYTES_PER_WARP;   // row epilogues: two 128-byte rows (fp32 residual) or one 256-byte row (bf16) per lane
+constexpr int ROW_PITCH2 = 272;               // 128 bf16 (256 B) + 16 B pad
+static_assert(32 * ROW_PITCH2 <= STG_BYTES_PER_WARP_RESID, "staging");
 constexpr int PAR_BYTES = 2 * 3 * 256 * 4;    // per-tile bias / gamma / beta, double buffered by accumulator parity
 constexpr int LN_BYTES = NUM_EPI_WARPS * 2 * 64 * 4;        // row epilogue: LayerNorm partials exchanged between the two warps of a quadrant
 constexpr int SMEM_BUDGET = 179 * 1024;       // operand stages; epilogue staging, parameters and barriers sit behind
@@ -433,13 +435,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     const int Cout = p.Cout, block_n = p.block_n, out_cs = p.out_cs;
     const int tile_w_log2 = p.tile_w_log2, tile_w_mask = p.tile_w - 1, pH = p.H, pW = p.W;
     bf16* const out_hi = p.out_hi;
-    uint8_t* const srow = stage_area + ew * p.stg_warp_bytes + lane * ROW_PITCH;      // (+ 32 * ROW_PITCH: second buffer, RESID only)
+    // RESID: two 128-byte rows per lane (pitch ROW_PITCH, second buffer at +32*ROW_PITCH); bf16 outputs: one 256-byte row (pitch ROW_PITCH2)
+    uint8_t* const srow = stage_area + ew * p.stg_warp_bytes + lane * (EPI == PRV2_EPI_RESID_F32 ? ROW_PITCH : ROW_PITCH2);
     const uint32_t srow_s = smem_u32(srow);
     float* const s_par = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * p.stg_warp_bytes);
     float* const s_ln = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * p.stg_warp_bytes + PAR_BYTES);
     int n_sub_done = 0;
     constexpr bool is_ln = EPI == PRV2_EPI_LN_GELU;
-    const int n_panels = (block_n + 63) >> 6;
+    // the two warps of a quadrant own contiguous halves of the tile's 16-column chunks: ONE bulk copy per lane and tile
+    const int n16 = block_n >> 4, q_half = (n16 + 1) >> 1;
+    const int q_start = csel ? q_half : 0, q_cnt = csel ? n16 - q_half : q_half;
     const uint32_t tempty_leader0 = CG == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     int it = 0;
     for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++it) {
@@ -471,20 +476,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         float v[16];
         float sum = 0.f;
         int cnt = 0;
-        for (int pn = csel; pn < n_panels; pn += 2)
-          for (int c0 = pn * 64; c0 < min(pn * 64 + 64, block_n); c0 += 16) {
-            tc_ld16(taddr + c0, v);
+        for (int q = q_start; q < q_start + q_cnt; ++q) {
+          const int c0 = q * 16;
+          tc_ld16(taddr + c0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { sum += v[j]; ++cnt; }
-          }
+          for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { sum += v[j]; ++cnt; }
+        }
         const float mean_a = cnt ? sum / (float)cnt : 0.f;
         float m2 = 0.f;
-        for (int pn = csel; pn < n_panels; pn += 2)
-          for (int c0 = pn * 64; c0 < min(pn * 64 + 64, block_n); c0 += 16) {
-            tc_ld16(taddr + c0, v);
+        for (int q = q_start; q < q_start + q_cnt; ++q) {
+          const int c0 = q * 16;
+          tc_ld16(taddr + c0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { const float d = v[j] - mean_a; m2 += d * d; }
-          }
+          for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { const float d = v[j] - mean_a; m2 += d * d; }
+        }
         float* const mine = s_ln + (ew * 2 + acc) * 64;
         const float* const theirs = s_ln + ((ew ^ 4) * 2 + acc) * 64;
         mine[lane] = mean_a;
@@ -528,17 +533,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           bulk_commit();
         }
       } else
-      for (int pn = csel; pn < n_panels; pn += 2) {
-        const int c0 = pn * 64;
-        const int cols = min(64, block_n - c0);
-        const int nq = cols >> 4;
-        bulk_wait_read0();                                    // this lane's previous copy has left its staging row
+      if (q_cnt > 0) {
+        const int c_first = q_start * 16;
+        bulk_wait_read0();                                    // this lane's copy of the previous tile has left its staging row
         uint32_t rr[16], rn[16];
-        tc_ld16_issue(taddr + c0, rr);
+        tc_ld16_issue(taddr + c_first, rr);
         tc_ld_wait();
-        for (int q = 0; q < nq; ++q) {
-          if (q + 1 < nq) tc_ld16_issue(taddr + c0 + (q + 1) * 16, rn);
-          const int nl = c0 + q * 16;
+        for (int q = 0; q < q_cnt; ++q) {
+          if (q + 1 < q_cnt) tc_ld16_issue(taddr + c_first + (q + 1) * 16, rn);
+          const int nl = c_first + q * 16;
           float t[16];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -558,15 +561,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           for (int j = 0; j < 8; ++j) h2[j] = __floats2bfloat162_rn(act_fn<ACT>(t[2 * j]), act_fn<ACT>(t[2 * j + 1]));
           *reinterpret_cast<uint4*>(srow + q * 32) = *reinterpret_cast<const uint4*>(&h2[0]);
           *reinterpret_cast<uint4*>(srow + q * 32 + 16) = *reinterpret_cast<const uint4*>(&h2[4]);
-          if (q + 1 < nq) {
+          if (q + 1 < q_cnt) {
             tc_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) rr[j] = rn[j];
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // staged row -> visible to the bulk copy engine
-        const int nvalid = min(cols, Cout - (n0 + c0));
-        if (valid && nvalid > 0 && !(p.debug & 4)) bulk_store(grow + c0, srow_s, (uint32_t)nvalid * 2u);
+        const int nvalid = min(q_cnt * 16, Cout - (n0 + c_first));
+        if (valid && nvalid > 0 && !(p.debug & 4)) bulk_store(grow + c_first, srow_s, (uint32_t)nvalid * 2u);
         bulk_commit();
       }
       tc_fence_before();
@@ -1028,7 +1031,8 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
                           d->row_map_period == 0 && d->out_f32_ld % 4 == 0 && d->Cout % 4 == 0 && ((uintptr_t)d->out_f32 & 15) == 0;
   const int resid_stages = (SMEM_BUDGET - NUM_EPI_WARPS * (STG_BYTES_PER_WARP_RESID - STG_BYTES_PER_WARP)) / (A_STAGE_BYTES + p.b_stage_bytes);
   const bool use_fast_resid = fast_resid && resid_stages >= 3;        // a two-stage operand ring costs more than the epilogue gains
-  if (use_fast_resid) {
+  fast = fast && resid_stages >= 3;
+  if (use_fast_resid || fast) {
     p.stg_warp_bytes = STG_BYTES_PER_WARP_RESID;
     if (resid_stages < p.stages) p.stages = resid_stages;
   }
