@@ -65,7 +65,8 @@ struct alignas(64) KParams {
   int32_t n_seg;
   int32_t N, H, W, Cout;
   int32_t tile_w, tile_h, tile_w_log2, tiles_w, tiles_h, tiles_n, total_tiles;   // total_tiles counts tile PAIRS when CG == 2
-  int32_t block_n, stages, b_stage_bytes, tmem_cols;
+  int32_t block_n, stages, b_stage_bytes, tmem_cols;   // b_stage_bytes: ONE 64-wide K block of this CTA's weight share
+  int32_t kb;                                          // 64-wide K blocks per pipeline stage (2 when the N tile is narrow)
   int32_t epi, act;
   const float* bias;
   const float* gamma;
@@ -295,7 +296,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int stages = p.stages;
-  const uint32_t stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;        // b_stage_bytes: this CTA's share (half the N tile when CG == 2)
+  // stage = kb x [A block 16 KB] | kb x [B block]: with a narrow N tile (<= 128) one 64-wide K block is only 256 tensor cycles
+  // and the per-stage barrier round trip of the issuing warp became the limit, so two K blocks share a stage there
+  const int kb = p.kb;
+  const uint32_t blk_bytes = A_STAGE_BYTES + p.b_stage_bytes;           // b_stage_bytes: this CTA's share (half the N tile when CG == 2)
+  const uint32_t stage_bytes = kb * blk_bytes;
+  const uint32_t b_off = kb * A_STAGE_BYTES;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const uint32_t n_workers = CG == 2 ? gridDim.x >> 1 : gridDim.x;      // CTAs (CG 1) or CTA pairs (CG 2) walking the tile list
   const uint32_t worker = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
@@ -352,7 +358,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           const CUtensorMap* map = &p.tmA[p.seg_src[s]];
           const int dh = p.seg_dh[s], dw = p.seg_dw[s];
           const int chunks = p.seg_chunks[s];
-          for (int c = 0; c < chunks; ++c) {
+          for (int c = 0; c < chunks; c += kb) {
+            const int nb = min(kb, chunks - c);                 // K blocks of this stage (a segment's odd last block travels alone)
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t a_dst = smem_base + stage * stage_bytes;
             if (elect_one()) {
@@ -361,17 +368,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
               } else if (CG == 2) {
                 // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of the pair
                 const uint32_t lbar = mapa_shared(full_bar(stage), 0);
-                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * stage_bytes);
-                tma_load_4d_pair(a_dst, map, lbar, c * BK, w0 + dw, h0 + dh, img);
-                tma_load_2d_pair(a_dst + A_STAGE_BYTES, &p.tmB, lbar, kcol, n0);
+                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * nb * blk_bytes);
+                for (int j = 0; j < nb; ++j) {
+                  tma_load_4d_pair(a_dst + j * A_STAGE_BYTES, map, lbar, (c + j) * BK, w0 + dw, h0 + dh, img);
+                  tma_load_2d_pair(a_dst + b_off + j * p.b_stage_bytes, &p.tmB, lbar, kcol + j * BK, n0);
+                }
               } else {
-                mbar_expect_tx(full_bar(stage), stage_bytes);
-                tma_load_4d(a_dst, map, full_bar(stage), c * BK, w0 + dw, h0 + dh, img);
-                tma_load_2d(a_dst + A_STAGE_BYTES, &p.tmB, full_bar(stage), kcol, n0);
+                mbar_expect_tx(full_bar(stage), nb * blk_bytes);
+                for (int j = 0; j < nb; ++j) {
+                  tma_load_4d(a_dst + j * A_STAGE_BYTES, map, full_bar(stage), (c + j) * BK, w0 + dw, h0 + dh, img);
+                  tma_load_2d(a_dst + b_off + j * p.b_stage_bytes, &p.tmB, full_bar(stage), kcol + j * BK, n0);
+                }
               }
             }
             __syncwarp();
-            kcol += BK;
+            kcol += nb * BK;
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -399,21 +410,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         for (int s = 0; s < p.n_seg; ++s) {
           const int chunks = p.seg_chunks[s];
           const int last = p.seg_last[s];
-          for (int c = 0; c < chunks; ++c) {
-            const int slices = (c == chunks - 1) ? last : 4;
+          for (int c = 0; c < chunks; c += kb) {
+            const int nb = min(kb, chunks - c);
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_addr = smem_base + stage * stage_bytes;
-            const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + A_STAGE_BYTES);
             if (elect_one()) {
-              // +32 bytes per 16-element K slice inside the 128-byte swizzle row (encoded >>4)
-              if (slices == 4) {
-                mma(tmem_d, adesc, bdesc, accumulate);
-                mma(tmem_d, adesc + 2, bdesc + 2, 1);
-                mma(tmem_d, adesc + 4, bdesc + 4, 1);
-                mma(tmem_d, adesc + 6, bdesc + 6, 1);
-              } else {
-                for (int k = 0; k < slices; ++k) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, k ? 1u : accumulate);
+              for (int j = 0; j < nb; ++j) {
+                const int slices = (c + j == chunks - 1) ? last : 4;
+                const uint64_t adesc = umma_desc_sw128(a_addr + j * A_STAGE_BYTES), bdesc = umma_desc_sw128(a_addr + b_off + j * p.b_stage_bytes);
+                // +32 bytes per 16-element K slice inside the 128-byte swizzle row (encoded >>4)
+                if (slices == 4) {
+                  mma(tmem_d, adesc, bdesc, accumulate);
+                  mma(tmem_d, adesc + 2, bdesc + 2, 1);
+                  mma(tmem_d, adesc + 4, bdesc + 4, 1);
+                  mma(tmem_d, adesc + 6, bdesc + 6, 1);
+                } else {
+                  for (int k = 0; k < slices; ++k) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, k ? 1u : accumulate);
+                }
+                accumulate = 1;
               }
               if (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
             }
@@ -967,7 +982,10 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   p.total_tiles = (int)total;
   p.block_n = d->block_n;
   p.b_stage_bytes = (d->block_n / cg) * BK * 2;
-  p.stages = SMEM_BUDGET / (A_STAGE_BYTES + p.b_stage_bytes);
+  static const char* kb_env = getenv("PRV2_GEMM_KB");             // diagnostics: force the K blocks per stage
+  p.kb = d->block_n <= 208 ? 2 : 1;
+  if (kb_env && (kb_env[0] == '1' || kb_env[0] == '2')) p.kb = kb_env[0] - '0';
+  p.stages = SMEM_BUDGET / (p.kb * (A_STAGE_BYTES + p.b_stage_bytes));
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   static const char* dbg_env = getenv("PRV2_GEMM_DEBUG");
   p.debug = dbg_env ? atoi(dbg_env) : 0;
@@ -1029,7 +1047,7 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   static const char* red_env = getenv("PRV2_GEMM_REDUCE");          // diagnostics: 0 keeps the register read-modify-write epilogue
   const bool fast_resid = d->epi == PRV2_EPI_RESID_F32 && !(fast_env && fast_env[0] == '0') && !(red_env && red_env[0] == '0') &&
                           d->row_map_period == 0 && d->out_f32_ld % 4 == 0 && d->Cout % 4 == 0 && ((uintptr_t)d->out_f32 & 15) == 0;
-  const int resid_stages = (SMEM_BUDGET - NUM_EPI_WARPS * (STG_BYTES_PER_WARP_RESID - STG_BYTES_PER_WARP)) / (A_STAGE_BYTES + p.b_stage_bytes);
+  const int resid_stages = (SMEM_BUDGET - NUM_EPI_WARPS * (STG_BYTES_PER_WARP_RESID - STG_BYTES_PER_WARP)) / (p.kb * (A_STAGE_BYTES + p.b_stage_bytes));
   const bool use_fast_resid = fast_resid && resid_stages >= 3;        // a two-stage operand ring costs more than the epilogue gains
   fast = fast && resid_stages >= 3;
   if (use_fast_resid || fast) {
