@@ -118,9 +118,13 @@ typedef struct {
 } prv2_src;
 
 /* One K-segment: all channels of source `src` seen through spatial offset (dh,dw).  The packed
- * weight matrix holds the segments back to back, each padded to a multiple of 64 columns. */
+ * weight matrix holds the segments back to back, each padded to a multiple of 64 columns.
+ * taps_h == 3 makes the segment a vertical tap GROUP: the three offsets (dh-1,dw), (dh,dw), (dh+1,dw)
+ * of a 3x3 conv share ONE activation fetch (a tile with a one-row halo above and below); its weight
+ * columns are interleaved per 64-channel block: [block c: tap dh-1 | tap dh | tap dh+1], c = 0, 1, ...
+ * A source is used either by groups or by single-tap segments, not both. */
 typedef struct {
-  int16_t src, dh, dw, pad_;
+  int16_t src, dh, dw, taps_h;   /* taps_h: 0 or 1 = single tap, 3 = vertical group */
 } prv2_seg;
 
 #define PRV2_ACT_NONE 0

@@ -29,7 +29,7 @@ class Src(C.Structure):
 
 
 class Seg(C.Structure):
-    _fields_ = [("src", C.c_int16), ("dh", C.c_int16), ("dw", C.c_int16), ("pad_", C.c_int16)]
+    _fields_ = [("src", C.c_int16), ("dh", C.c_int16), ("dw", C.c_int16), ("taps_h", C.c_int16)]
 
 
 class GemmDesc(C.Structure):

@@ -62,11 +62,13 @@ struct alignas(64) KParams {
   int16_t seg_dw[PRV2_MAX_SEG];
   uint8_t seg_chunks[PRV2_MAX_SEG];           // 64-wide chunks in this segment
   uint8_t seg_last[PRV2_MAX_SEG];             // 16-wide MMA slices in the last chunk (1..4)
+  uint8_t seg_taps[PRV2_MAX_SEG];             // 1 = single tap, 3 = vertical tap group sharing one halo fetch
   int32_t n_seg;
   int32_t N, H, W, Cout;
   int32_t tile_w, tile_h, tile_w_log2, tiles_w, tiles_h, tiles_n, total_tiles;   // total_tiles counts tile PAIRS when CG == 2
   int32_t block_n, stages, b_stage_bytes, tmem_cols;   // b_stage_bytes: ONE 64-wide K block of this CTA's weight share
   int32_t kb;                                          // 64-wide K blocks per pipeline stage (2 when the N tile is narrow)
+  int32_t stage_bytes, b_off, halo_bytes, halo_step;   // stage layout: [A region b_off bytes][B blocks]; halo tile bytes; bytes per dh step
   int32_t epi, act;
   const float* bias;
   const float* gamma;
@@ -300,8 +302,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   // and the per-stage barrier round trip of the issuing warp became the limit, so two K blocks share a stage there
   const int kb = p.kb;
   const uint32_t blk_bytes = A_STAGE_BYTES + p.b_stage_bytes;           // b_stage_bytes: this CTA's share (half the N tile when CG == 2)
-  const uint32_t stage_bytes = kb * blk_bytes;
-  const uint32_t b_off = kb * A_STAGE_BYTES;
+  const uint32_t stage_bytes = p.stage_bytes;
+  const uint32_t b_off = p.b_off;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const uint32_t n_workers = CG == 2 ? gridDim.x >> 1 : gridDim.x;      // CTAs (CG 1) or CTA pairs (CG 2) walking the tile list
   const uint32_t worker = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
@@ -358,6 +360,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           const CUtensorMap* map = &p.tmA[p.seg_src[s]];
           const int dh = p.seg_dh[s], dw = p.seg_dw[s];
           const int chunks = p.seg_chunks[s];
+          if (p.seg_taps[s] == 3) {
+            // vertical tap group: ONE (tile_h + 2)-row halo tile per 64-channel block serves the three dh taps; three weight blocks
+            const uint32_t group_bytes = p.halo_bytes + 3 * p.b_stage_bytes;
+            for (int c = 0; c < chunks; ++c) {
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              const uint32_t a_dst = smem_base + stage * stage_bytes;
+              if (elect_one()) {
+                if ((p.debug & 1) && (phase != 0 || tile != (int)worker)) {
+                  if (cta_rank == 0) mbar_arrive(full_bar(stage));
+                } else if (CG == 2) {
+                  const uint32_t lbar = mapa_shared(full_bar(stage), 0);
+                  if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * group_bytes);
+                  tma_load_4d_pair(a_dst, map, lbar, c * BK, w0 + dw, h0 + dh - 1, img);
+                  for (int r = 0; r < 3; ++r) tma_load_2d_pair(a_dst + b_off + r * p.b_stage_bytes, &p.tmB, lbar, kcol + r * BK, n0);
+                } else {
+                  mbar_expect_tx(full_bar(stage), group_bytes);
+                  tma_load_4d(a_dst, map, full_bar(stage), c * BK, w0 + dw, h0 + dh - 1, img);
+                  for (int r = 0; r < 3; ++r) tma_load_2d(a_dst + b_off + r * p.b_stage_bytes, &p.tmB, full_bar(stage), kcol + r * BK, n0);
+                }
+              }
+              __syncwarp();
+              kcol += 3 * BK;
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+            continue;
+          }
           for (int c = 0; c < chunks; c += kb) {
             const int nb = min(kb, chunks - c);                 // K blocks of this stage (a segment's odd last block travels alone)
             mbar_wait(empty_bar(stage), phase ^ 1);
@@ -410,6 +438,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         for (int s = 0; s < p.n_seg; ++s) {
           const int chunks = p.seg_chunks[s];
           const int last = p.seg_last[s];
+          if (p.seg_taps[s] == 3) {
+            for (int c = 0; c < chunks; ++c) {
+              const int slices = (c == chunks - 1) ? last : 4;
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint32_t a_addr = smem_base + stage * stage_bytes;
+              if (elect_one()) {
+                for (int r = 0; r < 3; ++r) {
+                  // tap dh-1+r reads the halo tile r image rows further down: a 1024-byte-aligned view of the same shared tile
+                  const uint64_t adesc = umma_desc_sw128(a_addr + r * p.halo_step), bdesc = umma_desc_sw128(a_addr + b_off + r * p.b_stage_bytes);
+                  if (slices == 4) {
+                    mma(tmem_d, adesc, bdesc, accumulate);
+                    mma(tmem_d, adesc + 2, bdesc + 2, 1);
+                    mma(tmem_d, adesc + 4, bdesc + 4, 1);
+                    mma(tmem_d, adesc + 6, bdesc + 6, 1);
+                  } else {
+                    for (int k = 0; k < slices; ++k) mma(tmem_d, adesc + 2 * k, bdesc + 2 * k, k ? 1u : accumulate);
+                  }
+                  accumulate = 1;
+                }
+                if (CG == 2) tc_commit_pair(empty_bar(stage)); else tc_commit(empty_bar(stage));
+              }
+              __syncwarp();
+              accumulate = 1;
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+            continue;
+          }
           for (int c = 0; c < chunks; c += kb) {
             const int nb = min(kb, chunks - c);
             mbar_wait(full_bar(stage), phase);
@@ -924,26 +980,36 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
 
   KParams p;
   memset(&p, 0, sizeof(p));
+  // sources read through vertical tap groups are fetched as tiles with a one-row halo above and below
+  bool src_halo[PRV2_MAX_SRC] = {false}, src_single[PRV2_MAX_SRC] = {false}, any_halo = false;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const prv2_seg& sg = d->seg[s];
+    PRV2_CHECK_ARG(sg.src >= 0 && sg.src < d->n_src, "prv2_umma_gemm: segment %d references source %d", s, sg.src);
+    PRV2_CHECK_ARG(sg.taps_h == 0 || sg.taps_h == 1 || sg.taps_h == 3, "prv2_umma_gemm: segment %d: taps_h must be 1 or 3", s);
+    if (sg.taps_h == 3) { src_halo[sg.src] = true; any_halo = true; } else src_single[sg.src] = true;
+  }
+  for (int s = 0; s < d->n_src; ++s)
+    PRV2_CHECK_ARG(!(src_halo[s] && src_single[s]), "prv2_umma_gemm: source %d is used by both tap groups and single taps", s);
   for (int s = 0; s < d->n_src; ++s) {
     const prv2_src& src = d->src[s];
     PRV2_CHECK_ARG(src.ptr && src.C > 0 && src.cs >= src.C && src.cs % 8 == 0 && ((uintptr_t)src.ptr & 15) == 0,
                    "prv2_umma_gemm: source %d needs C>0, pitch multiple of 8, 16-byte aligned", s);
     cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)src.cs * 2, (cuuint64_t)d->W * src.cs * 2, (cuuint64_t)d->H * d->W * src.cs * 2};
-    cuuint32_t box[4] = {BK, (cuuint32_t)d->tile_w, (cuuint32_t)d->tile_h, 1};
+    cuuint32_t box[4] = {BK, (cuuint32_t)d->tile_w, (cuuint32_t)(d->tile_h + (src_halo[s] ? 2 : 0)), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)src.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("prv2_umma_gemm: cuTensorMapEncodeTiled(A%d) failed (%d) C=%d cs=%d N=%d H=%d W=%d", s, (int)r, src.C, src.cs, d->N, d->H, d->W); return PRV2_ECUDA; }
   }
   for (int s = d->n_src; s < PRV2_MAX_SRC; ++s) p.tmA[s] = p.tmA[0];
-  // CTA pairs (cta_group::2) whenever there is enough work to fill the chip with pairs: each CTA of a pair stages its own
+  // CTA pairs (cta_group::2) whenever there are two M tiles: each CTA of a pair stages its own
   // A tile and half of the weight tile.  PRV2_GEMM_CG=1|2 forces the choice (diagnostics).
   const int tiles_w = cdiv(d->W, d->tile_w), tiles_h = cdiv(d->H, d->tile_h);
   const long long m_tiles = (long long)d->N * tiles_h * tiles_w;
   const int tiles_n = d->Cout_pad / d->block_n;
   static const char* cg_env = getenv("PRV2_GEMM_CG");
-  int cg = (m_tiles >= 2 && m_tiles * tiles_n >= 2 * 148) ? 2 : 1;
+  int cg = m_tiles >= 2 ? 2 : 1;            // a pair runs two M tiles side by side, so small problems lose no parallelism
   if (cg_env && (cg_env[0] == '1' || cg_env[0] == '2')) cg = cg_env[0] - '0';
   if (m_tiles < 2 || d->block_n % 16 != 0) cg = 1;
   {
@@ -958,15 +1024,15 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   int ktot = 0;
   for (int s = 0; s < d->n_seg; ++s) {
     const prv2_seg& sg = d->seg[s];
-    PRV2_CHECK_ARG(sg.src >= 0 && sg.src < d->n_src, "prv2_umma_gemm: segment %d references source %d", s, sg.src);
     const int C = d->src[sg.src].C;
     const int chunks = (C + BK - 1) / BK;
     PRV2_CHECK_ARG(chunks <= 255, "prv2_umma_gemm: segment too long");
     p.seg_src[s] = sg.src; p.seg_dh[s] = sg.dh; p.seg_dw[s] = sg.dw;
     p.seg_chunks[s] = (uint8_t)chunks;
+    p.seg_taps[s] = sg.taps_h == 3 ? 3 : 1;
     const int tail = C - (chunks - 1) * BK;
     p.seg_last[s] = (uint8_t)((tail + 15) / 16);
-    ktot += chunks * BK;
+    ktot += chunks * BK * p.seg_taps[s];
   }
   PRV2_CHECK_ARG(ktot == d->Ktot, "prv2_umma_gemm: Ktot %d does not match the segment table (%d)", d->Ktot, ktot);
   p.n_seg = d->n_seg;
@@ -985,7 +1051,13 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   static const char* kb_env = getenv("PRV2_GEMM_KB");             // diagnostics: force the K blocks per stage
   p.kb = d->block_n <= 208 ? 2 : 1;
   if (kb_env && (kb_env[0] == '1' || kb_env[0] == '2')) p.kb = kb_env[0] - '0';
-  p.stages = SMEM_BUDGET / (p.kb * (A_STAGE_BYTES + p.b_stage_bytes));
+  if (any_halo) p.kb = 1;
+  p.halo_step = d->tile_w * BK * 2;                                         // one image row of the tile (a multiple of 1024 B: tile_w >= 16)
+  p.halo_bytes = any_halo ? (d->tile_h + 2) * p.halo_step : 0;
+  PRV2_CHECK_ARG(!any_halo || d->tile_w >= 8, "prv2_umma_gemm: tap groups need tile_w >= 8");
+  p.b_off = any_halo ? p.halo_bytes : p.kb * A_STAGE_BYTES;
+  p.stage_bytes = p.b_off + (any_halo ? 3 : p.kb) * p.b_stage_bytes;
+  p.stages = SMEM_BUDGET / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   static const char* dbg_env = getenv("PRV2_GEMM_DEBUG");
   p.debug = dbg_env ? atoi(dbg_env) : 0;
@@ -1047,9 +1119,10 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   static const char* red_env = getenv("PRV2_GEMM_REDUCE");          // diagnostics: 0 keeps the register read-modify-write epilogue
   const bool fast_resid = d->epi == PRV2_EPI_RESID_F32 && !(fast_env && fast_env[0] == '0') && !(red_env && red_env[0] == '0') &&
                           d->row_map_period == 0 && d->out_f32_ld % 4 == 0 && d->Cout % 4 == 0 && ((uintptr_t)d->out_f32 & 15) == 0;
-  const int resid_stages = (SMEM_BUDGET - NUM_EPI_WARPS * (STG_BYTES_PER_WARP_RESID - STG_BYTES_PER_WARP)) / (p.kb * (A_STAGE_BYTES + p.b_stage_bytes));
-  const bool use_fast_resid = fast_resid && resid_stages >= 3;        // a two-stage operand ring costs more than the epilogue gains
-  fast = fast && resid_stages >= 3;
+  const int resid_stages = (SMEM_BUDGET - NUM_EPI_WARPS * (STG_BYTES_PER_WARP_RESID - STG_BYTES_PER_WARP)) / p.stage_bytes;
+  const int blocks_in_flight = resid_stages * (any_halo ? 3 : p.kb);      // 64-wide K blocks the ring holds with the larger staging
+  const bool use_fast_resid = fast_resid && resid_stages >= 2 && blocks_in_flight >= 3;   // a starved operand ring costs more than the epilogue gains
+  fast = fast && resid_stages >= 2 && blocks_in_flight >= 3;
   if (use_fast_resid || fast) {
     p.stg_warp_bytes = STG_BYTES_PER_WARP_RESID;
     if (resid_stages < p.stages) p.stages = resid_stages;

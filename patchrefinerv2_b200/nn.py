@@ -143,21 +143,28 @@ class GemmLayer:
         if bias is not None and cout != cout_real:
             bias = torch.cat([bias.detach().float().reshape(-1), torch.zeros(cout - cout_real)])
         blocks, table, src_c = [], [], {}
-        for si, dh, dw, w in segs:
-            w = w.detach().to(device=device, dtype=torch.float32)      # packing runs on the device (setup, not hot path)
-            assert w.shape[0] == cout_real
-            c = w.shape[1]
+        for seg in segs:
+            si, dh, dw, w = seg[:4]
+            grouped = isinstance(w, (list, tuple))          # vertical tap group: weights of taps (dh-1, dh, dh+1)
+            ws = [x.detach().to(device=device, dtype=torch.float32) for x in (w if grouped else [w])]   # packing runs on the device (setup, not hot path)
+            assert all(x.shape[0] == cout_real for x in ws) and (not grouped or len(ws) == 3)
+            c = ws[0].shape[1]
             assert src_c.setdefault(si, c) == c, "a source must present the same channel count in every segment"
-            wp = torch.zeros((self.cout_pad, ceil_to(c, 64)), dtype=torch.float32, device=device)
-            wp[:cout_real, :c] = w
+            cp = ceil_to(c, 64)
+            wp = torch.zeros((len(ws), self.cout_pad, cp), dtype=torch.float32, device=device)
+            for r, x in enumerate(ws):
+                wp[r, :cout_real, :c] = x
+            # group: columns interleaved per 64-channel block [block 0: tap -1 | tap 0 | tap +1][block 1: ...] (include/prv2_b200.h)
+            wp = wp.reshape(len(ws), self.cout_pad, cp // 64, 64).permute(1, 2, 0, 3).reshape(self.cout_pad, len(ws) * cp)
             wh = wp.to(BF16)
+            taps = 3 if grouped else 1
             if x3:
                 wl = (wp - wh.float()).to(BF16)
                 blocks += [wh, wl, wh]
-                table += [(2 * si, dh, dw), (2 * si, dh, dw), (2 * si + 1, dh, dw)]
+                table += [(2 * si, dh, dw, taps), (2 * si, dh, dw, taps), (2 * si + 1, dh, dw, taps)]
             else:
                 blocks.append(wh)
-                table.append((si, dh, dw))
+                table.append((si, dh, dw, taps))
         assert len(table) <= _lib.MAX_SEG and n_src * (2 if x3 else 1) <= _lib.MAX_SRC
         self.src_c = [src_c[i] for i in range(n_src)]
         self.weight = torch.cat(blocks, dim=1).contiguous()
@@ -167,8 +174,8 @@ class GemmLayer:
         d = GemmDesc()
         d.Cout, d.block_n, d.Cout_pad, d.Ktot = cout, self.block_n, self.cout_pad, self.ktot
         d.n_src, d.n_seg = n_src * (2 if x3 else 1), len(table)
-        for i, (si, dh, dw) in enumerate(table):
-            d.seg[i].src, d.seg[i].dh, d.seg[i].dw = si, dh, dw
+        for i, (si, dh, dw, taps) in enumerate(table):
+            d.seg[i].src, d.seg[i].dh, d.seg[i].dw, d.seg[i].taps_h = si, dh, dw, taps
         d.weight = self.weight.data_ptr()
         d.epi, d.act = epi, act
         d.bias = 0 if self.bias is None else self.bias.data_ptr()
@@ -176,7 +183,7 @@ class GemmLayer:
         d.beta = 0 if self.beta is None else self.beta.data_ptr()
         d.eps, d.head_scale, d.shuffle_k = eps, head_scale, shuffle_k
         self.desc = d
-        self.flops_per_pixel = 2 * cout * sum(w.shape[1] for _, _, _, w in segs)
+        self.flops_per_pixel = 2 * cout * sum((3 * w[0].shape[1]) if isinstance(w, (list, tuple)) else w.shape[1] for _, _, _, w in segs)
 
     def __call__(self, srcs: Sequence[Act], out: Optional[Act] = None, relu_out: Optional[Act] = None, res: Optional[Act] = None,
                  res2: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, out_f32_ld: int = 0,
@@ -209,12 +216,23 @@ class GemmLayer:
         _lib.call("prv2_umma_gemm", C.byref(d), stream_ptr(), work=("flop", float(self.flops_per_pixel) * a0.N * a0.H * a0.W, self.name))
 
 
-def conv_segments(w: torch.Tensor, splits: Sequence[int], pad: int = 1) -> List[Tuple[int, int, int, torch.Tensor]]:
+def conv_segments(w: torch.Tensor, splits: Sequence[int], pad: int = 1, group: bool = True) -> List[Tuple[int, int, int, object]]:
     """Segment list of a stride-1 conv with OIHW weight ``w`` whose input channels are the
-    concatenation of sources with ``splits`` channels (virtual concat): taps outer, sources inner."""
+    concatenation of sources with ``splits`` channels (virtual concat).
+
+    3x3 / pad 1 convs are emitted as vertical tap GROUPS (one per column offset and source): the kernel
+    fetches one activation tile with a one-row halo and runs the three row taps from it, which cuts
+    the activation traffic of the conv by 2.4x.  Otherwise: one segment per tap, taps outer, sources inner."""
     co, ci, R, S = w.shape
     assert sum(splits) == ci
     segs = []
+    if group and R == 3 and S == 3 and pad == 1:
+        for s in range(3):
+            o = 0
+            for si, c in enumerate(splits):
+                segs.append((si, 0, s - 1, [w[:, o:o + c, r, s] for r in range(3)]))
+                o += c
+        return segs
     for r in range(R):
         for s in range(S):
             o = 0
