@@ -245,6 +245,11 @@ extern "C" int prv2_roi_gather_act(const prv2_bf16* feat_hi, const prv2_bf16* fe
 #define PRV2_MAX_STAGES 8
 struct StageTable { int n; prv2_grid_stage s[PRV2_MAX_STAGES]; };
 
+// n / d for 0 <= n < 2^16 with the host-made magic m = floor(2^32 / d) + 1 (exact for d < 2^16): one IMAD.HI instead of the
+// ~20-instruction generic division, per stage and thread, in a kernel that is otherwise four loads and a store
+__device__ __forceinline__ int div_magic(int n, unsigned magic) { return (int)__umulhi((unsigned)n, magic); }
+static unsigned make_magic(int d) { return (unsigned)((1ull << 32) / (unsigned)d) + 1u; }
+
 // RunningAverageMap.update for one pixel, exactly as the tensor expression evaluates it:
 // avg = (pred*ct + cnt*avg) / (cnt + ct); cnt = cnt + ct      (all separately rounded)
 __device__ __forceinline__ void ram_update(float& avg, float& cnt, float pred, float ct) {
@@ -260,7 +265,7 @@ __device__ __forceinline__ void ram_update(float& avg, float& cnt, float pred, f
 template <int MODE>
 __global__ void __launch_bounds__(256) blend_canvas_kernel(const float* __restrict__ preds, const uint8_t* __restrict__ own,
                                                            const float* __restrict__ mask, int ph, int pw, StageTable st, int Hc,
-                                                           int Wc, float* __restrict__ avg_out, float* __restrict__ cnt_out,
+                                                           int Wc, unsigned magic_h, unsigned magic_w, float* __restrict__ avg_out, float* __restrict__ cnt_out,
                                                            const float* __restrict__ num_in, const float* __restrict__ m1_in) {
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y;
@@ -278,14 +283,14 @@ __global__ void __launch_bounds__(256) blend_canvas_kernel(const float* __restri
     const prv2_grid_stage g = st.s[s];
     const int yy = y - g.off_h;
     if (yy < 0) continue;
-    const int i = yy / ph;
+    const int i = div_magic(yy, magic_h);
     if (i >= g.n_h) continue;
     const int ly = yy - i * ph;
     const int xx0 = x0 - g.off_w;
     float ct[4], pv[4];
     bool ok[4];
     int j0 = 0, lx0 = 0;
-    if (xx0 >= 0) { j0 = xx0 / pw; lx0 = xx0 - j0 * pw; }
+    if (xx0 >= 0) { j0 = div_magic(xx0, magic_w); lx0 = xx0 - j0 * pw; }
     const bool fast = xx0 >= 0 && j0 < g.n_w && lx0 + 3 < pw && x0 + 3 < Wc && ((lx0 | pw) & 3) == 0;
     if (fast) {
       const int pidx = g.first + i * g.n_w + j0;
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(256) blend_canvas_kernel(const float* __restri
         const int xx = xx0 + k;
         ok[k] = false; ct[k] = 0.f; pv[k] = 0.f;
         if (xx < 0 || x0 + k >= Wc) continue;
-        const int j = xx / pw;
+        const int j = div_magic(xx, magic_w);
         if (j >= g.n_w) continue;
         const int lx = xx - j * pw, pidx = g.first + i * g.n_w + j;
         ct[k] = __ldg(mask + (size_t)ly * pw + lx);
@@ -345,11 +350,18 @@ __global__ void __launch_bounds__(256) blend_canvas_kernel(const float* __restri
   if (MODE == 1) {       // accumulate into num_c (avg_out) and the m1 plane (cnt_out)
     for (int k = 0; k < 4 && x0 + k < Wc; ++k) { avg_out[o + k] += r_a[k]; cnt_out[o + k] += r_c[k]; }
   } else if (vec_out) {
-    *reinterpret_cast<float4*>(avg_out + o) = make_float4(r_a[0], r_a[1], r_a[2], r_a[3]);
-    if (cnt_out) *reinterpret_cast<float4*>(cnt_out + o) = make_float4(r_c[0], r_c[1], r_c[2], r_c[3]);
+    __stcs(reinterpret_cast<float4*>(avg_out + o), make_float4(r_a[0], r_a[1], r_a[2], r_a[3]));
+    if (cnt_out) __stcs(reinterpret_cast<float4*>(cnt_out + o), make_float4(r_c[0], r_c[1], r_c[2], r_c[3]));
   } else {
     for (int k = 0; k < 4 && x0 + k < Wc; ++k) { avg_out[o + k] = r_a[k]; if (cnt_out) cnt_out[o + k] = r_c[k]; }
   }
+}
+
+// threads per CTA so that a canvas row splits into CTAs without a mostly idle last one (1792 / 4 = 448 = 2 x 224)
+static int blend_threads(int Wc) {
+  const int groups = cdiv(Wc, 4);
+  const int ctas = cdiv(groups, 256);
+  return cdiv(cdiv(groups, ctas), 32) * 32;
 }
 
 static int fill_stages(StageTable& t, const prv2_grid_stage* stages, int n) {
@@ -364,9 +376,10 @@ extern "C" int prv2_blend_canvas(const float* preds, const float* mask, int ph, 
   PRV2_CHECK_ARG(preds && mask && avg, "prv2_blend_canvas: null pointer");
   StageTable t;
   PRV2_CHECK_ARG(fill_stages(t, stages, n_stages) == 0, "prv2_blend_canvas: need 1..%d stages", PRV2_MAX_STAGES);
-  PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535, "prv2_blend_canvas: bad shape");
-  dim3 grid(cdiv(cdiv(Wc, 4), 256), Hc);
-  blend_canvas_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(preds, nullptr, mask, ph, pw, t, Hc, Wc, avg, cnt, nullptr, nullptr);
+  PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535 && Wc <= 65535 && ph < 65536 && pw < 65536, "prv2_blend_canvas: bad shape");
+  const int bt = blend_threads(Wc);
+  dim3 grid(cdiv(cdiv(Wc, 4), bt), Hc);
+  blend_canvas_kernel<0><<<grid, bt, 0, (cudaStream_t)stream>>>(preds, nullptr, mask, ph, pw, t, Hc, Wc, make_magic(ph), make_magic(pw), avg, cnt, nullptr, nullptr);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -378,8 +391,9 @@ extern "C" int prv2_blend_partial_canvas(const float* preds, const uint8_t* own,
   StageTable t;
   PRV2_CHECK_ARG(fill_stages(t, stages, n_stages) == 0, "prv2_blend_partial_canvas: need 1..%d stages", PRV2_MAX_STAGES);
   PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535, "prv2_blend_partial_canvas: bad shape");
-  dim3 grid(cdiv(cdiv(Wc, 4), 256), Hc);
-  blend_canvas_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(preds, own, mask, ph, pw, t, Hc, Wc, num_c, m1, nullptr, nullptr);
+  const int bt = blend_threads(Wc);
+  dim3 grid(cdiv(cdiv(Wc, 4), bt), Hc);
+  blend_canvas_kernel<1><<<grid, bt, 0, (cudaStream_t)stream>>>(preds, own, mask, ph, pw, t, Hc, Wc, make_magic(ph), make_magic(pw), num_c, m1, nullptr, nullptr);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -391,8 +405,9 @@ extern "C" int prv2_blend_finalize_canvas(const float* num_c, const float* m1, c
   StageTable t;
   PRV2_CHECK_ARG(fill_stages(t, stages, n_stages) == 0, "prv2_blend_finalize_canvas: need 1..%d stages", PRV2_MAX_STAGES);
   PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535, "prv2_blend_finalize_canvas: bad shape");
-  dim3 grid(cdiv(cdiv(Wc, 4), 256), Hc);
-  blend_canvas_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, mask, ph, pw, t, Hc, Wc, avg, cnt, num_c, m1);
+  const int bt = blend_threads(Wc);
+  dim3 grid(cdiv(cdiv(Wc, 4), bt), Hc);
+  blend_canvas_kernel<2><<<grid, bt, 0, (cudaStream_t)stream>>>(nullptr, nullptr, mask, ph, pw, t, Hc, Wc, make_magic(ph), make_magic(pw), avg, cnt, num_c, m1);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -438,9 +453,9 @@ __global__ void __launch_bounds__(256) blend_raw_kernel(const float* __restrict_
     if (threadIdx.x == 0) s_n = m;
   }
   __syncthreads();
-  const int xb = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (xb >= W) return;
   const int m = s_n;
+  // one CTA walks its whole row (the covering-patch list above is built once per row, not once per 1024 pixels)
+  for (int xb = threadIdx.x * 4; xb < W; xb += blockDim.x * 4) {
   const size_t o = (size_t)y * W + xb;
   float avg[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f}, num[4] = {0.f, 0.f, 0.f, 0.f}, c0[4] = {0.f, 0.f, 0.f, 0.f};
   if (MODE != 1) {
@@ -490,10 +505,11 @@ __global__ void __launch_bounds__(256) blend_raw_kernel(const float* __restrict_
   if (MODE == 1) {
     for (int q = 0; q < 4 && xb + q < W; ++q) out[o + q] += r_a[q];
   } else if ((W & 3) == 0) {
-    *reinterpret_cast<float4*>(out + o) = make_float4(r_a[0], r_a[1], r_a[2], r_a[3]);
-    if (out_cnt) *reinterpret_cast<float4*>(out_cnt + o) = make_float4(r_c[0], r_c[1], r_c[2], r_c[3]);
+    __stcs(reinterpret_cast<float4*>(out + o), make_float4(r_a[0], r_a[1], r_a[2], r_a[3]));
+    if (out_cnt) __stcs(reinterpret_cast<float4*>(out_cnt + o), make_float4(r_c[0], r_c[1], r_c[2], r_c[3]));
   } else {
     for (int q = 0; q < 4 && xb + q < W; ++q) { out[o + q] = r_a[q]; if (out_cnt) out_cnt[o + q] = r_c[q]; }
+  }
   }
 }
 
@@ -519,7 +535,7 @@ extern "C" int prv2_blend_raw(const float* avg_c, const float* cnt_c, int Hc, in
   PRV2_CHECK_ARG(n == 0 || (preds && starts && rmask), "prv2_blend_raw: null patch inputs");
   int rc = check_raw("prv2_blend_raw", n, ph, pw, rh, rw, H, W);
   if (rc) return rc;
-  dim3 grid(cdiv(cdiv(W, 4), 256), H);
+  dim3 grid(1, H);
   blend_raw_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(avg_c, cnt_c, Hc, Wc, preds, nullptr, starts, n, ph, pw, rmask, rh, rw, H, W,
                                                               out, out_cnt, nullptr, raw_scales(Hc, Wc, H, W, ph, pw, rh, rw));
   PRV2_LAUNCH_CHECK();
@@ -532,7 +548,7 @@ extern "C" int prv2_blend_partial_raw(const float* preds, const uint8_t* own, co
   int rc = check_raw("prv2_blend_partial_raw", n, ph, pw, rh, rw, H, W);
   if (rc) return rc;
   if (n == 0) return PRV2_OK;
-  dim3 grid(cdiv(cdiv(W, 4), 256), H);
+  dim3 grid(1, H);
   blend_raw_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, 1, 1, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W,
                                                               num_r, nullptr, nullptr, raw_scales(1, 1, H, W, ph, pw, rh, rw));
   PRV2_LAUNCH_CHECK();
@@ -546,7 +562,7 @@ extern "C" int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, i
   PRV2_CHECK_ARG(n == 0 || (starts && rmask), "prv2_blend_finalize_raw: null patch inputs");
   int rc = check_raw("prv2_blend_finalize_raw", n, 1, 1, rh, rw, H, W);
   if (rc) return rc;
-  dim3 grid(cdiv(cdiv(W, 4), 256), H);
+  dim3 grid(1, H);
   blend_raw_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(avg_c, cnt_c, Hc, Wc, nullptr, nullptr, starts, n, 1, 1, rmask, rh, rw, H, W,
                                                               out, out_cnt, num_r, raw_scales(Hc, Wc, H, W, 1, 1, rh, rw));
   PRV2_LAUNCH_CHECK();
