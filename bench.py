@@ -37,6 +37,18 @@ WORKLOADS = {
 METRIC = "frames_per_sec_2160x3840_cai_r32"
 
 
+def profiled_traffic():
+    """Average DRAM bytes per launch of the dominant kernel from the committed ncu launch list of this command
+    (profiles/traffic.json, written by scripts/summarize_launches.py); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -139,8 +151,9 @@ def main():
     ap.add_argument("--patch-batch", type=int, default=0, help="patches per network launch (0 = balance automatically, <= 27)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-run", action="store_true", help="run under ncu: fewer warm-up steps allowed; the printed number is NOT a bench value")
     args = ap.parse_args()
-    assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+    assert args.warmup >= 3 or args.impl == "reference" or args.profile_run, "timing rules: at least 3 warm-up steps"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -298,10 +311,23 @@ def main():
     gemm_layers = {k: {"tflops": v["flop"] / (v["ms"] * 1e-3) / 1e12, "frac": v["flop"] / (v["ms"] * 1e-3) / 1e12 / peaks["tf_sustained"],
                        "ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in sorted(layers.items())}
     gemm = kern.get("prv2_umma_gemm", {})
+    traffic = profiled_traffic() or {}
     roofline = {"kernel": "umma_gemm_kernel (prv2_umma_gemm)", "bound": "tensor", "achieved": gemm.get("achieved"), "peak": peaks["tf_sustained"],
-                "unit": "TFLOP/s", "frac": gemm.get("frac"), "traffic": None, "peak_source": f"{peaks['source']} bf16 sustained",
+                "unit": "TFLOP/s", "frac": gemm.get("frac"), "traffic": traffic.get("umma_gemm_kernel", {}).get("dram_bytes_per_launch"),
+                "traffic_source": traffic.get("source"), "peak_source": f"{peaks['source']} bf16 sustained",
                 "share_of_step": gemm.get("share_of_step"), "launches_per_step": gemm.get("launches_per_step"),
                 "note": "aggregate over all launches of the kernel in the timed region: sum(algorithmic FLOPs) / sum(CUDA-event durations)"}
+
+    # the CAI blend (north_star: HBM-bound target): both stages together, algorithmic bytes / CUDA-event time
+    bl = [kern[k] for k in ("prv2_blend_canvas", "prv2_blend_raw") if k in kern]
+    roofline_blend = None
+    if bl:
+        b_ms = sum(k["ms_per_step"] for k in bl)
+        b_bytes = sum(k["achieved"] * 1e9 * k["ms_per_step"] * 1e-3 for k in bl)
+        roofline_blend = {"kernel": "blend_canvas_kernel + blend_raw_kernel", "bound": "hbm", "achieved": b_bytes / (b_ms * 1e-3) / 1e9, "peak": peaks["hbm"],
+                          "unit": "GB/s", "frac": b_bytes / (b_ms * 1e-3) / 1e9 / peaks["hbm"], "ms_per_step": b_ms,
+                          "traffic": {k: traffic.get(k, {}).get("dram_bytes_per_launch") for k in ("blend_canvas_kernel", "blend_raw_kernel")},
+                          "note": "CUDA-event time of two ~20-60 us launches includes launch latency; ncu durations are in profiles/"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -316,7 +342,7 @@ def main():
             "patches_per_sec": fps * n_patches, "algorithmic_tflop_per_frame": flops_frame / 1e12,
             "model_tflops_per_gpu": flops_frame * fps / 1e12 / world,
             "l2_policy": "working set per step (activations, several GB) far exceeds the 126 MB L2; no explicit flush",
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "shard_check": shard_check, "roofline": roofline, "kernels": kern, "gemm_layers": gemm_layers, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "shard_check": shard_check, "roofline": roofline, "roofline_blend": roofline_blend, "kernels": kern, "gemm_layers": gemm_layers, "cpu_baseline": cpu_baseline,
             "workspace_gb": sum(w.nbytes() for eng in (model._engine["coarse"], model._engine["fine"], model._engine["fusion"]) for w in eng.ws.values()) / 1e9}
     print(json.dumps(line))
     if world > 1:

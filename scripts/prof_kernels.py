@@ -36,13 +36,16 @@ if which in ("all", "attn"):
     out = Act.empty(1, 1, M, D, False, DEV)
     run(lambda: ops.attention(qkv, B, T, heads, out))
 if which in ("all", "conv"):
-    # fusion.dec3.conv1-like: 2 sources (256, 264->258) at 256x256, Cout 514
-    a = Act.empty(4, 256, 256, 256, False, DEV); a.hi.normal_()
-    b = Act.empty(4, 256, 256, 258, False, DEV, cs=264); b.hi.normal_()
-    w = torch.randn(514, 514, 3, 3) / math.sqrt(514 * 9)
-    lay = GemmLayer(conv_segments(w, [256, 258]), 2, 514, False, DEV, act=_lib.ACT_GELU, name="dec3.conv1")
-    out = Act.empty(4, 256, 256, 514, False, DEV)
-    run(lambda: lay([a, b], out=out))
+    # fusion.dec4.conv1: cat[up(256), skip(128), depth taps] at 448x448 -> 386 channels, GELU (the largest single layer)
+    from patchrefinerv2_b200.fusion import depth_tap_weight
+    a = Act.empty(4, 448, 448, 256, False, DEV); a.hi.normal_()
+    b = Act.empty(4, 448, 448, 128, False, DEV); b.hi.normal_()
+    c = Act.empty(4, 448, 448, 18, False, DEV, cs=24); c.hi.normal_()
+    w = torch.randn(386, 386, 3, 3) / math.sqrt(386 * 9)
+    lay = GemmLayer(conv_segments(w[:, :384], [256, 128]) + [(2, 0, 0, depth_tap_weight(w[:, 384:386]))], 3, 386, False, DEV,
+                    act=_lib.ACT_GELU, name="dec4.conv1")
+    out = Act.empty(4, 448, 448, 386, False, DEV, cs=392)
+    run(lambda: lay([a, b, c], out=out))
 if which in ("all", "blend"):
     preds = torch.rand(81, 448, 448, device=DEV)
     mask = torch.rand(448, 448, device=DEV)
