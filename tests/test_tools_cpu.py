@@ -1,0 +1,150 @@
+"""tools/test.py surface on CPU: the mmengine-free config loader, --cfg-option overrides, frame ingest / egress
+(SURVEY.md 8(f) rows 1 and 4).  Model construction needs no GPU; the forward itself is covered by the -m gpu tests."""
+import importlib.util
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from patchrefinerv2_b200 import frames
+from patchrefinerv2_b200.config import Config, ConfigDict, merge_dict, parse_cfg_options
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CFG = "/root/reference/configs"
+
+
+def _tools_test():
+    spec = importlib.util.spec_from_file_location("prv2_tools_test", os.path.join(ROOT, "tools", "test.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+BASE_RUN = "work_dir = './work_dir'\nlog_name = 'base'\n"
+BASE_DATA = ("general_dataloader = dict(batch_size=1, num_workers=2,\n"
+             "    dataset=dict(type='ImageDataset', rgb_image_dir='', dataset_name='', network_process_size=(384, 512)))\n")
+CHILD = """
+_base_ = ['../_base_/run_time.py', '../_base_/datasets/general_dataset.py']
+min_depth = 1e-3
+max_depth = 80
+model = dict(
+    type='PatchRefiner',
+    config=dict(
+        image_raw_shape=[432, 768], patch_process_shape=[224, 224], patch_split_num=[2, 2],
+        fusion_feat_level=6, min_depth=1e-3, max_depth=80, strategy_refiner_target='offset_coarse',
+        pretrain_coarse_model=None, pretrain_fine_model=None,
+        coarse_branch=dict(type='DA2', pretrained=None, model_cfg=dict(encoder='vits', features=64, out_channels=[48, 96, 192, 384])),
+        refiner=dict(
+            fine_branch=dict(type='DA2', pretrained=None, model_cfg=dict(encoder='vits', features=64, out_channels=[48, 96, 192, 384])),
+            fusion_model=dict(type='FusionUnet', input_chl=[64, 128, 128, 128, 128, 128], temp_chl=[32, 64, 64, 64, 64, 64],
+                              dec_chl=[64, 64, 64, 64, 32])),
+        sigloss=dict(type='SILogLoss'), pre_norm_bbox=True))
+general_dataloader = dict(dataset=dict(network_process_size=(224, 224)))
+"""
+
+
+@pytest.fixture()
+def cfg_tree(tmp_path):
+    (tmp_path / "_base_" / "datasets").mkdir(parents=True)
+    (tmp_path / "_base_" / "run_time.py").write_text(BASE_RUN)
+    (tmp_path / "_base_" / "datasets" / "general_dataset.py").write_text(BASE_DATA)
+    (tmp_path / "pr").mkdir()
+    (tmp_path / "pr" / "tiny.py").write_text(CHILD)
+    return str(tmp_path / "pr" / "tiny.py")
+
+
+def test_config_base_inheritance_and_attribute_access(cfg_tree):
+    cfg = Config.fromfile(cfg_tree)
+    assert cfg.work_dir == "./work_dir" and cfg.log_name == "base"                 # from _base_/run_time.py
+    ds = cfg.general_dataloader.dataset
+    assert ds.type == "ImageDataset" and tuple(ds.network_process_size) == (224, 224)   # child merged INTO the base dict
+    assert cfg.general_dataloader.num_workers == 2
+    assert cfg.model.config.coarse_branch.model_cfg.encoder == "vits"
+    assert isinstance(cfg.model, ConfigDict) and isinstance(cfg.model.to_dict(), dict) and not isinstance(cfg.model.to_dict()["config"], ConfigDict)
+    assert "_base_" not in cfg
+
+
+def test_cfg_option_overrides_and_delete_key(cfg_tree):
+    cfg = Config.fromfile(cfg_tree)
+    opts = parse_cfg_options(["general_dataloader.dataset.rgb_image_dir='./examples/'", "model.config.patch_split_num=[4,4]",
+                              "model.config.max_depth=10", "new.key.path=abc"])
+    cfg.merge_from_dict(opts)
+    assert cfg.general_dataloader.dataset.rgb_image_dir == "./examples/"
+    assert cfg.model.config.patch_split_num == [4, 4] and cfg.model.config.max_depth == 10
+    assert cfg.new.key.path == "abc"
+    with pytest.raises(ValueError):
+        parse_cfg_options(["novalue"])
+    merged = merge_dict({"a": {"_delete_": True, "x": 1}}, {"a": {"y": 2}, "b": 3})
+    assert merged == {"a": {"x": 1}, "b": 3}
+    assert merge_dict({"a": {"x": 1}}, {"a": {"y": 2}}) == {"a": {"x": 1, "y": 2}}
+
+
+def test_circular_and_missing_base(tmp_path):
+    (tmp_path / "a.py").write_text("_base_ = ['b.py']\n")
+    (tmp_path / "b.py").write_text("_base_ = ['a.py']\n")
+    with pytest.raises(ValueError):
+        Config.fromfile(str(tmp_path / "a.py"))
+    (tmp_path / "c.py").write_text("_base_ = ['nope.py']\n")
+    with pytest.raises(FileNotFoundError):
+        Config.fromfile(str(tmp_path / "c.py"))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference tree not mounted (GPU box)")
+def test_every_reference_config_loads_unmodified():
+    import glob
+    files = [f for f in sorted(glob.glob(os.path.join(REF_CFG, "*", "*.py"))) if "/_base_/" not in f]
+    assert len(files) > 50
+    n_models = 0
+    for f in files:
+        cfg = Config.fromfile(f)                      # every file parses, _base_ chains included
+        if "model" in cfg:
+            n_models += 1
+            assert isinstance(cfg.model.type, str) and cfg.model.type.startswith(("Patch", "Baseline")), f
+    assert n_models > 50
+    u4k = Config.fromfile(os.path.join(REF_CFG, "patchrefiner_dav2", "pr_u4k.py"))
+    assert u4k.model.config.patch_process_shape == [448, 448] and u4k.model.config.coarse_branch.model_cfg.encoder == "vitl"
+    assert u4k.model.config.refiner.fusion_model.type == "FusionUnet"
+
+
+def test_tools_test_builds_the_registry_model_from_a_config(cfg_tree, tmp_path):
+    t = _tools_test()
+    args = t.parse_args([cfg_tree, "--cai-mode", "r4", "--image-raw-shape", "432", "768", "--patch-split-num", "2", "2",
+                         "--cfg-option", f"general_dataloader.dataset.rgb_image_dir={tmp_path}", "--save", "--work-dir", str(tmp_path / "out")])
+    cfg, model = t.build(args)
+    from patchrefinerv2_b200 import PatchRefiner
+    assert isinstance(model, PatchRefiner)
+    assert cfg.general_dataloader.dataset.rgb_image_dir == str(tmp_path)
+    assert model.tile_cfg["patch_raw_shape"] == (216, 384) or list(model.tile_cfg["patch_raw_shape"]) == [216, 384]
+    args2 = t.parse_args([cfg_tree, "--test-type", "normal"])
+    with pytest.raises(NotImplementedError):
+        t.build(args2)
+
+
+def test_frame_ingest_matches_the_reference_dataset_recipe(tmp_path):
+    rng = np.random.default_rng(0)
+    bgr = rng.integers(0, 256, (54, 96, 3), dtype=np.uint8)
+    cv2.imwrite(str(tmp_path / "b_img.png"), bgr)
+    cv2.imwrite(str(tmp_path / "a_img.jpg"), bgr)
+    (tmp_path / "notes.txt").write_text("not an image")
+    assert frames.list_frames(str(tmp_path)) == ["a_img.jpg", "b_img.png"]
+    out = dict(frames.iter_frames(str(tmp_path), (108, 192)))
+    assert set(out) == {"a_img", "b_img"}
+    t = out["b_img"]
+    assert t.shape == (3, 108, 192) and t.dtype == torch.float32
+    # general_dataset.py:52-59 restated inline: BGR->RGB, /255 (float64), bicubic align_corners=True, float()
+    rgb = torch.tensor(bgr[:, :, ::-1].copy() / 255.0).permute(2, 0, 1).unsqueeze(0)
+    ref = torch.nn.functional.interpolate(rgb, (108, 192), mode="bicubic", align_corners=True)[0].float()
+    assert torch.equal(t, ref)
+    with pytest.raises(FileNotFoundError):
+        frames.list_frames(str(tmp_path / "missing"))
+
+
+def test_save_prediction_uint16_contract(tmp_path):
+    d = torch.rand(1, 1, 40, 64) * 80
+    coarse = torch.rand(1, 1, 20, 32)
+    out = frames.save_prediction(d, str(tmp_path / "o"), "f0", gray_scale=True, coarse=coarse, image_raw_shape=(40, 64))
+    u16 = cv2.imread(out["uint16"], cv2.IMREAD_UNCHANGED)
+    assert u16.dtype == np.uint16 and np.array_equal(u16, (d.squeeze().numpy() * 256).astype("uint16"))   # tester.py:90-91
+    assert cv2.imread(out["preview"]).shape[:2] == (40, 64) and cv2.imread(out["coarse"]).shape[:2] == (40, 64)
