@@ -102,6 +102,9 @@ int prv2_blend_finalize_canvas(const float* num_c, const float* m1, const float*
 int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* num_r,
                             const int32_t* starts, int n, const float* rmask, int rh, int rw, int H, int W,
                             float* out, float* out_cnt, prv2_stream_t stream);
+/* Test / A-B hook: on != 0 routes every blend entry point through the any-alignment generic kernels instead of the
+ * aligned fast paths (both produce the same bits; tests assert it). */
+int prv2_debug_blend_generic(int on);
 
 /* ------------------------------------------------------------------------------------------
  * (2) per-patch network: tcgen05 implicit-GEMM (linear layers AND convolutions)

@@ -68,6 +68,7 @@ SIGNATURES = {
     "prv2_blend_partial_raw": [_p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p],
     "prv2_blend_finalize_canvas": [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p],
     "prv2_blend_finalize_raw": [_p, _p, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p],
+    "prv2_debug_blend_generic": [_i],
     "prv2_umma_gemm": [_p, _p],
     "prv2_attention": [_p, _p, _i, _i, _i, _p, _p, _p],
     "prv2_layernorm": [_p, _i, _i, _p, _p, _f, _i, _p, _p, _i, _p],

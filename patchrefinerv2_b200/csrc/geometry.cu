@@ -4,6 +4,7 @@
 // CPU kernels do it (see oracle/pr_oracle.py np_* for the pinned restatements).
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace prv2 {
@@ -364,6 +365,102 @@ static int blend_threads(int Wc) {
   return cdiv(cdiv(groups, ctas), 32) * 32;
 }
 
+// Aligned fast path (pw, Wc and every stage's off_w multiples of 4 -- true for every tiling the reference produces):
+// a 4-pixel group then lies inside exactly one patch of a stage or outside all of them, so a thread's whole working
+// set is NS (mask float4, prediction float4) pairs.  All 2*NS loads are issued before the first dependent use
+// (predicated, no branches between them): one DRAM latency per thread instead of one per stage.
+template <int MODE, int NS>
+__global__ void __launch_bounds__(256) blend_canvas_fast_kernel(const float* __restrict__ preds, const uint8_t* __restrict__ own,
+                                                                const float* __restrict__ mask, int ph, int pw, StageTable st, int Hc,
+                                                                int Wc, unsigned magic_h, unsigned magic_w, float* __restrict__ avg_out,
+                                                                float* __restrict__ cnt_out, const float* __restrict__ num_in,
+                                                                const float* __restrict__ m1_in) {
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  if (x0 >= Wc) return;
+  const size_t o = (size_t)y * Wc + x0;
+  float4 ct[NS], pv[NS];
+  bool ok[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const prv2_grid_stage g = st.s[s];
+    const int yy = y - g.off_h, xx = x0 - g.off_w;
+    const int i = div_magic(max(yy, 0), magic_h), j = div_magic(max(xx, 0), magic_w);
+    const bool in = (s < st.n) && yy >= 0 && xx >= 0 && i < g.n_h && j < g.n_w;
+    const int ly = yy - i * ph, lx = xx - j * pw, pidx = g.first + i * g.n_w + j;
+    bool mine = in;
+    if (MODE == 1) mine = in && own[in ? pidx : 0] != 0;
+    if (MODE == 2) mine = false;
+    ct[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pv[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in && (MODE != 1 || mine)) ct[s] = __ldg(reinterpret_cast<const float4*>(mask + (size_t)ly * pw + lx));
+    if (mine) pv[s] = __ldcs(reinterpret_cast<const float4*>(preds + ((size_t)pidx * ph + ly) * pw + lx));
+    ok[s] = (MODE == 1) ? mine : in;
+  }
+  float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_c = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (MODE == 1) { acc_a = *reinterpret_cast<const float4*>(avg_out + o); acc_c = *reinterpret_cast<const float4*>(cnt_out + o); }
+  if (MODE == 2) { acc_a = __ldcs(reinterpret_cast<const float4*>(num_in + o)); acc_c = __ldcs(reinterpret_cast<const float4*>(m1_in + o)); }
+  float r_a[4], r_c[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float avg = 0.f, cnt = 0.f, num = (MODE == 2) ? (&acc_a.x)[k] : 0.f, m1 = (MODE == 2) ? (&acc_c.x)[k] : 0.f, cnt0 = 0.f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float c = (&ct[s].x)[k], p = (&pv[s].x)[k];
+      if (!ok[s]) continue;
+      if (MODE == 0) {
+        if (s == 0) { avg = p; cnt = c; }
+        else if (c > 0.f) ram_update(avg, cnt, p, c);
+      } else if (MODE == 1) {
+        if (s == 0) m1 = p;
+        else if (c > 0.f) num = __fadd_rn(num, __fmul_rn(p, c));
+      } else {
+        if (s == 0) { cnt = c; cnt0 = c; }
+        else if (c > 0.f) cnt = __fadd_rn(cnt, c);
+      }
+    }
+    if (MODE == 0) { r_a[k] = avg; r_c[k] = cnt; }
+    else if (MODE == 1) { r_a[k] = (&acc_a.x)[k] + num; r_c[k] = (&acc_c.x)[k] + m1; }
+    else { r_a[k] = (cnt > cnt0) ? __fdiv_rn(__fadd_rn(__fmul_rn(m1, cnt0), num), cnt) : m1; r_c[k] = cnt; }
+  }
+  if (MODE == 1) {
+    *reinterpret_cast<float4*>(avg_out + o) = make_float4(r_a[0], r_a[1], r_a[2], r_a[3]);
+    *reinterpret_cast<float4*>(cnt_out + o) = make_float4(r_c[0], r_c[1], r_c[2], r_c[3]);
+  } else {
+    __stcs(reinterpret_cast<float4*>(avg_out + o), make_float4(r_a[0], r_a[1], r_a[2], r_a[3]));
+    if (cnt_out) __stcs(reinterpret_cast<float4*>(cnt_out + o), make_float4(r_c[0], r_c[1], r_c[2], r_c[3]));
+  }
+}
+
+// test / A-B hook: route every blend entry point through the generic (any-alignment) kernels
+static int g_blend_generic = -1;
+static bool blend_generic_forced() {
+  if (g_blend_generic < 0) { const char* e = getenv("PRV2_BLEND_GENERIC"); g_blend_generic = (e && e[0] == '1') ? 1 : 0; }
+  return g_blend_generic == 1;
+}
+extern "C" int prv2_debug_blend_generic(int on) { g_blend_generic = on ? 1 : 0; return PRV2_OK; }
+
+static bool canvas_aligned(const StageTable& t, int pw, int Wc) {
+  if (blend_generic_forced() || (pw & 3) || (Wc & 3) || t.n > 4) return false;
+  for (int i = 0; i < t.n; ++i) if (t.s[i].off_w & 3) return false;
+  return true;
+}
+
+template <int MODE>
+static void launch_canvas(const float* preds, const uint8_t* own, const float* mask, int ph, int pw, const StageTable& t, int Hc, int Wc,
+                          float* a, float* b, const float* num_in, const float* m1_in, cudaStream_t stream) {
+  const int bt = blend_threads(Wc);
+  dim3 grid(cdiv(cdiv(Wc, 4), bt), Hc);
+  const unsigned mh = make_magic(ph), mw = make_magic(pw);
+  if (canvas_aligned(t, pw, Wc)) {
+    if (t.n == 1) blend_canvas_fast_kernel<MODE, 1><<<grid, bt, 0, stream>>>(preds, own, mask, ph, pw, t, Hc, Wc, mh, mw, a, b, num_in, m1_in);
+    else if (t.n == 2) blend_canvas_fast_kernel<MODE, 2><<<grid, bt, 0, stream>>>(preds, own, mask, ph, pw, t, Hc, Wc, mh, mw, a, b, num_in, m1_in);
+    else blend_canvas_fast_kernel<MODE, 4><<<grid, bt, 0, stream>>>(preds, own, mask, ph, pw, t, Hc, Wc, mh, mw, a, b, num_in, m1_in);
+  } else {
+    blend_canvas_kernel<MODE><<<grid, bt, 0, stream>>>(preds, own, mask, ph, pw, t, Hc, Wc, mh, mw, a, b, num_in, m1_in);
+  }
+}
+
 static int fill_stages(StageTable& t, const prv2_grid_stage* stages, int n) {
   if (!stages || n < 1 || n > PRV2_MAX_STAGES) return -1;
   t.n = n;
@@ -377,9 +474,7 @@ extern "C" int prv2_blend_canvas(const float* preds, const float* mask, int ph, 
   StageTable t;
   PRV2_CHECK_ARG(fill_stages(t, stages, n_stages) == 0, "prv2_blend_canvas: need 1..%d stages", PRV2_MAX_STAGES);
   PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535 && Wc <= 65535 && ph < 65536 && pw < 65536, "prv2_blend_canvas: bad shape");
-  const int bt = blend_threads(Wc);
-  dim3 grid(cdiv(cdiv(Wc, 4), bt), Hc);
-  blend_canvas_kernel<0><<<grid, bt, 0, (cudaStream_t)stream>>>(preds, nullptr, mask, ph, pw, t, Hc, Wc, make_magic(ph), make_magic(pw), avg, cnt, nullptr, nullptr);
+  launch_canvas<0>(preds, nullptr, mask, ph, pw, t, Hc, Wc, avg, cnt, nullptr, nullptr, (cudaStream_t)stream);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -391,9 +486,7 @@ extern "C" int prv2_blend_partial_canvas(const float* preds, const uint8_t* own,
   StageTable t;
   PRV2_CHECK_ARG(fill_stages(t, stages, n_stages) == 0, "prv2_blend_partial_canvas: need 1..%d stages", PRV2_MAX_STAGES);
   PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535, "prv2_blend_partial_canvas: bad shape");
-  const int bt = blend_threads(Wc);
-  dim3 grid(cdiv(cdiv(Wc, 4), bt), Hc);
-  blend_canvas_kernel<1><<<grid, bt, 0, (cudaStream_t)stream>>>(preds, own, mask, ph, pw, t, Hc, Wc, make_magic(ph), make_magic(pw), num_c, m1, nullptr, nullptr);
+  launch_canvas<1>(preds, own, mask, ph, pw, t, Hc, Wc, num_c, m1, nullptr, nullptr, (cudaStream_t)stream);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -405,9 +498,7 @@ extern "C" int prv2_blend_finalize_canvas(const float* num_c, const float* m1, c
   StageTable t;
   PRV2_CHECK_ARG(fill_stages(t, stages, n_stages) == 0, "prv2_blend_finalize_canvas: need 1..%d stages", PRV2_MAX_STAGES);
   PRV2_CHECK_ARG(ph > 0 && pw > 0 && Hc > 0 && Wc > 0 && Hc <= 65535, "prv2_blend_finalize_canvas: bad shape");
-  const int bt = blend_threads(Wc);
-  dim3 grid(cdiv(cdiv(Wc, 4), bt), Hc);
-  blend_canvas_kernel<2><<<grid, bt, 0, (cudaStream_t)stream>>>(nullptr, nullptr, mask, ph, pw, t, Hc, Wc, make_magic(ph), make_magic(pw), avg, cnt, num_c, m1);
+  launch_canvas<2>(nullptr, nullptr, mask, ph, pw, t, Hc, Wc, avg, cnt, num_c, m1, (cudaStream_t)stream);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -522,6 +613,218 @@ static RawScales raw_scales(int Hc, int Wc, int H, int W, int ph, int pw, int rh
   return s;
 }
 
+// Table-driven version of the rN stage (same CTA shape as blend_raw_kernel: one raw row per CTA, thread = 4 consecutive
+// pixels).  Everything that depends on the column only -- nearest column of the average canvas, bilinear tap (i0, l1) of
+// the count canvas, nearest column of a prediction for every in-patch x -- is read from small device tables that
+// prv2_blend_raw_* builds once per geometry (raw_tables_kernel), instead of being recomputed with int<->float conversions for
+// each of the H rows.  The arithmetic on pixel values is unchanged (same ops, same order) -> same bits as blend_raw_kernel.
+struct RawTables { const unsigned short* a_ix; const unsigned short* c_i0; const float* c_l1; const unsigned short* src_x; };
+
+__global__ void raw_tables_kernel(unsigned short* a_ix, unsigned short* c_i0, float* c_l1, unsigned short* src_x, int Wc, int W, int Wpad,
+                                  int pw, int rw, RawScales sc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Wpad) {
+    const int x = min(i, W - 1);
+    a_ix[i] = (unsigned short)nearest_src(x, sc.ns_x, Wc);
+    const BilinearTap tx = ac_tap(sc.bs_x, x, Wc);
+    c_i0[i] = (unsigned short)tx.i0;
+    c_l1[i] = tx.l1;
+  }
+  if (i < rw) src_x[i] = (unsigned short)nearest_src(i, sc.ps_x, pw);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) blend_raw_tab_kernel(const float* __restrict__ avg_c, const float* __restrict__ cnt_c, int Hc, int Wc,
+                                                            const float* __restrict__ preds, const uint8_t* __restrict__ own,
+                                                            const int32_t* __restrict__ starts, int n, int ph, int pw,
+                                                            const float* __restrict__ rmask, int rh, int rw, int H, int W,
+                                                            float* __restrict__ out, float* __restrict__ out_cnt,
+                                                            const float* __restrict__ num_in, RawScales sc, RawTables tb) {
+  __shared__ int s_x0[PRV2_MAX_RANDOM], s_prow[PRV2_MAX_RANDOM], s_mrow[PRV2_MAX_RANDOM];
+  __shared__ int s_n;
+  const int y = blockIdx.y;
+  if (threadIdx.x < 32) {
+    int m = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + threadIdx.x;
+      int y0 = 0, x0 = 0;
+      bool hit = false;
+      if (k < n) {
+        y0 = starts[k * 2 + 0]; x0 = starts[k * 2 + 1];
+        hit = (y >= y0 && y < y0 + rh) && (MODE != 1 || own[k]);
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = m + __popc(b & ((1u << threadIdx.x) - 1));
+        const int ly = y - y0;
+        s_x0[pos] = x0;
+        s_mrow[pos] = ly * rw;
+        s_prow[pos] = (MODE == 2) ? 0 : (k * ph + nearest_src(ly, sc.ps_y, ph)) * pw;    // baseline_pretrain.py:210 (nearest), row part
+      }
+      m += __popc(b);
+    }
+    if (threadIdx.x == 0) s_n = m;
+  }
+  // row-only resampling state (utils.py:42-43), uniform over the CTA
+  const float* arow = nullptr; const float* c_r0 = nullptr; const float* c_r1 = nullptr;
+  BilinearTap ty; ty.i0 = ty.i1 = 0; ty.l0 = ty.l1 = 0.f;
+  if (MODE != 1) {
+    arow = avg_c + (size_t)nearest_src(y, sc.ns_y, Hc) * Wc;
+    ty = ac_tap(sc.bs_y, y, Hc);
+    c_r0 = cnt_c + (size_t)ty.i0 * Wc;
+    c_r1 = cnt_c + (size_t)ty.i1 * Wc;
+  }
+  __syncthreads();
+  const int m = s_n;
+  const bool vec = (W & 3) == 0;
+  for (int xb = threadIdx.x * 4; xb < W; xb += blockDim.x * 4) {
+    const size_t o = (size_t)y * W + xb;
+    const bool full = xb + 3 < W;
+    float avg[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f}, num[4] = {0.f, 0.f, 0.f, 0.f}, c0[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE != 1) {
+      // tables are padded to a multiple of 4 columns (clamped to W-1), so the vector loads are always in bounds
+      const uint2 ta = __ldg(reinterpret_cast<const uint2*>(tb.a_ix + xb));
+      const uint2 ti = __ldg(reinterpret_cast<const uint2*>(tb.c_i0 + xb));
+      const float4 tl = __ldg(reinterpret_cast<const float4*>(tb.c_l1 + xb));
+      const int a_ix[4] = {(int)(ta.x & 0xffffu), (int)(ta.x >> 16), (int)(ta.y & 0xffffu), (int)(ta.y >> 16)};
+      const int i0[4] = {(int)(ti.x & 0xffffu), (int)(ti.x >> 16), (int)(ti.y & 0xffffu), (int)(ti.y >> 16)};
+      float va[4], v00[4], v01[4], v10[4], v11[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i1 = i0[q] + (i0[q] < Wc - 1 ? 1 : 0);
+        va[q] = __ldg(arow + a_ix[q]);
+        v00[q] = __ldg(c_r0 + i0[q]); v01[q] = __ldg(c_r0 + i1);
+        v10[q] = __ldg(c_r1 + i0[q]); v11[q] = __ldg(c_r1 + i1);
+      }
+      float4 nin = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 2) {
+        if (full && vec) nin = __ldcs(reinterpret_cast<const float4*>(num_in + o));
+        else { for (int q = 0; q < 4; ++q) if (xb + q < W) (&nin.x)[q] = num_in[o + q]; }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        BilinearTap tx;
+        tx.l1 = (&tl.x)[q]; tx.l0 = __fsub_rn(1.0f, tx.l1);
+        avg[q] = va[q];
+        cnt[q] = ac_blend(ty, tx, v00[q], v01[q], v10[q], v11[q]);
+        c0[q] = cnt[q];
+        num[q] = (&nin.x)[q];
+      }
+    }
+    for (int i = 0; i < m; ++i) {
+      const int l0 = xb - s_x0[i];
+      if (l0 + 3 < 0 || l0 >= rw) continue;                    // group entirely outside this patch
+      const float* mrow = rmask + s_mrow[i];
+      const float* prow = preds + s_prow[i];
+      if (l0 >= 0 && l0 + 3 < rw && full) {
+        float ct[4], p[4];
+        int sx[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ct[q] = __ldg(mrow + l0 + q); sx[q] = (MODE != 2) ? (int)__ldg(tb.src_x + l0 + q) : 0; }
+        if (MODE != 2) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) p[q] = __ldg(prow + sx[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (!(ct[q] > 0.f)) continue;
+          if (MODE == 2) cnt[q] = __fadd_rn(cnt[q], ct[q]);
+          else if (MODE == 0) ram_update(avg[q], cnt[q], p[q], ct[q]);
+          else num[q] = __fadd_rn(num[q], __fmul_rn(p[q], ct[q]));
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int lx = l0 + q;
+          if (lx < 0 || lx >= rw || xb + q >= W) continue;
+          const float ct = __ldg(mrow + lx);
+          if (!(ct > 0.f)) continue;
+          if (MODE == 2) { cnt[q] = __fadd_rn(cnt[q], ct); continue; }
+          const float p = __ldg(prow + (int)__ldg(tb.src_x + lx));
+          if (MODE == 0) ram_update(avg[q], cnt[q], p, ct);
+          else num[q] = __fadd_rn(num[q], __fmul_rn(p, ct));
+        }
+      }
+    }
+    float r_a[4], r_c[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (MODE == 0) { r_a[q] = avg[q]; r_c[q] = cnt[q]; }
+      else if (MODE == 1) { r_a[q] = num[q]; r_c[q] = 0.f; }
+      else { r_a[q] = (cnt[q] > c0[q]) ? __fdiv_rn(__fadd_rn(__fmul_rn(avg[q], c0[q]), num[q]), cnt[q]) : avg[q]; r_c[q] = cnt[q]; }
+    }
+    if (MODE == 1) {
+      for (int q = 0; q < 4 && xb + q < W; ++q) out[o + q] += r_a[q];
+    } else if (full && vec) {
+      __stcs(reinterpret_cast<float4*>(out + o), make_float4(r_a[0], r_a[1], r_a[2], r_a[3]));
+      if (out_cnt) __stcs(reinterpret_cast<float4*>(out_cnt + o), make_float4(r_c[0], r_c[1], r_c[2], r_c[3]));
+    } else {
+      for (int q = 0; q < 4 && xb + q < W; ++q) { out[o + q] = r_a[q]; if (out_cnt) out_cnt[o + q] = r_c[q]; }
+    }
+  }
+}
+
+// Column tables live in a small per-geometry device cache owned by the library (<= 64 KB each, built by one tiny kernel the
+// first time a geometry is seen on a device; an event orders later use from other streams after the build).
+struct RawTableEntry {
+  int dev, Wc, W, pw, rw, used;
+  void* mem;
+  cudaEvent_t ready;
+  RawTables tb;
+};
+#define PRV2_RAW_TABLE_SLOTS 64
+static RawTableEntry g_raw_tables[PRV2_RAW_TABLE_SLOTS];
+
+static bool raw_tables_get(int Wc, int W, int pw, int rw, const RawScales& sc, cudaStream_t stream, RawTables* tb) {
+  if (Wc > 65535 || pw > 65535 || W <= 0) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  RawTableEntry* slot = nullptr;
+  for (int i = 0; i < PRV2_RAW_TABLE_SLOTS; ++i) {
+    RawTableEntry& e = g_raw_tables[i];
+    if (e.used && e.dev == dev && e.Wc == Wc && e.W == W && e.pw == pw && e.rw == rw) {
+      if (cudaStreamWaitEvent(stream, e.ready, 0) != cudaSuccess) return false;
+      *tb = e.tb;
+      return true;
+    }
+    if (!e.used && !slot) slot = &e;
+  }
+  if (!slot) return false;                                      // cache full: the caller falls back to the generic kernel
+  const int Wpad = (W + 3) & ~3, rwpad = (rw + 7) & ~7;
+  const size_t bytes = (size_t)Wpad * (2 + 2 + 4) + (size_t)rwpad * 2 + 64;
+  void* mem = nullptr;
+  if (cudaMalloc(&mem, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+  char* base = (char*)mem;
+  float* c_l1 = (float*)base;                                   // 16-byte aligned first
+  unsigned short* a_ix = (unsigned short*)(base + (size_t)Wpad * 4);
+  unsigned short* c_i0 = a_ix + Wpad;
+  unsigned short* src_x = c_i0 + Wpad;
+  const int nthr = Wpad > rw ? Wpad : rw;
+  raw_tables_kernel<<<cdiv(nthr, 256), 256, 0, stream>>>(a_ix, c_i0, c_l1, src_x, Wc, W, Wpad, pw, rw, sc);
+  cudaEvent_t ev;
+  if (cudaGetLastError() != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaFree(mem); return false; }
+  cudaEventRecord(ev, stream);
+  slot->dev = dev; slot->Wc = Wc; slot->W = W; slot->pw = pw; slot->rw = rw; slot->mem = mem; slot->ready = ev;
+  slot->tb.a_ix = a_ix; slot->tb.c_i0 = c_i0; slot->tb.c_l1 = c_l1; slot->tb.src_x = src_x;
+  slot->used = 1;
+  *tb = slot->tb;
+  return true;
+}
+
+template <int MODE>
+static void launch_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* preds, const uint8_t* own, const int32_t* starts,
+                       int n, int ph, int pw, const float* rmask, int rh, int rw, int H, int W, float* out, float* out_cnt,
+                       const float* num_in, const RawScales& sc, cudaStream_t stream) {
+  dim3 grid(1, H);
+  RawTables tb;
+  if (!blend_generic_forced() && raw_tables_get(Wc, W, pw, rw, sc, stream, &tb)) {
+    blend_raw_tab_kernel<MODE><<<grid, 256, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W, out, out_cnt,
+                                                         num_in, sc, tb);
+  } else {
+    blend_raw_kernel<MODE><<<grid, 256, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W, out, out_cnt, num_in, sc);
+  }
+}
+
 static int check_raw(const char* fn, int n, int ph, int pw, int rh, int rw, int H, int W) {
   if (!(n >= 0 && n <= PRV2_MAX_RANDOM)) { set_error("%s: 0 <= n <= %d required (got %d)", fn, PRV2_MAX_RANDOM, n); return PRV2_EINVAL; }
   if (!(ph > 0 && pw > 0 && rh > 0 && rw > 0 && H > 0 && W > 0 && H <= 65535)) { set_error("%s: bad shape", fn); return PRV2_EINVAL; }
@@ -535,9 +838,8 @@ extern "C" int prv2_blend_raw(const float* avg_c, const float* cnt_c, int Hc, in
   PRV2_CHECK_ARG(n == 0 || (preds && starts && rmask), "prv2_blend_raw: null patch inputs");
   int rc = check_raw("prv2_blend_raw", n, ph, pw, rh, rw, H, W);
   if (rc) return rc;
-  dim3 grid(1, H);
-  blend_raw_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(avg_c, cnt_c, Hc, Wc, preds, nullptr, starts, n, ph, pw, rmask, rh, rw, H, W,
-                                                              out, out_cnt, nullptr, raw_scales(Hc, Wc, H, W, ph, pw, rh, rw));
+  launch_raw<0>(avg_c, cnt_c, Hc, Wc, preds, nullptr, starts, n, ph, pw, rmask, rh, rw, H, W, out, out_cnt, nullptr,
+                raw_scales(Hc, Wc, H, W, ph, pw, rh, rw), (cudaStream_t)stream);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -548,9 +850,8 @@ extern "C" int prv2_blend_partial_raw(const float* preds, const uint8_t* own, co
   int rc = check_raw("prv2_blend_partial_raw", n, ph, pw, rh, rw, H, W);
   if (rc) return rc;
   if (n == 0) return PRV2_OK;
-  dim3 grid(1, H);
-  blend_raw_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, 1, 1, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W,
-                                                              num_r, nullptr, nullptr, raw_scales(1, 1, H, W, ph, pw, rh, rw));
+  launch_raw<1>(nullptr, nullptr, 1, 1, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W, num_r, nullptr, nullptr,
+                raw_scales(1, 1, H, W, ph, pw, rh, rw), (cudaStream_t)stream);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -562,9 +863,8 @@ extern "C" int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, i
   PRV2_CHECK_ARG(n == 0 || (starts && rmask), "prv2_blend_finalize_raw: null patch inputs");
   int rc = check_raw("prv2_blend_finalize_raw", n, 1, 1, rh, rw, H, W);
   if (rc) return rc;
-  dim3 grid(1, H);
-  blend_raw_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(avg_c, cnt_c, Hc, Wc, nullptr, nullptr, starts, n, 1, 1, rmask, rh, rw, H, W,
-                                                              out, out_cnt, num_r, raw_scales(Hc, Wc, H, W, 1, 1, rh, rw));
+  launch_raw<2>(avg_c, cnt_c, Hc, Wc, nullptr, nullptr, starts, n, 1, 1, rmask, rh, rw, H, W, out, out_cnt, num_r,
+                raw_scales(Hc, Wc, H, W, 1, 1, rh, rw), (cudaStream_t)stream);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

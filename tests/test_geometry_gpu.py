@@ -172,3 +172,46 @@ def test_blend_rejects_bad_arguments(dev):
     out, oc = ops.blend_raw(avg, cnt, None, None, None, 4, 4, 3, 3, 6, 6)
     want = torch.nn.functional.interpolate(avg.cpu()[None, None], (6, 6))[0, 0]
     assert torch.equal(out.cpu(), want)
+
+
+def _set_generic(on):
+    from patchrefinerv2_b200 import _lib
+    _lib.call("prv2_debug_blend_generic", 1 if on else 0)
+
+
+@pytest.mark.parametrize("case", [
+    # (shape, raw, split, mode, pn): aligned fast paths vs the generic kernels -- identical bits required
+    ((448, 448), (2160, 3840), (4, 4), "r32", 4),
+    ((224, 224), (432, 768), (2, 2), "r4", 2),
+    ((384, 512), (2160, 3840), (4, 4), "r64", 4),          # two ballot rounds per row list
+    ((224, 224), (434, 774), (2, 2), "r6", 2),             # raw width not a multiple of 4 (ragged last group), odd patch size
+])
+def test_blend_fast_paths_equal_generic_kernels(dev, case):
+    from patchrefinerv2_b200 import ops
+    shape, raw, split, mode, pn = case
+    tc, preds, grid, n_reg, mask, rmask, starts = _blend_inputs(dev, shape, mode, pn, raw, split)
+    preds = torch.rand_like(preds) * 10
+    Hc, Wc = tc["patch_reensemble_shape"]
+    H, W = tc["image_raw_shape"]
+    rh, rw = tc["patch_raw_shape"]
+    own = torch.from_numpy((np.arange(preds.shape[0]) % 3 == 1).astype(np.uint8)).to(dev)
+    outs = []
+    try:
+        for generic in (True, False):
+            _set_generic(generic)
+            a, c = ops.blend_canvas(preds[:n_reg], mask, grid, Hc, Wc)
+            a_r, c_r = ops.blend_raw(a, c, preds[n_reg:], starts, rmask, shape[0], shape[1], rh, rw, H, W)
+            packed = torch.zeros(2 * Hc * Wc + H * W, device=dev)
+            num_c, m1, num_r = packed[:Hc * Wc].view(Hc, Wc), packed[Hc * Wc:2 * Hc * Wc].view(Hc, Wc), packed[2 * Hc * Wc:].view(H, W)
+            ops.blend_partial_canvas(preds[:n_reg], own[:n_reg].contiguous(), mask, grid, Hc, Wc, num_c, m1)
+            ops.blend_partial_raw(preds[n_reg:], own[n_reg:].contiguous(), starts, rmask, shape[0], shape[1], H, W, num_r)
+            fa, fc = ops.blend_finalize_canvas(num_c, m1, mask, grid, Hc, Wc)
+            fr, fcr = ops.blend_finalize_raw(fa, fc, num_r, starts, rmask, rh, rw, H, W)
+            pure, pure_c = ops.blend_raw(a, c, None, None, None, shape[0], shape[1], rh, rw, H, W)     # n = 0: resize only
+            outs.append([t.clone() for t in (a, c, a_r, c_r, packed, fa, fc, fr, fcr, pure, pure_c)])
+    finally:
+        _set_generic(False)
+    names = "avg cnt avg_raw cnt_raw packed fin_avg fin_cnt fin_raw fin_cnt_raw resize_avg resize_cnt".split()
+    for nm, g, f in zip(names, outs[0], outs[1]):
+        assert torch.equal(g, f), nm
+    assert torch.equal(outs[1][1], outs[1][6]) and torch.equal(outs[1][3], outs[1][8])          # count maps: sharded == sequential, bit-exact
