@@ -134,9 +134,10 @@ typedef struct {
 #define PRV2_ACT_RELU 1
 #define PRV2_ACT_GELU 2       /* exact erf GELU (torch.nn.GELU default)                 */
 #define PRV2_ACT_GELU_TANH 3  /* tanh-form GELU (|diff| <= 1e-3 abs vs erf); one-pass bf16 mode only */
+#define PRV2_ACT_SIGMOID_GATE 4 /* EPI_STORE only: out = res * sigmoid(acc+bias)  (GatedConvUnit, bi_directional_fusion_model.py:70-78) */
 
 #define PRV2_EPI_STORE 0      /* act(acc+bias) [+ residual act] -> out (and optional relu copy) */
-#define PRV2_EPI_LN_GELU 1    /* channels-first LayerNorm over Cout then GELU (convs.py:21-29,64-75); act = GELU or GELU_TANH */
+#define PRV2_EPI_LN_GELU 1    /* channels-first LayerNorm over Cout of (acc+bias), then act = GELU | GELU_TANH (convs.py:21-29,64-75) | RELU (GatedConvUnit.fusion_conv) */
 #define PRV2_EPI_RESID_F32 2  /* x_f32[m,n] += gamma[n]*(acc+bias[n])  (block.py:105-106, layer_scale.py:27) */
 #define PRV2_EPI_F32 3        /* out_f32[m,n] = acc+bias                                 */
 #define PRV2_EPI_SHUFFLE 4    /* ConvTranspose2d k==stride: n=(ky,kx,co) scattered to [N,H*k,W*k,Cout] (dpt.py:62-73) */
@@ -187,6 +188,10 @@ int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, int B, int 
  * is compacted (block.py:56,68; dinov2.py:309-312). */
 int prv2_layernorm(const float* x, int rows, int D, const float* w, const float* b, float eps,
                    int drop_period, prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
+/* Channels-first LayerNorm + exact GELU of a conv output held as fp32 rows [pixels, D] (SingleConvCNNLN, convs.py:64-75) for
+ * channel counts the GEMM's fused LN epilogue cannot hold in one N tile (D > 256; BiDirectionalFusion's 512-channel level). */
+int prv2_layernorm_gelu(const float* x, int rows, int D, const float* w, const float* b, float eps,
+                        prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
 
 /* dpt.py:183 + patch_embed.py:69-82 im2col: crops [B,3,H,W] fp32 in [0,1] -> (x-mean)/std ->
  * rows (b,ty,tx), cols c*196+ky*14+kx, zero padded to Kp columns. */

@@ -152,9 +152,39 @@ def geom(ph, pw):
         print("geom", ph, pw, mode, dn.shape, float(dn.min()), float(dn.max()))
 
 
+#: BiDirectionalFusion fixture (V2 family, SURVEY.md row a9'): the reference module itself on seeded stand-in features
+BIFUSION = dict(coarse_chl=[32, 256, 256, 256, 256, 256], fine_chl=[32, 32, 64, 96, 960],
+                fine_chl_after_coarse2fine=[32, 256, 256, 256, 256, 256], temp_chl=[32, 64, 64, 128, 256, 512], dec_chl=[512, 256, 128, 64, 32])
+BIFUSION_SIZES_C = [(64, 64), (36, 36), (18, 18), (9, 9), (5, 5), (3, 3)]      # coarse ROI maps (resized to the fine sizes inside)
+BIFUSION_SIZES_F = [(64, 64), (32, 32), (16, 16), (8, 8), (4, 4), (2, 2)]
+BIFUSION_TYPES = ("coarse-gated", "coarse-fusion", "self-agg")
+
+
+def bifusion():
+    """bifusion_<type>.npz: output of the reference's BiDirectionalFusion (bi_directional_fusion_model.py) on
+    oracle.synthetic_fusion_inputs(seed 3), weights init_bidirectional_fusion_state_dict(seed 5)."""
+    ref_shim.install()
+    from estimator.models.blocks.bi_directional_fusion_model import BiDirectionalFusion
+    for t in BIFUSION_TYPES:
+        m = BiDirectionalFusion(encoder_name="golden", coarse2fine_type=t, **{k: list(v) for k, v in BIFUSION.items()}).eval()
+        sd = O.init_bidirectional_fusion_state_dict(seed=5, coarse2fine_type=t, **BIFUSION)
+        m.load_state_dict(sd, strict=True)
+        c, f, p1, p2 = O.synthetic_fusion_inputs(BIFUSION["coarse_chl"], BIFUSION["fine_chl"], BIFUSION_SIZES_C, BIFUSION_SIZES_F, 2, 3)
+        with torch.no_grad():
+            out = m(c_feat=[x.clone() for x in c], f_feat=[x.clone() for x in f], pred1=p1, pred2=p2, update_base=p1)
+            off = m(c_feat=[x.clone() for x in c], f_feat=[x.clone() for x in f], pred1=p1, pred2=p2, update_base=None)
+        np.savez_compressed(os.path.join(OUT, f"bifusion_{t}.npz"), coarse2fine_type=t, depth=out.numpy(), offset=off.numpy(),
+                            sd_sha=sd_digest(sd), pred1_sha=O.sha256_f32(p1.numpy()), keys=np.array(sorted(m.state_dict().keys())))
+        print("bifusion", t, tuple(out.shape), float(out.mean()), float(off.std()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if "--bifusion-only" in sys.argv:
+        bifusion()
+        sys.exit(0)
+    bifusion()
     tiny()
     geom(448, 448)
     geom(384, 512)

@@ -383,6 +383,165 @@ def fusion_unet(sd: Dict[str, Tensor], pre: str, c_feat: List[Tensor], f_feat: L
 
 
 # ---------------------------------------------------------------------------------------------
+# BiDirectionalFusion -- the V2 ("PatchRefinerPlus") fusion model
+# (estimator/models/blocks/bi_directional_fusion_model.py ; SURVEY.md row a9')
+# ---------------------------------------------------------------------------------------------
+
+#: coarse2fine_type -> (C2FModule fusion, gate) (bi_directional_fusion_model.py:366-374)
+C2F_TYPES = {"self-agg": (False, False), "coarse-gated": (True, True), "coarse-fusion": (True, False)}
+C2F_FEATURES = 256            # C2FModule default `features` (:149); no config overrides it
+
+
+def init_bidirectional_fusion_state_dict(coarse_chl, fine_chl, fine_chl_after_coarse2fine, temp_chl, dec_chl, seed: int,
+                                         coarse2fine_type: str = "coarse-gated", features: int = C2F_FEATURES) -> Dict[str, Tensor]:
+    """Random BiDirectionalFusion weights with the reference's state-dict keys (glb_att=False, coarse2fine=True;
+    bi_directional_fusion_model.py:285-374, C2FModule :148-184, GatedFusionBlock :84-116, GatedConvUnit :24-54)."""
+    fusion, _gate = C2F_TYPES[coarse2fine_type]
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    for idx, (cc, fc, tc) in enumerate(zip(coarse_chl, fine_chl_after_coarse2fine, temp_chl)):
+        sd[f"fusion_layers_1.{idx}.single_conv.0.weight"] = _conv_w(g, tc, cc + fc, 3, gain=1.7)
+        sd[f"fusion_layers_1.{idx}.single_conv.1.weight"] = 1.0 + _vec(g, tc, 0.1)
+        sd[f"fusion_layers_1.{idx}.single_conv.1.bias"] = _vec(g, tc, 0.05)
+        sd[f"fusion_layers_2.{idx}.single_conv.0.weight"] = _conv_w(g, tc, tc + 2, 3, gain=1.7)
+        sd[f"fusion_layers_2.{idx}.single_conv.1.weight"] = 1.0 + _vec(g, tc, 0.1)
+        sd[f"fusion_layers_2.{idx}.single_conv.1.bias"] = _vec(g, tc, 0.05)
+    rev = list(temp_chl)[::-1]
+    _chl = rev[0]
+    for i, (tc, dc) in enumerate(zip(rev[1:], dec_chl)):
+        cin = tc + _chl + 2
+        sd[f"f2r_agg.{i}.conv.double_conv.0.weight"] = _conv_w(g, cin, cin, 3, gain=1.7)
+        sd[f"f2r_agg.{i}.conv.double_conv.2.weight"] = _conv_w(g, dc, cin, 3, gain=1.7)
+        _chl = dc
+    sd["final_conv.weight"] = _conv_w(g, 1, dec_chl[-1] if len(dec_chl) else _chl, 3, gain=6.0)
+
+    def unit(pre, feat):
+        sd[pre + "conv.weight"] = _conv_w(g, feat, feat, 3)
+        sd[pre + "conv.bias"] = _vec(g, feat, 0.05)
+        if fusion:
+            sd[pre + "fusion_conv.0.weight"] = _conv_w(g, feat, 2 * feat, 3, gain=1.7)
+            sd[pre + "fusion_conv.0.bias"] = _vec(g, feat, 0.05)
+            sd[pre + "fusion_conv.1.weight"] = 1.0 + _vec(g, feat, 0.1)
+            sd[pre + "fusion_conv.1.bias"] = _vec(g, feat, 0.05)
+            sd[pre + "fusion_conv.3.weight"] = _conv_w(g, feat, feat, 1, gain=2.0)
+
+    def block(pre, feat):
+        sd[pre + "out_conv.weight"] = _conv_w(g, feat, feat, 1)
+        sd[pre + "out_conv.bias"] = _vec(g, feat, 0.05)
+        unit(pre + "GateresConfUnit1.", feat)
+        unit(pre + "GateresConfUnit2.", feat)
+
+    s = "c2f.scratch."
+    for i, fc in enumerate(fine_chl):
+        sd[f"{s}layer{i + 1}_rn.weight"] = _conv_w(g, features, fc, 3)
+    for i in range(1, 6):
+        block(f"{s}refinenet{i}.", features)
+    h2 = coarse_chl[0]
+    sd[s + "output_conv1.weight"] = _conv_w(g, features // 2, features, 3)
+    sd[s + "output_conv1.bias"] = _vec(g, features // 2, 0.05)
+    sd[s + "output_conv2.0.weight"] = _conv_w(g, h2, features // 2, 3, gain=1.7)
+    sd[s + "output_conv2.0.bias"] = _vec(g, h2, 0.05)
+    block(s + "output_conv2_fusion.", h2)
+    sd[s + "output_conv3.0.weight"] = 1.0 + _conv_w(g, 1, h2, 1)       # nn.init.normal_(mean=1.0) (:181)
+    sd[s + "output_conv3.0.bias"] = torch.zeros(1)
+    return sd
+
+
+def _gated_conv_unit(sd, pre, x, c_feat, fusion: bool, gate: bool):
+    """GatedConvUnit.forward (bi_directional_fusion_model.py:56-82)."""
+    out = F.relu(x)
+    out = F.conv2d(out, sd[pre + "conv.weight"], sd[pre + "conv.bias"], padding=1)
+    out = out + x
+    if fusion:
+        fused = torch.cat([out, c_feat], dim=1)
+        fused = F.conv2d(fused, sd[pre + "fusion_conv.0.weight"], sd[pre + "fusion_conv.0.bias"], padding=1)
+        fused = F.relu(_ln_cf(fused, sd[pre + "fusion_conv.1.weight"], sd[pre + "fusion_conv.1.bias"]))
+        fused = F.conv2d(fused, sd[pre + "fusion_conv.3.weight"])
+        out = out * torch.sigmoid(fused) if gate else fused
+    return out
+
+
+def _gated_fusion_block(sd, pre, xs, size, coarse_feat, fusion: bool, gate: bool, upscale: bool = True):
+    """GatedFusionBlock.forward (bi_directional_fusion_model.py:116-146)."""
+    out = xs[0]
+    if len(xs) == 2:
+        out = out + _gated_conv_unit(sd, pre + "GateresConfUnit1.", xs[1], coarse_feat, fusion, gate)
+    out = _gated_conv_unit(sd, pre + "GateresConfUnit2.", out, coarse_feat, fusion, gate)
+    if upscale:
+        if size is None:
+            out = F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
+        else:
+            out = F.interpolate(out, size=tuple(size), mode="bilinear", align_corners=True)
+    return F.conv2d(out, sd[pre + "out_conv.weight"], sd[pre + "out_conv.bias"])
+
+
+def c2f_module(sd, pre, fine_features: List[Tensor], coarse_features: List[Tensor], fusion: bool, gate: bool):
+    """C2FModule.forward (bi_directional_fusion_model.py:184-208).  fine_features: 5 maps, finest first;
+    coarse_features: 6 maps, finest first.  Returns ([layer_5_rn, path_5, path_4, path_3, path_2, last_feat], depth)."""
+    s = pre + "scratch."
+    rn = [F.conv2d(f, sd[f"{s}layer{i + 1}_rn.weight"], padding=1) for i, f in enumerate(fine_features)]
+    fb = lambda i, xs, size, cf: _gated_fusion_block(sd, f"{s}refinenet{i}.", xs, size, cf, fusion, gate)
+    path_5 = fb(5, [rn[4]], rn[3].shape[2:], coarse_features[5])
+    path_4 = fb(4, [path_5, rn[3]], rn[2].shape[2:], coarse_features[4])
+    path_3 = fb(3, [path_4, rn[2]], rn[1].shape[2:], coarse_features[3])
+    path_2 = fb(2, [path_3, rn[1]], rn[0].shape[2:], coarse_features[2])
+    path_1 = fb(1, [path_2, rn[0]], None, coarse_features[1])
+    out = F.conv2d(path_1, sd[s + "output_conv1.weight"], sd[s + "output_conv1.bias"], padding=1)
+    last = F.relu(F.conv2d(out, sd[s + "output_conv2.0.weight"], sd[s + "output_conv2.0.bias"], padding=1))
+    last = _gated_fusion_block(sd, s + "output_conv2_fusion.", [last], None, coarse_features[0], fusion, gate, upscale=False)
+    out = F.conv2d(last, sd[s + "output_conv3.0.weight"], sd[s + "output_conv3.0.bias"])
+    return [rn[4], path_5, path_4, path_3, path_2, last], out
+
+
+def bidirectional_fusion(sd: Dict[str, Tensor], pre: str, c_feat: List[Tensor], f_feat: List[Tensor], pred1: Tensor, pred2: Tensor,
+                         update_base: Optional[Tensor], coarse2fine_type: str = "coarse-gated", trace: Optional[dict] = None) -> Tensor:
+    """BiDirectionalFusion.forward (bi_directional_fusion_model.py:379-446) with glb_att=False, coarse2fine=True.
+    c_feat / f_feat: 6 maps each, finest first (patchrefinerplus.py:318-326 reverses them); ``pred2`` is replaced by the
+    C2F module's depth (:409-414), exactly as the reference does."""
+    fusion, gate = C2F_TYPES[coarse2fine_type]
+    c_feat, f_feat = list(c_feat), list(f_feat)
+    if tuple(c_feat[-1].shape[-2:]) != tuple(f_feat[-1].shape[-2:]):
+        c_feat = [_bil(c, f.shape[-2:]) for c, f in zip(c_feat, f_feat)]                       # :392-395
+    feats, out_depth = c2f_module(sd, pre + "c2f.", f_feat[1:], c_feat, fusion, gate)
+    f_feat, pred2 = feats[::-1], out_depth
+    if trace is not None:
+        trace["c2f_feats"] = [t.clone() for t in f_feat]
+        trace["c2f_depth"] = out_depth.clone()
+    temp = []
+    for idx, (c, f) in enumerate(zip(c_feat, f_feat)):
+        f = _single_conv_ln(sd, f"{pre}fusion_layers_1.{idx}.", torch.cat([c, f], dim=1))
+        p1 = _bil(pred1, f.shape[-2:])
+        p2 = _bil(pred2, f.shape[-2:])
+        temp.append(_single_conv_ln(sd, f"{pre}fusion_layers_2.{idx}.", torch.cat([f, p1, p2], dim=1)))
+    if trace is not None:
+        trace["fusion_enc"] = [t.clone() for t in temp]
+    dec = temp[0]
+    temp = temp[::-1]
+    _feat = temp[0]
+    for i, feat in enumerate(temp[1:]):
+        x = torch.cat([_bil(_feat, feat.shape[-2:]), feat, _bil(pred1, feat.shape[-2:]), _bil(pred2, feat.shape[-2:])], dim=1)
+        x = F.gelu(F.conv2d(x, sd[f"{pre}f2r_agg.{i}.conv.double_conv.0.weight"], padding=1))
+        x = F.gelu(F.conv2d(x, sd[f"{pre}f2r_agg.{i}.conv.double_conv.2.weight"], padding=1))
+        dec = _feat = x
+    off = F.conv2d(dec, sd[pre + "final_conv.weight"], padding=1)
+    if update_base is not None:
+        return torch.clamp(update_base + off, min=0)
+    return off
+
+
+def synthetic_fusion_inputs(coarse_chl, fine_chl, sizes_c, sizes_f, B: int, seed: int):
+    """Seeded stand-ins for the tensors BiDirectionalFusion consumes: ROI-cropped coarse features, the light-weight
+    encoder's features (its timm arithmetic is not available offline: parity of the ENCODER is unpinned, the fusion
+    model is pinned on these inputs), the ROI coarse depth and the (ignored, see :409-414) refiner depth."""
+    g = torch.Generator().manual_seed(seed)
+    c = [torch.randn(B, ch, *sz, generator=g) for ch, sz in zip(coarse_chl, sizes_c)]
+    f = [torch.relu(torch.randn(B, ch, *sz, generator=g)) for ch, sz in zip([fine_chl[0]] + list(fine_chl), sizes_f)]
+    p1 = torch.rand(B, 1, *sizes_f[0], generator=g) * 10
+    p2 = torch.zeros(B, 1, *sizes_f[0])
+    return c, f, p1, p2
+
+
+# ---------------------------------------------------------------------------------------------
 # tiling geometry, masks, running average  (baseline_pretrain.py ; models/utils.py)
 # ---------------------------------------------------------------------------------------------
 

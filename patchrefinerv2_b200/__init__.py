@@ -2,5 +2,6 @@
 high-resolution inference hot path behind the reference's estimator-model API."""
 from .registry import MODELS, build_model  # noqa: F401
 from .model import PatchRefiner  # noqa: F401
+from .bifusion import BiDirectionalFusion  # noqa: F401
 
-__all__ = ["MODELS", "build_model", "PatchRefiner"]
+__all__ = ["MODELS", "build_model", "PatchRefiner", "BiDirectionalFusion"]

@@ -13,7 +13,7 @@ MAX_SRC = 12
 MAX_SEG = 128
 
 EPI_STORE, EPI_LN_GELU, EPI_RESID_F32, EPI_F32, EPI_SHUFFLE, EPI_HEAD = range(6)
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_TANH = range(4)
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_TANH, ACT_SIGMOID_GATE = range(5)
 
 
 class Prv2Error(RuntimeError):
@@ -72,6 +72,7 @@ SIGNATURES = {
     "prv2_umma_gemm": [_p, _p],
     "prv2_attention": [_p, _p, _i, _i, _i, _p, _p, _p],
     "prv2_layernorm": [_p, _i, _i, _p, _p, _f, _i, _p, _p, _i, _p],
+    "prv2_layernorm_gelu": [_p, _i, _i, _p, _p, _f, _p, _p, _i, _p],
     "prv2_patchify": [_p, _i, _i, _i, _p, _p, _i, _p],
     "prv2_assemble_tokens": [_p, _p, _p, _i, _i, _i, _p, _p],
     "prv2_resize_bilinear_act": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p],

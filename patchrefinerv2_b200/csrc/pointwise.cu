@@ -32,7 +32,7 @@ __device__ __forceinline__ void act_store4(bf16* hi, bf16* lo, size_t i, const f
 // warp per row, row kept in registers (D <= 1024), two-pass mean / variance.
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int rows, int D, const float* __restrict__ w,
                                                         const float* __restrict__ b, float eps, int drop_period, bf16* __restrict__ oh,
-                                                        bf16* __restrict__ ol, int out_cs) {
+                                                        bf16* __restrict__ ol, int out_cs, int gelu) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       const float4 ww = *reinterpret_cast<const float4*>(w + c0), bb = *reinterpret_cast<const float4*>(b + c0);
       float o[4] = {(v[j].x - mean) * rstd * ww.x + bb.x, (v[j].y - mean) * rstd * ww.y + bb.y, (v[j].z - mean) * rstd * ww.z + bb.z,
                     (v[j].w - mean) * rstd * ww.w + bb.w};
+      if (gelu) { o[0] = gelu_erf(o[0]); o[1] = gelu_erf(o[1]); o[2] = gelu_erf(o[2]); o[3] = gelu_erf(o[3]); }
       act_store4(oh, ol, (size_t)orow * out_cs + c0, o);
     }
 }
@@ -294,7 +295,17 @@ extern "C" int prv2_layernorm(const float* x, int rows, int D, const float* w, c
   PRV2_CHECK_ARG(x && w && b && out_hi, "prv2_layernorm: null pointer");
   PRV2_CHECK_ARG(rows >= 0 && D > 0 && D % 128 == 0 && D <= 1024 && out_cs % 4 == 0 && out_cs >= D, "prv2_layernorm: D must be a multiple of 128, <= 1024 (got %d)", D);
   if (rows == 0) return PRV2_OK;
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, drop_period, (bf16*)out_hi, (bf16*)out_lo, out_cs);
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, drop_period, (bf16*)out_hi, (bf16*)out_lo, out_cs, 0);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_layernorm_gelu(const float* x, int rows, int D, const float* w, const float* b, float eps,
+                                   prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(x && w && b && out_hi, "prv2_layernorm_gelu: null pointer");
+  PRV2_CHECK_ARG(rows >= 0 && D > 0 && D % 128 == 0 && D <= 1024 && out_cs % 4 == 0 && out_cs >= D, "prv2_layernorm_gelu: D must be a multiple of 128, <= 1024 (got %d)", D);
+  if (rows == 0) return PRV2_OK;
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, 0, (bf16*)out_hi, (bf16*)out_lo, out_cs, 1);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

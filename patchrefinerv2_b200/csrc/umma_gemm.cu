@@ -244,6 +244,7 @@ __device__ __forceinline__ float act_fn(float x) {
   if (ACT == PRV2_ACT_RELU) return fmaxf(x, 0.f);
   if (ACT == PRV2_ACT_GELU) return gelu_fast(x);
   if (ACT == PRV2_ACT_GELU_TANH) return gelu_tanh(x);
+  if (ACT == PRV2_ACT_SIGMOID_GATE) return 1.0f / (1.0f + __expf(-x));     // bi_directional_fusion_model.py:75-77 (gate, then * res below)
   return x;
 }
 
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           const int c0 = q * 16;
           tc_ld16(taddr + c0, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { sum += v[j]; ++cnt; }
+          for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { sum += v[j] + par[c0 + j]; ++cnt; }
         }
         const float mean_a = cnt ? sum / (float)cnt : 0.f;
         float m2 = 0.f;
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           const int c0 = q * 16;
           tc_ld16(taddr + c0, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { const float d = v[j] - mean_a; m2 += d * d; }
+          for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { const float d = v[j] + par[c0 + j] - mean_a; m2 += d * d; }
         }
         float* const mine = s_ln + (ew * 2 + acc) * 64;
         const float* const theirs = s_ln + ((ew ^ 4) * 2 + acc) * 64;
@@ -621,8 +622,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             t[g * 4 + 2] = __uint_as_float(rr[g * 4 + 2]); t[g * 4 + 3] = __uint_as_float(rr[g * 4 + 3]);
             if (is_ln) {
               const float4 g4 = *reinterpret_cast<const float4*>(par + 256 + nl + g * 4), e4 = *reinterpret_cast<const float4*>(par + 512 + nl + g * 4);
-              t[g * 4 + 0] = g4.x * ((t[g * 4 + 0] - mean) * rstd) + e4.x; t[g * 4 + 1] = g4.y * ((t[g * 4 + 1] - mean) * rstd) + e4.y;
-              t[g * 4 + 2] = g4.z * ((t[g * 4 + 2] - mean) * rstd) + e4.z; t[g * 4 + 3] = g4.w * ((t[g * 4 + 3] - mean) * rstd) + e4.w;
+              t[g * 4 + 0] = g4.x * ((t[g * 4 + 0] + b4.x - mean) * rstd) + e4.x; t[g * 4 + 1] = g4.y * ((t[g * 4 + 1] + b4.y - mean) * rstd) + e4.y;
+              t[g * 4 + 2] = g4.z * ((t[g * 4 + 2] + b4.z - mean) * rstd) + e4.z; t[g * 4 + 3] = g4.w * ((t[g * 4 + 3] + b4.w - mean) * rstd) + e4.w;
             } else {
               t[g * 4 + 0] += b4.x; t[g * 4 + 1] += b4.y; t[g * 4 + 2] += b4.z; t[g * 4 + 3] += b4.w;
             }
@@ -769,14 +770,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           for (int c = csel; c < n_chunks; c += 2) {
             tc_ld16(taddr + c * 16, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < Cout) { sum += v[j]; ++cnt; }
+            for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < Cout) { sum += v[j] + par[c * 16 + j]; ++cnt; }
           }
           const float mean_a = cnt ? sum / (float)cnt : 0.f;
           float m2 = 0.f;
           for (int c = csel; c < n_chunks; c += 2) {
             tc_ld16(taddr + c * 16, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < Cout) { const float d = v[j] - mean_a; m2 += d * d; }
+            for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < Cout) { const float d = v[j] + par[c * 16 + j] - mean_a; m2 += d * d; }
           }
           s_mine[lane] = mean_a;
           s_mine[32 + lane] = m2;
@@ -835,7 +836,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
                 const float b8[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
                 const float mean = s_fin[rl], rstd = s_fin[32 + rl];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = act_fn<ACT>(g8[j] * ((t[j] - mean) * rstd) + b8[j]);
+                for (int j = 0; j < 8; ++j) t[j] = act_fn<ACT>(g8[j] * ((t[j] + bias8[j] - mean) * rstd) + b8[j]);
                 act_store8(out_hi, out_lo, q.orow * out_cs + n, t);
                 continue;
               }
@@ -878,7 +879,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
                 float r8[8];
                 act_unpack8(pre.a[i], res_lo, q.m * res_cs + n, r8);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] += r8[j];
+                for (int j = 0; j < 8; ++j) t[j] = (ACT == PRV2_ACT_SIGMOID_GATE) ? t[j] * r8[j] : t[j] + r8[j];
               }
               if (res2_hi) {
                 float r8[8];
@@ -1138,7 +1139,9 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   const int act = d->act;
-  PRV2_CHECK_ARG(act >= PRV2_ACT_NONE && act <= PRV2_ACT_GELU_TANH, "prv2_umma_gemm: unknown activation %d", act);
+  PRV2_CHECK_ARG(act >= PRV2_ACT_NONE && act <= PRV2_ACT_SIGMOID_GATE, "prv2_umma_gemm: unknown activation %d", act);
+  PRV2_CHECK_ARG(act != PRV2_ACT_SIGMOID_GATE || (d->epi == PRV2_EPI_STORE && d->res_hi),
+                 "prv2_umma_gemm: SIGMOID_GATE needs the STORE epilogue with `res` = the gated tensor (res2 is then added, relu copy allowed)");
   cudaError_t err = cudaSuccess;
 #define PRV2_L2(E, A, F) (cg == 2 ? launch<E, A, 2, F>(cfg, p) : launch<E, A, 1, F>(cfg, p))
 #define PRV2_L(E, A) (fast ? PRV2_L2(E, A, true) : PRV2_L2(E, A, false))
@@ -1147,10 +1150,13 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
       err = act == PRV2_ACT_RELU ? PRV2_L(PRV2_EPI_STORE, PRV2_ACT_RELU)
             : act == PRV2_ACT_GELU ? PRV2_L(PRV2_EPI_STORE, PRV2_ACT_GELU)
             : act == PRV2_ACT_GELU_TANH ? PRV2_L(PRV2_EPI_STORE, PRV2_ACT_GELU_TANH)
+            : act == PRV2_ACT_SIGMOID_GATE ? PRV2_L2(PRV2_EPI_STORE, PRV2_ACT_SIGMOID_GATE, false)
                                         : PRV2_L(PRV2_EPI_STORE, PRV2_ACT_NONE);
       break;
     case PRV2_EPI_LN_GELU:
-      err = act == PRV2_ACT_GELU_TANH ? PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU_TANH) : PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU);
+      err = act == PRV2_ACT_GELU_TANH ? PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU_TANH)
+            : act == PRV2_ACT_RELU    ? PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_RELU)
+                                      : PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU);
       break;
     case PRV2_EPI_RESID_F32: err = use_fast_resid ? PRV2_L2(PRV2_EPI_RESID_F32, PRV2_ACT_NONE, true) : PRV2_L2(PRV2_EPI_RESID_F32, PRV2_ACT_NONE, false); break;
     case PRV2_EPI_F32: err = PRV2_L2(PRV2_EPI_F32, PRV2_ACT_NONE, false); break;

@@ -23,28 +23,44 @@ def depth_tap_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 class FusionUnetB200:
-    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, input_chl, temp_chl, dec_chl, x3: bool, device):
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, input_chl, temp_chl, dec_chl, x3: bool, device,
+                 in_splits=None, names=("encoder_layers_1", "encoder_layers_2", "decoder_layers")):
+        """``in_splits``: per level (coarse channels, fine channels) of the first conv's virtual concat (default: two equal
+        halves of ``input_chl``, the FusionUnet case); ``names``: state-dict module names of the two encoder lists and the
+        decoder list (BiDirectionalFusion calls them fusion_layers_1 / fusion_layers_2 / f2r_agg, same arithmetic)."""
         self.x3, self.device = x3, device
         self.input_chl, self.temp_chl, self.dec_chl = list(input_chl), list(temp_chl), list(dec_chl)
         self.ws: Dict[tuple, Workspace] = {}
         g = lambda k: sd[prefix + k].detach().float()
         mk = lambda segs, n_src, cout, **kw: GemmLayer(segs, n_src, cout, x3, device, **kw)
         self.enc1, self.enc2 = [], []
+        n_e1, n_e2, n_dec = names
         for idx, (ic, tc) in enumerate(zip(self.input_chl, self.temp_chl)):
-            assert ic % 2 == 0
-            q = f"encoder_layers_1.{idx}.single_conv."
-            self.enc1.append(mk(conv_segments(g(q + "0.weight"), [ic // 2, ic // 2]), 2, tc, epi=_lib.EPI_LN_GELU,
-                                gamma=g(q + "1.weight"), beta=g(q + "1.bias"), eps=LN_EPS, name=f"fusion.enc1.L{idx}"))
-            q = f"encoder_layers_2.{idx}.single_conv."
+            if in_splits is None:
+                assert ic % 2 == 0
+                split = [ic // 2, ic // 2]
+            else:
+                split = list(in_splits[idx])
+                assert sum(split) == ic
+            # conv -> LN over channels -> GELU is one kernel while a pixel's channel vector fits one N tile (Cout <= 256);
+            # wider levels (BiDirectionalFusion's 512-channel bottom level, a few hundred pixels) store fp32 rows and
+            # normalise in prv2_layernorm_gelu
+            ln = (lambda q: dict(epi=_lib.EPI_LN_GELU, gamma=g(q + "1.weight"), beta=g(q + "1.bias"), eps=LN_EPS)) if tc <= 256 else \
+                 (lambda q: dict(epi=_lib.EPI_F32))
+            q = f"{n_e1}.{idx}.single_conv."
+            self.enc1.append(mk(conv_segments(g(q + "0.weight"), split), 2, tc, name=f"fusion.enc1.L{idx}", **ln(q)))
+            self.enc1[-1].ln_split = None if tc <= 256 else (g(q + "1.weight").to(device), g(q + "1.bias").to(device))
+            q = f"{n_e2}.{idx}.single_conv."
             w2 = g(q + "0.weight")                     # [tc, tc + 2, 3, 3]: cat[f, pred1, pred2]
-            self.enc2.append(mk(conv_segments(w2[:, :tc], [tc]) + [(1, 0, 0, depth_tap_weight(w2[:, tc:tc + 2]))], 2, tc, epi=_lib.EPI_LN_GELU,
-                                gamma=g(q + "1.weight"), beta=g(q + "1.bias"), eps=LN_EPS, name=f"fusion.enc2.L{idx}"))
+            self.enc2.append(mk(conv_segments(w2[:, :tc], [tc]) + [(1, 0, 0, depth_tap_weight(w2[:, tc:tc + 2]))], 2, tc,
+                                name=f"fusion.enc2.L{idx}", **ln(q)))
+            self.enc2[-1].ln_split = None if tc <= 256 else (g(q + "1.weight").to(device), g(q + "1.bias").to(device))
         self.dec = []
         rev = self.temp_chl[::-1]
         chl = rev[0]
         for i, (tc, dc) in enumerate(zip(rev[1:], self.dec_chl)):
             cin = tc + chl + 2
-            q = f"decoder_layers.{i}.conv.double_conv."
+            q = f"{n_dec}.{i}.conv.double_conv."
             w1 = g(q + "0.weight")                     # [cin, cin, 3, 3]: cat[up(chl), skip(tc), pred1, pred2]
             c1 = mk(conv_segments(w1[:, :chl + tc], [chl, tc]) + [(2, 0, 0, depth_tap_weight(w1[:, chl + tc:chl + tc + 2]))], 3, cin,
                     act=_lib.ACT_GELU, name=f"fusion.dec{i}.conv1")
@@ -68,6 +84,16 @@ class FusionUnetB200:
         f += 2.0 * B * h * w * 9 * self.final_c
         return f
 
+    @staticmethod
+    def _conv_ln_gelu(ws: Workspace, layer: GemmLayer, srcs: List[Act], out: Act) -> None:
+        if layer.ln_split is None:
+            layer(srcs, out=out)
+            return
+        rows = out.N * out.H * out.W
+        tmp = ws.f32(f"ln_rows_{out.C}", rows, out.C)
+        layer(srcs, out_f32=tmp, out_f32_ld=out.C)
+        ops.layernorm_gelu(tmp, layer.ln_split[0], layer.ln_split[1], LN_EPS, out)
+
     def forward(self, c_feat: List[Act], f_feat: List[Act], pred1: torch.Tensor, pred2: torch.Tensor,
                 update_base: Optional[torch.Tensor], trace: Optional[dict] = None) -> torch.Tensor:
         """fusion_model.py:84-122.  c_feat / f_feat finest first; pred1/pred2/update_base fp32 [B,1,H,W]."""
@@ -80,11 +106,11 @@ class FusionUnetB200:
         for idx, (c, f) in enumerate(zip(c_feat, f_feat)):
             tc = self.temp_chl[idx]
             e1 = A(f"e1_{idx}", B, c.H, c.W, tc)
-            self.enc1[idx]([c, f], out=e1)
+            self._conv_ln_gelu(ws, self.enc1[idx], [c, f], e1)
             d18 = A(f"dtaps_{idx}", B, c.H, c.W, 18, cs=24)
             ops.depth_taps(pred1, pred2, d18)                 # shared by enc2 of this level and the decoder conv that takes it as skip
             t = A(f"t_{idx}", B, c.H, c.W, tc)
-            self.enc2[idx]([e1, d18], out=t)
+            self._conv_ln_gelu(ws, self.enc2[idx], [e1, d18], t)
             temp.append(t)
             dtaps.append(d18)
         if trace is not None:

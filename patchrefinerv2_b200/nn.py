@@ -129,7 +129,7 @@ class GemmLayer:
                  gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, eps: float = 1e-6,
                  head_scale: float = 1.0, shuffle_k: int = 0, name: str = "gemm"):
         self.x3, self.n_src, self.device, self.name = x3, n_src, device, name
-        if epi == _lib.EPI_LN_GELU:
+        if epi == _lib.EPI_LN_GELU and act == _lib.ACT_NONE:
             act = _lib.ACT_GELU
         if act == _lib.ACT_GELU and not x3:
             # one-pass bf16 mode: tanh-form GELU on MUFU.TANH (|diff| <= 1e-3 abs vs the erf form, below the bf16

@@ -127,6 +127,15 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out
     return out
 
 
+def layernorm_gelu(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out: Act) -> Act:
+    """fp32 conv rows [pixels, D] -> channels LayerNorm -> exact GELU -> act (convs.py:64-75 for D > 256)."""
+    rows, D = x.shape
+    planes = 2 if out.lo is not None else 1
+    _lib.call("prv2_layernorm_gelu", ptr(x), rows, D, ptr(w), ptr(b), C.c_float(eps), ptr(out.hi), ptr(out.lo), out.cs, stream_ptr(),
+              work=("byte", rows * D * (4.0 + 2.0 * planes)))
+    return out
+
+
 def patchify(crops: torch.Tensor, out: Act) -> Act:
     B, _, H, W = crops.shape
     _lib.call("prv2_patchify", ptr(crops), B, H, W, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr(),
