@@ -178,12 +178,41 @@ def bifusion():
         print("bifusion", t, tuple(out.shape), float(out.mean()), float(off.std()))
 
 
+PLUS_MODES = (("m1", 2), ("r2", 2))
+
+
+def plus():
+    """plus_<mode>.npz: the reference PatchRefinerPlus (patchrefinerplus.py) end to end -- DA2 ViT-S coarse branch with 256 decoder
+    features, LightWeightRefiner around oracle.ToyFineEncoder (timm stand-in), BiDirectionalFusion coarse-gated -- on the tiny frame."""
+    cfg = O.make_plus_config()
+    sd = O.init_patchrefinerplus_state_dict(cfg, 0)
+    d = tempfile.mkdtemp()
+    cp = os.path.join(d, "c.pth")
+    torch.save({k[len("coarse_branch."):]: v for k, v in sd.items() if k.startswith("coarse_branch.")}, cp)
+    ref = ref_shim.build_reference_patchrefinerplus(cfg, cp, lambda: O.ToyFineEncoder(3))
+    res = ref.load_state_dict(sd, strict=False)
+    assert not res.missing_keys and not res.unexpected_keys, res
+    lr, hr = O.synthetic_frame(cfg, 1)
+    for mode, pn in PLUS_MODES:
+        random.seed(1)
+        with torch.no_grad():
+            depth, log = ref(mode="infer", image_lr=lr, image_hr=hr, cai_mode=mode, process_num=pn, tile_cfg=None)
+        np.savez_compressed(os.path.join(OUT, f"plus_{mode}.npz"), mode=mode, process_num=pn, depth=depth.numpy(),
+                            coarse=log["coarse_prediction"].numpy(), sd_sha=sd_digest(sd), frame_sha=O.sha256_f32(hr.numpy()),
+                            keys=np.array(sorted(ref.state_dict().keys())))
+        print("plus", mode, tuple(depth.shape), float(depth.mean()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     if "--bifusion-only" in sys.argv:
         bifusion()
         sys.exit(0)
+    if "--plus-only" in sys.argv:
+        plus()
+        sys.exit(0)
+    plus()
     bifusion()
     tiny()
     geom(448, 448)

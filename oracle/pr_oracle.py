@@ -820,6 +820,127 @@ class PatchRefinerOracle:
         return depth, coarse, avg
 
 
+# ---------------------------------------------------------------------------------------------
+# PatchRefinerPlus (V2 family) tiled inference  (estimator/models/patchrefinerplus.py)
+# ---------------------------------------------------------------------------------------------
+
+TOY_ENCODER_NAME = "mobilenetv4_conv_small.e2400_r224_in1k"     # the name whose 4-channel stem surgery the reference knows (patchrefinerplus.py:158-164)
+TOY_ENCODER_CHL = (32, 32, 64, 96, 960)                         # == fine_chl of configs/patchrefinerv2_*/ *mobile* configs
+
+
+class ToyFineEncoder(torch.nn.Module):
+    """Stand-in for the timm ``features_only`` CNN inside ``LightWeightRefiner`` (blocks/lightweight_refiner.py:259-262).
+    timm is not installable offline, so the encoder's own arithmetic is UNPINNED; everything around
+    it -- pixel normalisation, coarse-depth conditioning, feature ordering, BiDirectionalFusion, tiling, blending --
+    is pinned by running the reference ``PatchRefinerPlus`` with this module injected as ``timm.create_model``'s result.
+    Five stride-2 stages with the channel counts / strides of mobilenetv4_conv_small; ``conv_stem`` and ``default_cfg``
+    are the attributes the reference touches (patchrefinerplus.py:158-164, lightweight_refiner.py:264-265)."""
+
+    default_cfg = {"mean": (0.485, 0.456, 0.406), "std": (0.229, 0.224, 0.225)}
+
+    def __init__(self, in_chans: int = 3):
+        super().__init__()
+        nn = torch.nn
+        c = TOY_ENCODER_CHL
+        self.conv_stem = nn.Conv2d(in_chans, c[0], 3, stride=2, padding=1, bias=False)
+        self.stages = nn.ModuleList([nn.Conv2d(c[i], c[i + 1], 3, stride=2, padding=1, bias=True) for i in range(4)])
+
+    def forward(self, x):
+        feats = [F.relu(self.conv_stem(x))]
+        for st in self.stages:
+            feats.append(F.relu(st(feats[-1])))
+        return feats
+
+
+def init_toy_encoder_state_dict(seed: int, in_chans: int = 4) -> Dict[str, Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    c = TOY_ENCODER_CHL
+    sd = {"conv_stem.weight": _conv_w(g, c[0], in_chans, 3, gain=1.7)}
+    for i in range(4):
+        sd[f"stages.{i}.weight"] = _conv_w(g, c[i + 1], c[i], 3, gain=1.7)
+        sd[f"stages.{i}.bias"] = _vec(g, c[i + 1], 0.05)
+    return sd
+
+
+def make_plus_config(encoder="vits", features=256, out_channels=(48, 96, 192, 384), patch_process_shape=(224, 224), image_raw_shape=(432, 768),
+                     patch_split_num=(2, 2), coarse2fine_type="coarse-gated", max_depth=80.0) -> dict:
+    """A config dict shaped like configs/patchrefinerv2_dav2/plus_mobile_u4k_base_coarse_e2e_c2f_pretrain.py (DA2 coarse branch
+    with 256 decoder features, LightWeightRefiner fine branch, BiDirectionalFusion)."""
+    return dict(
+        image_raw_shape=list(image_raw_shape), patch_process_shape=list(patch_process_shape), patch_split_num=list(patch_split_num),
+        fusion_feat_level=6, min_depth=1e-3, max_depth=max_depth, strategy_refiner_target="offset_coarse",
+        pretrain_stage=False, e2e_training=False, hack_strategy=None,
+        coarse_branch=dict(type="DA2", pretrained=None, model_cfg=dict(encoder=encoder, features=features, out_channels=list(out_channels))),
+        refiner=dict(
+            fine_branch=dict(type="LightWeightRefiner", coarse_condition=True, with_decoder=False, encoder_name=TOY_ENCODER_NAME),
+            fusion_model=dict(type="BiDirectionalFusion", encoder_name=TOY_ENCODER_NAME, coarse2fine=True, coarse2fine_type=coarse2fine_type,
+                              coarse_chl=[features // 2] + [features] * 5, fine_chl=list(TOY_ENCODER_CHL),
+                              fine_chl_after_coarse2fine=[features // 2] + [features] * 5,
+                              temp_chl=[32, 64, 64, 128, 256, 512], dec_chl=[512, 256, 128, 64, 32])),
+        sigloss=dict(type="SILogLoss"), gmloss=dict(type="GradMatchLoss"), sigweight=1, pre_norm_bbox=True,
+        pretrain_coarse_model=None, pretrained=None, whole_pretrained=None)
+
+
+def init_patchrefinerplus_state_dict(cfg: dict, seed: int = 0) -> Dict[str, Tensor]:
+    """State dict with the reference's PatchRefinerPlus prefixes: coarse_branch.* (DepthAnythingV2),
+    refiner_fine_branch.refiner_encoder.* (the encoder), refiner_fusion_model.* (BiDirectionalFusion)."""
+    cb = cfg["coarse_branch"]["model_cfg"]
+    fu = cfg["refiner"]["fusion_model"]
+    sd: Dict[str, Tensor] = {}
+    for k, v in init_dav2_state_dict(cb["encoder"], cb["features"], cb["out_channels"], seed * 3 + 21).items():
+        sd["coarse_branch." + k] = v
+    for k, v in init_toy_encoder_state_dict(seed * 3 + 22).items():
+        sd["refiner_fine_branch.refiner_encoder." + k] = v
+    for k, v in init_bidirectional_fusion_state_dict(fu["coarse_chl"], fu["fine_chl"], fu["fine_chl_after_coarse2fine"], fu["temp_chl"], fu["dec_chl"],
+                                                     seed * 3 + 23, fu["coarse2fine_type"]).items():
+        sd["refiner_fusion_model." + k] = v
+    return sd
+
+
+class PatchRefinerPlusOracle(PatchRefinerOracle):
+    """PatchRefinerPlus.forward(mode='infer') (patchrefinerplus.py:367-533): the tiling / blending is BaselinePretrain's
+    (shared with PatchRefiner); only ``infer_forward`` differs (:330-365): LightWeightRefiner (lightweight_refiner.py:285-322,
+    with_decoder=False, coarse_condition=True) then BiDirectionalFusion."""
+
+    def __init__(self, cfg: dict, state_dict: Dict[str, Tensor], encoder: torch.nn.Module):
+        self.cfg = cfg
+        self.sd = {k: v.float() for k, v in state_dict.items()}
+        self.patch_process_shape = tuple(cfg["patch_process_shape"])
+        self.max_depth = float(cfg["max_depth"])
+        self.enc_c = cfg["coarse_branch"]["model_cfg"]["encoder"]
+        self.level = cfg["fusion_feat_level"]
+        self.target = cfg["strategy_refiner_target"]
+        self.c2f_type = cfg["refiner"]["fusion_model"]["coarse2fine_type"]
+        self.tile_cfg = prepare_tile_cfg(self.patch_process_shape, cfg["image_raw_shape"], cfg["patch_split_num"])
+        self.trace = None
+        pre = "refiner_fine_branch.refiner_encoder."
+        encoder.load_state_dict({k[len(pre):]: v for k, v in self.sd.items() if k.startswith(pre)}, strict=True)
+        self.encoder = encoder.eval()
+
+    def infer_forward(self, imgs_crop, coarse_depth_roi, coarse_feats_roi, trace=None):
+        mean = torch.tensor(self.encoder.default_cfg["mean"]).view(-1, 1, 1)
+        std = torch.tensor(self.encoder.default_cfg["std"]).view(-1, 1, 1)
+        x = (imgs_crop - mean) / std                                                      # lightweight_refiner.py:293
+        feats = list(self.encoder(torch.cat([x, coarse_depth_roi], dim=1)))                # :296 (coarse_condition)
+        feats.insert(0, F.interpolate(feats[0], scale_factor=2, mode="bilinear", align_corners=True))   # :316-318
+        r_feats = feats[::-1]                                                             # :320
+        r_depth = torch.zeros_like(x[:, :1])                                              # :321
+        if trace is not None:
+            trace["fine_feats"] = [t.clone() for t in r_feats]
+        if self.target == "offset_fine":
+            base = r_depth
+        elif self.target == "offset_coarse":
+            base = coarse_depth_roi
+        else:
+            base = None
+        c_list = list(coarse_feats_roi[-self.level:])[::-1]
+        r_list = list(r_feats[-self.level:])[::-1]
+        pred = bidirectional_fusion(self.sd, "refiner_fusion_model.", c_list, r_list, coarse_depth_roi, r_depth, base, self.c2f_type, trace)
+        if self.target == "direct":
+            pred = torch.sigmoid(pred) * self.max_depth
+        return pred
+
+
 def synthetic_frame(cfg: dict, seed: int = 1, image_raw_shape=None) -> Tuple[Tensor, Tensor]:
     """Synthetic frame: smooth random structure + noise in [0,1]; image_lr = resizer(image_hr)
     (estimator/datasets/general_dataset.py:203-234 output contract)."""

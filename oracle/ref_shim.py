@@ -229,3 +229,22 @@ def build_reference_patchrefiner(cfg: dict, coarse_sd_path: str, fine_sd_path: s
     model = PatchRefiner(ConfigDict(c))
     model.eval()
     return model
+
+
+def build_reference_patchrefinerplus(cfg: dict, coarse_sd_path: str, encoder_factory):
+    """Build the reference ``PatchRefinerPlus`` (estimator/models/patchrefinerplus.py:59) from a plain dict shaped like
+    ``configs/patchrefinerv2_dav2/plus_mobile_u4k_*.py``.  ``timm.create_model`` (lightweight_refiner.py:259-262) is the one
+    call into the absent timm package: it is answered with ``encoder_factory()`` (a 3-channel-stem module exposing
+    ``conv_stem`` and ``default_cfg``; the reference then performs its own 4-channel stem surgery on it, :158-164)."""
+    install()
+    import copy
+    import timm
+    timm.create_model = lambda name, pretrained=False, features_only=True, **kw: encoder_factory()
+    import estimator.models.blocks.lightweight_refiner as lwr
+    lwr.timm.create_model = timm.create_model
+    from estimator.models.patchrefinerplus import PatchRefinerPlus
+    c = copy.deepcopy(cfg)
+    c["coarse_branch"]["pretrained"] = coarse_sd_path
+    model = PatchRefinerPlus(ConfigDict(c))
+    model.eval()
+    return model

@@ -356,3 +356,157 @@ class PatchRefiner(nn.Module):
         if self.output_device == "cpu":
             depth = depth.cpu()
         return depth, {"rgb": image_lr, "depth_pred": depth, "depth_gt": depth_gt, "coarse_prediction": coarse_depth}
+
+
+def _default_fine_encoder(encoder_name: str, in_chans: int):
+    """timm.create_model(..., features_only=True) like lightweight_refiner.py:259-262 -- only where timm exists.  The
+    encoder's arithmetic lives in timm (pinned ``timm==0.9.2`` in the reference's environment.yml:27), which is not
+    installable offline: parity of the ENCODER is unpinned; pass ``fine_encoder=`` to supply one."""
+    try:
+        import timm
+    except Exception as e:
+        raise NotImplementedError(
+            f"refiner.fine_branch encoder {encoder_name!r} is a timm model and timm is not installed: construct PatchRefinerPlus with "
+            "fine_encoder=<torch module returning the 5 feature maps> (see INTEGRATION.md)") from e
+    return timm.create_model(encoder_name, pretrained=False, features_only=True, in_chans=in_chans)
+
+
+@MODELS.register_module()
+class PatchRefinerPlus(PatchRefiner):
+    """B200-native PatchRefinerPlus (the V2 family: DA2 coarse branch + LightWeightRefiner + BiDirectionalFusion),
+    infer path only (estimator/models/patchrefinerplus.py:367-533).  Tiling, cropping, ROI gather, blending and the
+    sharded multi-GPU path are PatchRefiner's; ``refine_patches`` runs the light-weight encoder (a PyTorch module the
+    caller supplies or timm builds -- library code, not one of this package's kernels) and hands its features to
+    ``BiDirectionalFusionB200``, where 99 % of the V2 refiner's FLOPs are."""
+
+    def __init__(self, config, precision: str = "bf16", patch_batch: int = 8, output_device: str = "cpu", fine_encoder: Optional[nn.Module] = None):
+        nn.Module.__init__(self)
+        from .bifusion import C2F_TYPES, bifusion_weight_spec
+        if hasattr(config, "to_dict"):
+            config = config.to_dict()
+        self.config = config
+        if _get(config, "pretrain_stage", False):
+            raise NotImplementedError("pretrain_stage=True (training-time hack path, patchrefinerplus.py:383-425) is out of scope")
+        self.min_depth = _get(config, "min_depth")
+        self.max_depth = float(_get(config, "max_depth"))
+        self.patch_process_shape = tuple(_get(config, "patch_process_shape"))
+        self.tile_cfg = self.prepare_tile_cfg(_get(config, "image_raw_shape"), _get(config, "patch_split_num"))
+        cb, rf = _get(config, "coarse_branch"), _get(config, "refiner")
+        fb, fu = _get(rf, "fine_branch"), _get(rf, "fusion_model")
+        if _get(cb, "type") != "DA2":
+            raise NotImplementedError(f"coarse_branch.type={_get(cb, 'type')!r}: only the DA2 (DepthAnythingV2) coarse branch is implemented")
+        if _get(fb, "type") != "LightWeightRefiner" or _get(fb, "with_decoder", False):
+            raise NotImplementedError("refiner.fine_branch must be LightWeightRefiner(with_decoder=False)")
+        if _get(fu, "type") != "BiDirectionalFusion" or _get(fu, "coarse2fine_type") not in C2F_TYPES or _get(fu, "glb_att", False):
+            raise NotImplementedError(f"fusion_model {_get(fu, 'type')!r}/{_get(fu, 'coarse2fine_type')!r}: BiDirectionalFusion with coarse2fine_type in {sorted(C2F_TYPES)}")
+        self._cb_cfg, self._fu_cfg = dict(_get(cb, "model_cfg")), fu
+        self.coarse_condition = bool(_get(fb, "coarse_condition", True))
+        self.fusion_feat_level = int(_get(config, "fusion_feat_level"))
+        self.strategy_refiner_target = _get(config, "strategy_refiner_target")
+        if self.strategy_refiner_target == "direct":
+            raise NotImplementedError("strategy_refiner_target='direct' is not implemented")
+        self.pre_norm_bbox = _get(config, "pre_norm_bbox", True)
+        self.resizer = _Resizer(self.patch_process_shape)
+        if tuple(self.resizer.size) != tuple(self.patch_process_shape):
+            raise NotImplementedError("patch_process_shape must be a multiple of 14 for the DA2 coarse branch")
+        assert precision in ("bf16", "fp32")
+        self.precision, self.patch_batch, self.output_device = precision, int(patch_batch), output_device
+        if "convnext" in str(_get(fb, "encoder_name", "")):
+            raise NotImplementedError("convnext encoders add an upsample_convx stage (lightweight_refiner.py:276-283,307-314): not implemented")
+        self.refiner_fine_encoder = fine_encoder if fine_encoder is not None else _default_fine_encoder(_get(fb, "encoder_name"), 4 if self.coarse_condition else 3)
+        self.refiner_fine_encoder.eval()
+        cfgd = getattr(self.refiner_fine_encoder, "default_cfg", None) or {}
+        self._enc_mean = tuple(cfgd.get("mean", (0.485, 0.456, 0.406)))
+        self._enc_std = tuple(cfgd.get("std", (0.229, 0.224, 0.225)))
+        self._weights = OrderedDict()
+        for k, shp in dav2_weight_spec(self._cb_cfg["encoder"], self._cb_cfg["features"], self._cb_cfg["out_channels"]).items():
+            self._weights["coarse_branch." + k] = torch.zeros(shp)
+        keys = ("coarse_chl", "fine_chl", "fine_chl_after_coarse2fine", "temp_chl", "dec_chl")
+        for k, shp in bifusion_weight_spec(*[_get(fu, x) for x in keys], coarse2fine_type=_get(fu, "coarse2fine_type")).items():
+            self._weights["refiner_fusion_model." + k] = torch.zeros(shp)
+        path = _get(cb, "pretrained")
+        if path:
+            self._load({"coarse_branch." + k: v for k, v in torch.load(path, map_location="cpu").items()}, strict=False)
+        for key in ("pretrain_coarse_model", "pretrained", "whole_pretrained"):
+            path = _get(config, key)
+            if path:
+                sd = torch.load(path, map_location="cpu")["model_state_dict"]
+                self._load({("coarse_branch." + k if key == "pretrain_coarse_model" else k): v for k, v in sd.items()}, strict=False)
+        self._engine = None
+        self._device = torch.device("cpu")
+        self.last_stats = {}
+
+    ENC_PREFIX = "refiner_fine_branch.refiner_encoder."
+
+    def _load(self, sd, strict):
+        enc = {k[len(self.ENC_PREFIX):]: v for k, v in sd.items() if k.startswith(self.ENC_PREFIX)}
+        rest = {k: v for k, v in sd.items() if not k.startswith(self.ENC_PREFIX)}
+        res = super()._load(rest, strict)
+        missing, unexpected = list(res.missing_keys), list(res.unexpected_keys)
+        if enc or strict:
+            r2 = self.refiner_fine_encoder.load_state_dict(enc, strict=strict)
+            missing += [self.ENC_PREFIX + k for k in r2.missing_keys]
+            unexpected += [self.ENC_PREFIX + k for k in r2.unexpected_keys]
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def state_dict(self, *args, **kwargs):
+        sd = OrderedDict((k, v.clone()) for k, v in self._weights.items())
+        for k, v in self.refiner_fine_encoder.state_dict().items():
+            sd[self.ENC_PREFIX + k] = v.detach().cpu().clone()
+        return sd
+
+    def get_save_dict(self):                        # patchrefinerplus.py:215-216 (keeps the coarse branch)
+        return self.state_dict()
+
+    def _build_engine(self, device):
+        if device.type != "cuda":
+            raise RuntimeError("patchrefinerv2_b200 runs on CUDA (sm_100a) only; there is no CPU path. Call .cuda() first.")
+        from .bifusion import BiDirectionalFusionB200
+        _lib.load()
+        x3 = self.precision == "fp32"
+        sd, fu = self._weights, self._fu_cfg
+        keys = ("coarse_chl", "fine_chl", "fine_chl_after_coarse2fine", "temp_chl", "dec_chl")
+        self.refiner_fine_encoder.to(device)
+        return dict(
+            coarse=DepthAnythingV2B200(sd, "coarse_branch.", self._cb_cfg["encoder"], self._cb_cfg["features"], self._cb_cfg["out_channels"], self.max_depth, x3, device),
+            fusion=BiDirectionalFusionB200(sd, "refiner_fusion_model.", *[_get(fu, k) for k in keys], coarse2fine_type=_get(fu, "coarse2fine_type"),
+                                           x3=x3, device=device),
+            ws=Workspace(device, x3), device=device, masks={},
+            enc_mean=torch.tensor(self._enc_mean, device=device).view(1, -1, 1, 1), enc_std=torch.tensor(self._enc_std, device=device).view(1, -1, 1, 1))
+
+    def refine_patches(self, eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel: np.ndarray, preds: torch.Tensor, trace=None):
+        """patchrefinerplus.py:330-365 for the patches ``sel``, ``patch_batch`` at a time."""
+        dev = eng["device"]
+        ph, pw = self.patch_process_shape
+        level = self.fusion_feat_level
+        x3 = self.precision == "fp32"
+        for s in range(0, len(sel), self.patch_batch):
+            idx = sel[s:s + self.patch_batch]
+            pb = len(idx)
+            bb = torch.from_numpy(np.ascontiguousarray(bboxs_np[idx])).to(dev)
+            rois = torch.from_numpy(np.ascontiguousarray(rois_np[idx])).to(dev)
+            crops = ops.crop_resize(image_hr, bb, ph, pw)
+            ws = eng["ws"]
+            c_roi = [ops.roi_gather_act(f, rois, f.H / ph, ws.act(f"roi{li}", pb, f.H, f.W, f.C)) for li, f in enumerate(coarse_feats)]
+            d_roi = ops.roi_gather_f32(coarse_depth.reshape(ph, pw, 1), rois, 1.0).reshape(pb, 1, ph, pw)
+            # LightWeightRefiner.forward (lightweight_refiner.py:285-322): normalise, condition on the coarse depth, encode
+            x = (crops - eng["enc_mean"]) / eng["enc_std"]
+            feats = list(self.refiner_fine_encoder(torch.cat([x, d_roi], dim=1) if self.coarse_condition else x))
+            f_acts = [Act.from_nchw(f, x3) for f in feats]
+            top = f_acts[0]
+            up = ops.resize_bilinear(top, ws.act("enc_up", pb, top.H * 2, top.W * 2, top.C))       # :316-318
+            r_feats = ([up] + f_acts)[::-1]                                                        # :320, coarsest first
+            if self.strategy_refiner_target == "offset_fine":
+                base = torch.zeros_like(d_roi)                                                     # :321: the refiner depth is zeros
+            elif self.strategy_refiner_target == "offset_coarse":
+                base = d_roi
+            else:
+                base = None
+            c_list = c_roi[-level:][::-1]
+            f_list = r_feats[-level:][::-1]
+            pred = eng["fusion"].forward(c_list, f_list, d_roi, None, base, trace)
+            preds[torch.from_numpy(idx).to(dev)] = pred.reshape(pb, ph, pw)
+            if trace is not None:
+                trace.setdefault("crops", crops.clone()); trace.setdefault("roi_depth", d_roi.clone())
+                trace.setdefault("fine_feats", [a.to_nchw() for a in r_feats])
+                trace = None
