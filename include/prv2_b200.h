@@ -222,6 +222,11 @@ int prv2_depth_taps(const float* pred1, const float* pred2, int N, int H, int W,
  * out[p] = clamp(base[p] + sum_{r,s} taps[p + (r-1, s-1), r*3+s], 0) with zero padding (base may
  * be NULL -> offset only, no clamp).  out fp32 [N,H,W]. */
 int prv2_tap_stencil(const float* taps, int N, int H, int W, int ld, const float* base, float* out, prv2_stream_t stream);
+/* The whole final conv fused: out[n,y,x] = clamp(base + sum_{r,s,c} feat[n,y+r-1,x+s-1,c] * w9c[(r*3+s)*C + c], 0) (no clamp when
+ * base is NULL); feat is a channels-last act (hi [+lo]), w9c fp32 [9,C] (final_conv.weight [1,C,3,3] permuted), out fp32 [N,H,W].
+ * Replaces FusionUnet.final_conv (estimator/models/blocks/fusion_model.py:113-118) in one HBM-bound pass. */
+int prv2_final_conv3x3(const prv2_bf16* feat_hi, const prv2_bf16* feat_lo, int N, int H, int W, int C, int cs, const float* w9c,
+                       const float* base, float* out, prv2_stream_t stream);
 
 /* act <-> fp32 helpers (layout changes at the API edge and for tests). */
 int prv2_nchw_f32_to_act(const float* in, int N, int C, int H, int W,

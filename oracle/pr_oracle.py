@@ -314,8 +314,8 @@ def depth_anything_v2(sd: Dict[str, Tensor], pre: str, x: Tensor, encoder: str, 
                       trace: Optional[dict] = None):
     """DepthAnythingV2.forward (dpt.py:182-203).  x: RGB in [0,1], [B,3,H,W].
     Returns (metric_depth [B,1,H,W], [x_d0, x_blocks_feat_0..3, midas_final_feat])."""
-    mean = torch.tensor(PIXEL_MEAN).view(-1, 1, 1)
-    std = torch.tensor(PIXEL_STD).view(-1, 1, 1)
+    mean = torch.tensor(PIXEL_MEAN, device=x.device).view(-1, 1, 1)      # device-agnostic: bench.py also runs this port on the GPU as the eager baseline
+    std = torch.tensor(PIXEL_STD, device=x.device).view(-1, 1, 1)
     x = (x - mean) / std
     ph, pw = x.shape[-2] // PATCH, x.shape[-1] // PATCH
     taps = vit_intermediate(sd, pre + "pretrained.", x, encoder, trace)
@@ -627,7 +627,7 @@ def crop_resize(image_hr: Tensor, bboxs: Tensor, patch_process_shape) -> Tensor:
 def coarse_postprocess_test(coarse_prediction: Tensor, coarse_features: List[Tensor], bboxs_feat: Tensor, ph: int):
     """PatchRefiner.coarse_postprocess_test (patchrefiner.py:199-217).  ``repeat`` is replaced by
     batch index 0 for every ROI (identical result: every repeated copy equals the original)."""
-    rois = bboxs_feat.clone()
+    rois = bboxs_feat.clone().to(coarse_prediction.device)
     rois[:, 0] = 0
     feats = []
     for feat in coarse_features:
@@ -918,8 +918,8 @@ class PatchRefinerPlusOracle(PatchRefinerOracle):
         self.encoder = encoder.eval()
 
     def infer_forward(self, imgs_crop, coarse_depth_roi, coarse_feats_roi, trace=None):
-        mean = torch.tensor(self.encoder.default_cfg["mean"]).view(-1, 1, 1)
-        std = torch.tensor(self.encoder.default_cfg["std"]).view(-1, 1, 1)
+        mean = torch.tensor(self.encoder.default_cfg["mean"], device=imgs_crop.device).view(-1, 1, 1)
+        std = torch.tensor(self.encoder.default_cfg["std"], device=imgs_crop.device).view(-1, 1, 1)
         x = (imgs_crop - mean) / std                                                      # lightweight_refiner.py:293
         feats = list(self.encoder(torch.cat([x, coarse_depth_roi], dim=1)))                # :296 (coarse_condition)
         feats.insert(0, F.interpolate(feats[0], scale_factor=2, mode="bilinear", align_corners=True))   # :316-318

@@ -78,6 +78,7 @@ SIGNATURES = {
     "prv2_resize_bilinear_act": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p],
     "prv2_depth_taps": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p],
     "prv2_tap_stencil": [_p, _i, _i, _i, _i, _p, _p, _p],
+    "prv2_final_conv3x3": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p],
     "prv2_nchw_f32_to_act": [_p, _i, _i, _i, _i, _p, _p, _i, _p],
     "prv2_act_to_nchw_f32": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
     "prv2_phase_split": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p],

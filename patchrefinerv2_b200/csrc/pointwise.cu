@@ -236,6 +236,104 @@ __global__ void __launch_bounds__(256) tap_stencil_kernel(const float* __restric
   out[o] = acc;
 }
 
+// ------------------------------ final 3x3 conv to ONE channel + base + clamp, fused (fusion_model.py:113-118)
+// HBM-bound: the C-channel feature map is read once.  CTA = 30x30 output pixels = a 32x32 halo tile.  Phase 1: every halo
+// pixel gets its 9 tap responses Y[t] = sum_c feat[c] * w[t][c] (fp32) into shared memory; out-of-image pixels are the
+// conv's zero padding.  FOUR lanes share a pixel (lane `sub` owns the 8-channel groups sub, sub+4, ...), so a warp-wide
+// 16-byte load touches 8 cache lines instead of 32 (thread-per-pixel loads were L1-tag bound), and a thread works on four
+// pixels at a time so one weight vector from shared memory feeds all four (the weight reads were shared-memory-bandwidth bound at two); the four partial sums meet in two shuffle steps.
+// Phase 2: out = clamp(base + sum_{r,s} Y[(y+r-1, x+s-1)][r*3+s], 0).  Replaces a 9-column GEMM (tile overheads on a
+// K=128, N=16 problem left it at ~1 TB/s) plus the tap-stencil pass over its 64-byte-per-pixel output.
+#define FC_T 30
+#define FC_HALO (FC_T + 2)
+#define FC_PIX (FC_HALO * FC_HALO)
+#define FC_NPX 4                 // pixels a thread works on at once: one shared-memory weight vector feeds all of them
+template <bool X3>
+__global__ void __launch_bounds__(256) final_conv_kernel(const bf16* __restrict__ fh, const bf16* __restrict__ fl, int H, int W, int C, int cs,
+                                                         const float* __restrict__ wt, const float* __restrict__ base, float* __restrict__ out) {
+  extern __shared__ float fc_smem[];
+  float* const s_w = fc_smem;                 // [9][C]
+  float* const s_y = fc_smem + 9 * C;         // [9][FC_PIX]
+  const int n = blockIdx.z, y0 = blockIdx.y * FC_T, x0 = blockIdx.x * FC_T;
+  for (int i = threadIdx.x; i < 9 * C; i += 256) s_w[i] = wt[i];
+  __syncthreads();
+  const size_t img = (size_t)n * H * W;
+  const int sub = threadIdx.x & 3, grp = threadIdx.x >> 2;            // 64 pixel slots per pass, FC_NPX pixels per thread and iteration
+  for (int pbase = 0; pbase < FC_PIX; pbase += 64 * FC_NPX) {
+    int pi[FC_NPX];
+    const bf16* ph[FC_NPX];
+    const bf16* pl[FC_NPX];
+    bool ok[FC_NPX];
+#pragma unroll
+    for (int k = 0; k < FC_NPX; ++k) {
+      pi[k] = pbase + k * 64 + grp;
+      const int hy = pi[k] / FC_HALO, hx = pi[k] - hy * FC_HALO;
+      const int yy = y0 + hy - 1, xx = x0 + hx - 1;
+      ok[k] = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const size_t off = ok[k] ? (img + (size_t)yy * W + xx) * cs : 0;
+      ph[k] = fh + off;
+      pl[k] = X3 ? fl + off : nullptr;
+    }
+    float acc[FC_NPX][9];
+#pragma unroll
+    for (int k = 0; k < FC_NPX; ++k)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
+    for (int c0 = sub * 8; c0 < C; c0 += 32) {
+      float v[FC_NPX][8];
+#pragma unroll
+      for (int k = 0; k < FC_NPX; ++k) {
+        if (ok[k]) {
+          act_load8(ph[k], pl[k], c0, v[k]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s_w + t * C + c0), w1 = *reinterpret_cast<const float4*>(s_w + t * C + c0 + 4);
+#pragma unroll
+        for (int k = 0; k < FC_NPX; ++k) {
+          float a = acc[k][t];
+          a = fmaf(v[k][0], w0.x, a); a = fmaf(v[k][1], w0.y, a); a = fmaf(v[k][2], w0.z, a); a = fmaf(v[k][3], w0.w, a);
+          a = fmaf(v[k][4], w1.x, a); a = fmaf(v[k][5], w1.y, a); a = fmaf(v[k][6], w1.z, a); a = fmaf(v[k][7], w1.w, a);
+          acc[k][t] = a;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < FC_NPX; ++k)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float a = acc[k][t];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        acc[k][t] = a;
+      }
+    // lane `sub` stores taps sub, sub+4, sub+8 of both pixels
+#pragma unroll
+    for (int k = 0; k < FC_NPX; ++k)
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        if ((t & 3) == sub) s_y[t * FC_PIX + pi[k]] = acc[k][t];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < FC_T * FC_T; i += 256) {
+    const int ty = i / FC_T, tx = i - ty * FC_T;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= H || x >= W) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) a += s_y[(r * 3 + q) * FC_PIX + (ty + r) * FC_HALO + tx + q];
+    const size_t o = img + (size_t)y * W + x;
+    if (base) a = fmaxf(base[o] + a, 0.f);
+    out[o] = a;
+  }
+}
+
 __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ in, int N, int C, int H, int W, bf16* __restrict__ oh,
                                                           bf16* __restrict__ ol, int out_cs, long long total) {
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -364,6 +462,25 @@ extern "C" int prv2_tap_stencil(const float* taps, int N, int H, int W, int ld, 
   if (N == 0) return PRV2_OK;
   dim3 grid(cdiv(W, 256), H, N);
   tap_stencil_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(taps, H, W, ld, base, out);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_final_conv3x3(const prv2_bf16* feat_hi, const prv2_bf16* feat_lo, int N, int H, int W, int C, int cs, const float* w9c,
+                                  const float* base, float* out, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(feat_hi && w9c && out, "prv2_final_conv3x3: null pointer");
+  PRV2_CHECK_ARG(N >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && cs % 8 == 0 && cs >= C && N <= 65535, "prv2_final_conv3x3: C and pitch must be multiples of 8");
+  const size_t smem = (size_t)(9 * C + 9 * FC_PIX) * sizeof(float);
+  PRV2_CHECK_ARG(smem <= 200 * 1024, "prv2_final_conv3x3: C=%d too wide for the shared-memory weight table", C);
+  if (N == 0) return PRV2_OK;
+  dim3 grid(cdiv(W, FC_T), cdiv(H, FC_T), N);
+  if (feat_lo) {
+    PRV2_CUDA(cudaFuncSetAttribute(final_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    final_conv_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)feat_hi, (const bf16*)feat_lo, H, W, C, cs, w9c, base, out);
+  } else {
+    PRV2_CUDA(cudaFuncSetAttribute(final_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    final_conv_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)feat_hi, nullptr, H, W, C, cs, w9c, base, out);
+  }
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

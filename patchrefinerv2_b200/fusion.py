@@ -69,7 +69,7 @@ class FusionUnetB200:
             chl = dc
         wf = g("final_conv.weight")                       # [1, C, 3, 3] -> 1x1 conv with one output per tap: [9, C]
         self.final_c = wf.shape[1]
-        self.final_taps = mk([(0, 0, 0, wf[0].permute(1, 2, 0).reshape(9, self.final_c))], 1, 9, epi=_lib.EPI_F32, name="fusion.final_taps")
+        self.final_w = wf[0].permute(1, 2, 0).reshape(9, self.final_c).contiguous().to(device)
 
     def flops(self, B: int, sizes) -> float:
         """sizes: list of (h, w) per level, finest first."""
@@ -127,8 +127,6 @@ class FusionUnetB200:
             feat = o
         if trace is not None:
             trace["fusion_dec"] = feat.to_nchw()
-        taps = ws.f32("final_taps", B, feat.H, feat.W, 16)
-        self.final_taps([feat], out_f32=taps, out_f32_ld=16)
         out = ws.f32("pred", B, 1, feat.H, feat.W)
-        ops.tap_stencil(taps, update_base, out)
+        ops.final_conv3x3(feat, self.final_w, update_base, out)
         return out

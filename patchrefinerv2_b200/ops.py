@@ -170,6 +170,13 @@ def tap_stencil(taps: torch.Tensor, base: Optional[torch.Tensor], out: torch.Ten
     _lib.call("prv2_tap_stencil", ptr(taps), N, H, W, ld, ptr(base), ptr(out), stream_ptr(), work=("byte", N * H * W * (4.0 * 9 + 8.0)))
 
 
+def final_conv3x3(feat: Act, w9c: torch.Tensor, base: Optional[torch.Tensor], out: torch.Tensor):
+    """feat [N,H,W,C] act, w9c fp32 [9,C] -> out[N,1,H,W] = clamp(base + conv3x3(feat), 0)  (fusion_model.py:113-118), one pass."""
+    planes = 2 if feat.lo is not None else 1
+    _lib.call("prv2_final_conv3x3", ptr(feat.hi), ptr(feat.lo), feat.N, feat.H, feat.W, feat.C, feat.cs, ptr(w9c), ptr(base), ptr(out), stream_ptr(),
+              work=("byte", feat.N * feat.H * feat.W * (2.0 * planes * feat.C + 8.0)))
+
+
 def phase_split(a: Act, out: Act):
     """out is [4*N, H/2, W/2, C] (phase-major)."""
     _lib.call("prv2_phase_split", ptr(a.hi), ptr(a.lo), a.N, a.H, a.W, a.C, a.cs, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr(),

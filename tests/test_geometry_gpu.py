@@ -215,3 +215,31 @@ def test_blend_fast_paths_equal_generic_kernels(dev, case):
     for nm, g, f in zip(names, outs[0], outs[1]):
         assert torch.equal(g, f), nm
     assert torch.equal(outs[1][1], outs[1][6]) and torch.equal(outs[1][3], outs[1][8])          # count maps: sharded == sequential, bit-exact
+
+
+def test_blend_at_config5_size_vs_oracle(dev):
+    """BASELINE config 5 geometry, the largest in scope: 4320x7680 frame, 8x8 split (canvas 3584x3584, 225 regular patches),
+    r128 (128 random patches, four ballot rounds per row list).  Tiling, count map and depth of the sequential blend are
+    bit-exact against the CPU oracle (the reference's RunningAverageMap arithmetic); fast and generic kernels agree."""
+    from patchrefinerv2_b200 import ops
+    shape, raw, split, mode, pn = (448, 448), (4320, 7680), (8, 8), "r128", 4
+    tc, preds, grid, n_reg, mask, rmask, starts = _blend_inputs(dev, shape, mode, pn, raw, split)
+    assert n_reg == 64 + 56 + 56 + 49 and preds.shape[0] == n_reg + 128
+    Hc, Wc = tc["patch_reensemble_shape"]
+    H, W = tc["image_raw_shape"]
+    rh, rw = tc["patch_raw_shape"]
+    assert (Hc, Wc, rh, rw) == (3584, 3584, 540, 960)
+    res = []
+    try:
+        for generic in (True, False):
+            _set_generic(generic)
+            a, c = ops.blend_canvas(preds[:n_reg], mask, grid, Hc, Wc)
+            res.append(ops.blend_raw(a, c, preds[n_reg:], starts, rmask, shape[0], shape[1], rh, rw, H, W))
+    finally:
+        _set_generic(False)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    go = O.GeometryOracle(shape, raw, split)
+    random.seed(1)
+    depth, _, avg = go.infer(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, H, W), None, mode, pn)
+    assert torch.equal(res[1][1].cpu(), avg.count_map)                       # count map: bit-exact
+    assert torch.equal(res[1][0].cpu(), depth[0, 0])                          # sequential running mean: bit-exact

@@ -240,3 +240,20 @@ def test_resize_depth_taps_final_conv(x3, tol):
     out = torch.zeros(2, 1, 56, 56, device=DEV)
     ops.tap_stencil(taps, base.to(DEV), out)
     assert rel_err(out.cpu(), want) < tol
+
+
+@pytest.mark.parametrize("x3,tol", [(False, 1e-2), (True, 1e-4)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 56, 56), (3, 128, 70, 45), (1, 8, 5, 3)])
+def test_fused_final_conv3x3(x3, tol, B, C, H, W):
+    """prv2_final_conv3x3 (one pass) == clamp(base + conv2d(feat, w, padding=1), 0); ragged tiles, halo at every border."""
+    from patchrefinerv2_b200 import ops
+    g = torch.Generator().manual_seed(5 + C)
+    f = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(1, C, 3, 3, generator=g) / (3 * C ** 0.5)
+    base = torch.rand(B, 1, H, W, generator=g) - 0.3
+    w9c = w[0].permute(1, 2, 0).reshape(9, C).contiguous().to(DEV)
+    out = torch.zeros(B, 1, H, W, device=DEV)
+    ops.final_conv3x3(_act(f, x3), w9c, base.to(DEV), out)
+    assert rel_err(out.cpu(), torch.clamp(base + F.conv2d(f, w, padding=1), min=0)) < tol
+    ops.final_conv3x3(_act(f, x3), w9c, None, out)                        # no base: raw offset, no clamp
+    assert rel_err(out.cpu(), F.conv2d(f, w, padding=1)) < tol
