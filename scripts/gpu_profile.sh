@@ -4,16 +4,18 @@
 # Usage (under gpurun): bash scripts/gpu_profile.sh [tag]
 tag=${1:-r01}
 mkdir -p gpurun_out
-RX='regex:umma_gemm|attention_|layernorm_kernel|patchify|assemble_tokens|resize_act|depth_taps|tap_stencil|phase_split|crop_resize|roi_gather|blend_'
-# one frame = 979 launches of our kernels at ViT-L r32 with patch_batch 27; skip the warm-up frame
-timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$RX" -s 979 -c 979 --csv \
+RX='regex:umma_gemm|final_conv|attention_|layernorm_kernel|patchify|assemble_tokens|resize_act|depth_taps|tap_stencil|phase_split|crop_resize|roi_gather|blend_'
+# one frame = 976 launches of our kernels at ViT-L r32 with patch_batch 27; skip the warm-up frame
+timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$RX" -s 976 -c 976 --csv \
   --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 1 --warmup 1 --profile-run --no-cpu-baseline --no-e2e \
   > gpurun_out/bench_under_ncu_${tag}.log 2>&1
 echo "launch list rc=$?"
-for k in qkv conv attn blend resize; do
-  case $k in attn) rx=attention;; blend) rx=blend;; resize) rx=resize_act;; *) rx=umma_gemm;; esac
+for k in qkv fc1 fc2 proj conv attn blend resize finalconv; do
+  case $k in attn) rx=attention;; blend) rx=blend_;; resize) rx=resize_act;; finalconv) rx=final_conv;; *) rx=umma_gemm;; esac
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$rx -s 1 -c 3 -f -o gpurun_out/prof_${k}_${tag} \
     python scripts/prof_kernels.py $k > gpurun_out/prof_${k}_${tag}.log 2>&1
   echo "prof $k rc=$?"
+  # the raw page as CSV travels even when a large .ncu-rep does not
+  ncu -i gpurun_out/prof_${k}_${tag}.ncu-rep --page raw --csv > gpurun_out/prof_${k}_${tag}_raw.csv 2>/dev/null
 done
 ls -la gpurun_out | head -40

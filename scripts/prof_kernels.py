@@ -31,6 +31,22 @@ if which in ("all", "proj"):
     lay = GemmLayer([(0, 0, 0, torch.randn(D, D) / 32)], 1, D, False, DEV, epi=_lib.EPI_RESID_F32, bias=torch.randn(D), gamma=torch.rand(D), name="proj")
     x = torch.zeros(M, D, device=DEV)
     run(lambda: lay([y], out_f32=x, out_f32_ld=D))
+if which in ("all", "fc1"):
+    y = Act.empty(1, 1, M, D, False, DEV); y.hi.normal_()
+    lay = GemmLayer([(0, 0, 0, torch.randn(4 * D, D) / 32)], 1, 4 * D, False, DEV, act=_lib.ACT_GELU, bias=torch.randn(4 * D), name="fc1")
+    out = Act.empty(1, 1, M, 4 * D, False, DEV)
+    run(lambda: lay([y], out=out))
+if which in ("all", "fc2"):
+    y = Act.empty(1, 1, M, 4 * D, False, DEV); y.hi.normal_()
+    lay = GemmLayer([(0, 0, 0, torch.randn(D, 4 * D) / 64)], 1, D, False, DEV, epi=_lib.EPI_RESID_F32, bias=torch.randn(D), gamma=torch.rand(D), name="fc2")
+    x = torch.zeros(M, D, device=DEV)
+    run(lambda: lay([y], out_f32=x, out_f32_ld=D))
+if which in ("all", "finalconv"):
+    f = Act.empty(12, 448, 448, 128, False, DEV); f.hi.normal_()
+    w9c = torch.randn(9, 128, device=DEV) / 34
+    base = torch.rand(12, 1, 448, 448, device=DEV)
+    out = torch.empty(12, 1, 448, 448, device=DEV)
+    run(lambda: ops.final_conv3x3(f, w9c, base, out))
 if which in ("all", "attn"):
     qkv = Act.empty(1, 1, M, 3 * D, False, DEV); qkv.hi.normal_()
     out = Act.empty(1, 1, M, D, False, DEV)
@@ -47,15 +63,28 @@ if which in ("all", "conv"):
     out = Act.empty(4, 448, 448, 386, False, DEV, cs=392)
     run(lambda: lay([a, b, c], out=out))
 if which in ("all", "blend"):
-    preds = torch.rand(81, 448, 448, device=DEV)
-    mask = torch.rand(448, 448, device=DEV)
-    stages = [(0, 0, 4, 4, 0), (0, 224, 4, 3, 16), (224, 0, 3, 4, 28), (224, 224, 3, 3, 40)]
-    starts = torch.randint(0, 1600, (32, 2), dtype=torch.int32, device=DEV)
-    rmask = torch.rand(540, 960, device=DEV) + 1e-3
+    # the BASELINE frame's real schedule (2160x3840, 4x4, r32, seed 1) with random predictions
+    import random
+    import numpy as np
+    from patchrefinerv2_b200 import masks, tiling
+    tc = tiling.prepare_tile_cfg((448, 448), (2160, 3840), (4, 4))
+    st = tiling.schedule(tc, (448, 448), "r32", 4, random.Random(1))
+    bb = np.concatenate([s.bboxs for s in st])
+    stages, first = [], 0
+    for s_ in st:
+        if s_.kind == "regular":
+            stages.append((s_.off_process[0], s_.off_process[1], s_.grid[0], s_.grid[1], first))
+            first += s_.bboxs.shape[0]
+    preds = torch.rand(bb.shape[0], 448, 448, device=DEV) * 10
+    mask = torch.from_numpy(masks.generatemask((448, 448), 0.15).copy()).to(DEV)
+    rmask = torch.from_numpy(masks.random_patch_mask((540, 960), 0.15).copy()).to(DEV)
+    starts = torch.from_numpy(np.ascontiguousarray(bb[first:, [1, 0]])).to(DEV)
+    flush = torch.empty(64 * 1024 * 1024, device=DEV)
 
     def f():
-        avg, cnt = ops.blend_canvas(preds[:49], mask, stages, 1792, 1792)
-        ops.blend_raw(avg, cnt, preds[49:], starts, rmask, 448, 448, 540, 960, 2160, 3840)
+        flush.fill_(1.0)                                      # cold L2, as in the frame loop
+        avg, cnt = ops.blend_canvas(preds[:first], mask, stages, 1792, 1792)
+        ops.blend_raw(avg, cnt, preds[first:], starts, rmask, 448, 448, 540, 960, 2160, 3840)
     run(f)
 if which in ("all", "resize"):
     a = Act.empty(12, 256, 256, 256, False, DEV); a.hi.normal_()
