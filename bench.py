@@ -423,7 +423,7 @@ def main():
                           "unit": "GB/s", "frac": b_bytes / b_s / 1e9 / peaks["hbm"], "us_per_frame": b_s * 1e6,
                           "stages": {k: {"algorithmic_bytes": v["bytes"], "us": v["s"] * 1e6, "GBps": v["bytes"] / v["s"] / 1e9,
                                          "frac": v["bytes"] / v["s"] / 1e9 / peaks["hbm"]} for k, v in bt.items()},
-                          "traffic": {k: traffic.get(k, {}).get("dram_bytes_per_launch") for k in ("blend_canvas_kernel", "blend_raw_kernel")},
+                          "traffic": {k: traffic.get(k, {}).get("dram_bytes_per_launch") for k in ("blend_canvas_fast_kernel", "blend_raw_tab_kernel")},
                           "note": "median of 20 launches each, 256 MB L2 flush before every launch, own event pair per launch"}
     except Exception as e:
         roofline_blend = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
