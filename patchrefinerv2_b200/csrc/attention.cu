@@ -285,7 +285,9 @@ constexpr int KV_STAGES = 2;
 constexpr int KV_ROWS = 144;
 constexpr int KV_TILE_BYTES = KV_ROWS * 128;       // 18 KB
 constexpr int S_COLS = 160;                         // TMEM columns reserved per S accumulator (32-aligned)
-constexpr int V2_THREADS = 320;
+constexpr int V2_THREADS = 320;                    // SPLIT = 1: one softmax thread per query row
+constexpr int V4_THREADS = 64 + 2 * 256;            // SPLIT = 2: two threads per query row (16 softmax warps, 4 per SMSP)
+constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;      // row-statistics exchange between the two halves of a row: [tile][parity][half][row]
 constexpr int TAIL_MAX = 16;                        // leftover rows / keys folded away from a full extra tile
 constexpr int OUT_PITCH = 144;                      // staged output row: 64 bf16 + 16 B pad
 constexpr float RESCALE_LOG2 = 8.0f;                // lazy rescale threshold (log2 units)
@@ -323,6 +325,21 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
       : "memory");
 }
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+      "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 
 struct alignas(64) AttnParamsV2 {
   CUtensorMap tm_q, tm_kv;
@@ -330,7 +347,17 @@ struct alignas(64) AttnParamsV2 {
   int B, T, heads, D, n_chunks, last_width, tq_main;
 };
 
-__global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __grid_constant__ AttnParamsV2 p) {
+// SPLIT = 2 ("v4"): the softmax of a 128-row query tile is shared by TWO warpgroups -- the warps (tile, half, quadrant) with the same
+// quadrant may read the same TMEM lanes, so thread (half, row) owns columns [64*half, 64*half+64) of its row's scores, writes P
+// tile `half` and rescales / emits O columns [32*half, 32*half+32).  The halves meet once per chunk (row maximum, through shared
+// memory and a 256-thread named barrier) and once at the end (row sum).  v3 ran 2 softmax warps per SM sub-partition and was
+// latency-bound there (issue slots 45 % busy, MUFU 42 %); four warps per sub-partition hide the TMEM-load / MUFU / barrier latencies.
+// (18 warps put 5 on one sub-partition: 16384 / (5 * 32) caps the SPLIT = 2 kernel at 96 registers, so it walks its two
+// 32-column pieces through ONE register buffer; the other warps of the sub-partition cover the TMEM-load latency instead.
+// Keeping all 64 scores of a thread in registers between the two passes -- one TMEM read per chunk instead of two -- was
+// measured SLOWER (342 vs 292 us per 27-patch call): at 96 registers it spills.)
+template <int SPLIT>
+__global__ void __launch_bounds__(64 + 256 * SPLIT, 1) attention_v3_kernel(const __grid_constant__ AttnParamsV2 p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -344,6 +371,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __gri
   auto p_full = [&](int w) { return bars + 8u * (3 + 2 * KV_STAGES + w); };
   auto o_done = [&](int w) { return bars + 8u * (5 + 2 * KV_STAGES + w); };
   const uint32_t tmem_slot = bars + 8u * (7 + 2 * KV_STAGES);
+  float* const xch = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
@@ -354,7 +382,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __gri
   if (tid == 0) {
     mbar_init(bar_q, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full(w), 1); mbar_init(p_full(w), 128); mbar_init(o_done(w), 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(s_full(w), 1); mbar_init(p_full(w), 128 * SPLIT); mbar_init(o_done(w), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -435,11 +463,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __gri
     }
   } else {
     // ------------------------------------------------ softmax warpgroups
-    const int w = (warp - 2) >> 2;
+    const int w = (warp - 2) / (4 * SPLIT);
+    const int half = SPLIT == 2 ? ((warp - 2) >> 2) & 1 : 0;
+    constexpr int NP = 4 / SPLIT;                            // 32-column pieces of a full 128-key chunk per thread
+    const int col_base = half * (128 / SPLIT);               // first score column this thread owns
     if (w < n_wg) {
       const int row = (warp & 3) * 32 + lane;               // TMEM lane == query row of this tile
       const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t tS = tmem_base + w * S_COLS + lane_off, tO = tmem_base + 2 * S_COLS + w * 64 + lane_off;
+      const uint32_t tS = tmem_base + w * S_COLS + lane_off + col_base, tO = tmem_base + 2 * S_COLS + w * 64 + lane_off + half * 32;
+      auto xslot = [&](int parity, int h) { return xch + (((w * 2 + parity) * 2 + h) * 128 + row); };
+      auto pair_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory"); };
       uint8_t* const pP = base_ptr + (sP - base) + 3 * w * TILE_BYTES;
       const float c_log2 = 0.125f * 1.4426950408889634f;    // head_dim^-0.5 * log2(e)   (attention.py:41)
       const float tau = RESCALE_LOG2 / c_log2;
@@ -454,8 +487,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __gri
         constexpr bool GENERAL = decltype(general_tag)::value;
         const int n_valid = GENERAL ? T - j * 128 : 128;
         const int width = GENERAL ? p.last_width : 128;
-        const int n_pieces = GENERAL ? min(4, (width + 31) >> 5) : 4;     // 32-column pieces inside the first 128 columns
-        const bool wide = GENERAL && width > 128;                          // keys 128..143 of the wide last chunk
+        const int n_pieces = GENERAL ? max(1, min(NP, (min(width, 128) - col_base + 31) >> 5)) : NP;   // 32-column pieces of this thread inside the first 128 columns
+        const bool wide = GENERAL && width > 128 && half == SPLIT - 1;     // keys 128..143 of the wide last chunk
         mbar_wait(s_full(w), j & 1);
         tc_fence_after();
         // ---- pass 1: row maximum (TMEM loads double-buffered in registers)
@@ -471,17 +504,22 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __gri
         };
         tc_ld32_issue(tS, ra);
         tc_ld_wait();
-        if (n_pieces > 1) tc_ld32_issue(tS + 32, rb);
-        pmax(ra, 0);
-        if (n_pieces > 1) {
-          tc_ld_wait();
-          if (n_pieces > 2) tc_ld32_issue(tS + 64, ra);
-          pmax(rb, 32);
-          if (n_pieces > 2) {
+        if (SPLIT == 2) {
+          pmax(ra, col_base);
+          if (n_pieces > 1) { tc_ld32_issue(tS + 32, ra); tc_ld_wait(); pmax(ra, col_base + 32); }
+        } else {
+          if (n_pieces > 1) tc_ld32_issue(tS + 32, rb);
+          pmax(ra, 0);
+          if (n_pieces > 1) {
             tc_ld_wait();
-            if (n_pieces > 3) tc_ld32_issue(tS + 96, rb);
-            pmax(ra, 64);
-            if (n_pieces > 3) { tc_ld_wait(); pmax(rb, 96); }
+            if (n_pieces > 2) tc_ld32_issue(tS + 64, ra);
+            pmax(rb, 32);
+            if (n_pieces > 2) {
+              tc_ld_wait();
+              if (n_pieces > 3) tc_ld32_issue(tS + 96, rb);
+              pmax(ra, 64);
+              if (n_pieces > 3) { tc_ld_wait(); pmax(rb, 96); }
+            }
           }
         }
         uint32_t rw[16];
@@ -490,13 +528,18 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __gri
               "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
               : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]), "=r"(rw[8]), "=r"(rw[9]),
                 "=r"(rw[10]), "=r"(rw[11]), "=r"(rw[12]), "=r"(rw[13]), "=r"(rw[14]), "=r"(rw[15])
-              : "r"(tS + 128)
+              : "r"(tS - col_base + 128)
               : "memory");
           tc_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) if (128 + i < n_valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(rw[i]));
         }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        if (SPLIT == 2) {                                     // the row's other half: slots alternate by chunk parity, so a fast
+          *xslot(j & 1, half) = mx;                           // partner's write for chunk j+1 cannot overtake this chunk's read
+          pair_sync();
+          mx = fmaxf(mx, *xslot(j & 1, half ^ 1));
+        }
         // ---- lazy rescale decision: keep the stale maximum unless the new one is > 2^8 larger
         const bool need = mx > m_run + tau;
         float alpha = 1.f;
@@ -506,27 +549,36 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __gri
           l_run *= alpha;
         }
         const float mc = m_run * c_log2;
-        // first piece of pass 2 can be fetched while we wait for the previous P V product
-        tc_ld32_issue(tS, ra);
+        // first piece of pass 2 can be fetched while we wait for the previous P V product (SPLIT == 1: it has the registers for it)
+        if (SPLIT == 1) tc_ld32_issue(tS, ra);
         if (j > 0) {
           mbar_wait(o_done(w), (j - 1) & 1);                // P_w(j-1) V(j-1) has retired: P buffer and O_w are ours
           tc_fence_after();
           if (__any_sync(0xffffffffu, need)) {              // warp-uniform: tcgen05.ld / st are warp collectives
-            tc_ld_wait();                                     // (drains the prefetched S piece too)
-            uint32_t ro[32];
-            tc_ld32_issue(tO, ro);
-            tc_ld_wait();
+            if (SPLIT == 1) {
+              tc_ld_wait();                                   // (drains the prefetched S piece too)
+              uint32_t ro[32];
+              tc_ld32_issue(tO, ro);
+              tc_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-            tc_st32(tO, ro);
-            tc_ld32_issue(tO + 32, ro);
-            tc_ld_wait();
+              for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+              tc_st32(tO, ro);
+              tc_ld32_issue(tO + 32, ro);
+              tc_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-            tc_st32(tO + 32, ro);
+              for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+              tc_st32(tO + 32, ro);
+            } else {                                          // this half's 32 O columns, through the (still empty) S buffer
+              tc_ld32_issue(tO, ra);
+              tc_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ra[i] = __float_as_uint(__uint_as_float(ra[i]) * alpha);
+              tc_st32(tO, ra);
+            }
             tc_st_wait();
           }
         }
+        if (SPLIT == 2) tc_ld32_issue(tS, ra);
         // ---- pass 2: p = 2^(s*c - m*c) -> bf16 -> P tile (SW128 K-major), row sum
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         auto emit = [&](const uint32_t* r, int col0, int n) {
@@ -556,17 +608,22 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __gri
         };
         if (wide) emit(rw, 128, 16);
         tc_ld_wait();
-        if (n_pieces > 1) tc_ld32_issue(tS + 32, rb);
-        emit(ra, 0, 32);
-        if (n_pieces > 1) {
-          tc_ld_wait();
-          if (n_pieces > 2) tc_ld32_issue(tS + 64, ra);
-          emit(rb, 32, 32);
-          if (n_pieces > 2) {
+        if (SPLIT == 2) {
+          emit(ra, col_base, 32);
+          if (n_pieces > 1) { tc_ld32_issue(tS + 32, ra); tc_ld_wait(); emit(ra, col_base + 32, 32); }
+        } else {
+          if (n_pieces > 1) tc_ld32_issue(tS + 32, rb);
+          emit(ra, 0, 32);
+          if (n_pieces > 1) {
             tc_ld_wait();
-            if (n_pieces > 3) tc_ld32_issue(tS + 96, rb);
-            emit(ra, 64, 32);
-            if (n_pieces > 3) { tc_ld_wait(); emit(rb, 96, 32); }
+            if (n_pieces > 2) tc_ld32_issue(tS + 64, ra);
+            emit(rb, 32, 32);
+            if (n_pieces > 2) {
+              tc_ld_wait();
+              if (n_pieces > 3) tc_ld32_issue(tS + 96, rb);
+              emit(ra, 64, 32);
+              if (n_pieces > 3) { tc_ld_wait(); emit(rb, 96, 32); }
+            }
           }
         }
         l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
@@ -581,24 +638,32 @@ __global__ void __launch_bounds__(V2_THREADS, 1) attention_v3_kernel(const __gri
       // ---- epilogue: O / l -> bf16 -> staged row -> one bulk copy
       mbar_wait(o_done(w), (n_chunks - 1) & 1);
       tc_fence_after();
+      if (SPLIT == 2) {                                       // row sum = the two halves' partial sums (same rescale history)
+        *xslot(n_chunks & 1, half) = l_run;
+        pair_sync();
+        l_run += *xslot(n_chunks & 1, half ^ 1);
+      }
       const float inv = 1.0f / l_run;
       uint8_t* const srow = pP + row * OUT_PITCH;             // the P tiles are free now
       tc_ld32_issue(tO, ra);
-      tc_ld32_issue(tO + 32, rb);
+      if (SPLIT == 1) tc_ld32_issue(tO + 32, rb);
       tc_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         __nv_bfloat162 h2[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(__uint_as_float(ra[g * 8 + 2 * t]) * inv, __uint_as_float(ra[g * 8 + 2 * t + 1]) * inv);
-        *reinterpret_cast<uint4*>(srow + g * 16) = *reinterpret_cast<const uint4*>(h2);
+        *reinterpret_cast<uint4*>(srow + half * 64 + g * 16) = *reinterpret_cast<const uint4*>(h2);
+        if (SPLIT == 1) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(__uint_as_float(rb[g * 8 + 2 * t]) * inv, __uint_as_float(rb[g * 8 + 2 * t + 1]) * inv);
-        *reinterpret_cast<uint4*>(srow + 64 + g * 16) = *reinterpret_cast<const uint4*>(h2);
+          for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(__uint_as_float(rb[g * 8 + 2 * t]) * inv, __uint_as_float(rb[g * 8 + 2 * t + 1]) * inv);
+          *reinterpret_cast<uint4*>(srow + 64 + g * 16) = *reinterpret_cast<const uint4*>(h2);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (SPLIT == 2) pair_sync();                            // both halves of the staged row are written and fenced
       const int q = q0 + w * 128 + row;
-      if (q < p.tq_main) {
+      if (q < p.tq_main && half == 0) {
         bf16* const gdst = p.out_hi + ((size_t)b * T + q) * D + head * 64;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(gdst), "r"(smem_u32(srow)) : "memory");
       }
@@ -746,10 +811,13 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
   p.B = B; p.T = T; p.heads = heads; p.D = D;
   const int smem1 = 5 * TILE_BYTES + 1024 + 64, smem3 = 10 * TILE_BYTES + 1024 + 64;
-  const int smem_v2 = 2 * TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 6 * TILE_BYTES + 1024 + 256;
+  const int smem_v2 = 2 * TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 6 * TILE_BYTES + 1024 + 256 + XCH_BYTES;
+  static const char* split_env = getenv("PRV2_ATTN_SPLIT");            // diagnostics: 1 = one softmax thread per row (v3)
+  const bool split2 = !(split_env && split_env[0] == '1');
   static const bool force_v1 = getenv("PRV2_ATTN_V1") != nullptr;
   if (!g_attr_set) {
-    PRV2_CUDA(cudaFuncSetAttribute(attention_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v2));
+    PRV2_CUDA(cudaFuncSetAttribute(attention_v3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v2));
+    PRV2_CUDA(cudaFuncSetAttribute(attention_v3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v2));
     PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     g_attr_set = true;
@@ -773,7 +841,8 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
   // query rows: leftover rows (<= 16) go to the SIMT tail kernel instead of a mostly empty 128-row tile
   const int rem = T % 128;
   p2.tq_main = (rem != 0 && rem <= TAIL_MAX && T > 128 && T <= TAIL_MAX_T) ? T - rem : T;
-  attention_v3_kernel<<<dim3(cdiv(p2.tq_main, 256), heads, B), V2_THREADS, smem_v2, (cudaStream_t)stream>>>(p2);
+  if (split2) attention_v3_kernel<2><<<dim3(cdiv(p2.tq_main, 256), heads, B), V4_THREADS, smem_v2, (cudaStream_t)stream>>>(p2);
+  else attention_v3_kernel<1><<<dim3(cdiv(p2.tq_main, 256), heads, B), V2_THREADS, smem_v2, (cudaStream_t)stream>>>(p2);
   PRV2_LAUNCH_CHECK();
   if (p2.tq_main < T) {
     attention_tail_kernel<<<B * heads * (T - p2.tq_main), TAIL_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)qkv_hi, (bf16*)out_hi, B, T, heads, p2.tq_main);

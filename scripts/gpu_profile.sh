@@ -17,5 +17,9 @@ for k in qkv fc1 fc2 proj conv attn blend resize finalconv; do
   echo "prof $k rc=$?"
   # the raw page as CSV travels even when a large .ncu-rep does not
   ncu -i gpurun_out/prof_${k}_${tag}.ncu-rep --page raw --csv > gpurun_out/prof_${k}_${tag}_raw.csv 2>/dev/null
+  # gpurun copies back at most 64 MiB: keep the full report only for the small non-GEMM kernels, the top stall sites for all
+  python scripts/ncu_top_stalls.py gpurun_out/prof_${k}_${tag}.ncu-rep 30 > gpurun_out/prof_${k}_${tag}_stalls.txt 2>&1
+  case $k in attn|blend|finalconv) ;; *) rm -f gpurun_out/prof_${k}_${tag}.ncu-rep;; esac
 done
+du -sh gpurun_out
 ls -la gpurun_out | head -40
