@@ -159,9 +159,12 @@ __global__ void __launch_bounds__(256) roi_gather_f32_kernel(const float* __rest
 // the separable form hy*(hx*v1 + lx*v2) + ly*(hx*v3 + lx*v4); only the f32 variant replays torchvision's rounding order.
 constexpr int ROI_ROWS = 8;
 
-__global__ void __launch_bounds__(256) roi_gather_act_kernel(const bf16* __restrict__ fh, const bf16* __restrict__ fl, int h, int w,
+template <bool X3>   // compile-time (hi, lo) planes: a runtime lo pointer leaves the second plane's code predicated off but issued
+__global__ void __launch_bounds__(256) roi_gather_act_kernel(const bf16* __restrict__ fh, const bf16* __restrict__ fl_, int h, int w,
                                                              int C, int in_cs, const float* __restrict__ rois, float s,
-                                                             bf16* __restrict__ oh, bf16* __restrict__ ol, int out_cs) {
+                                                             bf16* __restrict__ oh, bf16* __restrict__ ol_, int out_cs) {
+  const bf16* const fl = X3 ? fl_ : nullptr;
+  bf16* const ol = X3 ? ol_ : nullptr;
   const unsigned cv = (unsigned)C >> 3, total = (unsigned)w * cv;
   const unsigned idx = blockIdx.x * 256u + threadIdx.x;
   if (idx >= total) return;
@@ -234,8 +237,13 @@ extern "C" int prv2_roi_gather_act(const prv2_bf16* feat_hi, const prv2_bf16* fe
   if (P == 0) return PRV2_OK;
   PRV2_CHECK_ARG(h <= 65535 && P <= 65535, "prv2_roi_gather_act: grid too large");
   dim3 grid(cdiv((long long)w * (C / 8), 256), cdiv(h, ROI_ROWS), P);
-  roi_gather_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)feat_hi, (const bf16*)feat_lo, h, w, C, in_cs, rois, spatial_scale,
-                                                               (bf16*)out_hi, (bf16*)out_lo, out_cs);
+  PRV2_CHECK_ARG((feat_lo == nullptr) == (out_lo == nullptr), "prv2_roi_gather_act: lo planes must both be present or absent");
+  if (feat_lo)
+    roi_gather_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)feat_hi, (const bf16*)feat_lo, h, w, C, in_cs, rois, spatial_scale,
+                                                                       (bf16*)out_hi, (bf16*)out_lo, out_cs);
+  else
+    roi_gather_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)feat_hi, nullptr, h, w, C, in_cs, rois, spatial_scale,
+                                                                        (bf16*)out_hi, nullptr, out_cs);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

@@ -30,9 +30,12 @@ __device__ __forceinline__ void act_store4(bf16* hi, bf16* lo, size_t i, const f
 
 // ------------------------------------------------------------------ LayerNorm (block.py:56,68)
 // warp per row, row kept in registers (D <= 1024), two-pass mean / variance.
+template <bool X3, bool GELU>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int rows, int D, const float* __restrict__ w,
                                                         const float* __restrict__ b, float eps, int drop_period, bf16* __restrict__ oh,
-                                                        bf16* __restrict__ ol, int out_cs, int gelu) {
+                                                        bf16* __restrict__ ol_, int out_cs) {
+  bf16* const ol = X3 ? ol_ : nullptr;
+  constexpr bool gelu = GELU;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -116,9 +119,15 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
 // version recomputed all four taps per output and was ALU-pipe bound (77 % ALU, 2.0 TB/s) on the unpack / index work.
 constexpr int RS_ROWS = 8;
 
-__global__ void __launch_bounds__(256) resize_act_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il, int h, int w, int C,
-                                                         int in_cs, bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW,
-                                                         int out_cs, int relu, float sy, float sx) {
+// X3 / RELU are compile-time: with a runtime `lo` pointer the (hi, lo) plane code was predicated off in bf16 mode but still
+// issued -- 645 of the kernel's ~2700 SASS instructions -- in a kernel that is ALU-pipe bound.
+template <bool X3, bool RELU>
+__global__ void __launch_bounds__(256) resize_act_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il_, int h, int w, int C,
+                                                         int in_cs, bf16* __restrict__ oh, bf16* __restrict__ ol_, int OH, int OW,
+                                                         int out_cs, float sy, float sx) {
+  const bf16* const il = X3 ? il_ : nullptr;
+  bf16* const ol = X3 ? ol_ : nullptr;
+  constexpr bool relu = RELU;
   const unsigned cv = (unsigned)C >> 3, total = (unsigned)OW * cv;
   const unsigned idx = blockIdx.x * 256u + threadIdx.x;
   if (idx >= total) return;
@@ -393,7 +402,8 @@ extern "C" int prv2_layernorm(const float* x, int rows, int D, const float* w, c
   PRV2_CHECK_ARG(x && w && b && out_hi, "prv2_layernorm: null pointer");
   PRV2_CHECK_ARG(rows >= 0 && D > 0 && D % 128 == 0 && D <= 1024 && out_cs % 4 == 0 && out_cs >= D, "prv2_layernorm: D must be a multiple of 128, <= 1024 (got %d)", D);
   if (rows == 0) return PRV2_OK;
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, drop_period, (bf16*)out_hi, (bf16*)out_lo, out_cs, 0);
+  if (out_lo) layernorm_kernel<true, false><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, drop_period, (bf16*)out_hi, (bf16*)out_lo, out_cs);
+  else layernorm_kernel<false, false><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, drop_period, (bf16*)out_hi, nullptr, out_cs);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -403,7 +413,8 @@ extern "C" int prv2_layernorm_gelu(const float* x, int rows, int D, const float*
   PRV2_CHECK_ARG(x && w && b && out_hi, "prv2_layernorm_gelu: null pointer");
   PRV2_CHECK_ARG(rows >= 0 && D > 0 && D % 128 == 0 && D <= 1024 && out_cs % 4 == 0 && out_cs >= D, "prv2_layernorm_gelu: D must be a multiple of 128, <= 1024 (got %d)", D);
   if (rows == 0) return PRV2_OK;
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, 0, (bf16*)out_hi, (bf16*)out_lo, out_cs, 1);
+  if (out_lo) layernorm_kernel<true, true><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, 0, (bf16*)out_hi, (bf16*)out_lo, out_cs);
+  else layernorm_kernel<false, true><<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D, w, b, eps, 0, (bf16*)out_hi, nullptr, out_cs);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -437,8 +448,12 @@ extern "C" int prv2_resize_bilinear_act(const prv2_bf16* in_hi, const prv2_bf16*
   const float sy = oh > 1 ? (float)(h - 1) / (float)(oh - 1) : 0.f, sx = ow > 1 ? (float)(w - 1) / (float)(ow - 1) : 0.f;
   PRV2_CHECK_ARG((long long)ow * (C / 8) < (1LL << 31), "prv2_resize_bilinear_act: row too long");
   dim3 grid(cdiv((long long)ow * (C / 8), 256), cdiv(oh, RS_ROWS), N);
-  resize_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, h, w, C, in_cs, (bf16*)out_hi, (bf16*)out_lo,
-                                                          oh, ow, out_cs, relu, sy, sx);
+  PRV2_CHECK_ARG((in_lo == nullptr) == (out_lo == nullptr), "prv2_resize_bilinear_act: lo planes must both be present or absent");
+#define PRV2_RS(X, R) resize_act_kernel<X, R><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, h, w, C, in_cs, \
+                                                                                       (bf16*)out_hi, (bf16*)out_lo, oh, ow, out_cs, sy, sx)
+  if (in_lo) { if (relu) PRV2_RS(true, true); else PRV2_RS(true, false); }
+  else { if (relu) PRV2_RS(false, true); else PRV2_RS(false, false); }
+#undef PRV2_RS
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

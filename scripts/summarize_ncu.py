@@ -6,6 +6,8 @@ import subprocess
 import sys
 
 KEYS = [
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 LSU data pipe %"),
     ("gpu__time_duration.sum", "duration"),
     ("dram__bytes_read.sum", "dram read"),
     ("dram__bytes_write.sum", "dram write"),
@@ -30,7 +32,11 @@ KEYS = [
 
 
 def rows_of(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """``rep``: an .ncu-rep, or the ``--page raw --csv`` export of one (what scripts/gpu_profile.sh brings back for the big GEMM reports)."""
+    if rep.endswith(".csv"):
+        out = open(rep, errors="ignore").read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
