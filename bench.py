@@ -417,6 +417,8 @@ def main():
     # the CAI blend (north_star: HBM-bound target): algorithmic bytes / CUDA-event launch duration, cold L2 (see blend_launch_times)
     roofline_blend = None
     try:
+        torch.cuda.synchronize(dev)
+        time.sleep(2.0)                      # let the power-capped clocks of the frame loop recover: these two kernels are timed alone
         bt = blend_launch_times(pshape, raw, split, cai_mode, process_num, dev)
         b_bytes, b_s = sum(v["bytes"] for v in bt.values()), sum(v["s"] for v in bt.values())
         roofline_blend = {"kernel": "blend_canvas_fast_kernel + blend_raw_tab_kernel", "bound": "hbm", "achieved": b_bytes / b_s / 1e9, "peak": peaks["hbm"],

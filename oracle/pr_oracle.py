@@ -1,14 +1,20 @@
 """CPU oracle: a plain PyTorch/NumPy restatement of PatchRefinerV2's tiled high-resolution
-inference path (``mode='infer'``, CAI modes m1 / m2 / rN) for the DAv2 + FusionUnet family.
+inference path (``mode='infer'``, CAI modes m1 / m2 / rN) for the DAv2 + FusionUnet family
+(``PatchRefiner``) and the V2 family (``PatchRefinerPlus`` = DAv2 coarse branch + LightWeightRefiner +
+``BiDirectionalFusion``).
 
 TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs may import this module; the product package
 ``patchrefinerv2_b200`` never does (the product fails loudly if its CUDA library is missing).
 
-Parity status: PINNED.  ``tests/test_oracle_vs_reference.py`` runs the reference's own classes
-(imported read-only from /root/reference through ``oracle/ref_shim.py``) against this file on
-identical weights/frames, and ``tests/golden/*.npz`` (made by ``oracle/make_golden.py`` from the
-reference itself) are checked on every run, with or without /root/reference.
+Parity status: PINNED.  ``tests/test_oracle_vs_reference.py``, ``tests/test_bifusion.py`` and
+``tests/test_plus.py`` run the reference's own classes (imported read-only from /root/reference
+through ``oracle/ref_shim.py``) against this file on identical weights/frames (bit-identical), and
+``tests/golden/*.npz`` (made by ``oracle/make_golden.py`` from the reference itself) are checked on
+every run, with or without /root/reference.  ONE piece is UNPINNED: the timm CNN inside
+``LightWeightRefiner`` (timm is not installable offline; pinned ``timm==0.9.2`` in the reference's
+environment.yml:27).  ``ToyFineEncoder`` stands in for it on both sides -- injected into the
+reference as ``timm.create_model``'s result -- so everything around the encoder is still pinned.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 Third-party arithmetic the reference itself calls is called here too, not restated:
