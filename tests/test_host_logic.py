@@ -119,3 +119,30 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("the oracle", "").replace("oracle/", ""), fn
+
+
+def test_schedule_at_config5_geometry_matches_oracle_draws():
+    """BASELINE config 5 (4320x7680, 8x8, r128): bboxes and roi coordinates of the whole schedule equal the oracle's
+    (= the reference's) regular grids and random draws, stage by stage, without running any network."""
+    shape, raw, split, pn = (448, 448), (4320, 7680), (8, 8), 4
+    tc = tiling.prepare_tile_cfg(shape, raw, split)
+    assert tc == O.prepare_tile_cfg(shape, raw, split) and tuple(tc["patch_reensemble_shape"]) == (3584, 3584)
+    rh, rw = tc["patch_raw_shape"]
+    random.seed(3)
+    stages = tiling.schedule(tc, shape, "r128", pn)
+    assert [s.bboxs.shape[0] for s in stages if s.kind == "regular"] == [64, 56, 56, 49]
+    assert sum(s.bboxs.shape[0] for s in stages if s.kind == "random") == 128
+    random.seed(3)
+    want = []
+    for off in ([0, 0], [0, rw // 2], [rh // 2, 0], [rh // 2, rw // 2]):
+        hs, ws = O.regular_bboxes(tc, off)
+        want.append(O.make_bboxs(hs, ws, rh, rw))
+    for _ in range(128 // pn):                                   # baseline_pretrain.py:160-161: pn rows, then ONE column
+        hs = [random.randint(0, raw[0] - rh - 1) for _ in range(pn)]
+        ws = [random.randint(0, raw[1] - rw - 1)]
+        want.append(O.make_bboxs(hs, ws, rh, rw))
+    want = torch.cat(want)
+    got = np.concatenate([s.bboxs for s in stages])
+    assert np.array_equal(got, want.numpy())
+    bf = np.concatenate([tiling.bboxs_to_feat(s.bboxs, raw, shape) for s in stages])
+    assert np.array_equal(bf[:, 1:], O.bboxs_to_feat(want, raw, shape).numpy()[:, 1:])
