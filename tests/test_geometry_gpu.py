@@ -243,3 +243,40 @@ def test_blend_at_config5_size_vs_oracle(dev):
     depth, _, avg = go.infer(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, H, W), None, mode, pn)
     assert torch.equal(res[1][1].cpu(), avg.count_map)                       # count map: bit-exact
     assert torch.equal(res[1][0].cpu(), depth[0, 0])                          # sequential running mean: bit-exact
+
+
+@pytest.mark.parametrize("case", [
+    # (patch shape, raw frame, split, mode, process_num): ragged frames, patch widths that are not multiples of 4 (any-alignment kernels),
+    # odd half-patch offsets, one-patch grids, more random patches than one ballot round
+    ((42, 42), (131, 257), (2, 3), "r6", 2),
+    ((28, 70), (97, 403), (2, 4), "m2", 2),
+    ((56, 42), (230, 171), (3, 2), "r40", 4),
+    ((14, 14), (64, 64), (1, 1), "m1", 1),            # (the reference itself cannot run m2 / rN on a one-row split: empty shifted stages)
+    ((112, 112), (300, 500), (2, 2), "r2", 2),
+])
+def test_blend_ragged_geometries_bit_exact_vs_oracle(dev, case):
+    """End-to-end geometry (tiling -> canvas blend -> raw blend) on awkward shapes against the CPU oracle's RunningAverageMap: depth and
+    count map bit-exact; the aligned fast paths (where the geometry allows them) and the generic kernels agree."""
+    from patchrefinerv2_b200 import ops
+    shape, raw, split, mode, pn = case
+    tc, preds, grid, n_reg, mask, rmask, starts = _blend_inputs(dev, shape, mode, pn, raw, split)
+    Hc, Wc = tc["patch_reensemble_shape"]
+    H, W = tc["image_raw_shape"]
+    rh, rw = tc["patch_raw_shape"]
+    is_r = mode[0] == "r"
+    res = []
+    try:
+        for generic in (True, False):
+            _set_generic(generic)
+            a, c = ops.blend_canvas(preds[:n_reg], mask, grid, Hc, Wc)
+            if is_r:
+                a, c = ops.blend_raw(a, c, preds[n_reg:], starts, rmask, shape[0], shape[1], rh, rw, H, W)
+            res.append((a.cpu(), c.cpu()))
+    finally:
+        _set_generic(False)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    go = O.GeometryOracle(shape, raw, split)
+    random.seed(1)
+    depth, _, avg = go.infer(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, H, W), None, mode, pn)
+    assert torch.equal(res[1][1], avg.count_map)
+    assert torch.equal(res[1][0], depth[0, 0])

@@ -146,3 +146,40 @@ def test_schedule_at_config5_geometry_matches_oracle_draws():
     assert np.array_equal(got, want.numpy())
     bf = np.concatenate([tiling.bboxs_to_feat(s.bboxs, raw, shape) for s in stages])
     assert np.array_equal(bf[:, 1:], O.bboxs_to_feat(want, raw, shape).numpy()[:, 1:])
+
+
+def test_tiling_matches_oracle_on_random_geometries():
+    """Property check over ragged geometries (frame sizes not divisible by the split, odd patch sizes, every CAI mode):
+    tile config, every stage's bboxes and the float32 roi coordinates equal the oracle's restatement of the reference."""
+    rng = np.random.default_rng(11)
+    for case in range(25):
+        sh, sw = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        ph, pw = int(rng.integers(2, 9)) * 14, int(rng.integers(2, 9)) * 14
+        H, W = int(rng.integers(sh * 24, sh * 200)), int(rng.integers(sw * 24, sw * 200))
+        mode = ["m1", "m2", f"r{int(rng.integers(1, 5)) * 2}"][case % 3]
+        pn = 2
+        tc = tiling.prepare_tile_cfg((ph, pw), (H, W), (sh, sw))
+        assert tc == O.prepare_tile_cfg((ph, pw), (H, W), (sh, sw)), (H, W, sh, sw)
+        rh, rw = tc["patch_raw_shape"]
+        if H - rh - 1 < 0 or W - rw - 1 < 0:
+            continue                                              # random.randint would raise in the reference too (1x1 split)
+        random.seed(case)
+        stages = tiling.schedule(tc, (ph, pw), mode, pn)
+        random.seed(case)
+        want = []
+        offs = [[0, 0]] + ([[0, rw // 2], [rh // 2, 0], [rh // 2, rw // 2]] if mode != "m1" else [])
+        for off in offs:
+            hs, ws = O.regular_bboxes(tc, off)
+            if hs and ws:
+                want.append(O.make_bboxs(hs, ws, rh, rw))
+        if mode[0] == "r":
+            for _ in range(int(mode[1:]) // pn):
+                hs = [random.randint(0, H - rh - 1) for _ in range(pn)]
+                ws = [random.randint(0, W - rw - 1)]
+                want.append(O.make_bboxs(hs, ws, rh, rw))
+        want = torch.cat(want)
+        got = np.concatenate([s.bboxs for s in stages if s.bboxs.shape[0]])
+        assert np.array_equal(got, want.numpy()), (case, H, W, sh, sw, mode)
+        bf = np.concatenate([tiling.bboxs_to_feat(s.bboxs, (H, W), (ph, pw)) for s in stages if s.bboxs.shape[0]])
+        assert np.array_equal(bf[:, 1:], O.bboxs_to_feat(want, (H, W), (ph, pw)).numpy()[:, 1:])
+        assert (got[:, 2] <= W).all() and (got[:, 3] <= H).all() and (got[:, :2] >= 0).all()
