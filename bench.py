@@ -8,7 +8,8 @@ reference's CPU path timed beside it.
 
 N > 1 is launched by torchrun (one rank per GPU); patches of each frame are sharded over the ranks
 and the packed partial canvases are combined by ONE NCCL sum-reduce ("strong" scaling of a frame).
-A step = one frame through the public model API.  `value` has the frame resident in HBM and the
+The measured arm builds its config, seeded random-init weights and synthetic frame itself; `oracle/` is imported only by
+the CPU / eager-GPU baseline legs and `--impl reference`.  A step = one frame through the public model API.  `value` has the frame resident in HBM and the
 result left on the device; `e2e` copies the frame from pinned host memory and the depth map back to
 the host inside the timed region.  Rank 0 prints one JSON line.
 """
@@ -35,6 +36,58 @@ WORKLOADS = {
     "dav2_vits_432x768_2x2_r4": ("vits", (224, 224), (432, 768), (2, 2), "r4", 2),
 }
 METRIC = "frames_per_sec_2160x3840_cai_r32"
+
+
+def make_config(encoder, patch_process_shape, image_raw_shape, patch_split_num, max_depth=80.0):
+    """Model config shaped like the reference's configs/patchrefiner_dav2/pr_u4k.py:10-53 (DAv2 coarse + DAv2 refiner + FusionUnet)."""
+    feats, oc = {"vitl": (256, [256, 512, 1024, 1024]), "vitb": (128, [96, 192, 384, 768]), "vits": (64, [48, 96, 192, 384])}[encoder]
+    half = feats // 2
+    branch = lambda: dict(type="DA2", pretrained=None, model_cfg=dict(encoder=encoder, features=feats, out_channels=list(oc)))
+    return dict(image_raw_shape=list(image_raw_shape), patch_process_shape=list(patch_process_shape), patch_split_num=list(patch_split_num),
+                fusion_feat_level=6, min_depth=1e-3, max_depth=max_depth, strategy_refiner_target="offset_coarse",
+                coarse_branch=branch(),
+                refiner=dict(fine_branch=branch(),
+                             fusion_model=dict(type="FusionUnet", input_chl=[half * 2] + [feats * 2] * 5, temp_chl=[half] + [feats] * 5,
+                                               dec_chl=[feats] * 4 + [half])),
+                sigloss=dict(type="SILogLoss"), pretrained=None, pre_norm_bbox=True, pretrain_coarse_model=None, pretrain_fine_model=None)
+
+
+def random_state_dict(spec, seed=0):
+    """Seeded random-init weights for every tensor of the model's own state dict (name -> shape): fan-in-scaled normals for
+    matrices / conv kernels, near-one LayerNorm scales, small biases, LayerScale around 0.2 -- numerically healthy, not trained.
+    The measured arm generates its inputs itself; `oracle/` is only used by the CPU / eager baseline legs."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in spec.items():
+        shp = tuple(shp)
+        u = lambda scale: (torch.rand(shp, generator=g) * 2 - 1) * scale
+        if k.endswith("mask_token"):
+            v = torch.zeros(shp)
+        elif k.endswith(("cls_token", "pos_embed")):
+            v = torch.randn(shp, generator=g) * 0.02
+        elif k.endswith(".gamma"):
+            v = 0.2 + u(0.1)
+        elif len(shp) == 1 and k.endswith(".weight"):
+            v = 1.0 + u(0.1)                                   # LayerNorm scales
+        elif k.endswith(".bias"):
+            v = u(0.05)
+        else:
+            fan_in = max(1, int(torch.tensor(shp[1:]).prod())) if len(shp) > 1 else shp[0]
+            v = torch.randn(shp, generator=g) * (1.3 / math.sqrt(fan_in))
+        sd[k] = v
+    return sd
+
+
+def synthetic_frame(image_raw_shape, seed=1):
+    """fp32 RGB frame in [0,1], [1,3,H,W]: smooth low-frequency structure + noise (host tensor)."""
+    import torch
+    import torch.nn.functional as F
+    H, W = image_raw_shape
+    g = torch.Generator().manual_seed(seed)
+    smooth = F.interpolate(torch.rand(1, 3, 9, 16, generator=g), (H, W), mode="bicubic", align_corners=True).clamp(0, 1)
+    return (0.7 * smooth + 0.3 * torch.rand(1, 3, H, W, generator=g)).contiguous()
 
 
 def profiled_traffic():
@@ -96,7 +149,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
 
 
-def cpu_reference_sample(cfg, sd, cai_mode, process_num, n_patches_frame, steps, warmup, log=lambda *a: None):
+def cpu_reference_sample(cfg, sd, hr, cai_mode, process_num, n_patches_frame, steps, warmup, log=lambda *a: None):
     """Times the oracle port of the reference's CPU path on the host cores: one coarse pass, `steps`
     single-patch refine passes (crop -> roi_align -> ViT + DPT -> FusionUnet) and the running-average
     blend update of one patch; extrapolates to a full frame.  Returns (frames/s, description)."""
@@ -105,7 +158,7 @@ def cpu_reference_sample(cfg, sd, cai_mode, process_num, n_patches_frame, steps,
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
     orc = O.PatchRefinerOracle(cfg, sd)
-    lr, hr = O.synthetic_frame(cfg, 1)
+    lr = O.resizer(tuple(cfg["patch_process_shape"]), hr)
     tc = orc.tile_cfg
     ph, pw = orc.patch_process_shape
     rh, rw = tc["patch_raw_shape"]
@@ -140,7 +193,7 @@ def cpu_reference_sample(cfg, sd, cai_mode, process_num, n_patches_frame, steps,
     return 1.0 / frame_s, cores, desc
 
 
-def eager_gpu_sample(cfg, sd, process_num, n_patches_frame, dev, steps=3, warmup=1):
+def eager_gpu_sample(cfg, sd, hr, process_num, n_patches_frame, dev, steps=3, warmup=1):
     """The same oracle port run as plain eager PyTorch (fp32, library kernels) on THIS GPU -- what the reference's own code
     path does on a CUDA device: network on the GPU, canvases and RunningAverageMap on the host after a D2H copy per patch
     (baseline_pretrain.py:340-373).  Bounded sample like the CPU one: 1 coarse pass + `steps` chunks of `process_num`
@@ -148,8 +201,8 @@ def eager_gpu_sample(cfg, sd, process_num, n_patches_frame, dev, steps=3, warmup
     import torch
     from oracle import pr_oracle as O
     orc = O.PatchRefinerOracle(cfg, {k: v.to(dev) for k, v in sd.items()})
-    lr, hr = O.synthetic_frame(cfg, 1)
-    lr, hr = lr.to(dev), hr.to(dev)
+    hr = hr.to(dev)
+    lr = O.resizer(tuple(cfg["patch_process_shape"]), hr)
     tc = orc.tile_cfg
     rh, rw = tc["patch_raw_shape"]
     H, W = tc["image_raw_shape"]
@@ -257,9 +310,8 @@ def main():
     enc, pshape, raw, split, cai_mode, process_num = WORKLOADS[args.workload]
 
     import torch
-    from oracle import pr_oracle as O          # weight / frame generators + the CPU baseline (never on the measured GPU path)
-    from patchrefinerv2_b200 import tiling
-    cfg = O.make_config(enc, pshape, raw, split)
+    from patchrefinerv2_b200 import build_model, tiling
+    cfg = make_config(enc, pshape, raw, split)
     tc = tiling.prepare_tile_cfg(pshape, raw, split)
     n_patches = sum(s.bboxs.shape[0] for s in tiling.schedule(tc, pshape, cai_mode, process_num, random.Random(0)))
     config = {"workload": args.workload, "image_raw_shape": list(raw), "patch_process_shape": list(pshape), "patch_split_num": list(split),
@@ -270,8 +322,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sd = O.init_patchrefiner_state_dict(cfg, 0)
-        fps, cores, desc = cpu_reference_sample(cfg, sd, cai_mode, process_num, n_patches, max(1, args.steps), max(0, args.warmup))
+        spec = {k: tuple(v.shape) for k, v in build_model(dict(type="PatchRefiner", config=cfg)).state_dict().items()}
+        sd = random_state_dict(spec, 0)
+        fps, cores, desc = cpu_reference_sample(cfg, sd, synthetic_frame(raw, 1), cai_mode, process_num, n_patches, max(1, args.steps), max(0, args.warmup))
         line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config, "patches_per_sec": fps * n_patches,
@@ -280,7 +333,7 @@ def main():
         print(json.dumps(line))
         return
 
-    from patchrefinerv2_b200 import _lib, build_model
+    from patchrefinerv2_b200 import _lib
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -297,16 +350,19 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-    sd = O.init_patchrefiner_state_dict(cfg, 0)
     n_local = -(-n_patches // world)
     pb = args.patch_batch or -(-n_local // (-(-n_local // 27)))
     config["patch_batch"] = pb
     model = build_model(dict(type="PatchRefiner", config=cfg, precision=args.precision, patch_batch=pb, output_device="cuda"))
-    model.load_dict(sd)
+    sd = random_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, 0)
+    res = model.load_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
     model = model.cuda().eval()
-    lr, hr = O.synthetic_frame(cfg, 1)
+    hr = synthetic_frame(raw, 1)
+    hr_dev = hr.to(dev)
+    lr_dev = model.resizer(hr_dev)                         # image_lr as the dataset builds it (general_dataset.py:218), on the device
+    lr = lr_dev.cpu()
     lr_pin, hr_pin = lr.pin_memory(), hr.pin_memory()
-    lr_dev, hr_dev = lr.to(dev), hr.to(dev)
     shard = world > 1
 
     def barrier():
@@ -432,10 +488,10 @@ def main():
 
     cpu_baseline = eager_gpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, cores, desc = cpu_reference_sample(cfg, sd, cai_mode, process_num, n_patches, 6, 1)
+        v, cores, desc = cpu_reference_sample(cfg, sd, hr, cai_mode, process_num, n_patches, 6, 1)
         cpu_baseline = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
         try:
-            eager_gpu = eager_gpu_sample(cfg, sd, process_num, n_patches, dev)
+            eager_gpu = eager_gpu_sample(cfg, sd, hr, process_num, n_patches, dev)
         except Exception as e:                                     # a baseline must never take the bench line down
             eager_gpu = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
