@@ -178,6 +178,43 @@ def bifusion():
         print("bifusion", t, tuple(out.shape), float(out.mean()), float(off.std()))
 
 
+ZOE_HEAD_SIZES = [(12, 16), (12, 16), (24, 32), (48, 64), (96, 128)]      # btlnck, then the four decoder blocks coarse -> fine
+
+
+def zoe_head_inputs(seed=2, B=2):
+    g = torch.Generator().manual_seed(seed)
+    btl = torch.randn(B, 256, *ZOE_HEAD_SIZES[0], generator=g)
+    xb = [torch.randn(B, 256, *s, generator=g) for s in ZOE_HEAD_SIZES[1:]]
+    outc = torch.relu(torch.randn(B, 32, 192, 256, generator=g))
+    rel = torch.rand(B, 192, 256, generator=g) * 5
+    return rel, btl, xb, outc
+
+
+def zoe_head():
+    """zoe_head.npz: the reference's ZoeDepth metric-bins head (zoedepth_v1.py:173-233) with a dummy core, fed through hack_feature."""
+    ref_shim.install()
+    from zoedepth.models.zoedepth.zoedepth_v1 import ZoeDepth
+
+    class DummyCore(torch.nn.Module):
+        output_channels = [256] * 5
+
+        def freeze_encoder(self, *a, **k):
+            pass
+
+    c = O.ZOE_HEAD_CFG
+    m = ZoeDepth(DummyCore(), n_bins=c["n_bins"], bin_centers_type=c["bin_centers_type"], bin_embedding_dim=c["bin_embedding_dim"], min_depth=1e-3,
+                 max_depth=80, n_attractors=list(c["n_attractors"]), attractor_alpha=c["attractor_alpha"], attractor_gamma=c["attractor_gamma"],
+                 attractor_kind=c["attractor_kind"], attractor_type=c["attractor_type"], min_temp=c["min_temp"], max_temp=c["max_temp"]).eval()
+    sd = O.init_zoe_head_state_dict([256] * 5, 7)
+    m.load_state_dict(sd, strict=False)
+    rel, btl, xb, outc = zoe_head_inputs()
+    with torch.no_grad():
+        r = m(None, hack_feature=[rel, [btl] + xb + [outc]], return_final_centers=True)
+    np.savez_compressed(os.path.join(OUT, "zoe_head.npz"), depth=r["metric_depth"].numpy(), centers_sub=r["bin_centers"][:, :, ::16, ::16].numpy(),
+                        sd_sha=sd_digest(sd), rel_sha=O.sha256_f32(rel.numpy()))
+    print("zoe_head", tuple(r["metric_depth"].shape), float(r["metric_depth"].mean()))
+
+
 PLUS_MODES = (("m1", 2), ("r2", 2))
 
 
@@ -209,10 +246,14 @@ if __name__ == "__main__":
     if "--bifusion-only" in sys.argv:
         bifusion()
         sys.exit(0)
+    if "--zoe-head-only" in sys.argv:
+        zoe_head()
+        sys.exit(0)
     if "--plus-only" in sys.argv:
         plus()
         sys.exit(0)
     plus()
+    zoe_head()
     bifusion()
     tiny()
     geom(448, 448)

@@ -548,6 +548,106 @@ def synthetic_fusion_inputs(coarse_chl, fine_chl, sizes_c, sizes_f, B: int, seed
 
 
 # ---------------------------------------------------------------------------------------------
+# ZoeDepth metric-bins head  (external/zoedepth/models/zoedepth/zoedepth_v1.py:173-233)
+# Oracle only so far: the product does not build this head yet (its BEiT-L core is unavailable offline).
+# ---------------------------------------------------------------------------------------------
+
+#: configs/patchrefiner_zoedepth/pr_u4k.py:10-66 (the values every ZoeDepth branch of the reference uses)
+ZOE_HEAD_CFG = dict(n_bins=64, bin_embedding_dim=128, n_attractors=(16, 8, 4, 1), attractor_alpha=1000, attractor_gamma=2,
+                    attractor_kind="mean", attractor_type="inv", min_temp=0.0212, max_temp=50.0, bin_centers_type="softplus")
+
+
+def init_zoe_head_state_dict(output_channels: Sequence[int], seed: int, cfg: dict = ZOE_HEAD_CFG, n_midas_out: int = 32) -> Dict[str, Tensor]:
+    """Random weights with the reference's keys for everything in ZoeDepth except ``core`` (zoedepth_v1.py:84-123)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    bt, outs, E, nb = output_channels[0], list(output_channels[1:]), cfg["bin_embedding_dim"], cfg["n_bins"]
+
+    def conv(name, co, ci, gain=1.0):
+        sd[name + ".weight"] = _conv_w(g, co, ci, 1, gain)
+        sd[name + ".bias"] = _vec(g, co, 0.05)
+
+    conv("conv2", bt, bt)
+    conv("seed_bin_regressor._net.0", 256, bt, 1.7); conv("seed_bin_regressor._net.2", nb, 256)
+    conv("seed_projector._net.0", 128, bt, 1.7); conv("seed_projector._net.2", E, 128)
+    for i, c in enumerate(outs):
+        conv(f"projectors.{i}._net.0", 128, c, 1.7); conv(f"projectors.{i}._net.2", E, 128)
+        conv(f"attractors.{i}._net.0", 128, E, 1.7); conv(f"attractors.{i}._net.2", cfg["n_attractors"][i], 128)
+    last_in = n_midas_out + 1
+    conv("conditional_log_binomial.mlp.0", (last_in + E) // 2, last_in + E, 1.7)
+    conv("conditional_log_binomial.mlp.2", 4, (last_in + E) // 2)
+    return sd
+
+
+def _mlp1x1(sd, pre, x, act_last=None):
+    x = F.relu(F.conv2d(x, sd[pre + "_net.0.weight"], sd[pre + "_net.0.bias"]))
+    x = F.conv2d(x, sd[pre + "_net.2.weight"], sd[pre + "_net.2.bias"])
+    return act_last(x) if act_last is not None else x
+
+
+def zoe_bins_head(sd: Dict[str, Tensor], pre: str, rel_depth: Tensor, btlnck: Tensor, x_blocks: List[Tensor], outconv: Tensor,
+                  cfg: dict = ZOE_HEAD_CFG, trace: Optional[dict] = None):
+    """ZoeDepth.forward after the core (zoedepth_v1.py:173-233) for bin_centers_type='softplus', inverse_midas=False:
+    seed bins (layers/localbins_layers.py:71-96), projectors (:99-118), AttractorLayerUnnormed (layers/attractor.py:139-208,
+    inv_attractor :45-57), ConditionalLogBinomial + LogBinomial (layers/dist_layers.py:29-122).
+    rel_depth [B,H,W]; btlnck / x_blocks / outconv as the core returns them.  Returns (metric_depth [B,1,h,w], temp_features)."""
+    assert cfg["bin_centers_type"] == "softplus" and cfg["attractor_type"] == "inv"
+    x_d0 = F.conv2d(btlnck, sd[pre + "conv2.weight"], sd[pre + "conv2.bias"])                     # :173
+    b_prev = _mlp1x1(sd, pre + "seed_bin_regressor.", x_d0, F.softplus)                             # :176, unnormed: centres themselves
+    prev_emb = _mlp1x1(sd, pre + "seed_projector.", x_d0)                                           # :184
+    # NB: AttractorLayerUnnormed.forward calls ``dist(A.unsqueeze(2) - b_centers.unsqueeze(1))`` WITHOUT alpha / gamma
+    # (attractor.py:194-197), so the jit function's defaults alpha=300, gamma=2 apply whatever the config says (1000 in
+    # every shipped config).  The oracle follows the code, not the config.
+    alpha, gamma, K = 300.0, 2, int(cfg["n_bins"])
+    b_centers = b_prev
+    emb = prev_emb
+    for i, x in enumerate(x_blocks):                                                               # :188-195
+        emb = _mlp1x1(sd, f"{pre}projectors.{i}.", x)
+        xa = emb + F.interpolate(prev_emb, x.shape[-2:], mode="bilinear", align_corners=True)      # attractor.py:176-180
+        A = _mlp1x1(sd, f"{pre}attractors.{i}.", xa, F.softplus)
+        b_c = F.interpolate(b_prev, A.shape[-2:], mode="bilinear", align_corners=True)
+        dx = A.unsqueeze(2) - b_c.unsqueeze(1)
+        dc = dx.div(1 + alpha * dx.pow(gamma))                                                      # inv_attractor
+        delta = dc.mean(dim=1) if cfg["attractor_kind"] == "mean" else dc.sum(dim=1)
+        b_centers = b_c + delta
+        b_prev, prev_emb = b_centers, emb
+    rel_cond = F.interpolate(rel_depth.unsqueeze(1), size=outconv.shape[2:], mode="bilinear", align_corners=True)   # :207-210
+    last = torch.cat([outconv, rel_cond], dim=1)
+    cond = F.interpolate(emb, last.shape[-2:], mode="bilinear", align_corners=True)
+    q = pre + "conditional_log_binomial.mlp."
+    pt = F.conv2d(torch.cat((last, cond), dim=1), sd[q + "0.weight"], sd[q + "0.bias"])
+    pt = F.softplus(F.conv2d(F.gelu(pt), sd[q + "2.weight"], sd[q + "2.bias"]))                   # dist_layers.py:95-103
+    p_eps = 1e-4
+    pp = pt[:, :2] + p_eps
+    prob = pp[:, 0] / (pp[:, 0] + pp[:, 1])
+    tt = pt[:, 2:] + p_eps
+    t = (tt[:, 0] / (tt[:, 0] + tt[:, 1])).unsqueeze(1)
+    t = (float(cfg["max_temp"]) - float(cfg["min_temp"])) * t + float(cfg["min_temp"])
+    xk = prob.unsqueeze(1)                                                                          # LogBinomial.forward (:52-69)
+    eps = 1e-4
+    one_minus = torch.clamp(1 - xk, eps, 1)
+    xk = torch.clamp(xk, eps, 1)
+    k_idx = torch.arange(0, K, device=xk.device).view(1, -1, 1, 1)
+    Km1 = torch.tensor([float(K - 1)], device=xk.device).view(1, -1, 1, 1)
+
+    def log_binom(n, k, e=1e-7):                                                                    # :29-33 (Stirling)
+        n = n + e
+        k = k + e
+        return n * torch.log(n) - k * torch.log(k) - (n - k) * torch.log(n - k + e)
+
+    y = log_binom(Km1, k_idx) + k_idx * torch.log(xk) + (K - 1 - k_idx) * torch.log(one_minus)
+    probs = torch.softmax(y / t, dim=1)
+    centers = F.interpolate(b_centers, probs.shape[-2:], mode="bilinear", align_corners=True)      # :217-218
+    depth = torch.sum(probs * centers, dim=1, keepdim=True)
+    feats = {"x_d0": x_d0, "midas_final_feat": outconv}
+    for i, x in enumerate(x_blocks):
+        feats[f"x_blocks_feat_{i}"] = x
+    if trace is not None:
+        trace.update(probs=probs, bin_centers=centers)
+    return depth, feats
+
+
+# ---------------------------------------------------------------------------------------------
 # tiling geometry, masks, running average  (baseline_pretrain.py ; models/utils.py)
 # ---------------------------------------------------------------------------------------------
 

@@ -95,3 +95,18 @@ def test_index_restatements_bit_exact_vs_torch():
         ref = roi_align(feat, rois, (h, w), h / ph, aligned=True).numpy()
         for i in range(bb.shape[0]):
             assert np.array_equal(ref[i], O.np_roi_align_1s(feat[0].numpy(), bf[i, 1:].numpy(), h / ph, h, w))
+
+
+def test_zoe_bins_head_matches_reference_golden(golden_dir):
+    """ZoeDepth metric-bins head (oracle only so far) against the output the reference's ZoeDepth produced (oracle/make_golden.py)."""
+    from oracle.make_golden import sd_digest, zoe_head_inputs
+    g = np.load(os.path.join(golden_dir, "zoe_head.npz"))
+    sd = O.init_zoe_head_state_dict([256] * 5, 7)
+    rel, btl, xb, outc = zoe_head_inputs()
+    assert str(g["sd_sha"]) == sd_digest(sd) and str(g["rel_sha"]) == O.sha256_f32(rel.numpy())
+    tr = {}
+    with torch.no_grad():
+        d, _ = O.zoe_bins_head(sd, "", rel, btl, xb, outc, O.ZOE_HEAD_CFG, tr)
+    np.testing.assert_allclose(d.numpy(), g["depth"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(tr["bin_centers"][:, :, ::16, ::16].numpy(), g["centers_sub"], rtol=1e-3, atol=1e-4)
+    assert float(tr["probs"].sum(1).sub(1).abs().max()) < 1e-5

@@ -52,3 +52,37 @@ def test_state_dict_keys_match_reference(pair):
     for k, v in ref.state_dict().items():
         assert tuple(mine.state_dict()[k].shape) == tuple(v.shape), k
     assert set(mine.get_save_dict().keys()) == set(ref.get_save_dict().keys())
+
+
+def test_zoe_bins_head_oracle_is_bit_identical_to_reference():
+    """ZoeDepth metric-bins head, oracle only so far: the reference's ZoeDepth with a dummy core and
+    ``hack_feature`` inputs (zoedepth_v1.py:164-171) against oracle.zoe_bins_head -- depth, probabilities, bin centres."""
+    ref_shim.install()
+    from zoedepth.models.zoedepth.zoedepth_v1 import ZoeDepth
+
+    class DummyCore(torch.nn.Module):
+        output_channels = [256] * 5                      # DPT_BEiT_L_384 (base_models/midas.py:377-380)
+
+        def freeze_encoder(self, *a, **k):
+            pass
+
+    c = O.ZOE_HEAD_CFG
+    m = ZoeDepth(DummyCore(), n_bins=c["n_bins"], bin_centers_type=c["bin_centers_type"], bin_embedding_dim=c["bin_embedding_dim"], min_depth=1e-3,
+                 max_depth=80, n_attractors=list(c["n_attractors"]), attractor_alpha=c["attractor_alpha"], attractor_gamma=c["attractor_gamma"],
+                 attractor_kind=c["attractor_kind"], attractor_type=c["attractor_type"], min_temp=c["min_temp"], max_temp=c["max_temp"]).eval()
+    sd = O.init_zoe_head_state_dict([256] * 5, 7)
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all("log_binomial_transform" in k for k in res.missing_keys)      # only the two index buffers
+    g = torch.Generator().manual_seed(2)
+    sizes = [(12, 16), (12, 16), (24, 32), (48, 64), (96, 128)]                                          # btlnck, then coarse -> fine
+    btl = torch.randn(2, 256, *sizes[0], generator=g)
+    xb = [torch.randn(2, 256, *s, generator=g) for s in sizes[1:]]
+    outc = torch.relu(torch.randn(2, 32, 192, 256, generator=g))
+    rel = torch.rand(2, 192, 256, generator=g) * 5
+    with torch.no_grad():
+        r = m(None, hack_feature=[rel, [btl] + xb + [outc]], return_final_centers=True, return_probs=True)
+        tr = {}
+        d, feats = O.zoe_bins_head(sd, "", rel, btl, xb, outc, c, tr)
+    assert torch.equal(r["metric_depth"], d) and torch.equal(r["probs"], tr["probs"]) and torch.equal(r["bin_centers"], tr["bin_centers"])
+    assert set(feats) == {"x_d0", "x_blocks_feat_0", "x_blocks_feat_1", "x_blocks_feat_2", "x_blocks_feat_3", "midas_final_feat"}
+    assert torch.equal(r["temp_features"]["x_d0"], feats["x_d0"])
