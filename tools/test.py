@@ -8,7 +8,8 @@ docs/user_infer.md:113-130) for the B200 implementation: the ``--test-type gener
 
 CONFIG is one of the reference's own python configs (loaded unmodified by ``patchrefinerv2_b200.config``);
 the checkpoint is a ``torch.save`` dict with ``model_state_dict`` (estimator/trainer/trainer.py:276-294) or a
-bare state dict; the loop is ``Tester.run`` (estimator/tester/tester.py:52-106) for one rank.
+bare state dict; the loop is ``Tester.run`` (estimator/tester/tester.py:52-106).  Launched with ``torchrun --nproc-per-node N``
+the patches of every frame are sharded over the N GPUs (one NCCL sum-reduce per frame) instead of the frames over ranks.
 """
 from __future__ import annotations
 
@@ -75,6 +76,13 @@ def main(argv=None):
     from patchrefinerv2_b200 import frames
     if not torch.cuda.is_available():
         raise SystemExit("tools/test.py needs a CUDA device (sm_100a); there is no CPU path")
+    # under torchrun (one rank per GPU) every frame's patches are sharded over the ranks and combined with one NCCL sum-reduce
+    # (DESIGN.md section 6); all ranks walk the same files and draw the same random patches, rank 0 writes the outputs
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    shard = world > 1
+    if shard:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        torch.distributed.init_process_group("nccl")
     random.seed(args.seed); np.random.seed(args.seed); torch.manual_seed(args.seed)
     model = model.cuda().eval()
     img_dir = cfg.general_dataloader.dataset.rgb_image_dir
@@ -83,12 +91,16 @@ def main(argv=None):
         hr = image_hr.cuda().unsqueeze(0)
         lr = model.resizer(hr)                                           # general_dataset.py:218 (on the device)
         tile_cfg = {"image_raw_shape": list(args.image_raw_shape), "patch_split_num": list(args.patch_split_num)}
-        result, log = model(mode="infer", cai_mode=args.cai_mode, process_num=args.process_num, tile_cfg=tile_cfg, image_lr=lr, image_hr=hr)
-        if args.save:
+        result, log = model(mode="infer", cai_mode=args.cai_mode, process_num=args.process_num, tile_cfg=tile_cfg, image_lr=lr, image_hr=hr, shard=shard)
+        if args.save and rank == 0:
             print(torch.max(result))                                     # tester.py:73
             frames.save_prediction(result, args.work_dir, name, args.gray_scale, log["coarse_prediction"], args.image_raw_shape)
         n += 1
     dt = time.perf_counter() - t0
+    if shard:
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
     print(f"{n} frame(s) in {dt:.2f}s ({n / dt if dt > 0 else 0:.2f} img / s incl. file I/O) -> {args.work_dir if args.save else '(not saved)'}")
 
 
