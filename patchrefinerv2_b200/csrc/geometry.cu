@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <stdlib.h>
+#include <mutex>
 #include <string.h>
 
 namespace prv2 {
@@ -782,9 +783,11 @@ struct RawTableEntry {
 };
 #define PRV2_RAW_TABLE_SLOTS 64
 static RawTableEntry g_raw_tables[PRV2_RAW_TABLE_SLOTS];
+static std::mutex g_raw_tables_mu;                               // entry points may be called from several host threads
 
 static bool raw_tables_get(int Wc, int W, int pw, int rw, const RawScales& sc, cudaStream_t stream, RawTables* tb) {
   if (Wc > 65535 || pw > 65535 || W <= 0) return false;
+  std::lock_guard<std::mutex> lock(g_raw_tables_mu);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
   RawTableEntry* slot = nullptr;
