@@ -317,7 +317,8 @@ def main():
     config = {"workload": args.workload, "image_raw_shape": list(raw), "patch_process_shape": list(pshape), "patch_split_num": list(split),
               "cai_mode": cai_mode, "process_num": process_num, "patches_per_frame": n_patches, "precision": args.precision,
               "parallelism": f"patch-shard x{world} + 1 NCCL sum-reduce" if world > 1 else "single GPU",
-              "weights": "random-init (seeded), reference state-dict layout"}
+              "weights": "random-init (seeded), reference state-dict layout",
+              "l2": "no explicit flush: every step streams several GB of activations (>> 126 MB L2) between reuses of any input"}
 
     if args.impl == "reference":
         if rank != 0:
