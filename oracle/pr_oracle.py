@@ -394,30 +394,44 @@ def fusion_unet(sd: Dict[str, Tensor], pre: str, c_feat: List[Tensor], f_feat: L
 # ---------------------------------------------------------------------------------------------
 
 #: coarse2fine_type -> (C2FModule fusion, gate) (bi_directional_fusion_model.py:366-374)
-C2F_TYPES = {"self-agg": (False, False), "coarse-gated": (True, True), "coarse-fusion": (True, False)}
+C2F_TYPES = {"self-agg": (False, False), "coarse-gated": (True, True), "coarse-fusion": (True, False),
+             "only-gate": (True, False)}     # only-gate = C2FNOENCModule(fusion=True, gate=False) (:372-373): oracle only, the product does not build it
 C2F_FEATURES = 256            # C2FModule default `features` (:149); no config overrides it
 
 
 def init_bidirectional_fusion_state_dict(coarse_chl, fine_chl, fine_chl_after_coarse2fine, temp_chl, dec_chl, seed: int,
-                                         coarse2fine_type: str = "coarse-gated", features: int = C2F_FEATURES) -> Dict[str, Tensor]:
+                                         coarse2fine_type: str = "coarse-gated", features: int = C2F_FEATURES, heavy: bool = False) -> Dict[str, Tensor]:
     """Random BiDirectionalFusion weights with the reference's state-dict keys (glb_att=False, coarse2fine=True;
-    bi_directional_fusion_model.py:285-374, C2FModule :148-184, GatedFusionBlock :84-116, GatedConvUnit :24-54)."""
+    bi_directional_fusion_model.py:285-374, C2FModule :148-184, C2FNOENCModule :211-251, GatedFusionBlock :84-116, GatedConvUnit
+    :24-54).  ``heavy``: BiDirectionalFusionHeavy (:517-561) -- SingleConvCNNLNHeavy (:448-463) and DoubleConvHeavy (:465-485)."""
     fusion, _gate = C2F_TYPES[coarse2fine_type]
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, Tensor] = {}
-    for idx, (cc, fc, tc) in enumerate(zip(coarse_chl, fine_chl_after_coarse2fine, temp_chl)):
-        sd[f"fusion_layers_1.{idx}.single_conv.0.weight"] = _conv_w(g, tc, cc + fc, 3, gain=1.7)
-        sd[f"fusion_layers_1.{idx}.single_conv.1.weight"] = 1.0 + _vec(g, tc, 0.1)
-        sd[f"fusion_layers_1.{idx}.single_conv.1.bias"] = _vec(g, tc, 0.05)
-        sd[f"fusion_layers_2.{idx}.single_conv.0.weight"] = _conv_w(g, tc, tc + 2, 3, gain=1.7)
-        sd[f"fusion_layers_2.{idx}.single_conv.1.weight"] = 1.0 + _vec(g, tc, 0.1)
-        sd[f"fusion_layers_2.{idx}.single_conv.1.bias"] = _vec(g, tc, 0.05)
+
+    def single(pre, tc, cin):
+        sd[pre + "single_conv.0.weight"] = _conv_w(g, tc, cin, 3, gain=1.7)
+        sd[pre + "single_conv.1.weight"] = 1.0 + _vec(g, tc, 0.1)
+        sd[pre + "single_conv.1.bias"] = _vec(g, tc, 0.05)
+        if heavy:
+            sd[pre + "single_conv.2.weight"] = _conv_w(g, tc, tc, 3, gain=1.7)
+            sd[pre + "single_conv.3.weight"] = 1.0 + _vec(g, tc, 0.1)
+            sd[pre + "single_conv.3.bias"] = _vec(g, tc, 0.05)
+            sd[pre + "single_conv.4.weight"] = _conv_w(g, tc, tc, 3, gain=1.7)
+
+    for idx, (cc, fc, tc) in enumerate(zip(coarse_chl, fine_chl_after_coarse2fine, temp_chl)):      # (draw order is part of the golden fixtures)
+        single(f"fusion_layers_1.{idx}.", tc, cc + fc)
+        single(f"fusion_layers_2.{idx}.", tc, tc + 2)
     rev = list(temp_chl)[::-1]
     _chl = rev[0]
     for i, (tc, dc) in enumerate(zip(rev[1:], dec_chl)):
         cin = tc + _chl + 2
         sd[f"f2r_agg.{i}.conv.double_conv.0.weight"] = _conv_w(g, cin, cin, 3, gain=1.7)
-        sd[f"f2r_agg.{i}.conv.double_conv.2.weight"] = _conv_w(g, dc, cin, 3, gain=1.7)
+        if heavy:
+            for k in (2, 4, 6):
+                sd[f"f2r_agg.{i}.conv.double_conv.{k}.weight"] = _conv_w(g, cin, cin, 3, gain=1.7)
+            sd[f"f2r_agg.{i}.conv.double_conv.8.weight"] = _conv_w(g, dc, cin, 3, gain=1.7)
+        else:
+            sd[f"f2r_agg.{i}.conv.double_conv.2.weight"] = _conv_w(g, dc, cin, 3, gain=1.7)
         _chl = dc
     sd["final_conv.weight"] = _conv_w(g, 1, dec_chl[-1] if len(dec_chl) else _chl, 3, gain=6.0)
 
@@ -440,6 +454,18 @@ def init_bidirectional_fusion_state_dict(coarse_chl, fine_chl, fine_chl_after_co
     s = "c2f.scratch."
     for i, fc in enumerate(fine_chl):
         sd[f"{s}layer{i + 1}_rn.weight"] = _conv_w(g, features, fc, 3)
+    if coarse2fine_type == "only-gate":                                  # C2FNOENCModule (:211-251)
+        for lvl in range(1, 6):
+            unit(f"{s}layer{lvl}_gate1.", features)
+            unit(f"{s}layer{lvl}_gate2.", features)
+        sd[s + "upsample_conv.0.weight"] = (torch.rand(fine_chl[0], 32, 2, 2, generator=g) * 2 - 1) / math.sqrt(fine_chl[0])   # ConvTranspose2d [Cin, Cout, k, k]
+        sd[s + "upsample_conv.0.bias"] = _vec(g, 32, 0.05)
+        sd[s + "upsample_conv.2.weight"] = _conv_w(g, 32, 32, 3, gain=1.7)
+        unit(s + "layer6_gate1.", 32)
+        unit(s + "layer6_gate2.", 32)
+        sd[s + "output_conv.weight"] = _conv_w(g, 1, 32, 3, gain=3.0)
+        sd[s + "output_conv.bias"] = _vec(g, 1, 0.05)
+        return sd
     for i in range(1, 6):
         block(f"{s}refinenet{i}.", features)
     h2 = coarse_chl[0]
@@ -499,8 +525,33 @@ def c2f_module(sd, pre, fine_features: List[Tensor], coarse_features: List[Tenso
     return [rn[4], path_5, path_4, path_3, path_2, last], out
 
 
+def c2f_noenc_module(sd, pre, fine_features: List[Tensor], coarse_features: List[Tensor], fusion: bool, gate: bool):
+    """C2FNOENCModule.forward (bi_directional_fusion_model.py:253-282): no top-down path; every level is two gated units
+    against its coarse map, plus a transposed-conv level 0.  Returns ([path_5 .. path_0], depth)."""
+    s = pre + "scratch."
+    rn = [F.conv2d(f, sd[f"{s}layer{i + 1}_rn.weight"], padding=1) for i, f in enumerate(fine_features)]
+    l0 = F.conv_transpose2d(fine_features[0], sd[s + "upsample_conv.0.weight"], sd[s + "upsample_conv.0.bias"], stride=2)
+    l0 = F.conv2d(F.relu(l0), sd[s + "upsample_conv.2.weight"], padding=1)
+    paths = []
+    for lvl, (x, c) in enumerate(zip(rn[::-1], coarse_features[::-1][:5]), start=1):      # layer1_* works on layer_5_rn with c[5], ...
+        x = _gated_conv_unit(sd, f"{s}layer{lvl}_gate1.", x, c, fusion, gate)
+        paths.append(_gated_conv_unit(sd, f"{s}layer{lvl}_gate2.", x, c, fusion, gate))
+    p0 = _gated_conv_unit(sd, s + "layer6_gate1.", l0, coarse_features[0], fusion, gate)
+    p0 = _gated_conv_unit(sd, s + "layer6_gate2.", p0, coarse_features[0], fusion, gate)
+    out = F.conv2d(p0, sd[s + "output_conv.weight"], sd[s + "output_conv.bias"], padding=1)
+    return paths + [p0], out
+
+
+def _single_conv_ln_heavy(sd, pre, x):
+    """SingleConvCNNLNHeavy (bi_directional_fusion_model.py:448-463): conv -> LN -> conv -> LN -> conv -> GELU (no activation between)."""
+    x = _ln_cf(F.conv2d(x, sd[pre + "single_conv.0.weight"], padding=1), sd[pre + "single_conv.1.weight"], sd[pre + "single_conv.1.bias"])
+    x = _ln_cf(F.conv2d(x, sd[pre + "single_conv.2.weight"], padding=1), sd[pre + "single_conv.3.weight"], sd[pre + "single_conv.3.bias"])
+    return F.gelu(F.conv2d(x, sd[pre + "single_conv.4.weight"], padding=1))
+
+
 def bidirectional_fusion(sd: Dict[str, Tensor], pre: str, c_feat: List[Tensor], f_feat: List[Tensor], pred1: Tensor, pred2: Tensor,
-                         update_base: Optional[Tensor], coarse2fine_type: str = "coarse-gated", trace: Optional[dict] = None) -> Tensor:
+                         update_base: Optional[Tensor], coarse2fine_type: str = "coarse-gated", trace: Optional[dict] = None,
+                         heavy: bool = False) -> Tensor:
     """BiDirectionalFusion.forward (bi_directional_fusion_model.py:379-446) with glb_att=False, coarse2fine=True.
     c_feat / f_feat: 6 maps each, finest first (patchrefinerplus.py:318-326 reverses them); ``pred2`` is replaced by the
     C2F module's depth (:409-414), exactly as the reference does."""
@@ -508,17 +559,19 @@ def bidirectional_fusion(sd: Dict[str, Tensor], pre: str, c_feat: List[Tensor], 
     c_feat, f_feat = list(c_feat), list(f_feat)
     if tuple(c_feat[-1].shape[-2:]) != tuple(f_feat[-1].shape[-2:]):
         c_feat = [_bil(c, f.shape[-2:]) for c, f in zip(c_feat, f_feat)]                       # :392-395
-    feats, out_depth = c2f_module(sd, pre + "c2f.", f_feat[1:], c_feat, fusion, gate)
+    c2f = c2f_noenc_module if coarse2fine_type == "only-gate" else c2f_module
+    feats, out_depth = c2f(sd, pre + "c2f.", f_feat[1:], c_feat, fusion, gate)
     f_feat, pred2 = feats[::-1], out_depth
     if trace is not None:
         trace["c2f_feats"] = [t.clone() for t in f_feat]
         trace["c2f_depth"] = out_depth.clone()
     temp = []
+    single = _single_conv_ln_heavy if heavy else _single_conv_ln
     for idx, (c, f) in enumerate(zip(c_feat, f_feat)):
-        f = _single_conv_ln(sd, f"{pre}fusion_layers_1.{idx}.", torch.cat([c, f], dim=1))
+        f = single(sd, f"{pre}fusion_layers_1.{idx}.", torch.cat([c, f], dim=1))
         p1 = _bil(pred1, f.shape[-2:])
         p2 = _bil(pred2, f.shape[-2:])
-        temp.append(_single_conv_ln(sd, f"{pre}fusion_layers_2.{idx}.", torch.cat([f, p1, p2], dim=1)))
+        temp.append(single(sd, f"{pre}fusion_layers_2.{idx}.", torch.cat([f, p1, p2], dim=1)))
     if trace is not None:
         trace["fusion_enc"] = [t.clone() for t in temp]
     dec = temp[0]
@@ -526,8 +579,8 @@ def bidirectional_fusion(sd: Dict[str, Tensor], pre: str, c_feat: List[Tensor], 
     _feat = temp[0]
     for i, feat in enumerate(temp[1:]):
         x = torch.cat([_bil(_feat, feat.shape[-2:]), feat, _bil(pred1, feat.shape[-2:]), _bil(pred2, feat.shape[-2:])], dim=1)
-        x = F.gelu(F.conv2d(x, sd[f"{pre}f2r_agg.{i}.conv.double_conv.0.weight"], padding=1))
-        x = F.gelu(F.conv2d(x, sd[f"{pre}f2r_agg.{i}.conv.double_conv.2.weight"], padding=1))
+        for k in ((0, 2, 4, 6, 8) if heavy else (0, 2)):                       # DoubleConv (convs.py:31-45) / DoubleConvHeavy (:465-485)
+            x = F.gelu(F.conv2d(x, sd[f"{pre}f2r_agg.{i}.conv.double_conv.{k}.weight"], padding=1))
         dec = _feat = x
     off = F.conv2d(dec, sd[pre + "final_conv.weight"], padding=1)
     if update_base is not None:

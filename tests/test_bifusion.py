@@ -135,3 +135,22 @@ def test_b200_gate_and_ln_relu_epilogues_vs_torch(dev):
         lay([Act.from_nchw(fz.to(dev), x3)], out=out, relu_out=out_relu, res=Act.from_nchw(a.to(dev), x3), res2=Act.from_nchw(skip.to(dev), x3))
         assert float((out.to_nchw().cpu() - gated).abs().max()) < tol * float(gated.abs().max())
         assert float((out_relu.to_nchw().cpu() - F.relu(gated)).abs().max()) < tol * float(gated.abs().max())
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
+@pytest.mark.parametrize("t,heavy", [("only-gate", False), ("coarse-gated", True), ("self-agg", True)])
+def test_oracle_covers_the_ablation_variants_bit_identically(t, heavy):
+    """The four ablation configs' fusion models (C2FNOENCModule 'only-gate', BiDirectionalFusionHeavy): oracle only -- the product
+    raises NotImplementedError for them -- pinned against the reference modules so the next step has a checker."""
+    ref_shim.install()
+    from estimator.models.blocks import bi_directional_fusion_model as ref
+    cls = ref.BiDirectionalFusionHeavy if heavy else ref.BiDirectionalFusion
+    m = cls(encoder_name="x", coarse2fine_type=t, **{k: list(v) for k, v in BIFUSION.items()}).eval()
+    sd = O.init_bidirectional_fusion_state_dict(seed=5, coarse2fine_type=t, heavy=heavy, **BIFUSION)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    c, f, p1, p2 = O.synthetic_fusion_inputs(BIFUSION["coarse_chl"], BIFUSION["fine_chl"], BIFUSION_SIZES_C, BIFUSION_SIZES_F, 2, 3)
+    with torch.no_grad():
+        r = m(c_feat=[x.clone() for x in c], f_feat=[x.clone() for x in f], pred1=p1, pred2=p2, update_base=p1)
+        o = O.bidirectional_fusion(sd, "", c, f, p1, p2, p1, t, heavy=heavy)
+    assert torch.equal(r, o)
