@@ -183,3 +183,17 @@ def test_tiling_matches_oracle_on_random_geometries():
         bf = np.concatenate([tiling.bboxs_to_feat(s.bboxs, (H, W), (ph, pw)) for s in stages if s.bboxs.shape[0]])
         assert np.array_equal(bf[:, 1:], O.bboxs_to_feat(want, (H, W), (ph, pw)).numpy()[:, 1:])
         assert (got[:, 2] <= W).all() and (got[:, 3] <= H).all() and (got[:, :2] >= 0).all()
+
+
+def test_integration_doc_lists_every_c_abi_symbol():
+    """INTEGRATION.md section 2 is the binding table a maintainer reads: every entry point the header declares must appear in it."""
+    hdr = open(os.path.join(ROOT, "include", "prv2_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(prv2_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) >= 25
+    # the doc groups some families as `prv2_blend_partial_{canvas,raw}`: expand those
+    grouped = set()
+    for stem, alts in re.findall(r"`(prv2_[a-z0-9_]*)\{([a-z0-9_,]+)\}`", doc):
+        grouped.update(stem + a for a in alts.split(","))
+    missing = [s for s in syms if s not in doc and s not in grouped]
+    assert not missing, missing
