@@ -4,7 +4,8 @@
  * PyTorch / torchvision / OpenCV calls made inside the estimator model's infer forward.  Each
  * entry point below replaces one such call site; the citation is the reference file:line whose
  * arithmetic the kernel reproduces.  All pointers are DEVICE pointers unless stated; all sizes are
- * explicit; nothing allocates; every function is asynchronous on `stream` and returns 0 on
+ * explicit; nothing allocates (one documented exception: the rN blend's per-geometry column tables, see
+ * prv2_blend_raw); every function is asynchronous on `stream` and returns 0 on
  * success or a negative PRV2_E* code (prv2_last_error() gives the message).  No torch types.
  *
  * Activation tensors ("act") are channels-last bf16, optionally as a (hi, lo) pair of bf16 planes
@@ -27,7 +28,12 @@ typedef uint16_t prv2_bf16;            /* raw bfloat16 bits */
 #define PRV2_ECUDA (-2)                /* CUDA runtime / driver error */
 #define PRV2_EUNSUPPORTED (-3)         /* shape outside what the kernels implement */
 
+/* ABI version: bumped whenever a signature or the GemmDesc layout changes; the Python binding refuses any other value. */
+#define PRV2_ABI_VERSION 200
 int prv2_version(void);
+/* sha256 of the CUDA sources + flags this library was compiled from (stamped by build.py with -DPRV2_BUILD_DIGEST);
+ * the binding compares it with the digest of the sources it sits next to, so a stale .so is an error, not a silent mismatch. */
+const char* prv2_build_digest(void);
 const char* prv2_last_error(void);
 /* Device properties the host uses for grid sizing: out[0]=SM count, out[1]=cc major, out[2]=cc minor,
  * out[3]=max dynamic smem per block (opt-in).  Host pointer. */
@@ -78,7 +84,10 @@ int prv2_blend_canvas(const float* preds, const float* mask, int ph, int pw,
  * nearest(avg_c), C0 = bilinear_ac(cnt_c) to [H,W], then every random patch k (draw order) with
  * raw bbox origin (y0,x0) in `starts` [n,2] int32 (device), prediction preds[k] [ph,pw] nearest-
  * resized to [rh,rw], weight rmask [rh,rw] (already +1e-3): sequential update.  out/out_cnt [H,W]
- * (out_cnt may be NULL).  n may be 0 (pure resize). */
+ * (out_cnt may be NULL).  n may be 0 (pure resize).
+ * ALLOCATION NOTE (the one exception to "nothing allocates"): the first call for a new (Wc, W, pw, rw) geometry on a
+ * device cudaMalloc()s <= 64 KB of column tables that the library keeps for the life of the process (64 geometries per
+ * process; beyond that the table-free generic kernel runs).  Call once per geometry before capturing a CUDA graph. */
 int prv2_blend_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc,
                    const float* preds, const int32_t* starts, int n, int ph, int pw,
                    const float* rmask, int rh, int rw, int H, int W,

@@ -20,7 +20,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PRV2_REFERENCE_ROOT", "/root/reference")
+def _find_root() -> str:
+    """The reference tree: $PRV2_REFERENCE_ROOT, else /root/reference (build container), else the verbatim copy that
+    oracle/build_ref.py leaves under oracle/_ref (the only one that exists on the GPU box)."""
+    env = os.environ.get("PRV2_REFERENCE_ROOT")
+    if env:
+        return env
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    for cand in ("/root/reference", here):
+        if os.path.isdir(os.path.join(cand, "estimator")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _STUB_ROOTS = (
     "mmengine", "timm", "matplotlib", "kornia", "skimage", "imageio", "prettytable",

@@ -9,6 +9,7 @@ import os
 
 from . import build as _build
 
+ABI_VERSION = 200          # == PRV2_ABI_VERSION in include/prv2_b200.h
 MAX_SRC = 12
 MAX_SEG = 128
 
@@ -57,6 +58,7 @@ _i, _f, _p, _i64 = C.c_int, C.c_float, C.c_void_p, C.c_int64
 #: name -> argtypes (every symbol include/prv2_b200.h declares; tests check the export list)
 SIGNATURES = {
     "prv2_version": [],
+    "prv2_build_digest": [],
     "prv2_last_error": [],
     "prv2_device_info": [_p],
     "prv2_crop_resize": [_p, _i, _i, _p, _i, _p, _i, _i, _p],
@@ -107,7 +109,13 @@ def load():
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
-        fn.restype = C.c_char_p if name == "prv2_last_error" else C.c_int
+        fn.restype = C.c_char_p if name in ("prv2_last_error", "prv2_build_digest") else C.c_int
+    if lib.prv2_version() != ABI_VERSION:
+        raise Prv2Error(f"{path} has ABI version {lib.prv2_version()}, this binding needs {ABI_VERSION}: rebuild (python -m patchrefinerv2_b200.build --force)")
+    have, want = (lib.prv2_build_digest() or b"").decode(), _build.source_digest()
+    if have != want:
+        raise Prv2Error(f"{path} was built from other sources (digest {have[:12]} != {want[:12]}): rebuild "
+                        "(python -c 'import __graft_entry__ as g; g.build()')")
     _lib = lib
     return lib
 

@@ -39,19 +39,33 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def built_digest() -> str:
+    """Digest stamped into the existing .so, '' when there is none / it predates the stamp.  Read from the file's bytes
+    (marker ``PRV2_DIGEST=``), not through dlopen: a dlopen'ed handle would survive the rebuild that may follow."""
+    if not os.path.exists(LIB_PATH):
+        return ""
+    with open(LIB_PATH, "rb") as fh:
+        blob = fh.read()
+    i = blob.find(b"PRV2_DIGEST=")
+    return blob[i + 12:i + 12 + 64].decode("ascii", "replace") if i >= 0 else ""
+
+
+def source_digest() -> str:
+    return _digest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a and link the shared library.  Returns its path."""
     os.makedirs(LIB_DIR, exist_ok=True)
-    stamp = os.path.join(LIB_DIR, "build.sha256")
     dig = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+    if not force and os.path.exists(LIB_PATH) and built_digest() == dig:
         return LIB_PATH
     nvcc = _nvcc()
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, f'-DPRV2_BUILD_DIGEST="{dig}"', "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -66,8 +80,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
-    with open(stamp, "w") as fh:
-        fh.write(dig)
     return LIB_PATH
 
 

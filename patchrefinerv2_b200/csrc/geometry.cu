@@ -20,7 +20,12 @@ void set_error(const char* fmt, ...) {
 
 using namespace prv2;
 
-extern "C" int prv2_version(void) { return 100; }
+#ifndef PRV2_BUILD_DIGEST
+#define PRV2_BUILD_DIGEST "unstamped"
+#endif
+extern "C" int prv2_version(void) { return PRV2_ABI_VERSION; }
+static const char g_digest_marker[] = "PRV2_DIGEST=" PRV2_BUILD_DIGEST;       // build.py finds the stamp in the file by this marker
+extern "C" const char* prv2_build_digest(void) { return g_digest_marker + 12; }
 extern "C" const char* prv2_last_error(void) { return g_err; }
 extern "C" int prv2_device_info(int32_t* out4) {
   PRV2_CHECK_ARG(out4 != nullptr, "prv2_device_info: null out");

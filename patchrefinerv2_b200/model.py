@@ -280,6 +280,26 @@ class PatchRefiner(nn.Module):
                 trace = None if "fine_depth" in trace else trace
 
     @torch.no_grad()
+    def predict_patches(self, image_lr, image_hr, bboxs, tile_cfg=None, trace: Optional[dict] = None):
+        """The front half the reference shares between regular_tile and random_tile (baseline_pretrain.py:158-206 / :249-345):
+        coarse pass, then crop -> roi_align -> fine branch -> fusion for the raw-image boxes ``bboxs`` [P,4] int (x0,y0,x1,y1).
+        Returns (preds [P,ph,pw] fp32 on the device, coarse_prediction).  Used by the parity checks (bench.py, tests)."""
+        tile_cfg = self.tile_cfg if tile_cfg is None else self.prepare_tile_cfg(tile_cfg["image_raw_shape"], tile_cfg["patch_split_num"])
+        dev = image_hr.device
+        if self._engine is None or self._engine["device"] != dev:
+            self._engine = self._build_engine(dev)
+        eng = self._engine
+        ph, pw = self.patch_process_shape
+        H, W = tile_cfg["image_raw_shape"]
+        bboxs_np = np.ascontiguousarray(np.asarray(bboxs.cpu() if torch.is_tensor(bboxs) else bboxs, dtype=np.int32).reshape(-1, 4))
+        rois_np = tiling.bboxs_to_feat(bboxs_np, (H, W), (ph, pw))[:, 1:]
+        coarse_feats, coarse_depth = self.coarse_forward(image_lr)
+        preds = torch.empty((bboxs_np.shape[0], ph, pw), dtype=torch.float32, device=dev)
+        self.refine_patches(eng, image_hr[0].float().contiguous(), bboxs_np, rois_np, coarse_feats, coarse_depth,
+                            np.arange(bboxs_np.shape[0]), preds, trace)
+        return preds, coarse_depth
+
+    @torch.no_grad()
     def forward(self, mode=None, image_lr=None, image_hr=None, crops_image_hr=None, depth_gt=None, crop_depths=None, bboxs=None,
                 tile_cfg=None, cai_mode="m1", process_num=4, shard: bool = False, trace: Optional[dict] = None, **kwargs):
         if mode == "train":
@@ -289,10 +309,26 @@ class PatchRefiner(nn.Module):
         else:
             tile_cfg = self.prepare_tile_cfg(tile_cfg["image_raw_shape"], tile_cfg["patch_split_num"])
         assert image_hr.shape[0] == 1                                                        # patchrefiner.py:348
-        dev = image_hr.device
+        dev = image_hr.device if image_hr.is_cuda else self._device
         if self._engine is None or self._engine["device"] != dev:
             self._engine = self._build_engine(dev)
         eng = self._engine
+        hr_ready = None
+        if not image_hr.is_cuda:
+            # frame ingest: host frames are uploaded by the model -- image_lr first on the compute stream,
+            # the 100 MB image_hr on a copy stream UNDER the coarse pass (only the crop kernel needs it); pinned memory makes
+            # both copies asynchronous
+            if "copy_stream" not in eng:
+                eng["copy_stream"] = torch.cuda.Stream(device=dev)
+            image_lr = image_lr.to(dev, non_blocking=True)
+            cs = eng["copy_stream"]
+            cs.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cs):
+                image_hr = image_hr.to(dev, non_blocking=True)
+                hr_ready = torch.cuda.Event()
+                hr_ready.record(cs)
+        elif not image_lr.is_cuda:
+            image_lr = image_lr.to(dev, non_blocking=True)
         ph, pw = self.patch_process_shape
         rh, rw = tile_cfg["patch_raw_shape"]
         H, W = tile_cfg["image_raw_shape"]
@@ -307,13 +343,21 @@ class PatchRefiner(nn.Module):
         n_regular = sum(s.bboxs.shape[0] for s in stages if s.kind == "regular")
         n_random = P - n_regular
 
-        coarse_feats, coarse_depth = self.coarse_forward(image_lr)
-        hr = image_hr[0].float().contiguous()
-        preds = eng["ws"].f32("preds", P, ph, pw)
-
         world, rank = 1, 0
         if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
             world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        if world > 1 and n_random:
+            # every rank must blend the SAME random patches: rank 0's draw wins (ranks seeded differently -- seed+rank is
+            # common practice -- would otherwise add num_r for different bboxes and finalize against their own starts)
+            bboxs_np = _broadcast_bboxs(bboxs_np, dev)
+            rois_np = tiling.bboxs_to_feat(bboxs_np, (H, W), (ph, pw))[:, 1:]
+
+        coarse_feats, coarse_depth = self.coarse_forward(image_lr)
+        if hr_ready is not None:
+            torch.cuda.current_stream(dev).wait_event(hr_ready)
+            image_hr.record_stream(torch.cuda.current_stream(dev))
+        hr = image_hr[0].float().contiguous()
+        preds = eng["ws"].f32("preds", P, ph, pw)
         own_np = tiling.shard_patches(P, rank, world)
         sel = np.nonzero(own_np)[0]
         self.refine_patches(eng, hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel, preds, trace)
@@ -356,6 +400,16 @@ class PatchRefiner(nn.Module):
         if self.output_device == "cpu":
             depth = depth.cpu()
         return depth, {"rgb": image_lr, "depth_pred": depth, "depth_gt": depth_gt, "coarse_prediction": coarse_depth}
+
+
+def _broadcast_bboxs(bboxs_np: np.ndarray, dev) -> np.ndarray:
+    """Rank 0's patch list to every rank (tiny: P x 4 int32), over whatever backend the default group runs on."""
+    dist = torch.distributed
+    on_dev = dist.get_backend() == "nccl"
+    t = torch.from_numpy(np.ascontiguousarray(bboxs_np, dtype=np.int32))
+    t = t.to(dev) if on_dev else t.clone()
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy()
 
 
 def _default_fine_encoder(encoder_name: str, in_chans: int):

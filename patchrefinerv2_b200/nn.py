@@ -146,12 +146,12 @@ class GemmLayer:
         for seg in segs:
             si, dh, dw, w = seg[:4]
             grouped = isinstance(w, (list, tuple))          # vertical tap group: weights of taps (dh-1, dh, dh+1)
-            ws = [x.detach().to(device=device, dtype=torch.float32) for x in (w if grouped else [w])]   # packing runs on the device (setup, not hot path)
+            ws = [x.detach().to(device="cpu", dtype=torch.float32) for x in (w if grouped else [w])]   # packing runs on the HOST: one H2D copy per layer, no device kernels at setup
             assert all(x.shape[0] == cout_real for x in ws) and (not grouped or len(ws) == 3)
             c = ws[0].shape[1]
             assert src_c.setdefault(si, c) == c, "a source must present the same channel count in every segment"
             cp = ceil_to(c, 64)
-            wp = torch.zeros((len(ws), self.cout_pad, cp), dtype=torch.float32, device=device)
+            wp = torch.zeros((len(ws), self.cout_pad, cp), dtype=torch.float32)
             for r, x in enumerate(ws):
                 wp[r, :cout_real, :c] = x
             # group: columns interleaved per 64-channel block [block 0: tap -1 | tap 0 | tap +1][block 1: ...] (include/prv2_b200.h)
@@ -167,9 +167,9 @@ class GemmLayer:
                 table.append((si, dh, dw, taps))
         assert len(table) <= _lib.MAX_SEG and n_src * (2 if x3 else 1) <= _lib.MAX_SRC
         self.src_c = [src_c[i] for i in range(n_src)]
-        self.weight = torch.cat(blocks, dim=1).contiguous()
+        self.weight = (blocks[0] if len(blocks) == 1 else torch.cat(blocks, dim=1)).contiguous().to(device)
         self.ktot = self.weight.shape[1]
-        f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous().to(device)
+        f32 = lambda t: None if t is None else t.detach().to(device="cpu", dtype=torch.float32).contiguous().to(device)
         self.bias, self.gamma, self.beta = f32(bias), f32(gamma), f32(beta)
         d = GemmDesc()
         d.Cout, d.block_n, d.Cout_pad, d.Ktot = cout, self.block_n, self.cout_pad, self.ktot

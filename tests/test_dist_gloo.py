@@ -139,3 +139,34 @@ def test_every_rank_draws_the_same_schedule():
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
     owns = [tiling.shard_patches(sum(x.shape[0] for x in a), r, 2) for r in range(2)]
     assert np.array_equal(owns[0] + owns[1], np.ones_like(owns[0]))
+
+
+def _bcast_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from patchrefinerv2_b200.model import _broadcast_bboxs
+    tc = tiling.prepare_tile_cfg(SHAPE, RAW, SPLIT)
+    random.seed(100 + rank)                                    # the bad practice the broadcast guards against: seed + rank
+    bb = np.concatenate([s.bboxs for s in tiling.schedule(tc, SHAPE, MODE, PN)])
+    got = _broadcast_bboxs(bb, torch.device("cpu"))
+    q.put((rank, bb, got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ranks_seeded_differently_still_blend_rank0s_patches():
+    """the sharded forward must not assume identical `random` state on every rank -- rank 0's draw is broadcast."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(2):
+        r, own, got = q.get(timeout=120)
+        res[r] = (own, got)
+    for p in procs:
+        p.join(60)
+    assert not np.array_equal(res[0][0], res[1][0])            # the two ranks really drew different random patches
+    assert np.array_equal(res[0][1], res[0][0]) and np.array_equal(res[1][1], res[0][0])

@@ -110,7 +110,10 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib = _lib.load()                                   # loads; no compute call without a GPU
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.prv2_version() == 100
+    assert lib.prv2_version() == _lib.ABI_VERSION == int(re.search(r"#define PRV2_ABI_VERSION (\d+)", header).group(1))
+    # the library is stamped with the digest of the sources it was compiled from; a stale .so is refused at load time
+    from patchrefinerv2_b200 import build as B
+    assert lib.prv2_build_digest().decode() == B.source_digest() == B.built_digest()
 
 
 def test_product_never_imports_the_oracle():

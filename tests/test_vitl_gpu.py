@@ -1,0 +1,146 @@
+"""Parity on the configuration that is BENCHMARKED: DAv2 ViT-L coarse + ViT-L refiner + FusionUnet,
+448x448 patches (1025 tokens, 37^2 -> 32^2 bicubic pos-embed, 24 blocks, 16 heads, 1024-channel projections), 2160x3840 frame,
+4x4 split -- against the CPU oracle (bit-identical to the reference, tests/test_oracle_vs_reference.py) run on the GPU box's
+host; plus BASELINE config 1 (ViT-S, 1080x1920, 2x2, m1) as a whole frame and the FusionUnet conv shapes that carry most of the
+FLOPs (386 -> 386 @ 448^2, 514 -> 514: Cout > 256 = two N tiles in the GELU epilogue).
+
+Tolerances: fp32 mode (3-pass bf16 split): final depth within 1e-3 RELATIVE per pixel (the north-star bar), intermediates
+within 1e-3 .. 5e-3 of the tensor's max magnitude; bf16 mode: 5e-2 per pixel / 1.5e-2 mean, stated separately."""
+import math
+import random
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pr_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel_max(got, want):
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-6)).item()
+
+
+def px_rel(got, want, floor=1e-3):
+    return ((got - want).abs() / want.abs().clamp_min(floor))
+
+
+@pytest.fixture(scope="module")
+def vitl_case():
+    """Benchmark-shaped config with bench.py's weight generator (healthy activations through 24 blocks) and frame."""
+    import bench
+    enc, pshape, raw, split, cai_mode, pn = bench.WORKLOADS["dav2_vitl_2160x3840_4x4_r32"]
+    cfg = bench.make_config(enc, pshape, raw, split)
+    from patchrefinerv2_b200 import build_model
+    spec = {k: tuple(v.shape) for k, v in build_model(dict(type="PatchRefiner", config=cfg)).state_dict().items()}
+    sd = bench.random_state_dict(spec, 0)
+    hr = bench.synthetic_frame(raw, 1)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    orc = O.PatchRefinerOracle(cfg, sd)
+    orc.trace = {}
+    lr = O.resizer(pshape, hr)
+    tc = orc.tile_cfg
+    rh, rw = tc["patch_raw_shape"]
+    with torch.no_grad():
+        feats, coarse = orc.coarse_forward(lr)
+        tt = {"coarse_prediction": coarse, "coarse_features": feats}
+        bb = O.make_bboxs([137, 1619], [211], rh, rw)               # two random-stage style patches (odd offsets; second touches the bottom edge)
+        rec = {"bboxs": [], "bboxs_feat": [], "preds": []}
+        preds = orc._predict(hr[0], bb, tc, tt, 1, rec)
+    return dict(cfg=cfg, sd=sd, hr=hr, lr=lr, bb=bb, coarse=coarse, feats=feats, preds=preds, trace=orc.trace["first_patch"], rec=rec)
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("bf16", 5e-2)])
+def test_vitl_448_coarse_pass_and_refined_patches_vs_oracle(vitl_case, prec, tol):
+    from patchrefinerv2_b200 import build_model
+    c = vitl_case
+    m = build_model(dict(type="PatchRefiner", config=c["cfg"], precision=prec, patch_batch=2, output_device="cuda"))
+    m.load_dict(c["sd"])
+    m = m.cuda().eval()
+    tr = {}
+    got, coarse = m.predict_patches(c["lr"].to(DEV), c["hr"].to(DEV), c["bb"], trace=tr)
+    got, coarse = got.cpu(), coarse.cpu()
+    t = c["trace"]
+    # coarse pass (whole frame through ViT-L + DPT head)
+    assert rel_max(coarse, c["coarse"]) < tol
+    # geometry: bit-exact whatever the precision mode
+    assert torch.equal(tr["crops"].cpu(), c["rec"]["roi_first"]["crop"])
+    assert rel_max(tr["roi_depth"].cpu(), c["rec"]["roi_first"]["depth"]) < tol
+    # fine branch intermediates of the first patch: tokens (patch embed + cls + bicubic pos-embed), block 0, the four taps
+    # (blocks 4/11/17/23 + final norm), DPT features, fine depth
+    assert rel_max(tr["tokens0"].cpu()[:1], t["tokens0"]) < tol
+    assert rel_max(tr["block0"].cpu()[:1], t["block0"]) < tol
+    for a, b in zip(tr["taps"], t["taps"]):
+        assert rel_max(a.cpu()[:1], b) < tol * 3
+    for a, b in zip(tr["fine_feats"], t["fine_feats"]):
+        assert rel_max(a.cpu()[:1], b) < tol * 5
+    assert rel_max(tr["fine_depth"].cpu()[:1], t["fine_depth"]) < tol * 3
+    for a, b in zip(tr["fusion_enc"], t["fusion_enc"]):
+        assert rel_max(a.cpu()[:1], b) < tol * 5
+    assert rel_max(tr["fusion_dec"].cpu()[:1], t["fusion_dec"]) < tol * 5
+    # refined depth of both patches: per-pixel relative (north-star bar in fp32 mode) and the offset the refiner adds
+    want = c["preds"][:, 0]
+    rel = px_rel(got, want)
+    assert rel.max().item() < tol, rel.max().item()
+    roi = c["rec"]["roi_first"]["depth"][:, 0]
+    off_ref = want - roi
+    off_err = ((got - roi) - off_ref).abs().max() / off_ref.abs().max()
+    assert off_ref.abs().max() > 1e-2 * want.abs().max()           # the refiner really moves the depth at these weights
+    assert off_err.item() < (2e-3 if prec == "fp32" else 0.15), off_err.item()
+    if prec == "bf16":
+        assert rel.mean().item() < 1.5e-2
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("bf16", 5e-2)])
+def test_baseline_config1_vits_1080p_2x2_m1_full_frame(prec, tol):
+    """BASELINE.json configs[0]: DAv2 ViT-S coarse + refiner, synthetic 1080x1920, 2x2 split, m1 -- whole frame vs the oracle."""
+    from patchrefinerv2_b200 import build_model
+    cfg = O.make_config("vits", (448, 448), (1080, 1920), (2, 2))
+    sd = O.init_patchrefiner_state_dict(cfg, 0)
+    lr, hr = O.synthetic_frame(cfg, 1)
+    random.seed(1)
+    want, coarse, avg = O.PatchRefinerOracle(cfg, sd).infer(lr, hr, None, "m1", 4)
+    m = build_model(dict(type="PatchRefiner", config=cfg, precision=prec, patch_batch=4))
+    m.load_dict(sd)
+    m = m.cuda().eval()
+    random.seed(1)
+    depth, log = m(mode="infer", image_lr=lr.to(DEV), image_hr=hr.to(DEV), cai_mode="m1", process_num=4)
+    assert depth.shape == want.shape == (1, 1, 896, 896) and depth.device.type == "cpu"
+    assert px_rel(depth, want).max().item() < tol
+    assert torch.equal(m.last_stats["count_map"].cpu(), avg.count_map)
+    # host-frame ingest path: same result from CPU tensors (the model uploads them itself)
+    random.seed(1)
+    depth2, _ = m(mode="infer", image_lr=lr, image_hr=hr.pin_memory(), cai_mode="m1", process_num=4)
+    assert torch.equal(depth, depth2)
+
+
+MODES = [(False, 1.5e-2), (True, 3e-4)]
+
+
+@pytest.mark.parametrize("x3,tol", MODES)
+@pytest.mark.parametrize("B,H,W,splits,Cout", [(1, 448, 448, [256, 128, 2], 386), (1, 64, 64, [256, 256, 2], 514), (2, 32, 32, [514], 256)])
+def test_fusion_decoder_conv_shapes_gelu(x3, tol, B, H, W, splits, Cout):
+    """FusionUnet decoder convs at ViT-L widths (fusion_model.py:33-45): 386 -> 386 @ 448^2 (the 717-GFLOP stage), 514 -> 514
+    (two 257-wide N tiles), 514 -> 256; GELU epilogue, no bias."""
+    from patchrefinerv2_b200 import _lib
+    from patchrefinerv2_b200.nn import Act, GemmLayer, conv_segments
+    g = torch.Generator().manual_seed(H + Cout)
+    xs = [torch.randn(B, c, H, W, generator=g) for c in splits]
+    cin = sum(splits)
+    w = torch.randn(Cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    want = F.gelu(F.conv2d(torch.cat(xs, 1).to(DEV), w.to(DEV), padding=1)).cpu()       # fp32 reference conv (cuDNN TF32 off below)
+    srcs = [Act.from_nchw(x.to(DEV), x3) for x in xs]
+    lay = GemmLayer(conv_segments(w, splits), len(splits), Cout, x3, DEV, act=_lib.ACT_GELU)
+    out = Act.empty(B, H, W, Cout, x3, DEV)
+    lay(srcs, out=out)
+    assert rel_max(out.to_nchw().cpu(), want) < tol
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _strict_fp32_reference_convs():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
