@@ -1,12 +1,7 @@
-// Fused multi-head attention for the DINOv2 blocks (attention.py:49-62): softmax(q k^T / 8) v with
-// head_dim 64, on tcgen05.  One CTA = 128 query rows of one (image, head).  Per 128-key chunk:
-//   S = Q K^T      tcgen05.mma  (A = Q tile, B = K tile, both K-major SW128 straight from TMA)
-//   online softmax 128 threads, thread t owns query row t = TMEM lane t (no shuffles)
-//   O_c = P V      tcgen05.mma  (A = P written to smem as bf16 in the SW128 K-major layout,
-//                                B = V tile as MN-major operand: rows are keys, as TMA delivers it)
-//   acc = acc * alpha + O_c   in registers (fp32)
-// The 1025-token sequence is 9 chunks; keys >= T are masked.  X3 = (hi,lo) operand splitting for
-// the fp32-class precision mode (3 MMAs per product).
+// Fused multi-head attention for the DINOv2 blocks (attention.py:49-62): softmax(q k^T / 8) v with head_dim 64, on tcgen05:
+// S = Q K^T and O = P V on the tensor cores (S, P and O live in tensor memory), online softmax with one thread per query row.
+// The design notes are at the kernel (attention_v5_kernel).  X3 = (hi, lo) operand splitting for the fp32-class precision mode
+// (3 MMAs per product).
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -18,7 +13,7 @@ using namespace prv2;
 namespace {
 
 constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB: 128 rows x 64 bf16
-constexpr uint64_t SPIN_LIMIT_NS = 4000000000ull;
+constexpr long long SPIN_LIMIT_CLK = 8000000000ll;     // ~4 s of SM clocks: a deadlock traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -32,13 +27,21 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ uint64_t globaltimer_ns() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends the thread in hardware for a while by itself; the watchdog below costs nothing until a wait has spun 4096
+  // times and then only reads the SM clock (round 1 read %globaltimer in front of every contended wait)
   if (mbar_try(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try(bar, parity)) {
-    if ((++spins & 0x3fff) == 0 && globaltimer_ns() - t0 > SPIN_LIMIT_NS) {
-      printf("prv2_attention: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
+    if ((++spins & 0xfff) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > SPIN_LIMIT_CLK) {
+        if ((threadIdx.x & 31) == 0)
+          printf("prv2_attention: mbarrier wait timed out (block %d,%d,%d warp %d, barrier @%u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x >> 5,
+                 bar & 0x3ffu, parity);
+        __trap();
+      }
     }
   }
 }
@@ -57,239 +60,12 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
                "l"(bdesc), "r"(idesc), "r"(accumulate)
                : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
-      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-        "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 // both operand layouts use 128-byte rows, 8-row groups 1024 B apart, SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-struct alignas(64) AttnParams {
-  CUtensorMap tm_hi, tm_lo;
-  bf16* out_hi; bf16* out_lo;
-  int B, T, heads, D;
-};
-
-template <bool X3>
-__global__ void __launch_bounds__(128) attention_kernel(const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  // tiles: Q, K, V, P0, P1 [, Ql, Kl, Vl, Pl0, Pl1]
-  const uint32_t sQ = base, sK = base + TILE_BYTES, sV = base + 2 * TILE_BYTES, sP = base + 3 * TILE_BYTES;
-  const uint32_t sQl = base + 5 * TILE_BYTES, sKl = base + 6 * TILE_BYTES, sVl = base + 7 * TILE_BYTES, sPl = base + 8 * TILE_BYTES;
-  const uint32_t bars = base + (X3 ? 10 : 5) * TILE_BYTES;
-  const uint32_t bar_q = bars, bar_kv = bars + 8, bar_s = bars + 16, bar_o = bars + 24, tmem_slot = bars + 32;
-  uint8_t* pP = base_ptr + 3 * TILE_BYTES;
-  uint8_t* pPl = base_ptr + 8 * TILE_BYTES;
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
-  const int D = p.D;
-  const int n_chunks = (p.T + 127) / 128;
-
-  if (tid == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
-  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-
-  const uint32_t kv_bytes = (X3 ? 4 : 2) * TILE_BYTES;
-  if (tid == 0) {
-    mbar_expect_tx(bar_q, (X3 ? 2 : 1) * TILE_BYTES);
-    tma_load_3d(sQ, &p.tm_hi, bar_q, head * 64, q0, b);
-    if (X3) tma_load_3d(sQl, &p.tm_lo, bar_q, head * 64, q0, b);
-    mbar_expect_tx(bar_kv, kv_bytes);
-    tma_load_3d(sK, &p.tm_hi, bar_kv, D + head * 64, 0, b);
-    tma_load_3d(sV, &p.tm_hi, bar_kv, 2 * D + head * 64, 0, b);
-    if (X3) {
-      tma_load_3d(sKl, &p.tm_lo, bar_kv, D + head * 64, 0, b);
-      tma_load_3d(sVl, &p.tm_lo, bar_kv, 2 * D + head * 64, 0, b);
-    }
-  }
-  // instruction descriptors: c=F32, a=b=BF16, M=128; S: N=128 both K-major; PV: N=64, B MN-major (bit 16)
-  const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-  const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-  const float c_log2 = 0.125f * 1.4426950408889634f;    // head_dim^-0.5 * log2(e)   (attention.py:41)
-
-  float acc[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
-
-  mbar_wait(bar_q, 0);
-  for (int j = 0; j < n_chunks; ++j) {
-    const uint32_t ph = j & 1;
-    mbar_wait(bar_kv, ph);
-    if (tid == 0) {
-      tc_fence_after();
-      uint32_t accum = 0;
-      for (int k = 0; k < 4; ++k) { tc_mma_bf16(tS, umma_desc_sw128(sQ) + 2 * k, umma_desc_sw128(sK) + 2 * k, idesc_s, accum); accum = 1; }
-      if (X3) {
-        for (int k = 0; k < 4; ++k) tc_mma_bf16(tS, umma_desc_sw128(sQ) + 2 * k, umma_desc_sw128(sKl) + 2 * k, idesc_s, 1);
-        for (int k = 0; k < 4; ++k) tc_mma_bf16(tS, umma_desc_sw128(sQl) + 2 * k, umma_desc_sw128(sK) + 2 * k, idesc_s, 1);
-      }
-      tc_commit(bar_s);
-    }
-    mbar_wait(bar_s, ph);
-    tc_fence_after();
-    const int key0 = j * 128;
-    const int n_valid = min(128, p.T - key0);
-    float v[32];
-    // pass 1: row max over this chunk
-    float m_new = m_run;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      tc_ld32(tS + lane_off + c * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) if (c * 32 + i < n_valid) m_new = fmaxf(m_new, v[i]);
-    }
-    const float alpha = exp2f((m_run - m_new) * c_log2);
-    // pass 2: p = exp2((s - m) * c), write P (bf16) to smem in the SW128 K-major layout
-    float l_add = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      tc_ld32(tS + lane_off + c * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float pv = (c * 32 + i < n_valid) ? exp2f((v[i] - m_new) * c_log2) : 0.f;
-        v[i] = pv;
-        l_add += pv;
-      }
-      // keys c*32 .. c*32+31 of row tid: tile (c>>1), 16-byte chunks ((c&1)*4 + g), g = 0..3
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int chunk = (c & 1) * 4 + g;
-        const uint32_t off = (uint32_t)(c >> 1) * TILE_BYTES + tid * 128 + ((chunk ^ (tid & 7)) << 4);
-        bf16x8 hi8, lo8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          hi8.v[e] = f2bf(v[g * 8 + e]);
-          if (X3) lo8.v[e] = f2bf(v[g * 8 + e] - bf2f(hi8.v[e]));
-        }
-        *reinterpret_cast<bf16x8*>(pP + off) = hi8;
-        if (X3) *reinterpret_cast<bf16x8*>(pPl + off) = lo8;
-      }
-    }
-    l_run = l_run * alpha + l_add;
-    m_run = m_new;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      uint32_t accum = 0;
-      for (int k = 0; k < 8; ++k) {      // 8 slices of 16 keys: A advances 32 B inside tile (k>>2), B advances 16 rows (2048 B)
-        const uint64_t ad = umma_desc_sw128(sP + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
-        tc_mma_bf16(tO, ad, umma_desc_sw128(sV + k * 2048), idesc_o, accum);
-        accum = 1;
-        if (X3) {
-          tc_mma_bf16(tO, ad, umma_desc_sw128(sVl + k * 2048), idesc_o, 1);
-          tc_mma_bf16(tO, umma_desc_sw128(sPl + (k >> 2) * TILE_BYTES) + 2 * (k & 3), umma_desc_sw128(sV + k * 2048), idesc_o, 1);
-        }
-      }
-      tc_commit(bar_o);
-    }
-    mbar_wait(bar_o, ph);
-    tc_fence_after();
-    if (tid == 0 && j + 1 < n_chunks) {       // K/V/P buffers are free again: prefetch the next chunk under the accumulate
-      mbar_expect_tx(bar_kv, kv_bytes);
-      tma_load_3d(sK, &p.tm_hi, bar_kv, D + head * 64, key0 + 128, b);
-      tma_load_3d(sV, &p.tm_hi, bar_kv, 2 * D + head * 64, key0 + 128, b);
-      if (X3) {
-        tma_load_3d(sKl, &p.tm_lo, bar_kv, D + head * 64, key0 + 128, b);
-        tma_load_3d(sVl, &p.tm_lo, bar_kv, 2 * D + head * 64, key0 + 128, b);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      tc_ld32(tO + lane_off + c * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[c * 32 + i] = acc[c * 32 + i] * alpha + v[i];
-    }
-  }
-  const int q = q0 + tid;
-  if (q < p.T) {
-    const float inv = 1.0f / l_run;
-    const size_t o = ((size_t)b * p.T + q) * D + head * 64;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      float t[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) t[e] = acc[g * 8 + e] * inv;
-      act_store8(p.out_hi, X3 ? p.out_lo : nullptr, o + g * 8, t);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// v3: warp-specialised, software-pipelined kernel for the one-pass bf16 mode.
-//   warp 0        TMA producer: Q tiles once, then a 2-stage ring of K / V chunks
-//   warp 1        MMA issuer (converged warp, one elected lane): S_w = Q_w K^T, O_w += P_w V
-//   warps 2..5    softmax warpgroup 0 (query tile 0), warps 6..9 warpgroup 1 (query tile 1)
-// One CTA owns TWO 128-query tiles of one (image, head): every K/V chunk is loaded once and used twice, and
-// while one warpgroup runs its softmax the tensor core works for the other.
-// * O_w accumulates in TMEM over all key chunks (tcgen05.mma accumulate); the row owner rescales it in
-//   place (tcgen05.ld / st) only when its running maximum grows by more than 2^8 ("lazy rescale": the
-//   exponentials are taken against a stale maximum otherwise, which is exact after the final 1/l).
-// * TMEM reads of S are double-buffered in registers so the load of the next 32 columns overlaps the
-//   exponentials of the current ones.
-// * Key chunks are 128 wide except the LAST, which may be up to 144 wide (UMMA N = 16..144), so the 1025-token
-//   DINOv2 sequence is 7 x 128 + 129 keys in 8 chunks instead of 9; the leftover query rows (T mod 128 <= 16)
-//   go to a small SIMT kernel instead of a whole extra 128-row tile.
-// * Output rows are staged in shared memory and leave with one bulk async copy per row.
-// TMEM: S0 | S1 (160-col slots) | O0 | O1 (64 cols each).
-// ---------------------------------------------------------------------------------------------
-constexpr int KV_STAGES = 2;
-constexpr int KV_ROWS = 144;
-constexpr int KV_TILE_BYTES = KV_ROWS * 128;       // 18 KB
-constexpr int S_COLS = 160;                         // TMEM columns reserved per S accumulator (32-aligned)
-constexpr int V2_THREADS = 320;                    // SPLIT = 1: one softmax thread per query row
-constexpr int V4_THREADS = 64 + 2 * 256;            // SPLIT = 2: two threads per query row (16 softmax warps, 4 per SMSP)
-constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;      // row-statistics exchange between the two halves of a row: [tile][parity][half][row]
 constexpr int TAIL_MAX = 16;                        // leftover rows / keys folded away from a full extra tile
-constexpr int OUT_PITCH = 144;                      // staged output row: 64 bf16 + 16 B pad
 constexpr float RESCALE_LOG2 = 8.0f;                // lazy rescale threshold (log2 units)
 
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -333,6 +109,39 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr)
       : "memory");
 }
+
+// ---------------------------------------------------------------------------------------------
+// v5: one softmax THREAD per query row, P stays in tensor memory, scores double-buffered.
+//   warps 0..3    softmax warpgroup of query tile 0 (thread = TMEM lane = query row: no shuffles, no shared-memory exchange)
+//   warps 4..7    softmax warpgroup of query tile 1
+//   warp 8        MMA issuer (one elected lane): S_w = Q_w K^T (operands in shared memory), O_w += P_w V (A = P_w from TMEM)
+//   warp 9        TMA producer: Q tiles once, then a ring of K / V chunks          (warps 10, 11: idle, they only give registers back)
+// Keys are processed in 64-wide chunks and every query tile owns TWO score slots in tensor memory: S_w(j+1) is computed while the
+// softmax of S_w(j) runs, so a softmax warpgroup never waits for the tensor pipe (round 1's kernel, and the first version of this
+// one, spent a third of the softmax warps' time waiting for S: ncu, profiles/).  A softmax thread reads its 64 scores from TMEM
+// ONCE, takes the maximum, forms p = 2^(s*c - m*c), packs bf16 pairs and writes them back OVER the scores with tcgen05.st: P
+// aliases S, so the P V product takes its A operand straight from tensor memory (no shared-memory staging of P, no
+// generic->async proxy fence).  The tensor pipe executes in issue order, so S_w(j+2) -- issued after P_w(j) V(j) -- may
+// overwrite P_w(j) safely.  The row owner rescales O_w in place, lazily (only when the running maximum grew by more than 2^8),
+// after waiting for P_w(j-1) V(j-1) to retire.  With two tiles and two slots per tile in flight the MUFU pipe always has
+// exponentials to run; that pipe (16 ex2 / clock / SM) is the bound of this kernel at head_dim 64.
+// X3 = fp32-class mode: Q, K, V arrive as (hi, lo) 16-bit planes, S = Qh Kh + Qh Kl + Ql Kh, P is split into (hi, lo) planes that
+// together fill the score slot, O = Ph Vh + Ph Vl + Pl Vh; the output is written as (hi, lo) planes.
+// The last key chunk is 16..80 wide: 1025 tokens = 15 x 64 + 65.  Leftover query rows (T mod 128 <= 16) go to the SIMT tail kernel.
+// TMEM (512 columns): S slots [tile][buffer] at 96-column pitch | O0 | O1 (64 columns each).
+// ---------------------------------------------------------------------------------------------
+constexpr int CH = 64;                              // keys per chunk
+constexpr int CHW = 80;                             // widest (last) chunk
+constexpr int KVB = CHW * 128;                      // bytes of one K or V chunk buffer (10 KB, 1024-aligned)
+constexpr int SLOT = 96;                            // TMEM column pitch of a score slot
+constexpr int P_LO_COL = CHW / 2;                   // X3: P_lo plane starts 40 columns into the slot (P_hi of an 80-wide chunk ends there)
+constexpr float TRUNC_BIAS_LOG2 = 0.0028150156f;    // log2(1 + 2^-9)
+
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(tmem_d), "r"(tmem_a),
+               "l"(bdesc), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
@@ -340,375 +149,73 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
       "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-
-struct alignas(64) AttnParamsV2 {
-  CUtensorMap tm_q, tm_kv;
-  bf16* out_hi;
-  int B, T, heads, D, n_chunks, last_width, tq_main;
-};
-
-// SPLIT = 2 ("v4"): the softmax of a 128-row query tile is shared by TWO warpgroups -- the warps (tile, half, quadrant) with the same
-// quadrant may read the same TMEM lanes, so thread (half, row) owns columns [64*half, 64*half+64) of its row's scores, writes P
-// tile `half` and rescales / emits O columns [32*half, 32*half+32).  The halves meet once per chunk (row maximum, through shared
-// memory and a 256-thread named barrier) and once at the end (row sum).  v3 ran 2 softmax warps per SM sub-partition and was
-// latency-bound there (issue slots 45 % busy, MUFU 42 %); four warps per sub-partition hide the TMEM-load / MUFU / barrier latencies.
-// (18 warps put 5 on one sub-partition: 16384 / (5 * 32) caps the SPLIT = 2 kernel at 96 registers, so it walks its two
-// 32-column pieces through ONE register buffer; the other warps of the sub-partition cover the TMEM-load latency instead.
-// Keeping all 64 scores of a thread in registers between the two passes -- one TMEM read per chunk instead of two -- was
-// measured SLOWER (342 vs 292 us per 27-patch call): at 96 registers it spills.)
-template <int SPLIT>
-__global__ void __launch_bounds__(64 + 256 * SPLIT, 1) attention_v3_kernel(const __grid_constant__ AttnParamsV2 p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  // tiles: Q0 Q1 | K[2] | V[2] (18 KB each) | P0(3) P1(3)
-  const uint32_t sQ = base, sK = base + 2 * TILE_BYTES, sV = sK + KV_STAGES * KV_TILE_BYTES, sP = sV + KV_STAGES * KV_TILE_BYTES;
-  const uint32_t bars = sP + 6 * TILE_BYTES;
-  const uint32_t bar_q = bars;
-  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bars + 8u * (1 + KV_STAGES + s); };
-  auto s_full = [&](int w) { return bars + 8u * (1 + 2 * KV_STAGES + w); };
-  auto p_full = [&](int w) { return bars + 8u * (3 + 2 * KV_STAGES + w); };
-  auto o_done = [&](int w) { return bars + 8u * (5 + 2 * KV_STAGES + w); };
-  const uint32_t tmem_slot = bars + 8u * (7 + 2 * KV_STAGES);
-  float* const xch = reinterpret_cast<float*>(base_ptr + (bars - base) + 256);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
-  const int D = p.D, T = p.T;
-  const int n_chunks = p.n_chunks;
-  const int n_wg = (q0 + 128 < p.tq_main) ? 2 : 1;
-
-  if (tid == 0) {
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(s_full(w), 1); mbar_init(p_full(w), 128 * SPLIT); mbar_init(o_done(w), 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  auto width_of = [&](int j) { return j == n_chunks - 1 ? p.last_width : 128; };
-
-  if (warp == 0) {
-    // ------------------------------------------------ TMA producer (converged warp, elected lane issues)
-    if (elect_one()) {
-      mbar_expect_tx(bar_q, n_wg * TILE_BYTES);
-      for (int w = 0; w < n_wg; ++w) tma_load_3d(sQ + w * TILE_BYTES, &p.tm_q, bar_q, head * 64, q0 + w * 128, b);
-    }
-    __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < n_chunks; ++j) {
-      mbar_wait(kv_empty(stage), phase ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(kv_full(stage), 2 * KV_TILE_BYTES);
-        tma_load_3d(sK + stage * KV_TILE_BYTES, &p.tm_kv, kv_full(stage), D + head * 64, j * 128, b);
-        tma_load_3d(sV + stage * KV_TILE_BYTES, &p.tm_kv, kv_full(stage), 2 * D + head * 64, j * 128, b);
-      }
-      __syncwarp();
-      if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    auto issue_s = [&](int w, int stage, int width) {          // S_w = Q_w K^T
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(width >> 3) << 17) | ((128u >> 4) << 24);
-      const uint64_t qd = umma_desc_sw128(sQ + w * TILE_BYTES), kd = umma_desc_sw128(sK + stage * KV_TILE_BYTES);
-      tc_mma_bf16(tmem_base + w * S_COLS, qd, kd, idesc, 0);
-      tc_mma_bf16(tmem_base + w * S_COLS, qd + 2, kd + 2, idesc, 1);
-      tc_mma_bf16(tmem_base + w * S_COLS, qd + 4, kd + 4, idesc, 1);
-      tc_mma_bf16(tmem_base + w * S_COLS, qd + 6, kd + 6, idesc, 1);
-      tc_commit(s_full(w));
-    };
-    const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-    auto issue_o = [&](int w, int stage, int width, uint32_t accum) {     // O_w (+)= P_w V
-      for (int k = 0; k < (width >> 4); ++k) {     // 16-key slices: A advances 32 B inside P tile (k>>2), B advances 16 key rows
-        tc_mma_bf16(tmem_base + 2 * S_COLS + w * 64, umma_desc_sw128(sP + (3 * w + (k >> 2)) * TILE_BYTES) + 2 * (k & 3),
-                    umma_desc_sw128(sV + stage * KV_TILE_BYTES + k * 2048), idesc_o, accum);
-        accum = 1;
-      }
-      tc_commit(o_done(w));
-    };
-    mbar_wait(bar_q, 0);
-    mbar_wait(kv_full(0), 0);
-    tc_fence_after();
-    if (elect_one()) for (int w = 0; w < n_wg; ++w) issue_s(w, 0, width_of(0));
-    __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < n_chunks; ++j) {
-      int nstage = stage + 1;
-      uint32_t nphase = phase;
-      if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
-      const bool more = j + 1 < n_chunks;
-      for (int w = 0; w < n_wg; ++w) {
-        mbar_wait(p_full(w), j & 1);          // P_w(j) is in smem (and O_w rescaled); S_w(j) has been consumed
-        if (more && w == 0) mbar_wait(kv_full(nstage), nphase);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_o(w, stage, width_of(j), j > 0 ? 1u : 0u);
-          if (more) issue_s(w, nstage, width_of(j + 1));
-        }
-        __syncwarp();
-      }
-      if (elect_one()) tc_commit(kv_empty(stage));   // K_j / V_j are free once everything issued so far has retired
-      __syncwarp();
-      stage = nstage; phase = nphase;
-    }
-  } else {
-    // ------------------------------------------------ softmax warpgroups
-    const int w = (warp - 2) / (4 * SPLIT);
-    const int half = SPLIT == 2 ? ((warp - 2) >> 2) & 1 : 0;
-    constexpr int NP = 4 / SPLIT;                            // 32-column pieces of a full 128-key chunk per thread
-    const int col_base = half * (128 / SPLIT);               // first score column this thread owns
-    if (w < n_wg) {
-      const int row = (warp & 3) * 32 + lane;               // TMEM lane == query row of this tile
-      const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t tS = tmem_base + w * S_COLS + lane_off + col_base, tO = tmem_base + 2 * S_COLS + w * 64 + lane_off + half * 32;
-      auto xslot = [&](int parity, int h) { return xch + (((w * 2 + parity) * 2 + h) * 128 + row); };
-      auto pair_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory"); };
-      uint8_t* const pP = base_ptr + (sP - base) + 3 * w * TILE_BYTES;
-      const float c_log2 = 0.125f * 1.4426950408889634f;    // head_dim^-0.5 * log2(e)   (attention.py:41)
-      const float tau = RESCALE_LOG2 / c_log2;
-      float m_run = -INFINITY, l_run = 0.f;
-      uint32_t ra[32], rb[32];
-      // (Forcing the two warpgroups to alternate in the MUFU-heavy section with named barriers was measured 16 % SLOWER:
-      // one warpgroup alone is latency-bound, not MUFU-bound, so letting both run concurrently overlaps better.)
-      // One key chunk of this warpgroup's softmax.  GENERAL = the last chunk (ragged: masked keys, 16..144 wide); every other
-      // chunk runs the specialisation with compile-time width 128 and no per-element predicates (the generic code spent
-      // ~320 of its ~1350 instructions per chunk on ISETP / FSEL masking).
-      auto chunk_body = [&](auto general_tag, const int j) {
-        constexpr bool GENERAL = decltype(general_tag)::value;
-        const int n_valid = GENERAL ? T - j * 128 : 128;
-        const int width = GENERAL ? p.last_width : 128;
-        const int n_pieces = GENERAL ? max(1, min(NP, (min(width, 128) - col_base + 31) >> 5)) : NP;   // 32-column pieces of this thread inside the first 128 columns
-        const bool wide = GENERAL && width > 128 && half == SPLIT - 1;     // keys 128..143 of the wide last chunk
-        mbar_wait(s_full(w), j & 1);
-        tc_fence_after();
-        // ---- pass 1: row maximum (TMEM loads double-buffered in registers)
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // independent chains: 2 warps per SMSP hide little latency
-        auto pmax = [&](const uint32_t (&r)[32], int col0) {
-          if (!GENERAL || col0 + 32 <= n_valid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (col0 + i < n_valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
-          }
-        };
-        tc_ld32_issue(tS, ra);
-        tc_ld_wait();
-        if (SPLIT == 2) {
-          pmax(ra, col_base);
-          if (n_pieces > 1) { tc_ld32_issue(tS + 32, ra); tc_ld_wait(); pmax(ra, col_base + 32); }
-        } else {
-          if (n_pieces > 1) tc_ld32_issue(tS + 32, rb);
-          pmax(ra, 0);
-          if (n_pieces > 1) {
-            tc_ld_wait();
-            if (n_pieces > 2) tc_ld32_issue(tS + 64, ra);
-            pmax(rb, 32);
-            if (n_pieces > 2) {
-              tc_ld_wait();
-              if (n_pieces > 3) tc_ld32_issue(tS + 96, rb);
-              pmax(ra, 64);
-              if (n_pieces > 3) { tc_ld_wait(); pmax(rb, 96); }
-            }
-          }
-        }
-        uint32_t rw[16];
-        if (wide) {
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7]), "=r"(rw[8]), "=r"(rw[9]),
-                "=r"(rw[10]), "=r"(rw[11]), "=r"(rw[12]), "=r"(rw[13]), "=r"(rw[14]), "=r"(rw[15])
-              : "r"(tS - col_base + 128)
-              : "memory");
-          tc_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (128 + i < n_valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(rw[i]));
-        }
-        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        if (SPLIT == 2) {                                     // the row's other half: slots alternate by chunk parity, so a fast
-          *xslot(j & 1, half) = mx;                           // partner's write for chunk j+1 cannot overtake this chunk's read
-          pair_sync();
-          mx = fmaxf(mx, *xslot(j & 1, half ^ 1));
-        }
-        // ---- lazy rescale decision: keep the stale maximum unless the new one is > 2^8 larger
-        const bool need = mx > m_run + tau;
-        float alpha = 1.f;
-        if (need) {
-          alpha = ex2_ftz((m_run - mx) * c_log2);             // 0 on the first chunk (m_run = -inf)
-          m_run = mx;
-          l_run *= alpha;
-        }
-        const float mc = m_run * c_log2;
-        // first piece of pass 2 can be fetched while we wait for the previous P V product (SPLIT == 1: it has the registers for it)
-        if (SPLIT == 1) tc_ld32_issue(tS, ra);
-        if (j > 0) {
-          mbar_wait(o_done(w), (j - 1) & 1);                // P_w(j-1) V(j-1) has retired: P buffer and O_w are ours
-          tc_fence_after();
-          if (__any_sync(0xffffffffu, need)) {              // warp-uniform: tcgen05.ld / st are warp collectives
-            if (SPLIT == 1) {
-              tc_ld_wait();                                   // (drains the prefetched S piece too)
-              uint32_t ro[32];
-              tc_ld32_issue(tO, ro);
-              tc_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-              tc_st32(tO, ro);
-              tc_ld32_issue(tO + 32, ro);
-              tc_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-              tc_st32(tO + 32, ro);
-            } else {                                          // this half's 32 O columns, through the (still empty) S buffer
-              tc_ld32_issue(tO, ra);
-              tc_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ra[i] = __float_as_uint(__uint_as_float(ra[i]) * alpha);
-              tc_st32(tO, ra);
-            }
-            tc_st_wait();
-          }
-        }
-        if (SPLIT == 2) tc_ld32_issue(tS, ra);
-        // ---- pass 2: p = 2^(s*c - m*c) -> bf16 -> P tile (SW128 K-major), row sum
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-        auto emit = [&](const uint32_t* r, int col0, int n) {
-          const bool masked = GENERAL && col0 + n > n_valid;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g * 8 >= n) break;
-            float e[8];
-            if (!masked) {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) e[t] = ex2_ftz(fmaf(__uint_as_float(r[g * 8 + t]), c_log2, -mc));
-            } else {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                const float pv = ex2_ftz(fmaf(__uint_as_float(r[g * 8 + t]), c_log2, -mc));
-                e[t] = (col0 + g * 8 + t < n_valid) ? pv : 0.f;
-              }
-            }
-            l4[0] += e[0] + e[4]; l4[1] += e[1] + e[5]; l4[2] += e[2] + e[6]; l4[3] += e[3] + e[7];
-            const int key = col0 + g * 8;                  // 8 consecutive keys = one 16-byte chunk of the P row
-            const int tile = key >> 6, chunk = (key & 63) >> 3;
-            __nv_bfloat162 h2[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(e[2 * t], e[2 * t + 1]);
-            *reinterpret_cast<uint4*>(pP + tile * TILE_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(h2);
-          }
-        };
-        if (wide) emit(rw, 128, 16);
-        tc_ld_wait();
-        if (SPLIT == 2) {
-          emit(ra, col_base, 32);
-          if (n_pieces > 1) { tc_ld32_issue(tS + 32, ra); tc_ld_wait(); emit(ra, col_base + 32, 32); }
-        } else {
-          if (n_pieces > 1) tc_ld32_issue(tS + 32, rb);
-          emit(ra, 0, 32);
-          if (n_pieces > 1) {
-            tc_ld_wait();
-            if (n_pieces > 2) tc_ld32_issue(tS + 64, ra);
-            emit(rb, 32, 32);
-            if (n_pieces > 2) {
-              tc_ld_wait();
-              if (n_pieces > 3) tc_ld32_issue(tS + 96, rb);
-              emit(ra, 64, 32);
-              if (n_pieces > 3) { tc_ld_wait(); emit(rb, 96, 32); }
-            }
-          }
-        }
-        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // P rows -> visible to the tensor core
-        tc_fence_before();
-        mbar_arrive_local(p_full(w));
-      };
-      const bool last_general = p.last_width != 128 || T - (n_chunks - 1) * 128 < 128;
-      for (int j = 0; j < n_chunks - 1; ++j) chunk_body(std::false_type{}, j);
-      if (last_general) chunk_body(std::true_type{}, n_chunks - 1);
-      else chunk_body(std::false_type{}, n_chunks - 1);
-      // ---- epilogue: O / l -> bf16 -> staged row -> one bulk copy
-      mbar_wait(o_done(w), (n_chunks - 1) & 1);
-      tc_fence_after();
-      if (SPLIT == 2) {                                       // row sum = the two halves' partial sums (same rescale history)
-        *xslot(n_chunks & 1, half) = l_run;
-        pair_sync();
-        l_run += *xslot(n_chunks & 1, half ^ 1);
-      }
-      const float inv = 1.0f / l_run;
-      uint8_t* const srow = pP + row * OUT_PITCH;             // the P tiles are free now
-      tc_ld32_issue(tO, ra);
-      if (SPLIT == 1) tc_ld32_issue(tO + 32, rb);
-      tc_ld_wait();
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        __nv_bfloat162 h2[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(__uint_as_float(ra[g * 8 + 2 * t]) * inv, __uint_as_float(ra[g * 8 + 2 * t + 1]) * inv);
-        *reinterpret_cast<uint4*>(srow + half * 64 + g * 16) = *reinterpret_cast<const uint4*>(h2);
-        if (SPLIT == 1) {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(__uint_as_float(rb[g * 8 + 2 * t]) * inv, __uint_as_float(rb[g * 8 + 2 * t + 1]) * inv);
-          *reinterpret_cast<uint4*>(srow + 64 + g * 16) = *reinterpret_cast<const uint4*>(h2);
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (SPLIT == 2) pair_sync();                            // both halves of the staged row are written and fenced
-      const int q = q0 + w * 128 + row;
-      if (q < p.tq_main && half == 0) {
-        bf16* const gdst = p.out_hi + ((size_t)b * T + q) * D + head * 64;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(gdst), "r"(smem_u32(srow)) : "memory");
-      }
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// two independent fp32 FMAs per instruction (FFMA2 on sm_100)
+__device__ __forceinline__ void fma2(float& x0, float& x1, float a0, float a1, float b, float c) {
+  uint64_t d, av, bv, cv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(av) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cv) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(av), "l"(bv), "l"(cv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
 }
 
-// Leftover query rows [tq_main, T) (1 row for the 1025-token DINOv2 sequence): one 256-thread CTA per
-// (image, head, row).  Phase 1: thread-per-key scores into shared memory + block softmax statistics;
-// phase 2: thread (kgroup, 4 dims) accumulates p*V over its keys, 16 key groups reduced through smem.
-constexpr int TAIL_THREADS = 256;
+struct alignas(64) AttnParamsV5 {
+  CUtensorMap tmq_hi, tmq_lo, tm64_hi, tm64_lo, tm80_hi, tm80_lo;    // boxes {64 ch, 128 | 64 | 80 tokens, 1 image} over the qkv planes
+  bf16* out_hi; bf16* out_lo;
+  const bf16* qkv_hi; const bf16* qkv_lo;        // plain pointers for the leftover-row CTA (qkv_lo == nullptr in one-pass mode)
+  int B, T, heads, D, n_chunks, last_width, tq_main;
+  unsigned long long* trace;      // diagnostics (PRV2_ATTN_TRACE=1): clock64 stamps of CTA (0,0,0), [role 0..2][chunk][5]
+};
+#define TRACE(role, j, k)                                                                                             \
+  do {                                                                                                                \
+    if (p.trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 32) p.trace[((role) * 32 + (j)) * 5 + (k)] = clock64(); \
+  } while (0)
+
+// Leftover query rows [tq_main, T) (1 row for the 1025-token DINOv2 sequence) are computed in plain SIMT code by a small second
+// kernel, one 256-thread CTA per (row, head, image): a 128-row tensor-core tile for one row would cost an eighth of the whole
+// attention.  (Folding these rows into the main launch as extra CTAs was measured slower: a latency-bound SIMT CTA holds one of
+// the two 97 KB CTA slots of an SM for longer than a tile CTA.)  Phase 1: thread-per-key scores into shared memory + block softmax
+// statistics; phase 2: thread (key group, 4 dims) accumulates p*V over its keys, the key groups are reduced through smem.
+// lo == nullptr: plain bf16 planes; otherwise value = hi + lo (fp32-class mode) and the output is split the same way.
 constexpr int TAIL_MAX_T = 2048;
-__global__ void __launch_bounds__(TAIL_THREADS) attention_tail_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int T, int heads,
-                                                                      int tq_main) {
-  __shared__ float s_p[TAIL_MAX_T];
-  __shared__ float s_q[64];
-  __shared__ float s_red[TAIL_THREADS / 32];
-  __shared__ float s_acc[16][64];
-  const int n_tail = T - tq_main;
-  const int r = blockIdx.x % n_tail, head = (blockIdx.x / n_tail) % heads, b = blockIdx.x / (n_tail * heads);
+template <int NTHR>
+__device__ __forceinline__ void attention_tail_row(float* smem, const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_lo, bf16* __restrict__ out,
+                                                   bf16* __restrict__ out_lo, int T, int heads, int b, int head, int qrow) {
+  constexpr int KG = NTHR / 16;
+  float* s_p = smem;                         // [TAIL_MAX_T]
+  float* s_q = s_p + TAIL_MAX_T;             // [64]
+  float* s_red = s_q + 64;                   // [NTHR / 32]
+  float* s_acc = s_red + 32;                 // [KG][64]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = heads * 64;
   const size_t row_stride = (size_t)3 * D;
-  const bf16* base = qkv + (size_t)b * T * row_stride;
-  if (tid < 64) s_q[tid] = bf2f(base[(size_t)(tq_main + r) * row_stride + head * 64 + tid]);
+  const size_t img = (size_t)b * T * row_stride;
+  const bf16* base = qkv + img;
+  const bf16* base_lo = qkv_lo ? qkv_lo + img : nullptr;
+  __syncthreads();                            // (the previous row's reads of the shared arrays are done)
+  if (tid < 64) s_q[tid] = act_load(base, base_lo, (size_t)qrow * row_stride + head * 64 + tid);
   __syncthreads();
   const float c_log2 = 0.125f * 1.4426950408889634f;
   // phase 1: scores, thread per key (an 8-lanes-per-key "coalesced" variant with shuffle reduction measured 2x slower:
   // the K rows are L2 hits and the extra passes cost more than the uncoalesced lines)
   float m = -INFINITY;
-  for (int k = tid; k < T; k += TAIL_THREADS) {
-    const bf16* kp = base + (size_t)k * row_stride + D + head * 64;
+  for (int k = tid; k < T; k += NTHR) {
+    const size_t ko = (size_t)k * row_stride + D + head * 64;
     float sc = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       float t[8];
-      act_load8(kp, nullptr, g * 8, t);
+      act_load8(base + ko, base_lo ? base_lo + ko : nullptr, g * 8, t);
 #pragma unroll
       for (int e = 0; e < 8; ++e) sc = fmaf(s_q[g * 8 + e], t[e], sc);
     }
@@ -721,10 +228,10 @@ __global__ void __launch_bounds__(TAIL_THREADS) attention_tail_kernel(const bf16
   __syncthreads();
   m = s_red[0];
 #pragma unroll
-  for (int w = 1; w < TAIL_THREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+  for (int w = 1; w < NTHR / 32; ++w) m = fmaxf(m, s_red[w]);
   __syncthreads();
   float l = 0.f;
-  for (int k = tid; k < T; k += TAIL_THREADS) {
+  for (int k = tid; k < T; k += NTHR) {
     const float pv = exp2f((s_p[k] - m) * c_log2);
     s_p[k] = pv;
     l += pv;
@@ -735,38 +242,426 @@ __global__ void __launch_bounds__(TAIL_THREADS) attention_tail_kernel(const bf16
   __syncthreads();
   l = 0.f;
 #pragma unroll
-  for (int w = 0; w < TAIL_THREADS / 32; ++w) l += s_red[w];
+  for (int w = 0; w < NTHR / 32; ++w) l += s_red[w];
   // phase 2: out[d] = sum_k p_k V[k, d]
   const int kg = tid >> 4, d4 = (tid & 15) * 4;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  const bf16* vbase = base + 2 * D + head * 64 + d4;
-  int k = kg;
-  for (; k + 7 * 16 < T; k += 8 * 16) {                      // eight independent 8-byte loads in flight per thread
-    uint2 raw[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) raw[u] = *reinterpret_cast<const uint2*>(vbase + (size_t)(k + u * 16) * row_stride);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
-      const float2 f0 = __bfloat1622float2(v2[0]), f1 = __bfloat1622float2(v2[1]);
-      const float pv = s_p[k + u * 16];
-      a0 = fmaf(pv, f0.x, a0); a1 = fmaf(pv, f0.y, a1); a2 = fmaf(pv, f1.x, a2); a3 = fmaf(pv, f1.y, a3);
-    }
-  }
-  for (; k < T; k += 16) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(vbase + (size_t)k * row_stride);
+  const size_t voff = 2 * D + head * 64 + d4;
+  auto load4 = [&](const bf16* pl, int k, float (&f)[4], bool add) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(pl + voff + (size_t)k * row_stride);
     const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
     const float2 f0 = __bfloat1622float2(v2[0]), f1 = __bfloat1622float2(v2[1]);
-    const float pv = s_p[k];
-    a0 = fmaf(pv, f0.x, a0); a1 = fmaf(pv, f0.y, a1); a2 = fmaf(pv, f1.x, a2); a3 = fmaf(pv, f1.y, a3);
+    if (add) { f[0] += f0.x; f[1] += f0.y; f[2] += f1.x; f[3] += f1.y; }
+    else { f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; }
+  };
+  int k = kg;
+  for (; k + 7 * KG < T; k += 8 * KG) {                      // eight independent 8-byte loads in flight per thread (and plane)
+    float f[8][4];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) load4(base, k + u * KG, f[u], false);
+    if (base_lo) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) load4(base_lo, k + u * KG, f[u], true);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float pv = s_p[k + u * KG];
+      a0 = fmaf(pv, f[u][0], a0); a1 = fmaf(pv, f[u][1], a1); a2 = fmaf(pv, f[u][2], a2); a3 = fmaf(pv, f[u][3], a3);
+    }
   }
-  s_acc[kg][d4] = a0; s_acc[kg][d4 + 1] = a1; s_acc[kg][d4 + 2] = a2; s_acc[kg][d4 + 3] = a3;
+  for (; k < T; k += KG) {
+    float f[4];
+    load4(base, k, f, false);
+    if (base_lo) load4(base_lo, k, f, true);
+    const float pv = s_p[k];
+    a0 = fmaf(pv, f[0], a0); a1 = fmaf(pv, f[1], a1); a2 = fmaf(pv, f[2], a2); a3 = fmaf(pv, f[3], a3);
+  }
+  s_acc[kg * 64 + d4] = a0; s_acc[kg * 64 + d4 + 1] = a1; s_acc[kg * 64 + d4 + 2] = a2; s_acc[kg * 64 + d4 + 3] = a3;
   __syncthreads();
   if (tid < 64) {
     float a = 0.f;
 #pragma unroll
-    for (int g = 0; g < 16; ++g) a += s_acc[g][tid];
-    out[((size_t)b * T + tq_main + r) * D + head * 64 + tid] = f2bf(a / l);
+    for (int g = 0; g < KG; ++g) a += s_acc[g * 64 + tid];
+    act_store(out, out_lo, ((size_t)b * T + qrow) * D + head * 64 + tid, a / l);
+  }
+}
+
+__global__ void __launch_bounds__(256) attention_tail_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ qkv_lo, bf16* __restrict__ out,
+                                                             bf16* __restrict__ out_lo, int T, int heads, int tq_main) {
+  __shared__ float smem[TAIL_MAX_T + 64 + 32 + 16 * 64];
+  attention_tail_row<256>(smem, qkv, qkv_lo, out, out_lo, T, heads, blockIdx.z, blockIdx.y, tq_main + blockIdx.x);
+}
+
+// NT = query tiles per CTA.  One-pass mode: NT = 1 with TWO CTAs per SM (256 TMEM columns, 97 KB of shared memory each) -- two
+// tiles owned by one CTA fall into lockstep (both wait / load / hand over at the same time and then contend for the MUFU pipe),
+// two independent CTAs do not, and one CTA's prologue / epilogue hides under the other's main loop.  (hi, lo) mode: NT = 2, one
+// CTA per SM (its shared-memory ring is twice as large and it is bound by the tensor pipe, 3 MMAs per product).
+template <bool X3> struct V5Cfg {
+  static constexpr int NT = X3 ? 2 : 1;
+  static constexpr int PLANES = X3 ? 2 : 1;
+  static constexpr int STAGES = 4;
+  static constexpr int STAGE_BYTES = 2 * PLANES * KVB;             // K_hi | V_hi [| K_lo | V_lo]
+  static constexpr int SMEM = NT * PLANES * TILE_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int THREADS = 128 * NT + 128;                   // softmax warpgroup(s) + one warpgroup holding the MMA and TMA warps
+  static constexpr int TMEM_COLS = NT == 2 ? 512 : 256;            // 2 score slots per tile at 96-column pitch + 64 columns of O per tile
+  static constexpr int O_COL = 2 * NT * SLOT;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attention_v5_kernel(const __grid_constant__ AttnParamsV5 p) {
+  constexpr int PLANES = V5Cfg<X3>::PLANES, STAGES = V5Cfg<X3>::STAGES, STAGE_BYTES = V5Cfg<X3>::STAGE_BYTES, NT = V5Cfg<X3>::NT;
+  constexpr int O_COL = V5Cfg<X3>::O_COL, MMA_WARP = 4 * NT, TMA_WARP = 4 * NT + 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  // Q tiles: [plane][tile] 16 KB each | K/V ring
+  const uint32_t sQ = base, sRing = base + NT * PLANES * TILE_BYTES;
+  const uint32_t bars = sRing + STAGES * STAGE_BYTES;
+  const uint32_t bar_q = bars;
+  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (1 + STAGES + s); };
+  auto s_full = [&](int w, int sl) { return bars + 8u * (1 + 2 * STAGES + 2 * w + sl); };
+  auto p_full = [&](int w, int sl) { return bars + 8u * (5 + 2 * STAGES + 2 * w + sl); };
+  auto o_done = [&](int w) { return bars + 8u * (9 + 2 * STAGES + w); };
+  auto o_final = [&](int w) { return bars + 8u * (11 + 2 * STAGES + w); };
+  const uint32_t tmem_slot = bars + 8u * (13 + 2 * STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * (128 * NT), head = blockIdx.y, b = blockIdx.z;
+  const int D = p.D, T = p.T;
+  const int n_chunks = p.n_chunks;
+  const int n_wg = (NT == 2 && q0 + 128 < p.tq_main) ? 2 : 1;
+
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const long long cta_clk0 = clock64();
+  if (p.trace && tid == 0 && cta_lin < 8192) p.trace[480 + 3 * cta_lin] = globaltimer_ns();
+  if (tid == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int w = 0; w < NT; ++w) {
+      for (int sl = 0; sl < 2; ++sl) { mbar_init(s_full(w, sl), 1); mbar_init(p_full(w, sl), 4); }
+      mbar_init(o_done(w), 1);
+      mbar_init(o_final(w), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)V5Cfg<X3>::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  auto width_of = [&](int j) { return j == n_chunks - 1 ? p.last_width : CH; };
+  const bool last_wide = p.last_width > CH;
+
+  if (warp >= MMA_WARP) {
+  // (the register split must dominate each role's code, or ptxas applies the minimum to all of it)
+  if (NT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  if (warp == TMA_WARP) {
+    // ------------------------------------------------ TMA producer (converged warp, elected lane issues)
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, n_wg * PLANES * TILE_BYTES);
+      for (int w = 0; w < n_wg; ++w) {
+        tma_load_3d(sQ + w * TILE_BYTES, &p.tmq_hi, bar_q, head * 64, q0 + w * 128, b);
+        if (X3) tma_load_3d(sQ + (NT + w) * TILE_BYTES, &p.tmq_lo, bar_q, head * 64, q0 + w * 128, b);
+      }
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_chunks; ++j) {
+      mbar_wait(kv_empty(stage), phase ^ 1);
+      if (elect_one()) {
+        const bool wide = last_wide && j == n_chunks - 1;
+        const CUtensorMap* mh = wide ? &p.tm80_hi : &p.tm64_hi;
+        const CUtensorMap* ml = wide ? &p.tm80_lo : &p.tm64_lo;
+        const uint32_t dst = sRing + stage * STAGE_BYTES;
+        mbar_expect_tx(kv_full(stage), 2 * PLANES * (wide ? CHW : CH) * 128);
+        tma_load_3d(dst, mh, kv_full(stage), D + head * 64, j * CH, b);
+        tma_load_3d(dst + KVB, mh, kv_full(stage), 2 * D + head * 64, j * CH, b);
+        if (X3) {
+          tma_load_3d(dst + 2 * KVB, ml, kv_full(stage), D + head * 64, j * CH, b);
+          tma_load_3d(dst + 3 * KVB, ml, kv_full(stage), 2 * D + head * 64, j * CH, b);
+        }
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------ MMA issuer
+    // Everything the elected lane needs is warp-uniform and computed by the converged warp; the issue blocks are straight-line
+    // (descriptor + constant) so the operands stay in uniform registers -- a loop with per-iteration descriptor arithmetic cost
+    // ~75 clocks per MMA in R2UR round trips and made this warp, not the MUFU pipe, the bound of the first version.
+    const uint32_t idesc_s64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CH >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    auto issue_s = [&](uint32_t tS, uint64_t qh, uint64_t ql, uint64_t kh, uint64_t kl, uint32_t idesc, uint32_t bar) {   // S = Q K^T (X3: Qh Kh + Qh Kl + Ql Kh)
+      tc_mma_bf16(tS, qh, kh, idesc, 0u);
+      tc_mma_bf16(tS, qh + 2, kh + 2, idesc, 1u);
+      tc_mma_bf16(tS, qh + 4, kh + 4, idesc, 1u);
+      tc_mma_bf16(tS, qh + 6, kh + 6, idesc, 1u);
+      if (X3) {
+        tc_mma_bf16(tS, qh, kl, idesc, 1u);
+        tc_mma_bf16(tS, qh + 2, kl + 2, idesc, 1u);
+        tc_mma_bf16(tS, qh + 4, kl + 4, idesc, 1u);
+        tc_mma_bf16(tS, qh + 6, kl + 6, idesc, 1u);
+        tc_mma_bf16(tS, ql, kh, idesc, 1u);
+        tc_mma_bf16(tS, ql + 2, kh + 2, idesc, 1u);
+        tc_mma_bf16(tS, ql + 4, kh + 4, idesc, 1u);
+        tc_mma_bf16(tS, ql + 6, kh + 6, idesc, 1u);
+      }
+      tc_commit(bar);
+    };
+    // O (+)= P V, A = P from TMEM (X3: Ph Vh + Ph Vl + Pl Vh).  16-key slices: A advances 8 TMEM columns, B 16 key rows (2048 B = +128 in the descriptor)
+    auto issue_o_slice = [&](uint32_t tO, uint32_t tP, uint64_t vh, uint64_t vl, int k, uint32_t accum) {
+      tc_mma_bf16_ts(tO, tP + 8 * k, vh + 128 * k, idesc_o, accum);
+      if (X3) {
+        tc_mma_bf16_ts(tO, tP + 8 * k, vl + 128 * k, idesc_o, 1u);
+        tc_mma_bf16_ts(tO, tP + P_LO_COL + 8 * k, vh + 128 * k, idesc_o, 1u);
+      }
+    };
+    const uint64_t qd_h[2] = {umma_desc_sw128(sQ), umma_desc_sw128(sQ + TILE_BYTES)};
+    const uint64_t qd_l[2] = {umma_desc_sw128(sQ + NT * TILE_BYTES), umma_desc_sw128(sQ + (NT + 1) * TILE_BYTES)};
+    const uint64_t ring_d = umma_desc_sw128(sRing);          // descriptor of ring byte 0; stage s / buffer b add (s * STAGE_BYTES + b * KVB) >> 4
+    auto kv_desc = [&](int stage, int buf) { return ring_d + (uint64_t)((stage * STAGE_BYTES + buf * KVB) >> 4); };
+    const bool leader = elect_one();
+    mbar_wait(bar_q, 0);
+    // the ring position of chunk j is (j % STAGES, parity (j / STAGES) & 1)
+    for (int j = 0; j < 2 && j < n_chunks; ++j) {
+      mbar_wait(kv_full(j), 0);
+      tc_fence_after();
+      const int width = width_of(j);
+      const uint32_t idesc = (idesc_s64 & ~(0x3fu << 17)) | ((uint32_t)(width >> 3) << 17);
+      for (int w = 0; w < n_wg; ++w)
+        if (leader) issue_s(tmem_base + (2 * w + j) * SLOT, qd_h[w], qd_l[w], kv_desc(j, 0), kv_desc(j, 2), idesc, s_full(w, j));
+      __syncwarp();
+    }
+    int stage = 0, stage2 = 2 % STAGES;
+    uint32_t phase2 = (2 / STAGES) & 1;
+    for (int j = 0; j < n_chunks; ++j) {
+      const int sl = j & 1;
+      const bool more = j + 2 < n_chunks;
+      const bool fast = j < n_chunks - 1 || p.last_width == CH;          // 64-wide chunk: four straight-line slices
+      const bool fast2 = j + 2 < n_chunks - 1 || p.last_width == CH;
+      const uint64_t vh = kv_desc(stage, 1), vl = kv_desc(stage, 3), kh2 = kv_desc(stage2, 0), kl2 = kv_desc(stage2, 2);
+      const uint32_t idesc2 = fast2 ? idesc_s64 : ((idesc_s64 & ~(0x3fu << 17)) | ((uint32_t)(p.last_width >> 3) << 17));
+      const uint32_t accum = j > 0 ? 1u : 0u;
+      for (int w = 0; w < n_wg; ++w) {
+        const uint32_t tP = tmem_base + (2 * w + sl) * SLOT, tO = tmem_base + O_COL + w * 64;
+        if (lane == 0 && w == 0) TRACE(2, j, 0);
+        mbar_wait(p_full(w, sl), (j >> 1) & 1);          // P_w(j) is in TMEM over S_w(j), O_w rescaled if it had to be
+        if (more && w == 0) mbar_wait(kv_full(stage2), phase2);
+        tc_fence_after();
+        if (lane == 0) TRACE(2, j, w == 0 ? 1 : 3);
+        if (leader) {
+          if (fast) {
+            issue_o_slice(tO, tP, vh, vl, 0, accum);
+            issue_o_slice(tO, tP, vh, vl, 1, 1u);
+            issue_o_slice(tO, tP, vh, vl, 2, 1u);
+            issue_o_slice(tO, tP, vh, vl, 3, 1u);
+          } else {
+            for (int k = 0; k < (p.last_width >> 4); ++k) issue_o_slice(tO, tP, vh, vl, k, k > 0 ? 1u : accum);
+          }
+          tc_commit(o_done(w));
+          if (j == n_chunks - 1) tc_commit(o_final(w));
+          if (more) issue_s(tP, qd_h[w], qd_l[w], kh2, kl2, idesc2, s_full(w, sl));
+        }
+        __syncwarp();
+        if (lane == 0) TRACE(2, j, w == 0 ? 2 : 4);
+      }
+      if (leader) tc_commit(kv_empty(stage));   // K_j / V_j are free once everything issued so far has retired
+      __syncwarp();
+      if (++stage == STAGES) stage = 0;
+      if (++stage2 == STAGES) { stage2 = 0; phase2 ^= 1; }
+    }
+  }
+  } else {
+    // ------------------------------------------------ softmax warpgroups: thread = query row
+    if (NT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+    const int w = warp >> 2;
+    if (w < n_wg) {
+      const int row = (warp & 3) * 32 + lane;               // TMEM lane == query row of this tile
+      const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t tSw = tmem_base + 2 * w * SLOT + lane_off, tO = tmem_base + O_COL + w * 64 + lane_off;
+      const float c_log2 = 0.125f * 1.4426950408889634f;    // head_dim^-0.5 * log2(e)   (attention.py:41)
+      const float tau = RESCALE_LOG2 / c_log2;
+      float m_run = -INFINITY, l_run = 0.f;
+      constexpr int PIECE = X3 ? 16 : 64;                    // scores packed per tcgen05.st (x8 / x32 registers per plane)
+
+      const bool last_general = p.last_width != CH || T - (n_chunks - 1) * CH < CH;
+      // scores of chunk j: wait for S_w(j), issue the TMEM loads into `s` (+ `sx` for columns 64..79 of a wide last chunk); no wait
+      auto load_scores = [&](const int j, uint32_t (&s)[CH]) {
+        const int sl = j & 1;
+        const uint32_t tS = tSw + sl * SLOT;
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 0);
+        mbar_wait(s_full(w, sl), (j >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 1);
+        tc_ld32_issue(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tc_ld32_issue(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      };
+      // softmax of chunk j from registers: maximum, p = 2^(s*c - m*c) packed to 16 bits and written back over the scores, row sum
+      auto chunk_math = [&](auto general_tag, const int j, uint32_t (&s)[CH], uint32_t (&sx)[16]) {
+        constexpr bool GENERAL = decltype(general_tag)::value;
+        constexpr int NS = GENERAL ? CHW : CH;
+        const int n_valid = GENERAL ? T - j * CH : CH;         // keys of this chunk that exist
+        const int width = GENERAL ? p.last_width : CH;          // columns the MMA wrote / will read
+        const int sl = j & 1;
+        const uint32_t tS = tSw + sl * SLOT;
+        // scores by compile-time index: the 64 columns, then columns 64..79 of the wide last chunk
+        auto sc = [&](int i) { return __uint_as_float(i < CH ? s[i & (CH - 1)] : sx[i & 15]); };
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 2);
+        // ---- row maximum (four independent chains of 3-input maxima)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (!GENERAL) {
+#pragma unroll
+          for (int i = 0; i < NS; i += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mx4[u] = max3(mx4[u], sc(i + 2 * u), sc(i + 2 * u + 1));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) if (i < n_valid) mx4[i & 3] = fmaxf(mx4[i & 3], sc(i));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        // ---- lazy rescale decision: keep the stale maximum unless the new one is > 2^8 larger
+        const bool need = mx > m_run + tau;
+        float alpha = 1.f;
+        if (need) {
+          alpha = ex2_ftz((m_run - mx) * c_log2);             // 0 on the first chunk (m_run = -inf)
+          m_run = mx;
+          l_run *= alpha;
+        }
+        const float nmc = fmaf(-m_run, c_log2, X3 ? 0.f : TRUNC_BIAS_LOG2);
+        constexpr int PC = (GENERAL || X3) ? 16 : 32;           // scores per tcgen05.st piece (the ragged chunk is 16..80 wide)
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < NS / PC; ++q) {
+          if (GENERAL && q * PC >= width) break;
+          float e[PC];
+#pragma unroll
+          for (int t = 0; t < PC; t += 2) {
+            float x0, x1;
+            fma2(x0, x1, sc(q * PC + t), sc(q * PC + t + 1), c_log2, nmc);
+            e[t] = ex2_ftz(x0);
+            e[t + 1] = ex2_ftz(x1);
+            if (GENERAL) {
+              if (q * PC + t >= n_valid) e[t] = 0.f;
+              if (q * PC + t + 1 >= n_valid) e[t + 1] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < PC; t += 4) { l4[0] += e[t]; l4[1] += e[t + 1]; l4[2] += e[t + 2]; l4[3] += e[t + 3]; }
+          // 16-bit packing by TRUNCATION with one byte-permute per pair (ALU pipe): the F2FP conversions of the round-to-nearest
+          // form share the quarter-rate pipe with the exponentials.  One-pass mode: the exponent carries +log2(1 + 2^-9), which
+          // centres the truncation error (|rel| <= 2^-8, mean 0); the row sum is taken from the same values and corrected once
+          // at the end.  (hi, lo) mode: hi is exact by construction and lo = p - hi is truncated at 2^-16 of p.
+          uint32_t hi[PC / 2];
+#pragma unroll
+          for (int t = 0; t < PC / 2; ++t) {
+            hi[t] = __byte_perm(__float_as_uint(e[2 * t]), __float_as_uint(e[2 * t + 1]), 0x7632);
+            if (X3) {
+              e[2 * t] -= __uint_as_float(__float_as_uint(e[2 * t]) & 0xffff0000u);
+              e[2 * t + 1] -= __uint_as_float(__float_as_uint(e[2 * t + 1]) & 0xffff0000u);
+            }
+          }
+          if constexpr (X3) {
+            uint32_t lo[PC / 2];
+#pragma unroll
+            for (int t = 0; t < PC / 2; ++t) lo[t] = __byte_perm(__float_as_uint(e[2 * t]), __float_as_uint(e[2 * t + 1]), 0x7632);
+            tc_st8(tS + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[8]>(&hi[0]));
+            tc_st8(tS + P_LO_COL + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[8]>(&lo[0]));
+          } else if constexpr (PC == 16) {
+            tc_st8(tS + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[8]>(&hi[0]));
+          } else {
+            tc_st16(tS + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[16]>(&hi[0]));
+          }
+        }
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        // ---- O_w rescale by the row owner (rare): P_w(j-1) V(j-1) must have retired.  S_w(j) was issued after P_w(j-2) V(j-2), so
+        // o_done has completed j-1 or j phases by now and the parity wait is unambiguous.
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          mbar_wait(o_done(w), (j - 1) & 1);
+          tc_fence_after();
+          uint32_t ro[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tc_ld32_issue(tO + 32 * h, ro);
+            tc_ld_wait();                                       // (also drains the prefetched scores of the next chunk)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tc_st32(tO + 32 * h, ro);
+          }
+        }
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 3);
+        tc_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(p_full(w, sl));
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 4);
+      };
+      // (Fetching the scores of chunk j+1 into a second register set during the last exponentials of chunk j -- software
+      // pipelining inside the thread -- was measured 25 % SLOWER: 128 live score registers push the loop over the 184 registers a
+      // softmax thread can have with two CTAs per SM, and the spills land in the MUFU-bound section.)
+      uint32_t sA[CH], sx[16];
+      for (int j = 0; j < n_chunks; ++j) {
+        const bool general = last_general && j == n_chunks - 1;
+        load_scores(j, sA);
+        if (general) tc_ld16_issue(tSw + (j & 1) * SLOT + 64, sx);
+        tc_ld_wait();
+        if (general) chunk_math(std::true_type{}, j, sA, sx);
+        else chunk_math(std::false_type{}, j, sA, sx);
+      }
+      // ---- epilogue: O / l -> 16-bit (hi[, lo]) -> staged row -> one bulk copy per plane.  The rows are staged in this tile's own Q
+      // buffers (every S_w has retired).  o_final completes once, after the last P V (o_done's parity would be ambiguous here).
+      mbar_wait(o_final(w), 0);
+      tc_fence_after();
+      const float inv = (X3 ? 1.0f : 1.0f + 0x1p-9f) / l_run;    // one-pass mode: l was summed from values carrying the +2^-9 bias
+      uint8_t* const srow = base_ptr + w * TILE_BYTES + row * 128;
+      uint8_t* const srow_lo = srow + NT * TILE_BYTES;
+      uint32_t ro[64];
+      tc_ld32_issue(tO, *reinterpret_cast<uint32_t(*)[32]>(&ro[0]));
+      tc_ld32_issue(tO + 32, *reinterpret_cast<uint32_t(*)[32]>(&ro[32]));
+      tc_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        __nv_bfloat162 h2[4], l2[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float a = __uint_as_float(ro[g * 8 + 2 * t]) * inv, c = __uint_as_float(ro[g * 8 + 2 * t + 1]) * inv;
+          h2[t] = __floats2bfloat162_rn(a, c);
+          if (X3) {
+            const float2 f = __bfloat1622float2(h2[t]);
+            l2[t] = __floats2bfloat162_rn(a - f.x, c - f.y);
+          }
+        }
+        *reinterpret_cast<uint4*>(srow + g * 16) = *reinterpret_cast<const uint4*>(h2);
+        if (X3) *reinterpret_cast<uint4*>(srow_lo + g * 16) = *reinterpret_cast<const uint4*>(l2);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const int q = q0 + w * 128 + row;
+      if (q < p.tq_main) {
+        const size_t go = ((size_t)b * T + q) * D + head * 64;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(p.out_hi + go), "r"(smem_u32(srow)) : "memory");
+        if (X3) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(p.out_lo + go), "r"(smem_u32(srow_lo)) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.trace && tid == 0 && cta_lin < 8192) {
+    p.trace[480 + 3 * cta_lin + 1] = globaltimer_ns();
+    p.trace[480 + 3 * cta_lin + 2] = (unsigned long long)(clock64() - cta_clk0);
+  }
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)V5Cfg<X3>::TMEM_COLS) : "memory");
   }
 }
 
@@ -785,6 +680,15 @@ bool g_attr_set = false;
 
 }  // namespace
 
+static CUresult encode_qkv_map(PFN_cuTensorMapEncodeTiled_v12000 enc, CUtensorMap* tm, const void* ptr, int B, int T, int D, int box_rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)3 * D, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)3 * D * 2, (cuuint64_t)T * 3 * D * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, int B, int T, int heads, prv2_bf16* out_hi, prv2_bf16* out_lo,
                               prv2_stream_t stream) {
   PRV2_CHECK_ARG(qkv_hi && out_hi, "prv2_attention: null pointer");
@@ -793,59 +697,78 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
   auto enc = get_encode();
   if (!enc) { set_error("prv2_attention: cuTensorMapEncodeTiled unavailable"); return PRV2_ECUDA; }
   const int D = heads * 64;
-  AttnParams p;
+  const bool x3 = qkv_lo != nullptr;
+  AttnParamsV5 p;
   memset(&p, 0, sizeof(p));
-  cuuint64_t dims[3] = {(cuuint64_t)3 * D, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)3 * D * 2, (cuuint64_t)T * 3 * D * 2};
-  cuuint32_t box[3] = {64, 128, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(&p.tm_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)qkv_hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_qkv_map(enc, &p.tmq_hi, qkv_hi, B, T, D, 128);
+  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tm64_hi, qkv_hi, B, T, D, CH);
+  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tm80_hi, qkv_hi, B, T, D, CHW);
+  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tmq_lo, x3 ? qkv_lo : qkv_hi, B, T, D, 128);
+  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tm64_lo, x3 ? qkv_lo : qkv_hi, B, T, D, CH);
+  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tm80_lo, x3 ? qkv_lo : qkv_hi, B, T, D, CHW);
   if (r != CUDA_SUCCESS) { set_error("prv2_attention: cuTensorMapEncodeTiled failed (%d)", (int)r); return PRV2_ECUDA; }
-  p.tm_lo = p.tm_hi;
-  if (qkv_lo) {
-    r = enc(&p.tm_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)qkv_lo, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("prv2_attention: cuTensorMapEncodeTiled(lo) failed (%d)", (int)r); return PRV2_ECUDA; }
-  }
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
   p.B = B; p.T = T; p.heads = heads; p.D = D;
-  const int smem1 = 5 * TILE_BYTES + 1024 + 64, smem3 = 10 * TILE_BYTES + 1024 + 64;
-  const int smem_v2 = 2 * TILE_BYTES + 2 * KV_STAGES * KV_TILE_BYTES + 6 * TILE_BYTES + 1024 + 256 + XCH_BYTES;
-  static const char* split_env = getenv("PRV2_ATTN_SPLIT");            // diagnostics: 1 = one softmax thread per row (v3)
-  const bool split2 = !(split_env && split_env[0] == '1');
-  static const bool force_v1 = getenv("PRV2_ATTN_V1") != nullptr;
-  if (!g_attr_set) {
-    PRV2_CUDA(cudaFuncSetAttribute(attention_v3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v2));
-    PRV2_CUDA(cudaFuncSetAttribute(attention_v3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v2));
-    PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    PRV2_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    g_attr_set = true;
-  }
-  dim3 grid(cdiv(T, 128), heads, B);
-  if (qkv_lo) { attention_kernel<true><<<grid, 128, smem3, (cudaStream_t)stream>>>(p); PRV2_LAUNCH_CHECK(); return PRV2_OK; }
-  if (force_v1) { attention_kernel<false><<<grid, 128, smem1, (cudaStream_t)stream>>>(p); PRV2_LAUNCH_CHECK(); return PRV2_OK; }
-
-  AttnParamsV2 p2;
-  memset(&p2, 0, sizeof(p2));
-  p2.tm_q = p.tm_hi;
-  cuuint32_t box_kv[3] = {64, KV_ROWS, 1};
-  r = enc(&p2.tm_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)qkv_hi, dims, strides, box_kv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("prv2_attention: cuTensorMapEncodeTiled(kv) failed (%d)", (int)r); return PRV2_ECUDA; }
-  p2.out_hi = (bf16*)out_hi;
-  p2.B = B; p2.T = T; p2.heads = heads; p2.D = D;
-  // key chunks: 128 wide, the last one 16..144 (multiple of 16) so that T mod 128 <= 16 does not cost a whole chunk
-  p2.n_chunks = T <= KV_ROWS ? 1 : cdiv(T - TAIL_MAX, 128);
-  p2.last_width = ((T - 128 * (p2.n_chunks - 1)) + 15) / 16 * 16;
+  // key chunks: 64 wide, the last one 16..80 (multiple of 16) so that T mod 64 <= 16 does not cost a whole chunk
+  p.n_chunks = T <= CHW ? 1 : cdiv(T - TAIL_MAX, CH);
+  p.last_width = ((T - CH * (p.n_chunks - 1)) + 15) / 16 * 16;
   // query rows: leftover rows (<= 16) go to the SIMT tail kernel instead of a mostly empty 128-row tile
   const int rem = T % 128;
-  p2.tq_main = (rem != 0 && rem <= TAIL_MAX && T > 128 && T <= TAIL_MAX_T) ? T - rem : T;
-  if (split2) attention_v3_kernel<2><<<dim3(cdiv(p2.tq_main, 256), heads, B), V4_THREADS, smem_v2, (cudaStream_t)stream>>>(p2);
-  else attention_v3_kernel<1><<<dim3(cdiv(p2.tq_main, 256), heads, B), V2_THREADS, smem_v2, (cudaStream_t)stream>>>(p2);
+  p.tq_main = (rem != 0 && rem <= TAIL_MAX && T > 128 && T <= TAIL_MAX_T) ? T - rem : T;
+  const int smem_bf = V5Cfg<false>::SMEM, smem_x3 = V5Cfg<true>::SMEM;
+  if (!g_attr_set) {
+    PRV2_CUDA(cudaFuncSetAttribute(attention_v5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bf));
+    PRV2_CUDA(cudaFuncSetAttribute(attention_v5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x3));
+    g_attr_set = true;
+  }
+  static const bool want_trace = getenv("PRV2_ATTN_TRACE") != nullptr;
+  static unsigned long long* d_trace = nullptr;
+  if (want_trace) {
+    if (!d_trace) PRV2_CUDA(cudaMalloc(&d_trace, (480 + 3 * 8192) * 8));
+    PRV2_CUDA(cudaMemsetAsync(d_trace, 0, (480 + 3 * 8192) * 8, (cudaStream_t)stream));
+    p.trace = d_trace;
+  }
+  p.qkv_hi = (const bf16*)qkv_hi; p.qkv_lo = (const bf16*)qkv_lo;
+  if (x3) attention_v5_kernel<true><<<dim3(cdiv(p.tq_main, 128 * V5Cfg<true>::NT), heads, B), V5Cfg<true>::THREADS, smem_x3, (cudaStream_t)stream>>>(p);
+  else attention_v5_kernel<false><<<dim3(cdiv(p.tq_main, 128 * V5Cfg<false>::NT), heads, B), V5Cfg<false>::THREADS, smem_bf, (cudaStream_t)stream>>>(p);
   PRV2_LAUNCH_CHECK();
-  if (p2.tq_main < T) {
-    attention_tail_kernel<<<B * heads * (T - p2.tq_main), TAIL_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)qkv_hi, (bf16*)out_hi, B, T, heads, p2.tq_main);
+  if (want_trace) {
+    static unsigned long long h[3 * 32 * 5];
+    PRV2_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    PRV2_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (unsigned long long v : h) if (v && v < t0) t0 = v;
+    for (int j = 0; j < p.n_chunks && j < 32; ++j) {
+      fprintf(stderr, "chunk %2d |", j);
+      for (int role = 0; role < 3; ++role) {
+        fprintf(stderr, " %s", role == 0 ? "sm0:" : role == 1 ? "sm1:" : "mma:");
+        for (int k = 0; k < 5; ++k) fprintf(stderr, " %6lld", h[(role * 32 + j) * 5 + k] ? (long long)(h[(role * 32 + j) * 5 + k] - t0) : -1ll);
+        fprintf(stderr, " |");
+      }
+      fprintf(stderr, "\n");
+    }
+    // per-CTA wall time: how many CTAs, mean / max duration, kernel span, mean CTAs in flight
+    static unsigned long long hc[3 * 8192];
+    PRV2_CUDA(cudaMemcpy(hc, d_trace + 480, sizeof(hc), cudaMemcpyDeviceToHost));
+    unsigned long long first = ~0ull, last = 0, sum = 0, mx = 0, clk = 0;
+    int n = 0;
+    for (int i = 0; i < 8192; ++i) {
+      if (!hc[3 * i] || !hc[3 * i + 1]) continue;
+      const unsigned long long d = hc[3 * i + 1] - hc[3 * i];
+      sum += d; if (d > mx) mx = d; ++n; clk += hc[3 * i + 2];
+      if (hc[3 * i] < first) first = hc[3 * i];
+      if (hc[3 * i + 1] > last) last = hc[3 * i + 1];
+    }
+    if (n) {
+      fprintf(stderr, "tile CTAs %d: mean %.2f us = %.0f clocks (%.2f GHz), max %.2f us, kernel span %.2f us, mean CTAs in flight %.1f\n", n, sum / 1e3 / n,
+              (double)clk / n, (double)clk / (double)sum, mx / 1e3, (last - first) / 1e3, (double)sum / (double)(last - first));
+      for (int i = 0; i < n && i < 4000; i += n / 12 + 1)
+        fprintf(stderr, "  cta %4d start %8.2f us dur %6.2f us (%llu clocks)\n", i, (hc[3 * i] - first) / 1e3, (hc[3 * i + 1] - hc[3 * i]) / 1e3, hc[3 * i + 2]);
+    }
+  }
+  if (p.tq_main < T) {
+    attention_tail_kernel<<<dim3(T - p.tq_main, heads, B), 256, 0, (cudaStream_t)stream>>>((const bf16*)qkv_hi, (const bf16*)qkv_lo, (bf16*)out_hi, (bf16*)out_lo, T,
+                                                                                       heads, p.tq_main);
     PRV2_LAUNCH_CHECK();
   }
   return PRV2_OK;

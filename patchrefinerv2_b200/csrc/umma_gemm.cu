@@ -52,7 +52,7 @@ constexpr int LN_BYTES = NUM_EPI_WARPS * 2 * 64 * 4;        // row epilogue: Lay
 constexpr int SMEM_BUDGET = 179 * 1024;       // operand stages; epilogue staging, parameters and barriers sit behind
 constexpr int SMEM_TOTAL = SMEM_BUDGET + NUM_EPI_WARPS * STG_BYTES_PER_WARP + PAR_BYTES + LN_BYTES + 1024 + 256;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
-constexpr uint64_t SPIN_LIMIT_NS = 4000000000ull;   // a wedged pipeline traps instead of hanging the box
+constexpr long long SPIN_LIMIT_CLK = 8000000000ll;     // ~4 s of SM clocks: a deadlock traps instead of hanging the GPU
 
 struct alignas(64) KParams {
   CUtensorMap tmA[PRV2_MAX_SRC];
@@ -113,13 +113,21 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends the thread in hardware for a while by itself; the watchdog below costs nothing until a wait has spun 4096
+  // times and then only reads the SM clock (round 1 read %globaltimer in front of every contended wait)
   if (mbar_try(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try(bar, parity)) {
-    if ((++spins & 0x3fff) == 0 && globaltimer_ns() - t0 > SPIN_LIMIT_NS) {
-      printf("prv2_umma_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
+    if ((++spins & 0xfff) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > SPIN_LIMIT_CLK) {
+        if ((threadIdx.x & 31) == 0)
+          printf("prv2_umma_gemm: mbarrier wait timed out (block %d,%d,%d warp %d, barrier @%u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x >> 5,
+                 bar & 0x3ffu, parity);
+        __trap();
+      }
     }
   }
 }

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 rc=0
-for f in tests/test_geometry_gpu.py tests/test_network_gpu.py tests/test_bifusion.py tests/test_plus.py tests/test_tools_gpu.py tests/test_model_gpu.py; do
+for f in tests/test_geometry_gpu.py tests/test_network_gpu.py tests/test_bifusion.py tests/test_plus.py tests/test_tools_gpu.py tests/test_model_gpu.py tests/test_vitl_gpu.py; do
   name=$(basename $f .py)
   timeout 900 python -m pytest $f -q -m gpu -x --timeout 600 "$@" > gpurun_out/$name.log 2>&1
   r=$?

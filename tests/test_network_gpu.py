@@ -161,20 +161,31 @@ def test_head_epilogue(x3, tol):
 
 
 @pytest.mark.parametrize("x3,tol", [(False, 1.5e-2), (True, 5e-4)])
-@pytest.mark.parametrize("B,T,heads", [(1, 257, 6), (2, 1025, 6), (1, 128, 2), (1, 1025, 16)])
-def test_attention(x3, tol, B, T, heads):
+@pytest.mark.parametrize("B,T,heads,scale", [(1, 257, 6, 1.0), (2, 1025, 6, 1.0), (1, 128, 2, 1.0), (1, 1025, 16, 1.0), (3, 1025, 16, 1.0),
+                                             (1, 144, 2, 1.0), (1, 129, 2, 1.0), (1, 300, 2, 1.0), (2, 256, 3, 1.0), (2, 640, 3, 1.0), (1, 77, 2, 1.0),
+                                             (1, 1025, 4, 3.0), (2, 513, 2, 5.0)])
+def test_attention(x3, tol, B, T, heads, scale):
+    """softmax(q k^T / 8) v (attention.py:49-62).  Shapes cover: 1025 tokens (7 x 128 keys + a 129-wide last chunk, one leftover
+    query row in the tail kernel), exact multiples of 128, a single ragged chunk, narrow last chunks (300 = 2 x 128 + 44), one
+    CTA with a single query tile; scale > 1 makes the row maxima grow by more than 2^8 between chunks (lazy O rescale path)."""
     from patchrefinerv2_b200 import ops
     from patchrefinerv2_b200.nn import Act
     g = torch.Generator().manual_seed(T + heads)
     D = heads * 64
     qkv = torch.randn(B, T, 3 * D, generator=g)
+    qkv[..., :2 * D] *= scale
     q, k, v = qkv.reshape(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     attn = ((q * 64 ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
     want = (attn @ v).transpose(1, 2).reshape(B, T, D)
     A = _act(qkv.reshape(B * T, 3 * D).t().reshape(1, 3 * D, 1, B * T), x3)
+    if not x3:                                               # the kernel sees bf16-rounded operands: compare against the same inputs
+        qb = qkv.to(torch.bfloat16).float()
+        q, k, v = qb.reshape(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+        want = (((q * 64 ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1) @ v).transpose(1, 2).reshape(B, T, D)
     out = Act.empty(1, 1, B * T, D, x3, DEV)
     ops.attention(A, B, T, heads, out)
     got = out.to_nchw()[0, :, 0, :].t().reshape(B, T, D).cpu()
+    assert torch.isfinite(got).all()
     assert rel_err(got, want) < tol
 
 
