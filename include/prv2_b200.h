@@ -8,8 +8,9 @@
  * prv2_blend_raw); every function is asynchronous on `stream` and returns 0 on
  * success or a negative PRV2_E* code (prv2_last_error() gives the message).  No torch types.
  *
- * Activation tensors ("act") are channels-last bf16, optionally as a (hi, lo) pair of bf16 planes
- * whose sum carries ~16 mantissa bits ("x3" precision mode; lo == NULL selects plain bf16).
+ * Activation tensors ("act") are channels-last 16-bit planes: ONE bf16 plane (lo == NULL, one-pass mode) or a (hi, lo) pair of
+ * FP16 planes whose sum carries ~22 mantissa bits ("x3" / fp32-class precision mode).  prv2_bf16 is the raw 16-bit storage type
+ * of both.
  */
 #ifndef PRV2_B200_H_
 #define PRV2_B200_H_
@@ -29,7 +30,7 @@ typedef uint16_t prv2_bf16;            /* raw bfloat16 bits */
 #define PRV2_EUNSUPPORTED (-3)         /* shape outside what the kernels implement */
 
 /* ABI version: bumped whenever a signature or the GemmDesc layout changes; the Python binding refuses any other value. */
-#define PRV2_ABI_VERSION 200
+#define PRV2_ABI_VERSION 201
 int prv2_version(void);
 /* sha256 of the CUDA sources + flags this library was compiled from (stamped by build.py with -DPRV2_BUILD_DIGEST);
  * the binding compares it with the digest of the sources it sits next to, so a stale .so is an error, not a silent mismatch. */
@@ -176,6 +177,11 @@ typedef struct {
   float* out_f32; int32_t out_f32_ld;                          /* RESID_F32 / F32 / HEAD  */
   int32_t shuffle_k;         /* EPI_SHUFFLE: kernel==stride                              */
   int32_t row_map_period, row_map_extra, row_map_offset;       /* out row = m + (m/period)*extra + offset (0 period = identity) */
+  /* fp32-class ("x3") mode: sources and weights are (hi, lo) pairs of FP16 planes (f16 = 1; bf16 planes when 0).  FP16 has a
+   * narrow exponent, so the host scales each layer's weights by a power of two that centres them in the fp16 range (the lo plane
+   * stays normal) and passes the inverse here: every accumulator is multiplied by acc_scale before bias / activation (0 = 1). */
+  float acc_scale;
+  int32_t f16;
 } prv2_gemm_desc;
 
 /* attention.py:44-46 / mlp.py:30-32 (nn.Linear), patch_embed.py:69-82, dpt.py:48-80,116-150,

@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 200          # == PRV2_ABI_VERSION in include/prv2_b200.h
+ABI_VERSION = 201          # == PRV2_ABI_VERSION in include/prv2_b200.h
 MAX_SRC = 12
 MAX_SEG = 128
 
@@ -50,6 +50,7 @@ class GemmDesc(C.Structure):
         ("out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
         ("shuffle_k", C.c_int32),
         ("row_map_period", C.c_int32), ("row_map_extra", C.c_int32), ("row_map_offset", C.c_int32),
+        ("acc_scale", C.c_float), ("f16", C.c_int32),
     ]
 
 

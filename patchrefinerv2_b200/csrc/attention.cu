@@ -4,6 +4,7 @@
 // (3 MMAs per product).
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 #include <type_traits>
@@ -249,8 +250,14 @@ __device__ __forceinline__ void attention_tail_row(float* smem, const bf16* __re
   const size_t voff = 2 * D + head * 64 + d4;
   auto load4 = [&](const bf16* pl, int k, float (&f)[4], bool add) {
     const uint2 raw = *reinterpret_cast<const uint2*>(pl + voff + (size_t)k * row_stride);
-    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-    const float2 f0 = __bfloat1622float2(v2[0]), f1 = __bfloat1622float2(v2[1]);
+    float2 f0, f1;
+    if (base_lo) {                            // (hi, lo) planes are FP16
+      const __half2* v2 = reinterpret_cast<const __half2*>(&raw);
+      f0 = __half22float2(v2[0]); f1 = __half22float2(v2[1]);
+    } else {
+      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      f0 = __bfloat1622float2(v2[0]); f1 = __bfloat1622float2(v2[1]);
+    }
     if (add) { f[0] += f0.x; f[1] += f0.y; f[2] += f1.x; f[3] += f1.y; }
     else { f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; }
   };
@@ -396,15 +403,14 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
     // Everything the elected lane needs is warp-uniform and computed by the converged warp; the issue blocks are straight-line
     // (descriptor + constant) so the operands stay in uniform registers -- a loop with per-iteration descriptor arithmetic cost
     // ~75 clocks per MMA in R2UR round trips and made this warp, not the MUFU pipe, the bound of the first version.
-    const uint32_t idesc_s64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CH >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-    auto issue_s = [&](uint32_t tS, uint64_t qh, uint64_t ql, uint64_t kh, uint64_t kl, uint32_t idesc, uint32_t bar) {   // S = Q K^T (X3: Qh Kh + Qh Kl + Ql Kh)
-      tc_mma_bf16(tS, qh, kh, idesc, 0u);
-      tc_mma_bf16(tS, qh + 2, kh + 2, idesc, 1u);
-      tc_mma_bf16(tS, qh + 4, kh + 4, idesc, 1u);
-      tc_mma_bf16(tS, qh + 6, kh + 6, idesc, 1u);
+    constexpr uint32_t FMT = X3 ? 0u : 1u;              // operand format: F16 for the (hi, lo) pair planes, BF16 in one-pass mode
+    const uint32_t idesc_s64 = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(CH >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_o = (1u << 4) | (FMT << 7) | (FMT << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    // The tensor core adds every MMA into the fp32 accumulator with round-toward-zero (a bias of ~2^-24 of the running sum per
+    // MMA, scripts/diag_accum.py), so in (hi, lo) mode the two small cross terms go FIRST and the main term last.
+    auto issue_s = [&](uint32_t tS, uint64_t qh, uint64_t ql, uint64_t kh, uint64_t kl, uint32_t idesc, uint32_t bar) {   // S = Q K^T (X3: Qh Kl + Ql Kh + Qh Kh)
       if (X3) {
-        tc_mma_bf16(tS, qh, kl, idesc, 1u);
+        tc_mma_bf16(tS, qh, kl, idesc, 0u);
         tc_mma_bf16(tS, qh + 2, kl + 2, idesc, 1u);
         tc_mma_bf16(tS, qh + 4, kl + 4, idesc, 1u);
         tc_mma_bf16(tS, qh + 6, kl + 6, idesc, 1u);
@@ -413,15 +419,19 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
         tc_mma_bf16(tS, ql + 4, kh + 4, idesc, 1u);
         tc_mma_bf16(tS, ql + 6, kh + 6, idesc, 1u);
       }
+      tc_mma_bf16(tS, qh, kh, idesc, X3 ? 1u : 0u);
+      tc_mma_bf16(tS, qh + 2, kh + 2, idesc, 1u);
+      tc_mma_bf16(tS, qh + 4, kh + 4, idesc, 1u);
+      tc_mma_bf16(tS, qh + 6, kh + 6, idesc, 1u);
       tc_commit(bar);
     };
-    // O (+)= P V, A = P from TMEM (X3: Ph Vh + Ph Vl + Pl Vh).  16-key slices: A advances 8 TMEM columns, B 16 key rows (2048 B = +128 in the descriptor)
+    // O (+)= P V, A = P from TMEM (X3: Ph Vl + Pl Vh + Ph Vh).  16-key slices: A advances 8 TMEM columns, B 16 key rows (2048 B = +128 in the descriptor)
     auto issue_o_slice = [&](uint32_t tO, uint32_t tP, uint64_t vh, uint64_t vl, int k, uint32_t accum) {
-      tc_mma_bf16_ts(tO, tP + 8 * k, vh + 128 * k, idesc_o, accum);
       if (X3) {
-        tc_mma_bf16_ts(tO, tP + 8 * k, vl + 128 * k, idesc_o, 1u);
+        tc_mma_bf16_ts(tO, tP + 8 * k, vl + 128 * k, idesc_o, accum);
         tc_mma_bf16_ts(tO, tP + P_LO_COL + 8 * k, vh + 128 * k, idesc_o, 1u);
       }
+      tc_mma_bf16_ts(tO, tP + 8 * k, vh + 128 * k, idesc_o, X3 ? 1u : accum);
     };
     const uint64_t qd_h[2] = {umma_desc_sw128(sQ), umma_desc_sw128(sQ + TILE_BYTES)};
     const uint64_t qd_l[2] = {umma_desc_sw128(sQ + NT * TILE_BYTES), umma_desc_sw128(sQ + (NT + 1) * TILE_BYTES)};
@@ -556,23 +566,29 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
           }
 #pragma unroll
           for (int t = 0; t < PC; t += 4) { l4[0] += e[t]; l4[1] += e[t + 1]; l4[2] += e[t + 2]; l4[3] += e[t + 3]; }
-          // 16-bit packing by TRUNCATION with one byte-permute per pair (ALU pipe): the F2FP conversions of the round-to-nearest
-          // form share the quarter-rate pipe with the exponentials.  One-pass mode: the exponent carries +log2(1 + 2^-9), which
-          // centres the truncation error (|rel| <= 2^-8, mean 0); the row sum is taken from the same values and corrected once
-          // at the end.  (hi, lo) mode: hi is exact by construction and lo = p - hi is truncated at 2^-16 of p.
+          // One-pass mode: bf16 packing by TRUNCATION with one byte-permute per pair (ALU pipe) -- the exponent carries
+          // +log2(1 + 2^-9), which centres the truncation error (|rel| <= 2^-8, mean 0); the row sum is taken from the same
+          // values and corrected once at the end.  (hi, lo) mode: FP16 pair, hi = rn(p), lo = rn(p - hi): ~22 bits of p.
           uint32_t hi[PC / 2];
 #pragma unroll
           for (int t = 0; t < PC / 2; ++t) {
-            hi[t] = __byte_perm(__float_as_uint(e[2 * t]), __float_as_uint(e[2 * t + 1]), 0x7632);
-            if (X3) {
-              e[2 * t] -= __uint_as_float(__float_as_uint(e[2 * t]) & 0xffff0000u);
-              e[2 * t + 1] -= __uint_as_float(__float_as_uint(e[2 * t + 1]) & 0xffff0000u);
+            if constexpr (X3) {
+              const __half2 h = __floats2half2_rn(e[2 * t], e[2 * t + 1]);
+              hi[t] = *reinterpret_cast<const uint32_t*>(&h);
+              const float2 f = __half22float2(h);
+              e[2 * t] -= f.x;
+              e[2 * t + 1] -= f.y;
+            } else {
+              hi[t] = __byte_perm(__float_as_uint(e[2 * t]), __float_as_uint(e[2 * t + 1]), 0x7632);
             }
           }
           if constexpr (X3) {
             uint32_t lo[PC / 2];
 #pragma unroll
-            for (int t = 0; t < PC / 2; ++t) lo[t] = __byte_perm(__float_as_uint(e[2 * t]), __float_as_uint(e[2 * t + 1]), 0x7632);
+            for (int t = 0; t < PC / 2; ++t) {
+              const __half2 h = __floats2half2_rn(e[2 * t], e[2 * t + 1]);
+              lo[t] = *reinterpret_cast<const uint32_t*>(&h);
+            }
             tc_st8(tS + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[8]>(&hi[0]));
             tc_st8(tS + P_LO_COL + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[8]>(&lo[0]));
           } else if constexpr (PC == 16) {
@@ -629,14 +645,19 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
       tc_ld_wait();
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        __nv_bfloat162 h2[4], l2[4];
+        uint32_t h2[4], l2[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float a = __uint_as_float(ro[g * 8 + 2 * t]) * inv, c = __uint_as_float(ro[g * 8 + 2 * t + 1]) * inv;
-          h2[t] = __floats2bfloat162_rn(a, c);
-          if (X3) {
-            const float2 f = __bfloat1622float2(h2[t]);
-            l2[t] = __floats2bfloat162_rn(a - f.x, c - f.y);
+          if constexpr (X3) {                                    // (hi, lo) FP16 pair (|O| <= max |v|: no saturation needed beyond V's own)
+            const __half2 h = __floats2half2_rn(a, c);
+            const float2 f = __half22float2(h);
+            const __half2 l = __floats2half2_rn(a - f.x, c - f.y);
+            h2[t] = *reinterpret_cast<const uint32_t*>(&h);
+            l2[t] = *reinterpret_cast<const uint32_t*>(&l);
+          } else {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
+            h2[t] = *reinterpret_cast<const uint32_t*>(&h);
           }
         }
         *reinterpret_cast<uint4*>(srow + g * 16) = *reinterpret_cast<const uint4*>(h2);

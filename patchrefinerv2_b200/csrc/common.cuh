@@ -34,47 +34,73 @@ typedef __nv_bfloat16 bf16;
 __device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
 
-// (hi, lo) activation element access.  lo == nullptr -> plain bf16.
+// Activation element access.  Two storage formats share the 16-bit planes:
+//   lo == nullptr : ONE plane of bf16 (one-pass mode);
+//   lo != nullptr : a (hi, lo) pair of FP16 planes, value = hi + lo (fp32-class mode).  fp16 pairs carry ~22 mantissa bits
+//                   (bf16 pairs: 16) for |x| >= 2^-3; below that the lo plane goes subnormal and the ABSOLUTE error floors at
+//                   3e-8, which is what matters for operands of dot products.  Stores saturate at +-65504 instead of overflowing.
+#include <cuda_fp16.h>
+constexpr float F16_MAX = 65504.0f;
+__device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -F16_MAX), F16_MAX); }
 __device__ __forceinline__ float act_load(const bf16* hi, const bf16* lo, size_t i) {
-  float v = bf2f(hi[i]);
-  if (lo) v += bf2f(lo[i]);
-  return v;
+  if (lo) return __half2float(reinterpret_cast<const __half*>(hi)[i]) + __half2float(reinterpret_cast<const __half*>(lo)[i]);
+  return bf2f(hi[i]);
 }
 __device__ __forceinline__ void act_store(bf16* hi, bf16* lo, size_t i, float v) {
-  bf16 h = f2bf(v);
-  hi[i] = h;
-  if (lo) lo[i] = f2bf(v - bf2f(h));
+  if (lo) {
+    v = sat16(v);
+    const __half h = __float2half_rn(v);
+    reinterpret_cast<__half*>(hi)[i] = h;
+    reinterpret_cast<__half*>(lo)[i] = __float2half_rn(v - __half2float(h));
+  } else {
+    hi[i] = f2bf(v);
+  }
 }
 
 // 8-wide (16 byte) vector access
 struct alignas(16) bf16x8 { bf16 v[8]; };
 
+// 8 packed 16-bit values already in registers -> floats (f16 = the plane pair format, else bf16)
+__device__ __forceinline__ void unpack8(const uint4& a, bool f16, float (&out)[8], bool add) {
+  float t[8];
+  if (f16) {
+    const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(a2[k]); t[2 * k] = f.x; t[2 * k + 1] = f.y; }
+  } else {
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(a2[k]); t[2 * k] = f.x; t[2 * k + 1] = f.y; }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[k] = add ? out[k] + t[k] : t[k];
+}
 __device__ __forceinline__ void act_load8(const bf16* hi, const bf16* lo, size_t i, float (&out)[8]) {
   const uint4 a = *reinterpret_cast<const uint4*>(hi + i);
-  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(a2[k]); out[2 * k] = f.x; out[2 * k + 1] = f.y; }
+  unpack8(a, lo != nullptr, out, false);
   if (lo) {
     const uint4 b = *reinterpret_cast<const uint4*>(lo + i);
-    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(b2[k]); out[2 * k] += f.x; out[2 * k + 1] += f.y; }
+    unpack8(b, true, out, true);
   }
 }
 __device__ __forceinline__ void act_store8(bf16* hi, bf16* lo, size_t i, const float (&in)[8]) {
-  // packed conversions (F2FP.BF16.PACK_AB: two values per instruction on the FMA pipe)
-  __nv_bfloat162 h2[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(in[2 * k], in[2 * k + 1]);
-  *reinterpret_cast<uint4*>(hi + i) = *reinterpret_cast<const uint4*>(h2);
   if (lo) {
-    __nv_bfloat162 l2[4];
+    __half2 h2[4], l2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 f = __bfloat1622float2(h2[k]);
-      l2[k] = __floats2bfloat162_rn(in[2 * k] - f.x, in[2 * k + 1] - f.y);
+      const float a = sat16(in[2 * k]), b = sat16(in[2 * k + 1]);
+      h2[k] = __floats2half2_rn(a, b);
+      const float2 f = __half22float2(h2[k]);
+      l2[k] = __floats2half2_rn(a - f.x, b - f.y);
     }
+    *reinterpret_cast<uint4*>(hi + i) = *reinterpret_cast<const uint4*>(h2);
     *reinterpret_cast<uint4*>(lo + i) = *reinterpret_cast<const uint4*>(l2);
+  } else {
+    // packed conversions (F2FP.BF16.PACK_AB: two values per instruction)
+    __nv_bfloat162 h2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(in[2 * k], in[2 * k + 1]);
+    *reinterpret_cast<uint4*>(hi + i) = *reinterpret_cast<const uint4*>(h2);
   }
 }
 

@@ -16,15 +16,22 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 struct alignas(8) bf16x4 { bf16 v[4]; };
 __device__ __forceinline__ void act_store4(bf16* hi, bf16* lo, size_t i, const float (&in)[4]) {
-  bf16x4 a;
+  if (lo) {                                   // (hi, lo) fp16 pair, see common.cuh
+    __half2 h2[2], l2[2];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) a.v[k] = f2bf(in[k]);
-  *reinterpret_cast<bf16x4*>(hi + i) = a;
-  if (lo) {
-    bf16x4 b;
+    for (int k = 0; k < 2; ++k) {
+      const float a = sat16(in[2 * k]), b = sat16(in[2 * k + 1]);
+      h2[k] = __floats2half2_rn(a, b);
+      const float2 f = __half22float2(h2[k]);
+      l2[k] = __floats2half2_rn(a - f.x, b - f.y);
+    }
+    *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<const uint2*>(h2);
+    *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l2);
+  } else {
+    bf16x4 a;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) b.v[k] = f2bf(in[k] - bf2f(a.v[k]));
-    *reinterpret_cast<bf16x4*>(lo + i) = b;
+    for (int k = 0; k < 4; ++k) a.v[k] = f2bf(in[k]);
+    *reinterpret_cast<bf16x4*>(hi + i) = a;
   }
 }
 

@@ -81,6 +81,8 @@ struct alignas(64) KParams {
   float* out_f32; int32_t out_f32_ld;
   int32_t shuffle_k;
   int32_t row_map_period, row_map_extra, row_map_offset;
+  float acc_scale;          // accumulators are multiplied by this on their way out of TMEM (weights pre-scaled by its inverse, see the header)
+  int32_t f16;              // operand planes are FP16 (the (hi, lo) pair format) instead of bf16
   int32_t stg_warp_bytes;   // epilogue staging per warp (row epilogue of the fp32 residual stream double-buffers its row)
   int32_t debug;      // diagnostics (PRV2_GEMM_DEBUG): bit0 = no TMA after the first ring pass, bit1 = epilogue drains TMEM only
 };
@@ -203,7 +205,7 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16], float scale) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -213,7 +215,7 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * scale;
 }
 
 // K-major, 128-byte-swizzled operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16
@@ -285,16 +287,12 @@ struct Row {              // one output pixel handled by this lane in the coales
 
 struct Pre { uint4 a[4]; };   // one chunk's worth of prefetched epilogue operands of this lane (2 rows)
 
-// bf16x8 already in registers (hi plane) [+ lo plane read from memory in the 3-pass precision mode]
+// 8 packed values already in registers (hi plane) [+ lo plane read from memory in the 3-pass precision mode: fp16 pair]
 __device__ __forceinline__ void act_unpack8(const uint4& hi, const bf16* lo, size_t i, float (&out)[8]) {
-  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(a2[k]); out[2 * k] = f.x; out[2 * k + 1] = f.y; }
+  unpack8(hi, lo != nullptr, out, false);
   if (lo) {
     const uint4 b = *reinterpret_cast<const uint4*>(lo + i);
-    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(b2[k]); out[2 * k] += f.x; out[2 * k + 1] += f.y; }
+    unpack8(b, true, out, true);
   }
 }
 
@@ -430,7 +428,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     if (cta_rank == 0) {
       // cute::UMMA::InstrDescriptor: c=F32(1)<<4 | a=BF16(1)<<7 | b=BF16(1)<<10 | N>>3 <<17 | M>>4 <<24, both K-major
       // (CG == 2: M = 256 = 128 rows in each CTA of the pair)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+      // c = F32; a / b format: 1 = BF16 (one-pass mode), 0 = F16 (the (hi, lo) pair planes)
+      const uint32_t fmt = p.f16 ? 0u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accum) {
         if (CG == 2) tc_mma_bf16_pair(d, a, b, idesc, accum); else tc_mma_bf16(d, a, b, idesc, accum);
       };
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         int cnt = 0;
         for (int q = q_start; q < q_start + q_cnt; ++q) {
           const int c0 = q * 16;
-          tc_ld16(taddr + c0, v);
+          tc_ld16(taddr + c0, v, p.acc_scale);
 #pragma unroll
           for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { sum += v[j] + par[c0 + j]; ++cnt; }
         }
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         float m2 = 0.f;
         for (int q = q_start; q < q_start + q_cnt; ++q) {
           const int c0 = q * 16;
-          tc_ld16(taddr + c0, v);
+          tc_ld16(taddr + c0, v, p.acc_scale);
 #pragma unroll
           for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { const float d = v[j] + par[c0 + j] - mean_a; m2 += d * d; }
         }
@@ -603,8 +603,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
             const float4 b4 = *reinterpret_cast<const float4*>(par + c0 + g * 4), g4 = *reinterpret_cast<const float4*>(par + 256 + c0 + g * 4);
             const uint32_t* rsrc = g < 4 ? &ra[g * 4] : &rb[(g - 4) * 4];
             float4 o;
-            o.x = g4.x * (__uint_as_float(rsrc[0]) + b4.x); o.y = g4.y * (__uint_as_float(rsrc[1]) + b4.y);
-            o.z = g4.z * (__uint_as_float(rsrc[2]) + b4.z); o.w = g4.w * (__uint_as_float(rsrc[3]) + b4.w);
+            const float sc = p.acc_scale;
+            o.x = g4.x * fmaf(__uint_as_float(rsrc[0]), sc, b4.x); o.y = g4.y * fmaf(__uint_as_float(rsrc[1]), sc, b4.y);
+            o.z = g4.z * fmaf(__uint_as_float(rsrc[2]), sc, b4.z); o.w = g4.w * fmaf(__uint_as_float(rsrc[3]), sc, b4.w);
             *reinterpret_cast<float4*>(dst + g * 16) = o;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -750,7 +751,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       float v[16];
 
       if (p.debug & 2) {
-        tc_ld16(taddr + csel * 16, v);
+        tc_ld16(taddr + csel * 16, v, 1.0f);
         if (v[0] == 123.456f && out_f32) out_f32[0] = v[1];             // keep the load alive
       } else if (EPI == PRV2_EPI_HEAD) {
         if (csel == 0) {                           // one float per pixel: lane-per-row stores are already coalesced
@@ -758,7 +759,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           const int h = h0 + (tr >> tile_w_log2), w = w0 + (tr & tile_w_mask);
           float dot = 0.f;
           for (int c = 0; c < n_chunks; ++c) {
-            tc_ld16(taddr + c * 16, v);
+            tc_ld16(taddr + c * 16, v, p.acc_scale);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (n0 + c * 16 + j < Cout) dot += fmaxf(v[j] + par[c * 16 + j], 0.f) * par[256 + c * 16 + j];
@@ -776,14 +777,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           float sum = 0.f;
           int cnt = 0;
           for (int c = csel; c < n_chunks; c += 2) {
-            tc_ld16(taddr + c * 16, v);
+            tc_ld16(taddr + c * 16, v, p.acc_scale);
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < Cout) { sum += v[j] + par[c * 16 + j]; ++cnt; }
           }
           const float mean_a = cnt ? sum / (float)cnt : 0.f;
           float m2 = 0.f;
           for (int c = csel; c < n_chunks; c += 2) {
-            tc_ld16(taddr + c * 16, v);
+            tc_ld16(taddr + c * 16, v, p.acc_scale);
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (n0 + c * 16 + j < Cout) { const float d = v[j] + par[c * 16 + j] - mean_a; m2 += d * d; }
           }
@@ -800,7 +801,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         }
         // (3) chunk loop, software pipelined: the TMEM load of chunk c+2 is in flight while chunk c goes
         //     through its coalesced phase.
-        if (csel < n_chunks) tc_ld16(taddr + csel * 16, v);
+        if (csel < n_chunks) tc_ld16(taddr + csel * 16, v, p.acc_scale);
         auto chunk = [&](const int c, const Pre& pre) {
           float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD);
           dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -907,7 +908,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           if (more) {
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]) * p.acc_scale;
           }
         };
         if (EPI == PRV2_EPI_RESID_F32) {
@@ -1084,6 +1085,8 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   p.res2_hi = (const bf16*)d->res2_hi; p.res2_lo = (const bf16*)d->res2_lo; p.res2_cs = d->res2_cs;
   p.out_f32 = d->out_f32; p.out_f32_ld = d->out_f32_ld;
   p.shuffle_k = d->shuffle_k;
+  p.acc_scale = d->acc_scale == 0.f ? 1.f : d->acc_scale;
+  p.f16 = d->f16;
   p.row_map_period = d->row_map_period; p.row_map_extra = d->row_map_extra; p.row_map_offset = d->row_map_offset;
 
   switch (d->epi) {

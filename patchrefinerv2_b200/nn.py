@@ -4,6 +4,8 @@ device memory and streams; every FLOP runs in the hand-written kernels behind th
 from __future__ import annotations
 
 import ctypes as C
+import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -27,8 +29,9 @@ def ceil_to(x: int, m: int) -> int:
 
 
 class Act:
-    """Channels-last activation [N,H,W,C] stored with channel pitch ``cs`` as bf16 ``hi`` plus an
-    optional ``lo`` plane (x3 precision mode: value = hi + lo)."""
+    """Channels-last activation [N,H,W,C] stored with channel pitch ``cs``: ONE bf16 plane ``hi`` (one-pass mode) or a pair of
+    FP16 planes ``hi``, ``lo`` with value = hi + lo (x3 / fp32-class mode).  The torch dtype of the planes is just 16-bit storage
+    (allocated as bfloat16 in both cases); only the kernels interpret them."""
 
     __slots__ = ("N", "H", "W", "C", "cs", "hi", "lo")
 
@@ -143,6 +146,15 @@ class GemmLayer:
         if bias is not None and cout != cout_real:
             bias = torch.cat([bias.detach().float().reshape(-1), torch.zeros(cout - cout_real)])
         blocks, table, src_c = [], [], {}
+        corr_blocks, corr_table = [], []          # x3: the two small cross passes of every segment, issued BEFORE all main passes
+        # fp32-class mode: (hi, lo) FP16 weight planes.  FP16's exponent is narrow, so the whole layer is scaled by a power of two
+        # that puts its largest weight near 2^14: hi keeps 11 bits, lo = w - hi stays a NORMAL fp16 number for everything within
+        # 2^-13 of the maximum (~22 bits in all), and the kernel multiplies the accumulators by the inverse (exact).
+        self.w_scale = 1.0
+        if x3:
+            wmax = max(float(x.detach().abs().max()) for seg in segs for x in (seg[3] if isinstance(seg[3], (list, tuple)) else [seg[3]]))
+            if wmax > 0 and math.isfinite(wmax):
+                self.w_scale = 2.0 ** math.floor(math.log2(16384.0 / wmax))
         for seg in segs:
             si, dh, dw, w = seg[:4]
             grouped = isinstance(w, (list, tuple))          # vertical tap group: weights of taps (dh-1, dh, dh+1)
@@ -156,15 +168,26 @@ class GemmLayer:
                 wp[r, :cout_real, :c] = x
             # group: columns interleaved per 64-channel block [block 0: tap -1 | tap 0 | tap +1][block 1: ...] (include/prv2_b200.h)
             wp = wp.reshape(len(ws), self.cout_pad, cp // 64, 64).permute(1, 2, 0, 3).reshape(self.cout_pad, len(ws) * cp)
-            wh = wp.to(BF16)
             taps = 3 if grouped else 1
             if x3:
-                wl = (wp - wh.float()).to(BF16)
-                blocks += [wh, wl, wh]
-                table += [(2 * si, dh, dw, taps), (2 * si, dh, dw, taps), (2 * si + 1, dh, dw, taps)]
+                wp = wp * self.w_scale
+                wh = wp.to(torch.float16)
+                wl = (wp - wh.float()).to(torch.float16)
+                if os.environ.get("PRV2_X3_ORDER", "main_last") == "main_first":      # diagnostics (scripts/diag_accum.py)
+                    blocks += [wh, wl, wh]
+                    table += [(2 * si, dh, dw, taps), (2 * si, dh, dw, taps), (2 * si + 1, dh, dw, taps)]
+                else:
+                    corr_blocks += [wl, wh]
+                    corr_table += [(2 * si, dh, dw, taps), (2 * si + 1, dh, dw, taps)]
+                    blocks.append(wh)
+                    table.append((2 * si, dh, dw, taps))
             else:
-                blocks.append(wh)
+                blocks.append(wp.to(BF16))
                 table.append((si, dh, dw, taps))
+        # The tensor core adds every MMA into its fp32 accumulator with round-toward-zero: a bias of ~2^-24 of the running sum
+        # per MMA.  With the cross terms (2^-11 of the result) accumulated first, only the main pass's MMAs see a full-size
+        # running sum -- a third of the bias of the interleaved order (scripts/diag_accum.py).
+        blocks, table = corr_blocks + blocks, corr_table + table
         assert len(table) <= _lib.MAX_SEG and n_src * (2 if x3 else 1) <= _lib.MAX_SRC
         self.src_c = [src_c[i] for i in range(n_src)]
         self.weight = (blocks[0] if len(blocks) == 1 else torch.cat(blocks, dim=1)).contiguous().to(device)
@@ -182,6 +205,7 @@ class GemmLayer:
         d.gamma = 0 if self.gamma is None else self.gamma.data_ptr()
         d.beta = 0 if self.beta is None else self.beta.data_ptr()
         d.eps, d.head_scale, d.shuffle_k = eps, head_scale, shuffle_k
+        d.acc_scale, d.f16 = 1.0 / self.w_scale, 1 if x3 else 0
         self.desc = d
         self.flops_per_pixel = 2 * cout * sum((3 * w[0].shape[1]) if isinstance(w, (list, tuple)) else w.shape[1] for _, _, _, w in segs)
 

@@ -8,8 +8,8 @@ from patchrefinerv2_b200.nn import Act
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 x3 = "--x3" in sys.argv
 T, heads, D = 1025, 16, 1024
-qkv = Act.empty(1, 1, B * T, 3 * D, x3, "cuda"); qkv.hi.normal_()
-if x3: qkv.lo.normal_(std=2.0 ** -9)
+qkv = Act.empty(1, 1, B * T, 3 * D, x3, "cuda"); (qkv.hi.view(torch.float16) if x3 else qkv.hi).normal_()
+if x3: qkv.lo.view(torch.float16).normal_(std=2.0 ** -11)
 out = Act.empty(1, 1, B * T, D, x3, "cuda")
 for i in range(2):
     print(f"--- launch {i}", file=sys.stderr)

@@ -22,9 +22,10 @@ def main():
     sm = torch.cuda.get_device_properties(0).multi_processor_count
     x3 = "--x3" in sys.argv
     for B, T in ((1, 1025), (11, 1025), (12, 1025), (27, 1025), (27, 257)):
-        qkv = Act.empty(1, 1, B * T, 3 * D, x3, dev); qkv.hi.normal_()
+        qkv = Act.empty(1, 1, B * T, 3 * D, x3, dev)
+        (qkv.hi.view(torch.float16) if x3 else qkv.hi).normal_()
         if x3:
-            qkv.lo.normal_(std=2.0 ** -9)
+            qkv.lo.view(torch.float16).normal_(std=2.0 ** -11)
         out = Act.empty(1, 1, B * T, D, x3, dev)
         for _ in range(3):
             ops.attention(qkv, B, T, heads, out)
