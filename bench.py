@@ -379,8 +379,9 @@ def blend_launch_times(pshape, raw, split, cai_mode, process_num, dev, n=20):
         avg_c, cnt_c = ops.blend_canvas(preds[:first], mask, grid, Hc, Wc)
         rmask = torch.from_numpy(masks.random_patch_mask((rh, rw), 0.15).copy()).to(dev)
         starts = torch.from_numpy(np.ascontiguousarray(bb[first:, [1, 0]])).to(dev)
+        rprep = ops.blend_raw_prepare(rmask, pw)                # once per geometry, as the model does
         out["raw"] = {"bytes": 4.0 * (2 * Hc * Wc + (bb.shape[0] - first) * ph * pw + rh * rw + 2 * H * W),
-                      "s": run(lambda: ops.blend_raw(avg_c, cnt_c, preds[first:], starts, rmask, ph, pw, rh, rw, H, W))}
+                      "s": run(lambda: ops.blend_raw(avg_c, cnt_c, preds[first:], starts, rmask, ph, pw, rh, rw, H, W, prep=rprep))}
     return out
 
 

@@ -30,7 +30,7 @@ typedef uint16_t prv2_bf16;            /* raw bfloat16 bits */
 #define PRV2_EUNSUPPORTED (-3)         /* shape outside what the kernels implement */
 
 /* ABI version: bumped whenever a signature or the GemmDesc layout changes; the Python binding refuses any other value. */
-#define PRV2_ABI_VERSION 201
+#define PRV2_ABI_VERSION 202
 int prv2_version(void);
 /* sha256 of the CUDA sources + flags this library was compiled from (stamped by build.py with -DPRV2_BUILD_DIGEST);
  * the binding compares it with the digest of the sources it sits next to, so a stale .so is an error, not a silent mismatch. */
@@ -92,7 +92,15 @@ int prv2_blend_canvas(const float* preds, const float* mask, int ph, int pw,
 int prv2_blend_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc,
                    const float* preds, const int32_t* starts, int n, int ph, int pw,
                    const float* rmask, int rh, int rw, int H, int W,
-                   float* out, float* out_cnt, prv2_stream_t stream);
+                   float* out, float* out_cnt, const void* prep /*NULL or prv2_blend_raw_prepare output*/, prv2_stream_t stream);
+
+/* Optional one-time preparation of the random-patch weight map for the three *_raw entry points (same results, ~40 % fewer load
+ * instructions): `prep` (device, 16-byte aligned, prv2_blend_raw_prep_bytes(rh, rw) bytes) receives four column-shifted,
+ * zero-padded copies of rmask [rh, rw] and of the nearest-source-column table of a [*, pw] prediction (baseline_pretrain.py:210),
+ * so that the four weights / source columns of any aligned group of four output pixels are ONE 16-byte / 8-byte vector.  The
+ * weight map depends only on (rh, rw): prepare it once per geometry and pass it to every frame's calls. */
+int64_t prv2_blend_raw_prep_bytes(int rh, int rw);
+int prv2_blend_raw_prepare(const float* rmask, int rh, int rw, int pw, void* prep, prv2_stream_t stream);
 
 /* Patch-sharded form (multi-GPU): each rank adds ITS patches into packed partial
  * sums, one NCCL sum-reduce combines them, `finalize` normalises.  own[k]!=0 marks patches this
@@ -103,7 +111,7 @@ int prv2_blend_partial_canvas(const float* preds, const uint8_t* own, const floa
                               float* num_c, float* m1, prv2_stream_t stream);
 int prv2_blend_partial_raw(const float* preds, const uint8_t* own, const int32_t* starts, int n, int ph, int pw,
                            const float* rmask, int rh, int rw, int H, int W,
-                           float* num_r, prv2_stream_t stream);
+                           float* num_r, const void* prep, prv2_stream_t stream);
 /* avg = cnt>cnt0 ? (m1*cnt0 + num_c)/cnt : m1, cnt recomputed locally in reference order. */
 int prv2_blend_finalize_canvas(const float* num_c, const float* m1, const float* mask, int ph, int pw,
                                const prv2_grid_stage* stages /*host*/, int n_stages, int Hc, int Wc,
@@ -111,7 +119,7 @@ int prv2_blend_finalize_canvas(const float* num_c, const float* m1, const float*
 /* out = (A0*C0 + num_r)/(C0 + cnt_r) with cnt_r recomputed locally in draw order. */
 int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* num_r,
                             const int32_t* starts, int n, const float* rmask, int rh, int rw, int H, int W,
-                            float* out, float* out_cnt, prv2_stream_t stream);
+                            float* out, float* out_cnt, const void* prep, prv2_stream_t stream);
 /* Test / A-B hook: on != 0 routes every blend entry point through the any-alignment generic kernels instead of the
  * aligned fast paths (both produce the same bits; tests assert it). */
 int prv2_debug_blend_generic(int on);

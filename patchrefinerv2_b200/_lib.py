@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 201          # == PRV2_ABI_VERSION in include/prv2_b200.h
+ABI_VERSION = 202          # == PRV2_ABI_VERSION in include/prv2_b200.h
 MAX_SRC = 12
 MAX_SEG = 128
 
@@ -66,11 +66,13 @@ SIGNATURES = {
     "prv2_roi_gather_f32": [_p, _i, _i, _i, _p, _i, _f, _p, _p],
     "prv2_roi_gather_act": [_p, _p, _i, _i, _i, _i, _p, _i, _f, _p, _p, _i, _p],
     "prv2_blend_canvas": [_p, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p],
-    "prv2_blend_raw": [_p, _p, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p],
+    "prv2_blend_raw": [_p, _p, _i, _i, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "prv2_blend_raw_prep_bytes": [_i, _i],
+    "prv2_blend_raw_prepare": [_p, _i, _i, _i, _p, _p],
     "prv2_blend_partial_canvas": [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p],
-    "prv2_blend_partial_raw": [_p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p],
+    "prv2_blend_partial_raw": [_p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p],
     "prv2_blend_finalize_canvas": [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p],
-    "prv2_blend_finalize_raw": [_p, _p, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p],
+    "prv2_blend_finalize_raw": [_p, _p, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p],
     "prv2_debug_blend_generic": [_i],
     "prv2_umma_gemm": [_p, _p],
     "prv2_attention": [_p, _p, _i, _i, _i, _p, _p, _p],
@@ -110,7 +112,7 @@ def load():
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
-        fn.restype = C.c_char_p if name in ("prv2_last_error", "prv2_build_digest") else C.c_int
+        fn.restype = C.c_char_p if name in ("prv2_last_error", "prv2_build_digest") else C.c_int64 if name == "prv2_blend_raw_prep_bytes" else C.c_int
     if lib.prv2_version() != ABI_VERSION:
         raise Prv2Error(f"{path} has ABI version {lib.prv2_version()}, this binding needs {ABI_VERSION}: rebuild (python -m patchrefinerv2_b200.build --force)")
     have, want = (lib.prv2_build_digest() or b"").decode(), _build.source_digest()

@@ -633,6 +633,11 @@ static RawScales raw_scales(int Hc, int Wc, int H, int W, int ph, int pw, int rh
 // prv2_blend_raw_* builds once per geometry (raw_tables_kernel), instead of being recomputed with int<->float conversions for
 // each of the H rows.  The arithmetic on pixel values is unchanged (same ops, same order) -> same bits as blend_raw_kernel.
 struct RawTables { const unsigned short* a_ix; const unsigned short* c_i0; const float* c_l1; const unsigned short* src_x; };
+// Prepared patch mask (prv2_blend_raw_prepare): four copies of the [rh, rw] weight map, copy c shifted right by c columns and
+// zero-padded to `pitch` (a multiple of 4, >= rw + 8), and four equally shifted copies of the nearest-source-column table.  For
+// an output group starting l0 columns into a patch, copy c = (-l0) & 3 holds the group's four weights / source columns in ONE
+// aligned 16-byte / 8-byte vector -- also where the group straddles a patch edge (the padding weighs 0).
+struct RawPrep { const float* mask4; const unsigned short* srcx4; int pitch; };
 
 __global__ void raw_tables_kernel(unsigned short* a_ix, unsigned short* c_i0, float* c_l1, unsigned short* src_x, int Wc, int W, int Wpad,
                                   int pw, int rw, RawScales sc) {
@@ -653,7 +658,7 @@ __global__ void __launch_bounds__(256) blend_raw_tab_kernel(const float* __restr
                                                             const int32_t* __restrict__ starts, int n, int ph, int pw,
                                                             const float* __restrict__ rmask, int rh, int rw, int H, int W,
                                                             float* __restrict__ out, float* __restrict__ out_cnt,
-                                                            const float* __restrict__ num_in, RawScales sc, RawTables tb) {
+                                                            const float* __restrict__ num_in, RawScales sc, RawTables tb, RawPrep prep) {
   __shared__ int s_x0[PRV2_MAX_RANDOM], s_prow[PRV2_MAX_RANDOM], s_mrow[PRV2_MAX_RANDOM];
   __shared__ int s_n;
   const int y = blockIdx.y;
@@ -672,7 +677,7 @@ __global__ void __launch_bounds__(256) blend_raw_tab_kernel(const float* __restr
         const int pos = m + __popc(b & ((1u << threadIdx.x) - 1));
         const int ly = y - y0;
         s_x0[pos] = x0;
-        s_mrow[pos] = ly * rw;
+        s_mrow[pos] = ly * (prep.mask4 ? prep.pitch : rw);
         s_prow[pos] = (MODE == 2) ? 0 : (k * ph + nearest_src(ly, sc.ps_y, ph)) * pw;    // baseline_pretrain.py:210 (nearest), row part
       }
       m += __popc(b);
@@ -704,11 +709,30 @@ __global__ void __launch_bounds__(256) blend_raw_tab_kernel(const float* __restr
       const int i0[4] = {(int)(ti.x & 0xffffu), (int)(ti.x >> 16), (int)(ti.y & 0xffffu), (int)(ti.y >> 16)};
       float va[4], v00[4], v01[4], v10[4], v11[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int i1 = i0[q] + (i0[q] < Wc - 1 ? 1 : 0);
-        va[q] = __ldg(arow + a_ix[q]);
-        v00[q] = __ldg(c_r0 + i0[q]); v01[q] = __ldg(c_r0 + i1);
-        v10[q] = __ldg(c_r1 + i0[q]); v11[q] = __ldg(c_r1 + i1);
+      for (int q = 0; q < 4; ++q) va[q] = __ldg(arow + a_ix[q]);
+      if (i0[3] - i0[0] <= 2) {
+        // up-sampling: the four outputs' taps (i0, i0 + 1) lie in FOUR consecutive canvas columns -- 8 loads instead of 16
+        float r0[4], r1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int col = min(i0[0] + k, Wc - 1);               // (i1 clamps the same way at the right edge)
+          r0[k] = __ldg(c_r0 + col); r1[k] = __ldg(c_r1 + col);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int d = i0[q] - i0[0];
+          v00[q] = d == 0 ? r0[0] : d == 1 ? r0[1] : r0[2];
+          v01[q] = d == 0 ? r0[1] : d == 1 ? r0[2] : r0[3];
+          v10[q] = d == 0 ? r1[0] : d == 1 ? r1[1] : r1[2];
+          v11[q] = d == 0 ? r1[1] : d == 1 ? r1[2] : r1[3];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i1 = i0[q] + (i0[q] < Wc - 1 ? 1 : 0);
+          v00[q] = __ldg(c_r0 + i0[q]); v01[q] = __ldg(c_r0 + i1);
+          v10[q] = __ldg(c_r1 + i0[q]); v11[q] = __ldg(c_r1 + i1);
+        }
       }
       float4 nin = make_float4(0.f, 0.f, 0.f, 0.f);
       if (MODE == 2) {
@@ -728,9 +752,28 @@ __global__ void __launch_bounds__(256) blend_raw_tab_kernel(const float* __restr
     for (int i = 0; i < m; ++i) {
       const int l0 = xb - s_x0[i];
       if (l0 + 3 < 0 || l0 >= rw) continue;                    // group entirely outside this patch
-      const float* mrow = rmask + s_mrow[i];
+      const float* mrow = prep.mask4 ? prep.mask4 + s_mrow[i] : rmask + s_mrow[i];      // copy 0 of the prepared mask is unshifted
       const float* prow = preds + s_prow[i];
-      if (l0 >= 0 && l0 + 3 < rw && full) {
+      if (prep.mask4 && full) {
+        // one aligned float4 of weights and one uint2 of source columns from the copy shifted by (-l0) & 3 (edge groups too)
+        const int c = (-l0) & 3, j = l0 + c;
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(prep.mask4 + (size_t)c * rh * prep.pitch + s_mrow[i] + j));
+        const float ct[4] = {c4.x, c4.y, c4.z, c4.w};
+        float p[4] = {0.f, 0.f, 0.f, 0.f};
+        if (MODE != 2) {
+          const uint2 s2 = __ldg(reinterpret_cast<const uint2*>(prep.srcx4 + (size_t)c * prep.pitch + j));
+          const int sx[4] = {(int)(s2.x & 0xffffu), (int)(s2.x >> 16), (int)(s2.y & 0xffffu), (int)(s2.y >> 16)};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) p[q] = __ldg(prow + sx[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (!(ct[q] > 0.f)) continue;
+          if (MODE == 2) cnt[q] = __fadd_rn(cnt[q], ct[q]);
+          else if (MODE == 0) ram_update(avg[q], cnt[q], p[q], ct[q]);
+          else num[q] = __fadd_rn(num[q], __fmul_rn(p[q], ct[q]));
+        }
+      } else if (!prep.mask4 && l0 >= 0 && l0 + 3 < rw && full) {
         float ct[4], p[4];
         int sx[4];
 #pragma unroll
@@ -827,15 +870,53 @@ static bool raw_tables_get(int Wc, int W, int pw, int rw, const RawScales& sc, c
   return true;
 }
 
+static int raw_prep_pitch(int rw) { return ((rw + 3) & ~3) + 8; }
+static size_t raw_prep_bytes(int rh, int rw) { return (size_t)4 * rh * raw_prep_pitch(rw) * sizeof(float) + (size_t)4 * raw_prep_pitch(rw) * sizeof(unsigned short); }
+
+__global__ void raw_prepare_kernel(const float* __restrict__ rmask, int rh, int rw, int pw, int pitch, float ps_x, float* __restrict__ mask4,
+                                   unsigned short* __restrict__ srcx4) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y, c = blockIdx.z;
+  if (j >= pitch) return;
+  const int src = j - c;                                         // copy c is shifted right by c columns, zero elsewhere
+  const bool in = src >= 0 && src < rw;
+  mask4[((size_t)c * rh + row) * pitch + j] = in ? rmask[(size_t)row * rw + src] : 0.f;
+  if (row == 0) srcx4[(size_t)c * pitch + j] = in ? (unsigned short)nearest_src(src, ps_x, pw) : (unsigned short)0;
+}
+
+static RawPrep raw_prep_view(const void* prep, int rh, int rw) {
+  RawPrep v;
+  v.mask4 = nullptr; v.srcx4 = nullptr; v.pitch = 0;
+  if (prep) {
+    v.pitch = raw_prep_pitch(rw);
+    v.mask4 = (const float*)prep;
+    v.srcx4 = (const unsigned short*)((const char*)prep + (size_t)4 * rh * v.pitch * sizeof(float));
+  }
+  return v;
+}
+
+extern "C" int64_t prv2_blend_raw_prep_bytes(int rh, int rw) { return (rh > 0 && rw > 0) ? (int64_t)raw_prep_bytes(rh, rw) : 0; }
+
+extern "C" int prv2_blend_raw_prepare(const float* rmask, int rh, int rw, int pw, void* prep, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(rmask && prep, "prv2_blend_raw_prepare: null pointer");
+  PRV2_CHECK_ARG(rh > 0 && rw > 0 && pw > 0 && pw <= 65535 && rh <= 65535, "prv2_blend_raw_prepare: bad shape");
+  PRV2_CHECK_ARG(((uintptr_t)prep & 15) == 0, "prv2_blend_raw_prepare: the buffer must be 16-byte aligned");
+  const int pitch = raw_prep_pitch(rw);
+  const RawPrep v = raw_prep_view(prep, rh, rw);
+  raw_prepare_kernel<<<dim3(cdiv(pitch, 256), rh, 4), 256, 0, (cudaStream_t)stream>>>(rmask, rh, rw, pw, pitch, (float)pw / (float)rw, (float*)v.mask4,
+                                                                                      (unsigned short*)v.srcx4);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
 template <int MODE>
 static void launch_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* preds, const uint8_t* own, const int32_t* starts,
                        int n, int ph, int pw, const float* rmask, int rh, int rw, int H, int W, float* out, float* out_cnt,
-                       const float* num_in, const RawScales& sc, cudaStream_t stream) {
+                       const float* num_in, const RawScales& sc, const void* prep, cudaStream_t stream) {
   dim3 grid(1, H);
   RawTables tb;
   if (!blend_generic_forced() && raw_tables_get(Wc, W, pw, rw, sc, stream, &tb)) {
     blend_raw_tab_kernel<MODE><<<grid, 256, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W, out, out_cnt,
-                                                         num_in, sc, tb);
+                                                         num_in, sc, tb, raw_prep_view(prep, rh, rw));
   } else {
     blend_raw_kernel<MODE><<<grid, 256, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W, out, out_cnt, num_in, sc);
   }
@@ -849,38 +930,38 @@ static int check_raw(const char* fn, int n, int ph, int pw, int rh, int rw, int 
 
 extern "C" int prv2_blend_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* preds, const int32_t* starts, int n,
                               int ph, int pw, const float* rmask, int rh, int rw, int H, int W, float* out, float* out_cnt,
-                              prv2_stream_t stream) {
+                              const void* prep, prv2_stream_t stream) {
   PRV2_CHECK_ARG(avg_c && cnt_c && out, "prv2_blend_raw: null pointer");
   PRV2_CHECK_ARG(n == 0 || (preds && starts && rmask), "prv2_blend_raw: null patch inputs");
   int rc = check_raw("prv2_blend_raw", n, ph, pw, rh, rw, H, W);
   if (rc) return rc;
   launch_raw<0>(avg_c, cnt_c, Hc, Wc, preds, nullptr, starts, n, ph, pw, rmask, rh, rw, H, W, out, out_cnt, nullptr,
-                raw_scales(Hc, Wc, H, W, ph, pw, rh, rw), (cudaStream_t)stream);
+                raw_scales(Hc, Wc, H, W, ph, pw, rh, rw), n ? prep : nullptr, (cudaStream_t)stream);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
 
 extern "C" int prv2_blend_partial_raw(const float* preds, const uint8_t* own, const int32_t* starts, int n, int ph, int pw,
-                                      const float* rmask, int rh, int rw, int H, int W, float* num_r, prv2_stream_t stream) {
+                                      const float* rmask, int rh, int rw, int H, int W, float* num_r, const void* prep, prv2_stream_t stream) {
   PRV2_CHECK_ARG(preds && own && starts && rmask && num_r, "prv2_blend_partial_raw: null pointer");
   int rc = check_raw("prv2_blend_partial_raw", n, ph, pw, rh, rw, H, W);
   if (rc) return rc;
   if (n == 0) return PRV2_OK;
   launch_raw<1>(nullptr, nullptr, 1, 1, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W, num_r, nullptr, nullptr,
-                raw_scales(1, 1, H, W, ph, pw, rh, rw), (cudaStream_t)stream);
+                raw_scales(1, 1, H, W, ph, pw, rh, rw), prep, (cudaStream_t)stream);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
 
 extern "C" int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* num_r, const int32_t* starts,
                                        int n, const float* rmask, int rh, int rw, int H, int W, float* out, float* out_cnt,
-                                       prv2_stream_t stream) {
+                                       const void* prep, prv2_stream_t stream) {
   PRV2_CHECK_ARG(avg_c && cnt_c && num_r && out, "prv2_blend_finalize_raw: null pointer");
   PRV2_CHECK_ARG(n == 0 || (starts && rmask), "prv2_blend_finalize_raw: null patch inputs");
   int rc = check_raw("prv2_blend_finalize_raw", n, 1, 1, rh, rw, H, W);
   if (rc) return rc;
   launch_raw<2>(avg_c, cnt_c, Hc, Wc, nullptr, nullptr, starts, n, 1, 1, rmask, rh, rw, H, W, out, out_cnt, num_r,
-                raw_scales(Hc, Wc, H, W, 1, 1, rh, rw), (cudaStream_t)stream);
+                raw_scales(Hc, Wc, H, W, 1, 1, rh, rw), n ? prep : nullptr, (cudaStream_t)stream);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

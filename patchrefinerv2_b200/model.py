@@ -368,16 +368,20 @@ class PatchRefiner(nn.Module):
                 grid_stages.append((s.off_process[0], s.off_process[1], s.grid[0], s.grid[1], first))
                 first += s.bboxs.shape[0]
         mask = self._mask_dev(eng, "p", (ph, pw))
-        starts = rmask = None
+        starts = rmask = rprep = None
         if n_random:
             starts = torch.from_numpy(np.ascontiguousarray(bboxs_np[n_regular:, [1, 0]])).to(dev)     # (y0, x0)
             rmask = self._mask_dev(eng, "r", (rh, rw))
+            key = ("rprep", rh, rw, pw)
+            if key not in eng["masks"]:
+                eng["masks"][key] = ops.blend_raw_prepare(rmask, pw)                               # once per geometry
+            rprep = eng["masks"][key]
         is_r = cai_mode[0] == "r"
 
         if not shard:
             avg_c, cnt_c = ops.blend_canvas(preds[:n_regular], mask, grid_stages, Hc, Wc, want_count=True)
             if is_r:
-                depth, cnt = ops.blend_raw(avg_c, cnt_c, preds[n_regular:] if n_random else None, starts, rmask, ph, pw, rh, rw, H, W)
+                depth, cnt = ops.blend_raw(avg_c, cnt_c, preds[n_regular:] if n_random else None, starts, rmask, ph, pw, rh, rw, H, W, prep=rprep)
             else:
                 depth, cnt = avg_c, cnt_c
         else:
@@ -387,12 +391,12 @@ class PatchRefiner(nn.Module):
             ops.blend_partial_canvas(preds[:n_regular], own[:n_regular], mask, grid_stages, Hc, Wc, num_c, m1)
             if is_r and n_random:
                 num_r = packed[2 * Hc * Wc:].view(H, W)
-                ops.blend_partial_raw(preds[n_regular:], own[n_regular:].contiguous(), starts, rmask, ph, pw, H, W, num_r)
+                ops.blend_partial_raw(preds[n_regular:], own[n_regular:].contiguous(), starts, rmask, ph, pw, H, W, num_r, prep=rprep)
             if world > 1:
                 torch.distributed.all_reduce(packed)                                         # ONE sum-reduce of the packed partial canvases
             avg_c, cnt_c = ops.blend_finalize_canvas(num_c, m1, mask, grid_stages, Hc, Wc)
             if is_r:
-                depth, cnt = ops.blend_finalize_raw(avg_c, cnt_c, packed[2 * Hc * Wc:].view(H, W), starts, rmask, rh, rw, H, W)
+                depth, cnt = ops.blend_finalize_raw(avg_c, cnt_c, packed[2 * Hc * Wc:].view(H, W), starts, rmask, rh, rw, H, W, prep=rprep)
             else:
                 depth, cnt = avg_c, cnt_c
         self.last_stats = dict(patches=P, patches_local=int(len(sel)), count_map=cnt, n_regular=n_regular, n_random=n_random)

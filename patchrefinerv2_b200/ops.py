@@ -71,8 +71,19 @@ def blend_canvas(preds: torch.Tensor, mask: torch.Tensor, stages: Sequence[tuple
     return avg, cnt
 
 
+def blend_raw_prepare(rmask: torch.Tensor, pw: int) -> torch.Tensor:
+    """One-time preparation of the random-patch weight map [rh, rw] for predictions of width ``pw`` (prv2_blend_raw_prepare):
+    returns the opaque device buffer the *_raw blend calls accept as ``prep``."""
+    _chk(rmask, torch.float32, "rmask")
+    rh, rw = rmask.shape
+    nbytes = int(_lib.load().prv2_blend_raw_prep_bytes(rh, rw))
+    prep = torch.empty(nbytes, dtype=torch.uint8, device=rmask.device)
+    _lib.call("prv2_blend_raw_prepare", ptr(rmask), rh, rw, pw, ptr(prep), stream_ptr())
+    return prep
+
+
 def blend_raw(avg_c: torch.Tensor, cnt_c: torch.Tensor, preds: Optional[torch.Tensor], starts: Optional[torch.Tensor],
-              rmask: Optional[torch.Tensor], ph: int, pw: int, rh: int, rw: int, H: int, W: int, want_count: bool = True):
+              rmask: Optional[torch.Tensor], ph: int, pw: int, rh: int, rw: int, H: int, W: int, want_count: bool = True, prep=None):
     """rN stage: resize canvas to raw resolution and fold the random patches in, in draw order."""
     _chk(avg_c, torch.float32, "avg_c"); _chk(cnt_c, torch.float32, "cnt_c")
     Hc, Wc = avg_c.shape
@@ -83,7 +94,7 @@ def blend_raw(avg_c: torch.Tensor, cnt_c: torch.Tensor, preds: Optional[torch.Te
     cnt = torch.empty((H, W), dtype=torch.float32, device=avg_c.device) if want_count else None
     nbytes = 4.0 * (2 * Hc * Wc + n * ph * pw + (rh * rw if n else 0) + (2 if want_count else 1) * H * W)
     _lib.call("prv2_blend_raw", ptr(avg_c), ptr(cnt_c), Hc, Wc, ptr(preds), ptr(starts), n, ph, pw, ptr(rmask), rh, rw, H, W,
-              ptr(out), ptr(cnt), stream_ptr(), work=("byte", nbytes))
+              ptr(out), ptr(cnt), ptr(prep), stream_ptr(), work=("byte", nbytes))
     return out, cnt
 
 
@@ -93,10 +104,10 @@ def blend_partial_canvas(preds, own, mask, stages, Hc, Wc, num_c, m1):
               ptr(num_c), ptr(m1), stream_ptr())
 
 
-def blend_partial_raw(preds, own, starts, rmask, ph, pw, H, W, num_r):
+def blend_partial_raw(preds, own, starts, rmask, ph, pw, H, W, num_r, prep=None):
     rh, rw = rmask.shape
     _lib.call("prv2_blend_partial_raw", ptr(preds), ptr(own), ptr(starts), preds.shape[0], ph, pw, ptr(rmask), rh, rw, H, W,
-              ptr(num_r), stream_ptr())
+              ptr(num_r), ptr(prep), stream_ptr())
 
 
 def blend_finalize_canvas(num_c, m1, mask, stages, Hc, Wc):
@@ -108,13 +119,13 @@ def blend_finalize_canvas(num_c, m1, mask, stages, Hc, Wc):
     return avg, cnt
 
 
-def blend_finalize_raw(avg_c, cnt_c, num_r, starts, rmask, rh, rw, H, W):
+def blend_finalize_raw(avg_c, cnt_c, num_r, starts, rmask, rh, rw, H, W, prep=None):
     Hc, Wc = avg_c.shape
     n = 0 if starts is None else starts.shape[0]
     out = torch.empty((H, W), dtype=torch.float32, device=avg_c.device)
     cnt = torch.empty((H, W), dtype=torch.float32, device=avg_c.device)
     _lib.call("prv2_blend_finalize_raw", ptr(avg_c), ptr(cnt_c), Hc, Wc, ptr(num_r), ptr(starts), n, ptr(rmask), rh, rw, H, W,
-              ptr(out), ptr(cnt), stream_ptr())
+              ptr(out), ptr(cnt), ptr(prep), stream_ptr())
     return out, cnt
 
 

@@ -62,7 +62,10 @@ def main():
         _lib.call("prv2_debug_blend_generic", generic)
         for fl_label, fl in (("flushed", flush), ("warm", None)):
             c = time_launches(lambda: ops.blend_canvas(preds[:first], mask, grid, Hc, Wc), flush=fl)
-            r = time_launches(lambda: ops.blend_raw(avg_c, cnt_c, preds[first:], starts, rmask, ph, pw, rh, rw, H, W), flush=fl)
+            rprep = ops.blend_raw_prepare(rmask, pw)
+            r0 = time_launches(lambda: ops.blend_raw(avg_c, cnt_c, preds[first:], starts, rmask, ph, pw, rh, rw, H, W), flush=fl)
+            print(f"   (raw stage without the prepared weight map: {r0})")
+            r = time_launches(lambda: ops.blend_raw(avg_c, cnt_c, preds[first:], starts, rmask, ph, pw, rh, rw, H, W, prep=rprep), flush=fl)
             c["GBps"] = bytes_canvas / c["median_us"] / 1e3
             r["GBps"] = bytes_raw / r["median_us"] / 1e3
             out[f"{label}_{fl_label}"] = {"canvas": c, "raw": r}

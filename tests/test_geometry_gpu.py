@@ -105,9 +105,10 @@ def _blend_inputs(dev, shape, mode, pn, raw=(2160, 3840), split=(4, 4)):
     return tc, preds, grid, first, mask, rmask, starts
 
 
+@pytest.mark.parametrize("prepared", [False, True])
 @pytest.mark.parametrize("shape", [(448, 448), (384, 512)])
 @pytest.mark.parametrize("mode", ["m1", "m2", "r32"])
-def test_blend_bit_exact_vs_reference_golden(dev, golden_dir, shape, mode):
+def test_blend_bit_exact_vs_reference_golden(dev, golden_dir, shape, mode, prepared):
     """Depth canvas AND count map of the sequential blend, at full 2160x3840 / r32 size, against the
     sha256 of what the reference's RunningAverageMap produced."""
     from patchrefinerv2_b200 import ops
@@ -118,7 +119,9 @@ def test_blend_bit_exact_vs_reference_golden(dev, golden_dir, shape, mode):
     rh, rw = tc["patch_raw_shape"]
     avg, cnt = ops.blend_canvas(preds[:n_reg], mask, grid, Hc, Wc)
     if mode[0] == "r":
-        avg, cnt = ops.blend_raw(avg, cnt, preds[n_reg:], starts, rmask, shape[0], shape[1], rh, rw, H, W)
+        # prepared = the per-geometry shifted weight-map copies (prv2_blend_raw_prepare): same bits either way
+        prep = ops.blend_raw_prepare(rmask, shape[1]) if prepared else None
+        avg, cnt = ops.blend_raw(avg, cnt, preds[n_reg:], starts, rmask, shape[0], shape[1], rh, rw, H, W, prep=prep)
     d = avg.cpu().numpy()
     assert tuple(d.shape) == tuple(g["depth_shape"])
     assert np.array_equal(d[::8, ::8], g["depth_sub"])
@@ -150,11 +153,14 @@ def test_sharded_blend_matches_sequential(dev, mode, world):
         garbage[own == 0] = float("nan")                     # a rank never reads predictions it does not own
         ops.blend_partial_canvas(garbage[:n_reg], own[:n_reg].contiguous(), mask, grid, Hc, Wc, packed[:Hc * Wc].view(Hc, Wc), packed[Hc * Wc:2 * Hc * Wc].view(Hc, Wc))
         if mode[0] == "r":
-            ops.blend_partial_raw(garbage[n_reg:], own[n_reg:].contiguous(), starts, rmask, 448, 448, H, W, packed[2 * Hc * Wc:].view(H, W))
+            prep = ops.blend_raw_prepare(rmask, 448) if r % 2 else None           # both forms on alternating ranks
+            ops.blend_partial_raw(garbage[n_reg:], own[n_reg:].contiguous(), starts, rmask, 448, 448, H, W, packed[2 * Hc * Wc:].view(H, W), prep=prep)
         total += packed
     a2, c2 = ops.blend_finalize_canvas(total[:Hc * Wc].view(Hc, Wc), total[Hc * Wc:2 * Hc * Wc].view(Hc, Wc), mask, grid, Hc, Wc)
     if mode[0] == "r":
-        a2, c2 = ops.blend_finalize_raw(a2, c2, total[2 * Hc * Wc:].view(H, W), starts, rmask, rh, rw, H, W)
+        a3, c3 = ops.blend_finalize_raw(a2, c2, total[2 * Hc * Wc:].view(H, W), starts, rmask, rh, rw, H, W)
+        a2, c2 = ops.blend_finalize_raw(a2, c2, total[2 * Hc * Wc:].view(H, W), starts, rmask, rh, rw, H, W, prep=ops.blend_raw_prepare(rmask, 448))
+        assert torch.equal(a2, a3) and torch.equal(c2, c3)
     assert torch.equal(c2, cnt)
     rel = ((a2 - avg).abs() / avg.abs().clamp_min(1e-6)).max().item()
     assert rel < 1e-3, rel
@@ -270,7 +276,11 @@ def test_blend_ragged_geometries_bit_exact_vs_oracle(dev, case):
             _set_generic(generic)
             a, c = ops.blend_canvas(preds[:n_reg], mask, grid, Hc, Wc)
             if is_r:
+                if not generic:                               # table kernel with the prepared (shifted) weight map as well
+                    a2, c2 = ops.blend_raw(a, c, preds[n_reg:], starts, rmask, shape[0], shape[1], rh, rw, H, W, prep=ops.blend_raw_prepare(rmask, shape[1]))
                 a, c = ops.blend_raw(a, c, preds[n_reg:], starts, rmask, shape[0], shape[1], rh, rw, H, W)
+                if not generic:
+                    assert torch.equal(a, a2) and torch.equal(c, c2)
             res.append((a.cpu(), c.cpu()))
     finally:
         _set_generic(False)
