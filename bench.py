@@ -424,6 +424,7 @@ def main():
     ap.add_argument("--workload", default="dav2_vitl_2160x3840_4x4_r32", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--patch-batch", type=int, default=0, help="patches per network launch (0 = balance automatically, <= 27)")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames in one model call (0 = one per GPU: the batch-of-frames work list, weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp32-mode", action="store_true", help="skip the second (fp32-class) model timed beside the bf16 headline")
@@ -497,13 +498,21 @@ def main():
             dist.init_process_group("nccl", device_id=dev)
             dist.all_reduce(torch.zeros(1, device=dev))
             torch.cuda.synchronize()
-    n_local = -(-n_patches // world)
+    # A step = ONE model call on a batch of F frames (default F = number of GPUs): the F x 81 patches form one work list that is
+    # sharded round-robin over the ranks, every frame keeps its own canvases, ONE sum-reduce combines the batch.  Per-GPU work
+    # is one frame's worth at every N (weak scaling); at N = 1 this is the single-frame call of BASELINE config 4.
+    F_ = args.frames_per_step or world
+    n_local = -(-(n_patches * F_) // world)
     pb = args.patch_batch or -(-n_local // (-(-n_local // 27)))
     config["patch_batch"] = pb
-    hr = synthetic_frame(raw, 1)
+    config["frames_per_step"] = F_
+    config["parallelism"] = (f"batch of {F_} frames = {F_ * n_patches} patches sharded round-robin over {world} ranks + 1 NCCL sum-reduce per batch"
+                             if world > 1 else "single GPU")
+    import torch as _t
+    hr = _t.cat([synthetic_frame(raw, 1 + f) for f in range(F_)])
     hr_dev = hr.to(dev)
     shard = world > 1
-    out_shape = (1, 1) + ((raw[0], raw[1]) if cai_mode[0] == "r" else tuple(tc["patch_reensemble_shape"]))
+    out_shape = (F_, 1) + ((raw[0], raw[1]) if cai_mode[0] == "r" else tuple(tc["patch_reensemble_shape"]))
     host_out = torch.empty(out_shape, dtype=torch.float32).pin_memory()
     peaks = measured_peaks()
 
@@ -557,10 +566,10 @@ def main():
             return host_out
 
         ms, launches, _ = timed(step_resident, steps, warmup)
-        res = {"ms": ms, "steps": steps, "launches": launches, "fps": steps / (ms / 1e3), "step_resident": step_resident}
+        res = {"ms": ms, "steps": steps, "launches": launches, "fps": F_ * steps / (ms / 1e3), "step_resident": step_resident}
         if want_e2e:
             ms_e, _, _ = timed(step_e2e, steps, 2)
-            res["e2e"] = {"value": steps / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": lr_pin.numel() * 4 + hr_pin.numel() * 4,
+            res["e2e"] = {"value": F_ * steps / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": lr_pin.numel() * 4 + hr_pin.numel() * 4,
                           "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e / steps,
                           "note": "pinned host frame in, pinned host depth out; image_hr upload overlaps the coarse pass on a copy stream; D2H on rank 0"}
         psteps = min(steps, 3)
@@ -593,10 +602,11 @@ def main():
     # multi-GPU parity evidence (untimed): the sharded frame against the same frame refined by this rank alone
     shard_check = None
     if world > 1:
-        d_sh = main_res["step_resident"]().clone()
+        d_sh = main_res["step_resident"]()[:1].clone()
         random.seed(1)
-        d_one, _ = model(mode="infer", image_lr=lr_dev, image_hr=hr_dev, cai_mode=cai_mode, process_num=process_num, shard=False)
-        shard_check = {"max_rel_diff_vs_unsharded": float(((d_sh - d_one).abs() / d_one.abs().clamp_min(1e-3)).max().item())}
+        d_one, _ = model(mode="infer", image_lr=lr_dev[:1], image_hr=hr_dev[:1], cai_mode=cai_mode, process_num=process_num, shard=False)
+        shard_check = {"max_rel_diff_vs_unsharded": float(((d_sh - d_one).abs() / d_one.abs().clamp_min(1e-3)).max().item()),
+                       "what": "frame 0 of the sharded batch against the same frame refined by this rank alone"}
         torch.distributed.barrier()
 
     traffic = profiled_traffic() or {}
@@ -605,7 +615,7 @@ def main():
     if rank == 0:
         eng = model._engine
         flops_frame = eng["coarse"].flops(1, *pshape) + n_patches * (eng["fine"].flops(1, *pshape) +
-                      eng["fusion"].flops(1, [(f.H, f.W) for f in eng["coarse"].forward(lr_dev)[1]][::-1]))
+                      eng["fusion"].flops(1, [(f.H, f.W) for f in eng["coarse"].forward(lr_dev[:1])[1]][::-1]))
         workspace_gb = sum(w.nbytes() for e in (eng["coarse"], eng["fine"], eng["fusion"]) for w in e.ws.values()) / 1e9
 
     # the CAI blend (north_star: HBM-bound target): algorithmic bytes / CUDA-event launch duration, cold L2 (see blend_launch_times)
@@ -691,9 +701,9 @@ def main():
             eager_gpu = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if F_ == world else "strong", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-class split)", "data": "synthetic", "config": config,
-            "patches_per_sec": fps * n_patches, "algorithmic_tflop_per_frame": flops_frame / 1e12,
+            "patches_per_sec": fps * n_patches, "frames_per_step": F_, "algorithmic_tflop_per_frame": flops_frame / 1e12,
             "model_tflops_per_gpu": flops_frame * fps / 1e12 / world,
             "l2_policy": "working set per step (activations, several GB) far exceeds the 126 MB L2; no explicit flush",
             "clocks": clocks, "e2e": main_res.get("e2e"), "gpu_launches": main_res["launches"], "parity": parity, f"{other}_mode": other_line,

@@ -243,25 +243,41 @@ class PatchRefiner(nn.Module):
         depth, feats = eng["coarse"].forward(image_lr.float().contiguous())
         return feats, depth
 
-    def refine_patches(self, eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel: np.ndarray, preds: torch.Tensor, trace=None):
-        """crop -> ROI gather -> fine branch -> fusion for the patches ``sel`` (indices into the
-        flattened schedule), ``patch_batch`` at a time; results land in ``preds[sel]``."""
+    def _gather_batch(self, eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, idx: np.ndarray, P: int):
+        """Crops and coarse ROIs of the work items ``idx`` (global indices frame * P + patch, ascending) into one batch: every
+        frame present in the batch contributes a contiguous run of rows (baseline_pretrain.py:272-296, patchrefiner.py:199-217)."""
+        dev = eng["device"]
+        ph, pw = self.patch_process_shape
+        ws = eng["ws"]
+        pb = len(idx)
+        crops = ws.f32(f"crops{pb}", pb, 3, ph, pw)
+        d_roi = ws.f32(f"droi{pb}", pb, 1, ph, pw)
+        c_roi = [ws.act(f"roi{li}", pb, f.H, f.W, f.C) for li, f in enumerate(coarse_feats)]
+        bb = torch.from_numpy(np.ascontiguousarray(bboxs_np[idx])).to(dev, non_blocking=True)
+        rois = torch.from_numpy(np.ascontiguousarray(rois_np[idx])).to(dev, non_blocking=True)
+        frames = idx // P
+        a = 0
+        while a < pb:
+            f = int(frames[a])
+            b = a + int(np.searchsorted(frames[a:], f, side="right"))
+            ops.crop_resize(image_hr[f], bb[a:b], ph, pw, out=crops[a:b])
+            for li, feat in enumerate(coarse_feats):
+                ops.roi_gather_act(feat.batch_slice(slice(f, f + 1)), rois[a:b], feat.H / ph, c_roi[li].batch_slice(slice(a, b)))
+            ops.roi_gather_f32(coarse_depth[f].reshape(ph, pw, 1), rois[a:b], 1.0, out=d_roi[a:b].reshape(b - a, ph, pw, 1))
+            a = b
+        return crops, c_roi, d_roi
+
+    def refine_patches(self, eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel: np.ndarray, preds: torch.Tensor, P: int, trace=None):
+        """crop -> ROI gather -> fine branch -> fusion for the work items ``sel`` (global indices frame * P + patch into the
+        flattened schedule of a batch of frames), ``patch_batch`` at a time; results land in ``preds[sel]``.  ``image_hr`` is
+        [F,3,H,W], ``coarse_feats`` acts with N = F, ``coarse_depth`` [F,1,ph,pw]."""
         dev = eng["device"]
         ph, pw = self.patch_process_shape
         level = self.fusion_feat_level
         for s in range(0, len(sel), self.patch_batch):
             idx = sel[s:s + self.patch_batch]
             pb = len(idx)
-            bb = torch.from_numpy(np.ascontiguousarray(bboxs_np[idx])).to(dev)
-            rois = torch.from_numpy(np.ascontiguousarray(rois_np[idx])).to(dev)
-            crops = ops.crop_resize(image_hr, bb, ph, pw)                                    # baseline_pretrain.py:272-280
-            ws = eng["ws"]
-            c_roi = []
-            for li, f in enumerate(coarse_feats):                                           # patchrefiner.py:203-207
-                o = ws.act(f"roi{li}", pb, f.H, f.W, f.C)
-                c_roi.append(ops.roi_gather_act(f, rois, f.H / ph, o))
-            cd = coarse_depth.reshape(ph, pw, 1)
-            d_roi = ops.roi_gather_f32(cd, rois, 1.0).reshape(pb, 1, ph, pw)                # patchrefiner.py:209-210
+            crops, c_roi, d_roi = self._gather_batch(eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, idx, P)
             r_depth, r_feats = eng["fine"].forward(crops, trace)                             # patchrefiner.py:219-232
             if self.strategy_refiner_target == "offset_fine":
                 base = r_depth
@@ -272,7 +288,7 @@ class PatchRefiner(nn.Module):
             c_list = c_roi[-level:][::-1]                                                   # patchrefiner.py:245-251
             f_list = r_feats[-level:][::-1]
             pred = eng["fusion"].forward(c_list, f_list, d_roi, r_depth, base, trace)        # fusion_model.py:84-122
-            preds[torch.from_numpy(idx).to(dev)] = pred.reshape(pb, ph, pw)
+            preds[torch.from_numpy(idx).to(dev, non_blocking=True)] = pred.reshape(pb, ph, pw)
             if trace is not None:
                 trace.setdefault("crops", crops.clone()); trace.setdefault("roi_depth", d_roi.clone())
                 trace.setdefault("roi_feats", [a.to_nchw() for a in c_roi]); trace.setdefault("fine_depth", r_depth.clone())
@@ -295,8 +311,8 @@ class PatchRefiner(nn.Module):
         rois_np = tiling.bboxs_to_feat(bboxs_np, (H, W), (ph, pw))[:, 1:]
         coarse_feats, coarse_depth = self.coarse_forward(image_lr)
         preds = torch.empty((bboxs_np.shape[0], ph, pw), dtype=torch.float32, device=dev)
-        self.refine_patches(eng, image_hr[0].float().contiguous(), bboxs_np, rois_np, coarse_feats, coarse_depth,
-                            np.arange(bboxs_np.shape[0]), preds, trace)
+        self.refine_patches(eng, image_hr[:1].float().contiguous(), bboxs_np, rois_np, coarse_feats, coarse_depth,
+                            np.arange(bboxs_np.shape[0]), preds, bboxs_np.shape[0], trace)
         return preds, coarse_depth
 
     @torch.no_grad()
@@ -308,7 +324,12 @@ class PatchRefiner(nn.Module):
             tile_cfg = self.tile_cfg
         else:
             tile_cfg = self.prepare_tile_cfg(tile_cfg["image_raw_shape"], tile_cfg["patch_split_num"])
-        assert image_hr.shape[0] == 1                                                        # patchrefiner.py:348
+        # The reference asserts batch 1 (patchrefiner.py:348) and its Tester feeds frames one by one (tester.py:62-69).  Here a
+        # batch of F frames is ONE work list of F x P patches (BASELINE config 5): the schedules are drawn frame by
+        # frame in order (so the global `random` stream is consumed exactly as F successive reference calls would), the coarse
+        # pass runs once on the whole batch, the flattened patches are refined in mixed-frame batches (and sharded round-robin
+        # over the ranks), every frame keeps its own canvases and one sum-reduce combines the whole batch.
+        F_ = int(image_hr.shape[0])
         dev = image_hr.device if image_hr.is_cuda else self._device
         if self._engine is None or self._engine["device"] != dev:
             self._engine = self._build_engine(dev)
@@ -335,13 +356,15 @@ class PatchRefiner(nn.Module):
         Hc, Wc = tile_cfg["patch_reensemble_shape"]
         if tuple(image_hr.shape[-2:]) != (H, W):
             raise ValueError(f"image_hr is {tuple(image_hr.shape[-2:])} but tile_cfg.image_raw_shape is {(H, W)}")
+        if image_lr.shape[0] != F_:
+            raise ValueError(f"image_lr holds {image_lr.shape[0]} frames, image_hr {F_}")
 
-        stages = tiling.schedule(tile_cfg, self.patch_process_shape, cai_mode, process_num)   # consumes `random` like the reference
-        bboxs_np = np.concatenate([s.bboxs for s in stages], axis=0)
-        rois_np = np.concatenate([tiling.bboxs_to_feat(s.bboxs, (H, W), (ph, pw))[:, 1:] for s in stages], axis=0)
-        P = bboxs_np.shape[0]
+        sched = [tiling.schedule(tile_cfg, self.patch_process_shape, cai_mode, process_num) for _ in range(F_)]   # consumes `random` like F reference calls
+        stages = sched[0]
+        P = sum(s.bboxs.shape[0] for s in stages)
         n_regular = sum(s.bboxs.shape[0] for s in stages if s.kind == "regular")
         n_random = P - n_regular
+        bboxs_np = np.concatenate([s.bboxs for st in sched for s in st], axis=0)                 # [F*P, 4], frame-major
 
         world, rank = 1, 0
         if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -350,17 +373,18 @@ class PatchRefiner(nn.Module):
             # every rank must blend the SAME random patches: rank 0's draw wins (ranks seeded differently -- seed+rank is
             # common practice -- would otherwise add num_r for different bboxes and finalize against their own starts)
             bboxs_np = _broadcast_bboxs(bboxs_np, dev)
-            rois_np = tiling.bboxs_to_feat(bboxs_np, (H, W), (ph, pw))[:, 1:]
+        rois_np = tiling.bboxs_to_feat(bboxs_np, (H, W), (ph, pw))[:, 1:]
 
         coarse_feats, coarse_depth = self.coarse_forward(image_lr)
         if hr_ready is not None:
             torch.cuda.current_stream(dev).wait_event(hr_ready)
             image_hr.record_stream(torch.cuda.current_stream(dev))
-        hr = image_hr[0].float().contiguous()
-        preds = eng["ws"].f32("preds", P, ph, pw)
-        own_np = tiling.shard_patches(P, rank, world)
+        hr = image_hr.float().contiguous()
+        preds = eng["ws"].f32("preds", F_ * P, ph, pw)
+
+        own_np = tiling.shard_patches(F_ * P, rank, world)
         sel = np.nonzero(own_np)[0]
-        self.refine_patches(eng, hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel, preds, trace)
+        self.refine_patches(eng, hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel, preds, P, trace)
 
         grid_stages, first = [], 0
         for s in stages:
@@ -368,39 +392,51 @@ class PatchRefiner(nn.Module):
                 grid_stages.append((s.off_process[0], s.off_process[1], s.grid[0], s.grid[1], first))
                 first += s.bboxs.shape[0]
         mask = self._mask_dev(eng, "p", (ph, pw))
-        starts = rmask = rprep = None
+        rmask = rprep = None
         if n_random:
-            starts = torch.from_numpy(np.ascontiguousarray(bboxs_np[n_regular:, [1, 0]])).to(dev)     # (y0, x0)
             rmask = self._mask_dev(eng, "r", (rh, rw))
             key = ("rprep", rh, rw, pw)
             if key not in eng["masks"]:
                 eng["masks"][key] = ops.blend_raw_prepare(rmask, pw)                               # once per geometry
             rprep = eng["masks"][key]
+            starts_all = torch.from_numpy(np.ascontiguousarray(bboxs_np.reshape(F_, P, 4)[:, n_regular:, [1, 0]])).to(dev)   # [F, n_random, (y0, x0)]
         is_r = cai_mode[0] == "r"
-
-        if not shard:
-            avg_c, cnt_c = ops.blend_canvas(preds[:n_regular], mask, grid_stages, Hc, Wc, want_count=True)
-            if is_r:
-                depth, cnt = ops.blend_raw(avg_c, cnt_c, preds[n_regular:] if n_random else None, starts, rmask, ph, pw, rh, rw, H, W, prep=rprep)
-            else:
-                depth, cnt = avg_c, cnt_c
-        else:
-            packed = torch.zeros(2 * Hc * Wc + (H * W if is_r else 0), dtype=torch.float32, device=dev)
-            num_c, m1 = packed[:Hc * Wc].view(Hc, Wc), packed[Hc * Wc:2 * Hc * Wc].view(Hc, Wc)
+        n_c = Hc * Wc
+        per_frame = 2 * n_c + (H * W if is_r else 0)
+        packed = own = None
+        if shard:
+            packed = eng["ws"].f32("packed", F_, per_frame)
+            packed.zero_()
             own = torch.from_numpy(own_np).to(dev)
-            ops.blend_partial_canvas(preds[:n_regular], own[:n_regular], mask, grid_stages, Hc, Wc, num_c, m1)
-            if is_r and n_random:
-                num_r = packed[2 * Hc * Wc:].view(H, W)
-                ops.blend_partial_raw(preds[n_regular:], own[n_regular:].contiguous(), starts, rmask, ph, pw, H, W, num_r, prep=rprep)
+            for f in range(F_):
+                pf, of, pk = preds[f * P:(f + 1) * P], own[f * P:(f + 1) * P], packed[f]
+                ops.blend_partial_canvas(pf[:n_regular], of[:n_regular].contiguous(), mask, grid_stages, Hc, Wc, pk[:n_c].view(Hc, Wc), pk[n_c:2 * n_c].view(Hc, Wc))
+                if is_r and n_random:
+                    ops.blend_partial_raw(pf[n_regular:], of[n_regular:].contiguous(), starts_all[f], rmask, ph, pw, H, W, pk[2 * n_c:].view(H, W), prep=rprep)
             if world > 1:
-                torch.distributed.all_reduce(packed)                                         # ONE sum-reduce of the packed partial canvases
-            avg_c, cnt_c = ops.blend_finalize_canvas(num_c, m1, mask, grid_stages, Hc, Wc)
-            if is_r:
-                depth, cnt = ops.blend_finalize_raw(avg_c, cnt_c, packed[2 * Hc * Wc:].view(H, W), starts, rmask, rh, rw, H, W, prep=rprep)
+                torch.distributed.all_reduce(packed)                                         # ONE sum-reduce of the packed partial canvases of the whole batch
+        depths, cnts = [], []
+        for f in range(F_):
+            pf = preds[f * P:(f + 1) * P]
+            starts = starts_all[f] if n_random else None
+            if not shard:
+                avg_c, cnt_c = ops.blend_canvas(pf[:n_regular], mask, grid_stages, Hc, Wc, want_count=True)
+                if is_r:
+                    depth, cnt = ops.blend_raw(avg_c, cnt_c, pf[n_regular:] if n_random else None, starts, rmask, ph, pw, rh, rw, H, W, prep=rprep)
+                else:
+                    depth, cnt = avg_c, cnt_c
             else:
-                depth, cnt = avg_c, cnt_c
-        self.last_stats = dict(patches=P, patches_local=int(len(sel)), count_map=cnt, n_regular=n_regular, n_random=n_random)
-        depth = depth.unsqueeze(0).unsqueeze(0)
+                pk = packed[f]
+                avg_c, cnt_c = ops.blend_finalize_canvas(pk[:n_c].view(Hc, Wc), pk[n_c:2 * n_c].view(Hc, Wc), mask, grid_stages, Hc, Wc)
+                if is_r:
+                    depth, cnt = ops.blend_finalize_raw(avg_c, cnt_c, pk[2 * n_c:].view(H, W), starts, rmask, rh, rw, H, W, prep=rprep)
+                else:
+                    depth, cnt = avg_c, cnt_c
+            depths.append(depth)
+            cnts.append(cnt)
+        depth = depths[0].unsqueeze(0).unsqueeze(0) if F_ == 1 else torch.stack(depths).unsqueeze(1)
+        self.last_stats = dict(patches=P, frames=F_, patches_local=int(len(sel)), count_map=cnts[0] if F_ == 1 else torch.stack(cnts),
+                               n_regular=n_regular, n_random=n_random)
         if self.output_device == "cpu":
             depth = depth.cpu()
         return depth, {"rgb": image_lr, "depth_pred": depth, "depth_gt": depth_gt, "coarse_prediction": coarse_depth}
@@ -532,21 +568,17 @@ class PatchRefinerPlus(PatchRefiner):
             ws=Workspace(device, x3), device=device, masks={},
             enc_mean=torch.tensor(self._enc_mean, device=device).view(1, -1, 1, 1), enc_std=torch.tensor(self._enc_std, device=device).view(1, -1, 1, 1))
 
-    def refine_patches(self, eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel: np.ndarray, preds: torch.Tensor, trace=None):
-        """patchrefinerplus.py:330-365 for the patches ``sel``, ``patch_batch`` at a time."""
+    def refine_patches(self, eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel: np.ndarray, preds: torch.Tensor, P: int, trace=None):
+        """patchrefinerplus.py:330-365 for the work items ``sel`` (see PatchRefiner.refine_patches), ``patch_batch`` at a time."""
         dev = eng["device"]
         ph, pw = self.patch_process_shape
         level = self.fusion_feat_level
         x3 = self.precision == "fp32"
+        ws = eng["ws"]
         for s in range(0, len(sel), self.patch_batch):
             idx = sel[s:s + self.patch_batch]
             pb = len(idx)
-            bb = torch.from_numpy(np.ascontiguousarray(bboxs_np[idx])).to(dev)
-            rois = torch.from_numpy(np.ascontiguousarray(rois_np[idx])).to(dev)
-            crops = ops.crop_resize(image_hr, bb, ph, pw)
-            ws = eng["ws"]
-            c_roi = [ops.roi_gather_act(f, rois, f.H / ph, ws.act(f"roi{li}", pb, f.H, f.W, f.C)) for li, f in enumerate(coarse_feats)]
-            d_roi = ops.roi_gather_f32(coarse_depth.reshape(ph, pw, 1), rois, 1.0).reshape(pb, 1, ph, pw)
+            crops, c_roi, d_roi = self._gather_batch(eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, idx, P)
             # LightWeightRefiner.forward (lightweight_refiner.py:285-322): normalise, condition on the coarse depth, encode
             x = (crops - eng["enc_mean"]) / eng["enc_std"]
             feats = list(self.refiner_fine_encoder(torch.cat([x, d_roi], dim=1) if self.coarse_condition else x))
@@ -563,7 +595,7 @@ class PatchRefinerPlus(PatchRefiner):
             c_list = c_roi[-level:][::-1]
             f_list = r_feats[-level:][::-1]
             pred = eng["fusion"].forward(c_list, f_list, d_roi, None, base, trace)
-            preds[torch.from_numpy(idx).to(dev)] = pred.reshape(pb, ph, pw)
+            preds[torch.from_numpy(idx).to(dev, non_blocking=True)] = pred.reshape(pb, ph, pw)
             if trace is not None:
                 trace.setdefault("crops", crops.clone()); trace.setdefault("roi_depth", d_roi.clone())
                 trace.setdefault("fine_feats", [a.to_nchw() for a in r_feats])

@@ -17,25 +17,32 @@ def _chk(t: torch.Tensor, dtype, name: str):
         raise ValueError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.dtype} on {t.device}")
 
 
-def crop_resize(image_hr: torch.Tensor, bboxs: torch.Tensor, ph: int, pw: int) -> torch.Tensor:
+def crop_resize(image_hr: torch.Tensor, bboxs: torch.Tensor, ph: int, pw: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """image_hr [3,H,W] fp32, bboxs [P,4] int32 (device) -> [P,3,ph,pw] fp32 (baseline_pretrain.py:272-280)."""
     _chk(image_hr, torch.float32, "image_hr"); _chk(bboxs, torch.int32, "bboxs")
     _, H, W = image_hr.shape
     P = bboxs.shape[0]
-    out = torch.empty((P, 3, ph, pw), dtype=torch.float32, device=image_hr.device)
+    if out is None:
+        out = torch.empty((P, 3, ph, pw), dtype=torch.float32, device=image_hr.device)
+    else:
+        _chk(out, torch.float32, "out")
+        assert tuple(out.shape) == (P, 3, ph, pw)
     if P == 0:
         return out
-    bb = bboxs.shape[0]
     _lib.call("prv2_crop_resize", ptr(image_hr), H, W, ptr(bboxs), P, ptr(out), ph, pw, stream_ptr(), work=("byte", 12.0 * P * ph * pw))
     return out
 
 
-def roi_gather_f32(feat_hwc: torch.Tensor, rois: torch.Tensor, spatial_scale: float) -> torch.Tensor:
+def roi_gather_f32(feat_hwc: torch.Tensor, rois: torch.Tensor, spatial_scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """feat [h,w,C] fp32, rois [P,4] fp32 -> [P,h,w,C] fp32 (patchrefiner.py:199-217, bit-exact form)."""
     _chk(feat_hwc, torch.float32, "feat"); _chk(rois, torch.float32, "rois")
     h, w, Cc = feat_hwc.shape
     P = rois.shape[0]
-    out = torch.empty((P, h, w, Cc), dtype=torch.float32, device=feat_hwc.device)
+    if out is None:
+        out = torch.empty((P, h, w, Cc), dtype=torch.float32, device=feat_hwc.device)
+    else:
+        _chk(out, torch.float32, "out")
+        assert tuple(out.shape) == (P, h, w, Cc)
     _lib.call("prv2_roi_gather_f32", ptr(feat_hwc), h, w, Cc, ptr(rois), P, C.c_float(spatial_scale), ptr(out), stream_ptr(),
               work=("byte", 4.0 * P * h * w * Cc))
     return out

@@ -128,3 +128,28 @@ def test_batch_invariance_and_tile_cfg_override(models, tiny_setup):
     assert torch.equal(a, b)                                 # per-patch results do not depend on batch composition
     with pytest.raises(ValueError):
         m(mode="infer", image_lr=lr.to(DEV), image_hr=hr.to(DEV), cai_mode="m1", tile_cfg={"image_raw_shape": [400, 768], "patch_split_num": [2, 2]})
+
+
+@pytest.mark.parametrize("mode,pn", [("m2", 2), ("r4", 2)])
+def test_batch_of_frames_equals_frame_by_frame(models, tiny_setup, mode, pn):
+    """BASELINE config 5 / SURVEY 8(e): a batch of F frames is one flattened work list of F x P patches (mixed-frame network
+    batches, per-frame canvases).  It must give, frame for frame, what F successive single-frame calls give -- including the
+    order in which the global `random` stream is consumed by the rN stages -- in the plain and in the sharded (sum-reduce) form."""
+    cfg, sd, lr, hr = tiny_setup
+    m = models["bf16"]
+    lr2, hr2 = O.synthetic_frame(cfg, 7)
+    lrs, hrs = torch.cat([lr, lr2]).to(DEV), torch.cat([hr, hr2]).to(DEV)
+    random.seed(3)
+    singles = [m(mode="infer", image_lr=lrs[f:f + 1], image_hr=hrs[f:f + 1], cai_mode=mode, process_num=pn)[0] for f in range(2)]
+    cnt_single = m.last_stats["count_map"].clone()
+    random.seed(3)
+    both, log = m(mode="infer", image_lr=lrs, image_hr=hrs, cai_mode=mode, process_num=pn)
+    assert both.shape == (2,) + tuple(singles[0].shape[1:]) and log["coarse_prediction"].shape[0] == 2
+    assert m.last_stats["frames"] == 2 and m.last_stats["patches_local"] == 2 * m.last_stats["patches"]
+    for f in range(2):
+        assert torch.equal(both[f], singles[f][0]), f
+    assert torch.equal(m.last_stats["count_map"][1], cnt_single)
+    random.seed(3)
+    sharded, _ = m(mode="infer", image_lr=lrs, image_hr=hrs, cai_mode=mode, process_num=pn, shard=True)
+    assert torch.equal(m.last_stats["count_map"][1], cnt_single)
+    assert ((sharded - both).abs() / both.abs().clamp_min(1e-3)).max().item() < 1e-3
