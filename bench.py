@@ -602,11 +602,12 @@ def main():
     # multi-GPU parity evidence (untimed): the sharded frame against the same frame refined by this rank alone
     shard_check = None
     if world > 1:
-        d_sh = main_res["step_resident"]()[:1].clone()
+        d_sh = main_res["step_resident"]().clone()
         random.seed(1)
-        d_one, _ = model(mode="infer", image_lr=lr_dev[:1], image_hr=hr_dev[:1], cai_mode=cai_mode, process_num=process_num, shard=False)
+        d_one, _ = model(mode="infer", image_lr=lr_dev, image_hr=hr_dev, cai_mode=cai_mode, process_num=process_num, shard=False)
         shard_check = {"max_rel_diff_vs_unsharded": float(((d_sh - d_one).abs() / d_one.abs().clamp_min(1e-3)).max().item()),
-                       "what": "frame 0 of the sharded batch against the same frame refined by this rank alone"}
+                       "what": f"all {F_} frames of the sharded batch (sharded + all-gathered coarse passes, round-robin patches, one sum-reduce) against "
+                               "the same batch refined by this rank alone"}
         torch.distributed.barrier()
 
     traffic = profiled_traffic() or {}

@@ -30,7 +30,7 @@ typedef uint16_t prv2_bf16;            /* raw bfloat16 bits */
 #define PRV2_EUNSUPPORTED (-3)         /* shape outside what the kernels implement */
 
 /* ABI version: bumped whenever a signature or the GemmDesc layout changes; the Python binding refuses any other value. */
-#define PRV2_ABI_VERSION 202
+#define PRV2_ABI_VERSION 203
 int prv2_version(void);
 /* sha256 of the CUDA sources + flags this library was compiled from (stamped by build.py with -DPRV2_BUILD_DIGEST);
  * the binding compares it with the digest of the sources it sits next to, so a stale .so is an error, not a silent mismatch. */
@@ -153,6 +153,7 @@ typedef struct {
 #define PRV2_ACT_GELU 2       /* exact erf GELU (torch.nn.GELU default)                 */
 #define PRV2_ACT_GELU_TANH 3  /* tanh-form GELU (|diff| <= 1e-3 abs vs erf); one-pass bf16 mode only */
 #define PRV2_ACT_SIGMOID_GATE 4 /* EPI_STORE only: out = res * sigmoid(acc+bias)  (GatedConvUnit, bi_directional_fusion_model.py:70-78) */
+#define PRV2_ACT_IDENTITY 5   /* LN epilogue only: LayerNorm without an activation (bi_directional_fusion_model.py:448-463); act 0 there means GELU */
 
 #define PRV2_EPI_STORE 0      /* act(acc+bias) [+ residual act] -> out (and optional relu copy) */
 #define PRV2_EPI_LN_GELU 1    /* channels-first LayerNorm over Cout of (acc+bias), then act = GELU | GELU_TANH (convs.py:21-29,64-75) | RELU (GatedConvUnit.fusion_conv) */

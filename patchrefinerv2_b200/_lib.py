@@ -9,12 +9,12 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 202          # == PRV2_ABI_VERSION in include/prv2_b200.h
+ABI_VERSION = 203          # == PRV2_ABI_VERSION in include/prv2_b200.h
 MAX_SRC = 12
 MAX_SEG = 128
 
 EPI_STORE, EPI_LN_GELU, EPI_RESID_F32, EPI_F32, EPI_SHUFFLE, EPI_HEAD = range(6)
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_TANH, ACT_SIGMOID_GATE = range(5)
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_TANH, ACT_SIGMOID_GATE, ACT_IDENTITY = range(6)
 
 
 class Prv2Error(RuntimeError):

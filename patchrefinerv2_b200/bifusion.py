@@ -31,13 +31,14 @@ from .nn import Act, GemmLayer, Workspace, conv_segments
 from .registry import MODELS
 
 #: coarse2fine_type -> (fusion, gate) of the C2FModule (bi_directional_fusion_model.py:366-374)
-C2F_TYPES = {"self-agg": (False, False), "coarse-gated": (True, True), "coarse-fusion": (True, False)}
+C2F_TYPES = {"self-agg": (False, False), "coarse-gated": (True, True), "coarse-fusion": (True, False),
+             "only-gate": (True, False)}       # only-gate = C2FNOENCModule(fusion=True, gate=False) (:211-283, :372-373)
 C2F_FEATURES = 256                 # C2FModule(features=256) (:149)
 
 
 def bifusion_weight_spec(coarse_chl, fine_chl, fine_chl_after_coarse2fine, temp_chl, dec_chl, coarse2fine_type="coarse-gated",
-                         features: int = C2F_FEATURES) -> "OrderedDict[str, tuple]":
-    """State-dict names and shapes of BiDirectionalFusion(glb_att=False, coarse2fine=True)."""
+                         features: int = C2F_FEATURES, heavy: bool = False) -> "OrderedDict[str, tuple]":
+    """State-dict names and shapes of BiDirectionalFusion / BiDirectionalFusionHeavy (glb_att=False, coarse2fine=True)."""
     fusion, _ = C2F_TYPES[coarse2fine_type]
     s: "OrderedDict[str, tuple]" = OrderedDict()
     for name, extra in (("fusion_layers_1", None), ("fusion_layers_2", 2)):
@@ -46,12 +47,22 @@ def bifusion_weight_spec(coarse_chl, fine_chl, fine_chl_after_coarse2fine, temp_
             s[f"{name}.{idx}.single_conv.0.weight"] = (tc, cin, 3, 3)
             s[f"{name}.{idx}.single_conv.1.weight"] = (tc,)
             s[f"{name}.{idx}.single_conv.1.bias"] = (tc,)
+            if heavy:                                                    # SingleConvCNNLNHeavy (:448-463)
+                s[f"{name}.{idx}.single_conv.2.weight"] = (tc, tc, 3, 3)
+                s[f"{name}.{idx}.single_conv.3.weight"] = (tc,)
+                s[f"{name}.{idx}.single_conv.3.bias"] = (tc,)
+                s[f"{name}.{idx}.single_conv.4.weight"] = (tc, tc, 3, 3)
     rev = list(temp_chl)[::-1]
     chl = rev[0]
     for i, (tc, dc) in enumerate(zip(rev[1:], dec_chl)):
         cin = tc + chl + 2
         s[f"f2r_agg.{i}.conv.double_conv.0.weight"] = (cin, cin, 3, 3)
-        s[f"f2r_agg.{i}.conv.double_conv.2.weight"] = (dc, cin, 3, 3)
+        if heavy:                                                        # DoubleConvHeavy (:465-485)
+            for k in (2, 4, 6):
+                s[f"f2r_agg.{i}.conv.double_conv.{k}.weight"] = (cin, cin, 3, 3)
+            s[f"f2r_agg.{i}.conv.double_conv.8.weight"] = (dc, cin, 3, 3)
+        else:
+            s[f"f2r_agg.{i}.conv.double_conv.2.weight"] = (dc, cin, 3, 3)
         chl = dc
     s["final_conv.weight"] = (1, dec_chl[-1] if len(dec_chl) else chl, 3, 3)
 
@@ -74,6 +85,18 @@ def bifusion_weight_spec(coarse_chl, fine_chl, fine_chl_after_coarse2fine, temp_
     q = "c2f.scratch."
     for i, fc in enumerate(fine_chl):
         s[f"{q}layer{i + 1}_rn.weight"] = (features, fc, 3, 3)
+    if coarse2fine_type == "only-gate":                                  # C2FNOENCModule (:211-251)
+        for lvl in range(1, 6):
+            unit(f"{q}layer{lvl}_gate1.", features)
+            unit(f"{q}layer{lvl}_gate2.", features)
+        s[q + "upsample_conv.0.weight"] = (fine_chl[0], 32, 2, 2)        # ConvTranspose2d [Cin, Cout, k, k]
+        s[q + "upsample_conv.0.bias"] = (32,)
+        s[q + "upsample_conv.2.weight"] = (32, 32, 3, 3)
+        unit(q + "layer6_gate1.", 32)
+        unit(q + "layer6_gate2.", 32)
+        s[q + "output_conv.weight"] = (1, 32, 3, 3)
+        s[q + "output_conv.bias"] = (1,)
+        return s
     for i in range(1, 6):
         block(f"{q}refinenet{i}.", features)
     h2 = coarse_chl[0]
@@ -151,11 +174,12 @@ class _GatedBlock:
 class BiDirectionalFusionB200:
     def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, coarse_chl: Sequence[int], fine_chl: Sequence[int],
                  fine_chl_after_coarse2fine: Sequence[int], temp_chl: Sequence[int], dec_chl: Sequence[int], coarse2fine_type: str,
-                 x3: bool, device, features: int = C2F_FEATURES):
+                 x3: bool, device, features: int = C2F_FEATURES, heavy: bool = False):
         if coarse2fine_type not in C2F_TYPES:
             raise NotImplementedError(f"coarse2fine_type={coarse2fine_type!r}: implemented {sorted(C2F_TYPES)}")
         fusion, gate = C2F_TYPES[coarse2fine_type]
         self.x3, self.device, self.features = x3, device, features
+        self.only_gate = coarse2fine_type == "only-gate"
         self.coarse_chl, self.fine_chl = list(coarse_chl), list(fine_chl)
         assert len(self.coarse_chl) == 6 and len(self.fine_chl) == 5
         if fusion:
@@ -166,6 +190,24 @@ class BiDirectionalFusionB200:
         q = "c2f.scratch."
         self.layer_rn = [mk(conv_segments(g(f"{q}layer{i + 1}_rn.weight"), [fc]), 1, features, name=f"c2f.layer{i + 1}_rn")
                          for i, fc in enumerate(self.fine_chl)]
+        after = list(fine_chl_after_coarse2fine)
+        self.f2c = FusionUnetB200(sd, prefix, [c + f for c, f in zip(self.coarse_chl, after)], temp_chl, dec_chl, x3, device,
+                                  in_splits=list(zip(self.coarse_chl, after)), names=("fusion_layers_1", "fusion_layers_2", "f2r_agg"), heavy=heavy)
+        self.ws: Dict[tuple, Workspace] = {}
+        if self.only_gate:
+            # C2FNOENCModule (:211-283): no top-down path -- two gated units per level against that level's coarse map, and a
+            # transposed-conv level 0 (deconv k = stride = 2 -> ReLU -> 3x3 conv) with two 32-channel units
+            assert self.coarse_chl[0] == 32, "C2FNOENCModule hard-codes a 32-channel level 0 (:238-247)"
+            self.gates = {lvl: (_GatedUnit(g, f"{q}layer{lvl}_gate1.", features, fusion, gate, x3, device, f"c2f.layer{lvl}_gate1"),
+                                _GatedUnit(g, f"{q}layer{lvl}_gate2.", features, fusion, gate, x3, device, f"c2f.layer{lvl}_gate2")) for lvl in range(1, 6)}
+            self.gates[6] = (_GatedUnit(g, q + "layer6_gate1.", 32, fusion, gate, x3, device, "c2f.layer6_gate1"),
+                             _GatedUnit(g, q + "layer6_gate2.", 32, fusion, gate, x3, device, "c2f.layer6_gate2"))
+            wt = g(q + "upsample_conv.0.weight")                             # [Cin, 32, 2, 2]
+            self.up_deconv = mk([(0, 0, 0, wt.permute(2, 3, 1, 0).reshape(4 * 32, wt.shape[0]))], 1, 4 * 32, epi=_lib.EPI_SHUFFLE, act=_lib.ACT_RELU,
+                                bias=g(q + "upsample_conv.0.bias"), shuffle_k=2, name="c2f.upsample_deconv")
+            self.up_conv = mk(conv_segments(g(q + "upsample_conv.2.weight"), [32]), 1, 32, name="c2f.upsample_conv")
+            self.out_ng = mk(conv_segments(g(q + "output_conv.weight"), [32]), 1, 1, epi=_lib.EPI_F32, bias=g(q + "output_conv.bias"), name="c2f.output_conv")
+            return
         self.refine = {i: _GatedBlock(g, f"{q}refinenet{i}.", features, fusion, gate, x3, device, f"c2f.refinenet{i}", two_inputs=i != 5)
                        for i in range(1, 6)}
         h2 = self.coarse_chl[0]
@@ -176,16 +218,17 @@ class BiDirectionalFusionB200:
         self.out2_fusion = _GatedBlock(g, q + "output_conv2_fusion.", h2, fusion, gate, x3, device, "c2f.output_conv2_fusion", two_inputs=False)
         self.out3 = mk([(0, 0, 0, g(q + "output_conv3.0.weight")[:, :, 0, 0])], 1, 1, epi=_lib.EPI_F32, bias=g(q + "output_conv3.0.bias"),
                        name="c2f.output_conv3")
-        after = list(fine_chl_after_coarse2fine)
-        self.f2c = FusionUnetB200(sd, prefix, [c + f for c, f in zip(self.coarse_chl, after)], temp_chl, dec_chl, x3, device,
-                                  in_splits=list(zip(self.coarse_chl, after)), names=("fusion_layers_1", "fusion_layers_2", "f2r_agg"))
-        self.ws: Dict[tuple, Workspace] = {}
 
     def flops(self, B: int, sizes) -> float:
         """sizes: (h, w) of the six fine levels, finest first (level 0 = twice level 1)."""
         F_ = self.features
         px = [B * h * w for h, w in sizes]
         f = sum(2.0 * px[i + 1] * 9 * fc * F_ for i, fc in enumerate(self.fine_chl))
+        if self.only_gate:
+            for lvl in range(1, 6):                                  # layer<lvl>_gate* work on level 6 - lvl
+                f += px[6 - lvl] * (self.gates[lvl][0].flops_per_pixel() + self.gates[lvl][1].flops_per_pixel())
+            f += px[1] * 2.0 * self.fine_chl[0] * 128 + px[0] * (2.0 * 9 * 32 * 32 + self.gates[6][0].flops_per_pixel() + self.gates[6][1].flops_per_pixel() + 2.0 * 9 * 32)
+            return f + self.f2c.flops(B, sizes)
         for r in range(1, 6):                                    # refinenet r works at level r, its out_conv at level r-1
             blk = self.refine[r]
             units = (blk.u1.flops_per_pixel() if blk.u1 else 0.0) + blk.u2.flops_per_pixel()
@@ -213,6 +256,30 @@ class BiDirectionalFusionB200:
             o, orl = A(f"l{i + 1}_rn", B, src.H, src.W, Fe), A(f"l{i + 1}_rn_relu", B, src.H, src.W, Fe)
             self.layer_rn[i]([src], out=o, relu_out=orl)
             rn.append(o); rn_relu.append(orl)
+        if self.only_gate:
+            def two_units(lvl, x, x_relu, c, feat):
+                u1, u2 = self.gates[lvl]
+                m, m_relu = A(f"g{lvl}_m", B, x.H, x.W, feat), A(f"g{lvl}_m_relu", B, x.H, x.W, feat)
+                u1(A, f"g{lvl}_u1", x, x_relu, c, None, m, m_relu)                          # :262-263 (gate1 then gate2 on the same coarse map)
+                o = A(f"g{lvl}_o", B, x.H, x.W, feat)
+                u2(A, f"g{lvl}_u2", m, m_relu, c, None, o, None)
+                return o
+            paths = [two_units(lvl, rn[5 - lvl], rn_relu[5 - lvl], c_feat[6 - lvl], Fe) for lvl in range(1, 6)]   # layer1_* : layer_5_rn with coarse[5], ...
+            H0, W0 = fine[0].H * 2, fine[0].W * 2
+            if (c_feat[0].H, c_feat[0].W) != (H0, W0):
+                raise ValueError(f"finest coarse map is {(c_feat[0].H, c_feat[0].W)} but the transposed conv ends at {(H0, W0)}")
+            up_relu = A("ng_up_relu", B, H0, W0, 32)
+            self.up_deconv([fine[0]], out=up_relu)                                         # :256 ConvTranspose2d(k=2, s=2) + bias -> ReLU
+            l0, l0_relu = A("ng_l0", B, H0, W0, 32), A("ng_l0_relu", B, H0, W0, 32)
+            self.up_conv([up_relu], out=l0, relu_out=l0_relu)                              # 3x3 conv, no bias
+            p0 = two_units(6, l0, l0_relu, c_feat[0], 32)
+            depth = ws.f32("c2f_depth", B, 1, H0, W0)
+            self.out_ng([p0], out_f32=depth, out_f32_ld=1)                                 # :280 output_conv (3x3, bias)
+            feats = [p0] + paths[::-1]                                                     # [::-1] of [path_5 .. path_1, path_0]
+            if trace is not None:
+                trace["c2f_feats"] = [t.to_nchw() for t in feats]
+                trace["c2f_depth"] = depth.clone()
+            return self.f2c.forward(c_feat, feats, pred1, depth, update_base, trace)
         size_of = lambda a: (a.H, a.W)
         path_5 = self.refine[5](A, "r5", rn[4], rn_relu[4], None, None, c_feat[5], size_of(rn[3]), A("path_5", B, rn[3].H, rn[3].W, Fe))
         path_4 = self.refine[4](A, "r4", path_5, None, rn[3], rn_relu[3], c_feat[4], size_of(rn[2]), A("path_4", B, rn[2].H, rn[2].W, Fe))
@@ -240,6 +307,7 @@ class BiDirectionalFusionB200:
 class BiDirectionalFusion(nn.Module):
     """Operator-level drop-in for the reference's registered ``BiDirectionalFusion`` (same keywords, same state dict,
     same forward arguments); CUDA only.  ``glb_att=True`` (dead in every shipped config) is not implemented."""
+    HEAVY = False
 
     def __init__(self, encoder_name="", coarse2fine=True, coarse2fine_type="self-agg", fine2coarse=True,
                  coarse_chl=(32, 256, 256, 256, 256, 256), fine_chl=(32, 32, 64, 96, 960),
@@ -247,6 +315,7 @@ class BiDirectionalFusion(nn.Module):
                  dec_chl=(512, 256, 128, 64, 32), glb_att=False, att_dim=256, select_feat_index=(-1,), pe_type="none",
                  precision: str = "bf16"):
         super().__init__()
+        self.heavy = type(self).HEAVY
         if glb_att or not coarse2fine:
             raise NotImplementedError("BiDirectionalFusion: glb_att=True / coarse2fine=False are not implemented")
         if coarse2fine_type not in C2F_TYPES:
@@ -256,7 +325,7 @@ class BiDirectionalFusion(nn.Module):
         self.cfg = dict(coarse_chl=list(coarse_chl), fine_chl=list(fine_chl), fine_chl_after_coarse2fine=list(fine_chl_after_coarse2fine),
                         temp_chl=list(temp_chl), dec_chl=list(dec_chl))
         self._weights: "OrderedDict[str, torch.Tensor]" = OrderedDict(
-            (k, torch.zeros(shp)) for k, shp in bifusion_weight_spec(coarse2fine_type=coarse2fine_type, **self.cfg).items())
+            (k, torch.zeros(shp)) for k, shp in bifusion_weight_spec(coarse2fine_type=coarse2fine_type, heavy=self.heavy, **self.cfg).items())
         self._engine: Optional[BiDirectionalFusionB200] = None
 
     def state_dict(self, *args, **kwargs):
@@ -281,7 +350,7 @@ class BiDirectionalFusion(nn.Module):
         if self._engine is None or self._engine.device != device:
             _lib.load()
             self._engine = BiDirectionalFusionB200(self._weights, "", coarse2fine_type=self.coarse2fine_type, x3=self.precision == "fp32",
-                                                   device=device, **self.cfg)
+                                                   device=device, heavy=self.heavy, **self.cfg)
         return self._engine
 
     @torch.no_grad()
@@ -294,3 +363,10 @@ class BiDirectionalFusion(nn.Module):
         f = [to_act(t) for t in f_feat]
         out = eng.forward(c, f, pred1.float().contiguous(), None, None if update_base is None else update_base.float().contiguous(), trace)
         return out.clone()
+
+
+@MODELS.register_module()
+class BiDirectionalFusionHeavy(BiDirectionalFusion):
+    """``BiDirectionalFusionHeavy`` (bi_directional_fusion_model.py:517-677): the same model with three-conv encoder blocks
+    (SingleConvCNNLNHeavy) and five-conv decoder blocks (DoubleConvHeavy)."""
+    HEAVY = True

@@ -852,6 +852,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 8; ++j) t[j] += bias8[j];
               if (EPI == PRV2_EPI_SHUFFLE) {
+                if (ACT != PRV2_ACT_NONE) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) t[j] = act_fn<ACT>(t[j]);
+                }
                 const int k = p.shuffle_k;
                 const size_t opix = ((size_t)q.img * (pH * k) + (q.h * k + sh_ky)) * (pW * k) + (q.w * k + sh_kx);
                 act_store8(out_hi, out_lo, opix * out_cs + sh_co, t);
@@ -1150,7 +1154,7 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   const int act = d->act;
-  PRV2_CHECK_ARG(act >= PRV2_ACT_NONE && act <= PRV2_ACT_SIGMOID_GATE, "prv2_umma_gemm: unknown activation %d", act);
+  PRV2_CHECK_ARG(act >= PRV2_ACT_NONE && act <= PRV2_ACT_IDENTITY, "prv2_umma_gemm: unknown activation %d", act);
   PRV2_CHECK_ARG(act != PRV2_ACT_SIGMOID_GATE || (d->epi == PRV2_EPI_STORE && d->res_hi),
                  "prv2_umma_gemm: SIGMOID_GATE needs the STORE epilogue with `res` = the gated tensor (res2 is then added, relu copy allowed)");
   cudaError_t err = cudaSuccess;
@@ -1167,11 +1171,12 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
     case PRV2_EPI_LN_GELU:
       err = act == PRV2_ACT_GELU_TANH ? PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU_TANH)
             : act == PRV2_ACT_RELU    ? PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_RELU)
+            : act == PRV2_ACT_IDENTITY ? PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_NONE)         // LayerNorm only (SingleConvCNNLNHeavy)
                                       : PRV2_L(PRV2_EPI_LN_GELU, PRV2_ACT_GELU);
       break;
     case PRV2_EPI_RESID_F32: err = use_fast_resid ? PRV2_L2(PRV2_EPI_RESID_F32, PRV2_ACT_NONE, true) : PRV2_L2(PRV2_EPI_RESID_F32, PRV2_ACT_NONE, false); break;
     case PRV2_EPI_F32: err = PRV2_L2(PRV2_EPI_F32, PRV2_ACT_NONE, false); break;
-    case PRV2_EPI_SHUFFLE: err = PRV2_L2(PRV2_EPI_SHUFFLE, PRV2_ACT_NONE, false); break;
+    case PRV2_EPI_SHUFFLE: err = act == PRV2_ACT_RELU ? PRV2_L2(PRV2_EPI_SHUFFLE, PRV2_ACT_RELU, false) : PRV2_L2(PRV2_EPI_SHUFFLE, PRV2_ACT_NONE, false); break;
     default: err = PRV2_L2(PRV2_EPI_HEAD, PRV2_ACT_NONE, false); break;
   }
 #undef PRV2_L

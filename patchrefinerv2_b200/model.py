@@ -243,6 +243,25 @@ class PatchRefiner(nn.Module):
         depth, feats = eng["coarse"].forward(image_lr.float().contiguous())
         return feats, depth
 
+    def _coarse_forward_sharded(self, eng, image_lr, rank: int, world: int):
+        """Coarse pass of frames [rank * F/world, (rank + 1) * F/world) on this rank, then all_gather of the six feature maps
+        (16-bit planes) and the coarse depth: every rank ends with the whole batch's coarse results in frame order."""
+        dist = torch.distributed
+        F_ = image_lr.shape[0]
+        fl = F_ // world
+        feats, depth = self.coarse_forward(image_lr[rank * fl:(rank + 1) * fl])
+        ws = eng["ws"]
+        out = []
+        for li, f in enumerate(feats):
+            g = ws.act(f"cg{li}_{F_}", F_, f.H, f.W, f.C, cs=f.cs)
+            dist.all_gather_into_tensor(g.hi, f.hi.contiguous())
+            if f.lo is not None:
+                dist.all_gather_into_tensor(g.lo, f.lo.contiguous())
+            out.append(g)
+        gd = ws.f32(f"cgd_{F_}", F_, 1, depth.shape[-2], depth.shape[-1])
+        dist.all_gather_into_tensor(gd, depth.contiguous())
+        return out, gd
+
     def _gather_batch(self, eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, idx: np.ndarray, P: int):
         """Crops and coarse ROIs of the work items ``idx`` (global indices frame * P + patch, ascending) into one batch: every
         frame present in the batch contributes a contiguous run of rows (baseline_pretrain.py:272-296, patchrefiner.py:199-217)."""
@@ -375,7 +394,12 @@ class PatchRefiner(nn.Module):
             bboxs_np = _broadcast_bboxs(bboxs_np, dev)
         rois_np = tiling.bboxs_to_feat(bboxs_np, (H, W), (ph, pw))[:, 1:]
 
-        coarse_feats, coarse_depth = self.coarse_forward(image_lr)
+        if world > 1 and F_ % world == 0:
+            # the coarse passes of a batch are sharded too (a contiguous block of frames per rank) and all-gathered: ~100 MB of
+            # features per frame over NVLink instead of F replicated 0.94-TFLOP passes on every rank
+            coarse_feats, coarse_depth = self._coarse_forward_sharded(eng, image_lr, rank, world)
+        else:
+            coarse_feats, coarse_depth = self.coarse_forward(image_lr)
         if hr_ready is not None:
             torch.cuda.current_stream(dev).wait_event(hr_ready)
             image_hr.record_stream(torch.cuda.current_stream(dev))
@@ -491,8 +515,9 @@ class PatchRefinerPlus(PatchRefiner):
             raise NotImplementedError(f"coarse_branch.type={_get(cb, 'type')!r}: only the DA2 (DepthAnythingV2) coarse branch is implemented")
         if _get(fb, "type") != "LightWeightRefiner" or _get(fb, "with_decoder", False):
             raise NotImplementedError("refiner.fine_branch must be LightWeightRefiner(with_decoder=False)")
-        if _get(fu, "type") != "BiDirectionalFusion" or _get(fu, "coarse2fine_type") not in C2F_TYPES or _get(fu, "glb_att", False):
-            raise NotImplementedError(f"fusion_model {_get(fu, 'type')!r}/{_get(fu, 'coarse2fine_type')!r}: BiDirectionalFusion with coarse2fine_type in {sorted(C2F_TYPES)}")
+        if _get(fu, "type") not in ("BiDirectionalFusion", "BiDirectionalFusionHeavy") or _get(fu, "coarse2fine_type") not in C2F_TYPES or _get(fu, "glb_att", False):
+            raise NotImplementedError(f"fusion_model {_get(fu, 'type')!r}/{_get(fu, 'coarse2fine_type')!r}: BiDirectionalFusion[Heavy] with coarse2fine_type in {sorted(C2F_TYPES)}")
+        self._fu_heavy = _get(fu, "type") == "BiDirectionalFusionHeavy"
         self._cb_cfg, self._fu_cfg = dict(_get(cb, "model_cfg")), fu
         self.coarse_condition = bool(_get(fb, "coarse_condition", True))
         self.fusion_feat_level = int(_get(config, "fusion_feat_level"))
@@ -516,7 +541,7 @@ class PatchRefinerPlus(PatchRefiner):
         for k, shp in dav2_weight_spec(self._cb_cfg["encoder"], self._cb_cfg["features"], self._cb_cfg["out_channels"]).items():
             self._weights["coarse_branch." + k] = torch.zeros(shp)
         keys = ("coarse_chl", "fine_chl", "fine_chl_after_coarse2fine", "temp_chl", "dec_chl")
-        for k, shp in bifusion_weight_spec(*[_get(fu, x) for x in keys], coarse2fine_type=_get(fu, "coarse2fine_type")).items():
+        for k, shp in bifusion_weight_spec(*[_get(fu, x) for x in keys], coarse2fine_type=_get(fu, "coarse2fine_type"), heavy=self._fu_heavy).items():
             self._weights["refiner_fusion_model." + k] = torch.zeros(shp)
         path = _get(cb, "pretrained")
         if path:
@@ -564,7 +589,7 @@ class PatchRefinerPlus(PatchRefiner):
         return dict(
             coarse=DepthAnythingV2B200(sd, "coarse_branch.", self._cb_cfg["encoder"], self._cb_cfg["features"], self._cb_cfg["out_channels"], self.max_depth, x3, device),
             fusion=BiDirectionalFusionB200(sd, "refiner_fusion_model.", *[_get(fu, k) for k in keys], coarse2fine_type=_get(fu, "coarse2fine_type"),
-                                           x3=x3, device=device),
+                                           x3=x3, device=device, heavy=self._fu_heavy),
             ws=Workspace(device, x3), device=device, masks={},
             enc_mean=torch.tensor(self._enc_mean, device=device).view(1, -1, 1, 1), enc_std=torch.tensor(self._enc_std, device=device).view(1, -1, 1, 1))
 

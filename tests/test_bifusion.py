@@ -11,6 +11,9 @@ from oracle import ref_shim
 from oracle.make_golden import BIFUSION, BIFUSION_SIZES_C, BIFUSION_SIZES_F, BIFUSION_TYPES, sd_digest
 
 
+ABLATIONS = [("only-gate", False), ("coarse-gated", True), ("self-agg", True)]     # (coarse2fine_type, heavy)
+
+
 def _case(t, seed_w=5, seed_x=3, B=2):
     sd = O.init_bidirectional_fusion_state_dict(seed=seed_w, coarse2fine_type=t, **BIFUSION)
     c, f, p1, p2 = O.synthetic_fusion_inputs(BIFUSION["coarse_chl"], BIFUSION["fine_chl"], BIFUSION_SIZES_C, BIFUSION_SIZES_F, B, seed_x)
@@ -60,8 +63,14 @@ def test_product_state_dict_and_registry_surface():
         assert not res.missing_keys and not res.unexpected_keys
         with pytest.raises(RuntimeError):
             m.load_state_dict({"nope": torch.zeros(1)}, strict=True)
+    for t, heavy in ABLATIONS:                                                    # the four ablation configs' fusion models
+        m = build_model(dict(type="BiDirectionalFusionHeavy" if heavy else "BiDirectionalFusion", encoder_name="x", coarse2fine_type=t,
+                             **{k: list(v) for k, v in BIFUSION.items()}))
+        sd = O.init_bidirectional_fusion_state_dict(seed=5, coarse2fine_type=t, heavy=heavy, **BIFUSION)
+        assert set(m.state_dict().keys()) == set(sd.keys())
+        assert all(tuple(v.shape) == tuple(sd[k].shape) for k, v in m.state_dict().items())
     with pytest.raises(NotImplementedError):
-        build_model(dict(type="BiDirectionalFusion", coarse2fine_type="only-gate"))
+        build_model(dict(type="BiDirectionalFusion", coarse2fine_type="no-such-type"))
     with pytest.raises(NotImplementedError):
         build_model(dict(type="BiDirectionalFusion", glb_att=True))
     m = build_model(dict(type="BiDirectionalFusion", coarse2fine_type="coarse-gated"))
@@ -107,6 +116,36 @@ def test_b200_bifusion_matches_reference_golden_and_oracle(dev, golden_dir, t, p
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("t,heavy", ABLATIONS)
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 6e-2)])
+def test_b200_ablation_variants_match_oracle(dev, t, heavy, precision, tol):
+    """C2FNOENCModule ('only-gate': transposed-conv level 0, two gated units per level, no top-down path) and
+    BiDirectionalFusionHeavy (conv-LN-conv-LN-conv-GELU encoder blocks, five-conv decoder blocks) on the kernels, against the
+    oracle that tests/test_bifusion.py::test_oracle_covers_the_ablation_variants_bit_identically pins to the reference modules."""
+    from patchrefinerv2_b200 import build_model
+    sd = O.init_bidirectional_fusion_state_dict(seed=5, coarse2fine_type=t, heavy=heavy, **BIFUSION)
+    c, f, p1, p2 = O.synthetic_fusion_inputs(BIFUSION["coarse_chl"], BIFUSION["fine_chl"], BIFUSION_SIZES_C, BIFUSION_SIZES_F, 2, 3)
+    m = build_model(dict(type="BiDirectionalFusionHeavy" if heavy else "BiDirectionalFusion", encoder_name="x", coarse2fine_type=t, precision=precision,
+                         **{k: list(v) for k, v in BIFUSION.items()}))
+    m.load_state_dict(sd)
+    m = m.cuda()
+    tr, otr = {}, {}
+    cd, fd = [x.to(dev) for x in c], [x.to(dev) for x in f]
+    off = m(c_feat=cd, f_feat=fd, pred1=p1.to(dev), pred2=p2.to(dev), update_base=None, trace=tr).cpu()
+    depth = m(c_feat=cd, f_feat=fd, pred1=p1.to(dev), pred2=p2.to(dev), update_base=p1.to(dev)).cpu()
+    with torch.no_grad():
+        ref_off = O.bidirectional_fusion(sd, "", c, f, p1, p2, None, t, otr, heavy=heavy)
+        ref_depth = O.bidirectional_fusion(sd, "", c, f, p1, p2, p1, t, heavy=heavy)
+    assert _rel(tr["c2f_depth"].cpu(), otr["c2f_depth"]) < tol
+    for a, b in zip(tr["c2f_feats"], otr["c2f_feats"]):
+        assert a.shape == b.shape and _rel(a.cpu(), b) < tol
+    for a, b in zip(tr["fusion_enc"], otr["fusion_enc"]):
+        assert _rel(a.cpu(), b) < tol * 3
+    assert off.shape == ref_off.shape and _rel(off, ref_off) < tol * (3 if heavy else 1)
+    assert float((depth - ref_depth).abs().max()) < tol * (3 if heavy else 1) * float(ref_off.abs().max()) and depth.min() >= 0
+
+
+@pytest.mark.gpu
 def test_b200_gate_and_ln_relu_epilogues_vs_torch(dev):
     """The two epilogues BiDirectionalFusion adds to prv2_umma_gemm, each against a plain PyTorch fp32 reference:
     LN(acc + bias) -> ReLU over a virtual concat, and res * sigmoid(acc) (+ res2, + ReLU copy)."""
@@ -140,7 +179,7 @@ def test_b200_gate_and_ln_relu_epilogues_vs_torch(dev):
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
 @pytest.mark.parametrize("t,heavy", [("only-gate", False), ("coarse-gated", True), ("self-agg", True)])
 def test_oracle_covers_the_ablation_variants_bit_identically(t, heavy):
-    """The four ablation configs' fusion models (C2FNOENCModule 'only-gate', BiDirectionalFusionHeavy): oracle only -- the product
+    """The four ablation configs' fusion models (C2FNOENCModule 'only-gate', BiDirectionalFusionHeavy): the oracle against the reference -- the product
     raises NotImplementedError for them -- pinned against the reference modules so the next step has a checker."""
     ref_shim.install()
     from estimator.models.blocks import bi_directional_fusion_model as ref

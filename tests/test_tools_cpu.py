@@ -188,3 +188,54 @@ def test_reference_configs_construct_or_fail_loudly():
             why[key] += 1
     assert ok == {"PatchRefiner": 3, "PatchRefinerPlus": 4}
     assert why == {"ZoeDepth coarse branch": 46, "pretrain_stage": 14, "convnext encoder": 1, "other model family": 31}
+
+
+def test_compute_metrics_matches_reference_and_hand_values():
+    """Frame egress: compute_errors / compute_metrics against hand-computed values and, where the reference tree
+    is present, against estimator/utils/metric.py itself on random depth maps (crops, clamps, masks, soft edge error)."""
+    import numpy as np
+    import torch
+    from patchrefinerv2_b200 import metrics
+    gt, pred = np.array([1.0, 2.0, 4.0]), np.array([1.0, 2.5, 2.0])
+    e = metrics.compute_errors(gt, pred)
+    assert abs(e["a1"] - 1 / 3) < 1e-12 and abs(e["a2"] - 2 / 3) < 1e-12 and abs(e["a3"] - 2 / 3) < 1e-12      # ratios 1, 1.25 (not < 1.25), 2 (not < 1.953)
+    assert abs(e["abs_rel"] - (0 + 0.25 + 0.5) / 3) < 1e-12 and abs(e["rmse"] - np.sqrt((0 + 0.25 + 4) / 3)) < 1e-12
+    g = torch.Generator().manual_seed(0)
+    gt_t = torch.rand(1, 1, 480, 640, generator=g) * 12
+    pr_t = (gt_t * (1 + 0.1 * torch.randn(1, 1, 480, 640, generator=g))).clamp_min(0)
+    pr_small = torch.nn.functional.interpolate(pr_t, (240, 320), mode="bilinear", align_corners=False)
+    edges = torch.from_numpy(metrics.get_boundaries(gt_t[0, 0].numpy(), th=3.0, dilation=3))
+    mine = metrics.compute_metrics(gt_t, pr_small, disp_gt_edges=edges)
+    assert set(mine) == {"a1", "a2", "a3", "abs_rel", "rmse", "log_10", "rmse_log", "silog", "sq_rel", "see"} and 0 < mine["a1"] < 1
+    from oracle import ref_shim
+    if ref_shim.reference_available():
+        cwd = os.getcwd()
+        try:
+            ref_shim.install()
+            from estimator.utils import metric as R
+            for kw in (dict(), dict(garg_crop=True, eigen_crop=False), dict(eigen_crop=False, garg_crop=False, min_depth_eval=1e-3, max_depth_eval=80), dict(dataset="kitti")):
+                theirs = R.compute_metrics(gt_t, pr_small.clone(), disp_gt_edges=edges, **kw)
+                ours = metrics.compute_metrics(gt_t, pr_small.clone(), disp_gt_edges=edges, **kw)
+                for k in theirs:
+                    assert np.allclose(float(ours[k]), float(theirs[k]), rtol=0, atol=0), (k, kw)
+            assert np.array_equal(R.get_boundaries(gt_t[0, 0].numpy(), th=3.0, dilation=3), edges.numpy())
+        finally:
+            os.chdir(cwd)
+
+
+def test_benchmark_reporter_counts_and_file(tmp_path):
+    """Tester.benchmark's bookkeeping (tester.py:325-404) with a stand-in model: warm-up forwards are not timed, every run reports
+    (total - warm-up) / time, the summary carries the average and variance, benchmark.txt is written."""
+    import torch
+    from patchrefinerv2_b200 import metrics
+    calls = []
+
+    class Fake:
+        patch_process_shape = (14, 14)
+
+        def __call__(self, **kw):
+            calls.append(kw["cai_mode"])
+            return torch.zeros(1), {}
+    res = metrics.benchmark(Fake(), [{"image_lr": None, "image_hr": None}], cai_mode="m1", repeat_times=2, num_warmup=3, total_iters=5, work_dir=str(tmp_path), log=lambda *a: None)
+    assert len(calls) == 10 and set(res) == {"unit", "overall_fps_1", "overall_fps_2", "average_fps", "fps_variance"}
+    assert "Average fps of 2 evaluations" in open(tmp_path / "benchmark.txt").read()

@@ -33,7 +33,9 @@ def parse_args(argv=None):
     ap.add_argument("--cfg-option", nargs="+", default=[], help="dotted key=value overrides of the config")
     ap.add_argument("--save", action="store_true")
     ap.add_argument("--work-dir", default="./work_dir/predictions")
-    ap.add_argument("--test-type", default="general", choices=["general", "normal"])
+    ap.add_argument("--test-type", default="general", choices=["general", "benchmark", "normal"],
+                    help="general: image directory -> depth maps (Tester.run); benchmark: Tester.benchmark on the same images (frames/s, benchmark.txt)")
+    ap.add_argument("--repeat-times", type=int, default=10, help="--test-type benchmark: number of runs (tester.py:326)")
     ap.add_argument("--gray-scale", action="store_true")
     ap.add_argument("--image-raw-shape", nargs=2, type=int, default=[2160, 3840])
     ap.add_argument("--patch-split-num", nargs=2, type=int, default=[4, 4])
@@ -49,8 +51,8 @@ def build(args):
     from patchrefinerv2_b200.config import Config, parse_cfg_options
     cfg = Config.fromfile(args.config)
     cfg.merge_from_dict(parse_cfg_options(args.cfg_option))
-    if args.test_type != "general":
-        raise NotImplementedError("only --test-type general (image directory) is implemented; dataset evaluation is out of scope")
+    if args.test_type not in ("general", "benchmark"):
+        raise NotImplementedError("--test-type general (image directory) and benchmark are implemented; dataset evaluation is out of scope")
     mcfg = cfg.model.to_dict()
     # weights come from --ckp-path: the per-branch 'pretrained' / pretrain_* files named by the training configs are optional here
     for br in (mcfg["config"].get("coarse_branch", {}), mcfg["config"].get("refiner", {}).get("fine_branch", {})):
@@ -86,6 +88,21 @@ def main(argv=None):
     random.seed(args.seed); np.random.seed(args.seed); torch.manual_seed(args.seed)
     model = model.cuda().eval()
     img_dir = cfg.general_dataloader.dataset.rgb_image_dir
+    if args.test_type == "benchmark":                                      # Tester.benchmark (tester.py:325-404)
+        from patchrefinerv2_b200 import metrics
+        batches = []
+        for name, image_hr in frames.iter_frames(img_dir, args.image_raw_shape):
+            hr = image_hr.cuda().unsqueeze(0)
+            batches.append({"image_lr": model.resizer(hr), "image_hr": hr})
+            if len(batches) >= 50:
+                break
+        res = metrics.benchmark(model, batches, args.cai_mode, args.process_num, args.image_raw_shape, args.patch_split_num, repeat_times=args.repeat_times,
+                                work_dir=args.work_dir if rank == 0 else None, shard=shard, log=print if rank == 0 else (lambda *a: None))
+        if shard:
+            torch.distributed.destroy_process_group()
+        if rank == 0:
+            print(res)
+        return
     n, t0 = 0, time.perf_counter()
     for name, image_hr in frames.iter_frames(img_dir, args.image_raw_shape):
         hr = image_hr.cuda().unsqueeze(0)
