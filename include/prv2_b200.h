@@ -30,7 +30,7 @@ typedef uint16_t prv2_bf16;            /* raw bfloat16 bits */
 #define PRV2_EUNSUPPORTED (-3)         /* shape outside what the kernels implement */
 
 /* ABI version: bumped whenever a signature or the GemmDesc layout changes; the Python binding refuses any other value. */
-#define PRV2_ABI_VERSION 203
+#define PRV2_ABI_VERSION 204
 int prv2_version(void);
 /* sha256 of the CUDA sources + flags this library was compiled from (stamped by build.py with -DPRV2_BUILD_DIGEST);
  * the binding compares it with the digest of the sources it sits next to, so a stale .so is an error, not a silent mismatch. */
@@ -252,12 +252,30 @@ int prv2_tap_stencil(const float* taps, int N, int H, int W, int ld, const float
 int prv2_final_conv3x3(const prv2_bf16* feat_hi, const prv2_bf16* feat_lo, int N, int H, int W, int C, int cs, const float* w9c,
                        const float* base, float* out, prv2_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * ZoeDepth metric-bins head, per-pixel part (the head's 1x1 convolutions run on prv2_umma_gemm)    [HBM-bound, fp32]
+ * ------------------------------------------------------------------------------------------ */
+
+/* AttractorLayerUnnormed.forward (external/zoedepth/models/layers/attractor.py:139-208) after its 1x1-conv MLP: a_raw [B,h,w,a_ld]
+ * holds the MLP output (pre-softplus; the first n_attractors columns are used), b_prev [B,hp,wp,n_bins] the previous level's bin
+ * centres (prev_is_raw != 0: they are the seed regressor's PRE-softplus output, localbins_layers.py:71-96).  b_out [B,h,w,n_bins] =
+ * bilinear_ac(b_prev) + mean_i (or sum_i) inv_attractor(softplus(a_i) - bilinear_ac(b_prev)), inv_attractor(dx) = dx / (1 + alpha dx^2)
+ * (attractor.py:45-57; the reference calls it with its default alpha = 300 whatever the config says, :194-197). */
+int prv2_zoe_attractor(const float* a_raw, int a_ld, int n_attractors, const float* b_prev, int hp, int wp, int prev_is_raw,
+                       float* b_out, int B, int h, int w, int n_bins, float alpha, int mean, prv2_stream_t stream);
+/* ConditionalLogBinomial tail + LogBinomial + expectation (layers/dist_layers.py:29-122, zoedepth_v1.py:212-219): pt_raw [B,H,W,pt_ld]
+ * = the 4 pre-softplus outputs of the conditional MLP; centers [B,hb,wb,n_bins] the final bin centres; depth [B,1,H,W] =
+ * sum_k softmax((log C(K-1,k) + k log p + (K-1-k) log(1-p)) / T)_k * bilinear_ac(centers)_k. */
+int prv2_zoe_logbinomial_depth(const float* pt_raw, int pt_ld, const float* centers, int hb, int wb, float* depth,
+                               int B, int H, int W, int n_bins, float min_temp, float max_temp, prv2_stream_t stream);
+
 /* act <-> fp32 helpers (layout changes at the API edge and for tests). */
 int prv2_nchw_f32_to_act(const float* in, int N, int C, int H, int W,
                          prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
 int prv2_act_to_nchw_f32(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int C, int H, int W, int in_cs,
                          float* out, prv2_stream_t stream);
-/* 2x2 space-to-depth phase split for the stride-2 conv (dpt.py:75-80): out[p] [N,H/2,W/2,C], p=(py,px). */
+/* 2x2 space-to-depth phase split for the stride-2 conv (dpt.py:75-80): out[p] [N,ceil(H/2),ceil(W/2),C], p=(py,px); zero where an odd
+ * H / W leaves a phase one row / column short (that row / column is the conv's padding). */
 int prv2_phase_split(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int H, int W, int C, int in_cs,
                      prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
 /* fp32 [rows, cols] -> bf16 hi[,lo] with pitch (weights packing helper). */

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libprv2_b200.so")
-SOURCES = ["geometry.cu", "pointwise.cu", "umma_gemm.cu", "attention.cu"]
+SOURCES = ["geometry.cu", "pointwise.cu", "umma_gemm.cu", "attention.cu", "zoe_head.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "prv2_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -372,22 +372,27 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const bf16* __restrict
   }
 }
 
+// out[(py*2+px)*N + n, y2, x2, :] = in[n, 2*y2 + py, 2*x2 + px, :], zero where that source pixel does not exist: with odd H or W
+// the four phases of a stride-2 conv have ceil / floor sizes, all are stored at the conv's output size ceil(H/2) x ceil(W/2)
+// (the missing row / column is exactly the conv's zero padding, dpt.py:72-80).
 __global__ void __launch_bounds__(256) phase_split_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il, int N, int H, int W,
                                                           int C, int in_cs, bf16* __restrict__ oh, bf16* __restrict__ ol, int out_cs,
                                                           long long total) {
-  const int cv = C / 8, H2 = H / 2, W2 = W / 2;
+  const int cv = C / 8, H2 = (H + 1) / 2, W2 = (W + 1) / 2;
   const size_t plane = (size_t)N * H2 * W2 * out_cs;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(idx % cv) * 8;
     long long pix = idx / cv;
-    const int x = (int)(pix % W);
-    pix /= W;
-    const int y = (int)(pix % H);
-    const int n = (int)(pix / H);
-    const int ph = (y & 1) * 2 + (x & 1);
-    float v[8];
-    act_load8(ih, il, (((size_t)n * H + y) * W + x) * in_cs + c8, v);
-    act_store8(oh, ol ? ol : nullptr, ph * plane + (((size_t)n * H2 + (y >> 1)) * W2 + (x >> 1)) * out_cs + c8, v);
+    const int x2 = (int)(pix % W2);
+    pix /= W2;
+    const int y2 = (int)(pix % H2);
+    pix /= H2;
+    const int n = (int)(pix % N);
+    const int ph = (int)(pix / N);
+    const int y = 2 * y2 + (ph >> 1), x = 2 * x2 + (ph & 1);
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (y < H && x < W) act_load8(ih, il, (((size_t)n * H + y) * W + x) * in_cs + c8, v);
+    act_store8(oh, ol ? ol : nullptr, ph * plane + (((size_t)n * H2 + y2) * W2 + x2) * out_cs + c8, v);
   }
 }
 
@@ -530,9 +535,9 @@ extern "C" int prv2_act_to_nchw_f32(const prv2_bf16* in_hi, const prv2_bf16* in_
 extern "C" int prv2_phase_split(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int H, int W, int C, int in_cs, prv2_bf16* out_hi,
                                 prv2_bf16* out_lo, int out_cs, prv2_stream_t stream) {
   PRV2_CHECK_ARG(in_hi && out_hi, "prv2_phase_split: null pointer");
-  PRV2_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0, "prv2_phase_split: H,W even; C,pitches multiples of 8");
+  PRV2_CHECK_ARG(H > 0 && W > 0 && C % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0, "prv2_phase_split: C and the pitches must be multiples of 8");
   PRV2_CHECK_ARG((in_lo == nullptr) == (out_lo == nullptr), "prv2_phase_split: lo planes must both be present or absent");
-  const long long total = (long long)N * H * W * (C / 8);
+  const long long total = 4LL * N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   if (total == 0) return PRV2_OK;
   phase_split_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, N, H, W, C, in_cs,
                                                                            (bf16*)out_hi, (bf16*)out_lo, out_cs, total);

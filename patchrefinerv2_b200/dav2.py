@@ -124,7 +124,7 @@ class DepthAnythingV2B200:
         oc, Fe = self.oc, self.features
         px = lambda s: B * (gh * s) * (gw * s)
         f += sum(2.0 * px(1) * D * oc[i] for i in range(4))
-        f += 2.0 * px(1) * oc[0] * oc[0] * 16 + 2.0 * px(1) * oc[1] * oc[1] * 4 + 2.0 * px(0.5) * oc[3] * oc[3] * 9
+        f += 2.0 * px(1) * oc[0] * oc[0] * 16 + 2.0 * px(1) * oc[1] * oc[1] * 4 + 2.0 * px(0.5) * oc[3] * oc[3] * 9      # (even grids; odd ones round the half level up)
         sizes = [4, 2, 1, 0.5]
         f += sum(2.0 * px(sizes[i]) * oc[i] * Fe * 9 for i in range(4))
         conv = lambda s: 2.0 * px(s) * Fe * Fe * 9
@@ -139,8 +139,6 @@ class DepthAnythingV2B200:
         B, _, H, W = x.shape
         assert H % PATCH == 0 and W % PATCH == 0
         gh, gw = H // PATCH, W // PATCH
-        if gh % 2 or gw % 2:
-            raise NotImplementedError("odd token grids (stride-2 reassemble conv) are not implemented")
         T = gh * gw
         D, x3 = self.D, self.x3
         M = B * (T + 1)
@@ -188,9 +186,10 @@ class DepthAnythingV2B200:
         l2_in = A("rs1", B, gh * 2, gw * 2, oc[1])
         self.resize1([pr[1]], out=l2_in)
         l3_in = pr[2]
-        ph4 = A("rs3_phase", 4 * B, gh // 2, gw // 2, oc[3])
+        gh2, gw2 = (gh + 1) // 2, (gw + 1) // 2              # 3x3 stride-2 pad-1 conv (dpt.py:72-80): odd grids round up
+        ph4 = A("rs3_phase", 4 * B, gh2, gw2, oc[3])
         ops.phase_split(pr[3], ph4)
-        l4_in = A("rs3", B, gh // 2, gw // 2, oc[3])
+        l4_in = A("rs3", B, gh2, gw2, oc[3])
         self.resize3([ph4.batch_slice(slice(k * B, (k + 1) * B)) for k in range(4)], out=l4_in)
 
         rn, rn_relu = [], []

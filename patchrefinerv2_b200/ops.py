@@ -196,7 +196,7 @@ def final_conv3x3(feat: Act, w9c: torch.Tensor, base: Optional[torch.Tensor], ou
 
 
 def phase_split(a: Act, out: Act):
-    """out is [4*N, H/2, W/2, C] (phase-major)."""
+    """out is [4*N, ceil(H/2), ceil(W/2), C] (phase-major; zero where an odd H / W leaves a phase one row / column short)."""
     _lib.call("prv2_phase_split", ptr(a.hi), ptr(a.lo), a.N, a.H, a.W, a.C, a.cs, ptr(out.hi), ptr(out.lo), out.cs, stream_ptr(),
               work=("byte", 4.0 * a.N * a.H * a.W * a.C * (2 if a.lo is not None else 1)))
 
@@ -204,3 +204,27 @@ def phase_split(a: Act, out: Act):
 def attention(qkv: Act, B: int, T: int, heads: int, out: Act):
     _lib.call("prv2_attention", ptr(qkv.hi), ptr(qkv.lo), B, T, heads, ptr(out.hi), ptr(out.lo), stream_ptr(),
               work=("flop", 4.0 * B * heads * T * T * 64))
+
+
+def zoe_attractor(a_raw: torch.Tensor, n_attractors: int, b_prev: torch.Tensor, prev_is_raw: bool, alpha: float, mean: bool) -> torch.Tensor:
+    """a_raw fp32 [B,h,w,ld] (attractor MLP output, pre-softplus), b_prev fp32 [B,hp,wp,K] -> new bin centres fp32 [B,h,w,K]
+    (external/zoedepth/models/layers/attractor.py:139-208)."""
+    _chk(a_raw, torch.float32, "a_raw"); _chk(b_prev, torch.float32, "b_prev")
+    B, h, w, ld = a_raw.shape
+    _, hp, wp, K = b_prev.shape
+    out = torch.empty((B, h, w, K), dtype=torch.float32, device=a_raw.device)
+    _lib.call("prv2_zoe_attractor", ptr(a_raw), ld, n_attractors, ptr(b_prev), hp, wp, 1 if prev_is_raw else 0, ptr(out), B, h, w, K,
+              C.c_float(alpha), 1 if mean else 0, stream_ptr(), work=("byte", 4.0 * B * h * w * (2 * K + ld)))
+    return out
+
+
+def zoe_logbinomial_depth(pt_raw: torch.Tensor, centers: torch.Tensor, min_temp: float, max_temp: float) -> torch.Tensor:
+    """pt_raw fp32 [B,H,W,ld>=4] (conditional MLP output, pre-softplus), centers fp32 [B,hb,wb,K] -> metric depth fp32 [B,1,H,W]
+    (layers/dist_layers.py:29-122, zoedepth_v1.py:212-219)."""
+    _chk(pt_raw, torch.float32, "pt_raw"); _chk(centers, torch.float32, "centers")
+    B, H, W, ld = pt_raw.shape
+    _, hb, wb, K = centers.shape
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=pt_raw.device)
+    _lib.call("prv2_zoe_logbinomial_depth", ptr(pt_raw), ld, ptr(centers), hb, wb, ptr(out), B, H, W, K, C.c_float(min_temp), C.c_float(max_temp),
+              stream_ptr(), work=("byte", 4.0 * B * H * W * (ld + 1 + K)))
+    return out

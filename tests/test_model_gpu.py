@@ -153,3 +153,25 @@ def test_batch_of_frames_equals_frame_by_frame(models, tiny_setup, mode, pn):
     sharded, _ = m(mode="infer", image_lr=lrs, image_hr=hrs, cai_mode=mode, process_num=pn, shard=True)
     assert torch.equal(m.last_stats["count_map"][1], cnt_single)
     assert ((sharded - both).abs() / both.abs().clamp_min(1e-3)).max().item() < 1e-3
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("hw", [(98, 126), (112, 154)])
+def test_dav2_non_square_and_odd_token_grids(prec, tol, hw):
+    """DepthAnythingV2 on inputs whose token grid is not square and has odd sides (98x126 -> 7x9 tokens, as 392x518 -> 28x37 does at
+    ZoeDepth's geometry): bicubic position-embedding resampling to a non-square grid, attention over an arbitrary token count, and
+    the 3x3 stride-2 reassemble conv (dpt.py:72-80) on an odd grid, against the oracle -- depth and all six feature maps."""
+    from patchrefinerv2_b200.dav2 import DepthAnythingV2B200
+    sd = O.init_dav2_state_dict("vits", 64, [48, 96, 192, 384], 3)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, *hw, generator=g)
+    with torch.no_grad():
+        want_d, want_f = O.depth_anything_v2(sd, "", x, "vits", 80.0)
+    net = DepthAnythingV2B200(sd, "", "vits", 64, [48, 96, 192, 384], 80.0, prec == "fp32", torch.device(DEV))
+    got_d, got_f = net.forward(x.to(DEV))
+    assert got_d.shape == want_d.shape
+    assert rel_max(got_d.cpu(), want_d) < tol * 3
+    for a, b in zip(got_f, want_f):
+        a = a.to_nchw().cpu()
+        assert a.shape == b.shape, (a.shape, b.shape)
+        assert rel_max(a, b) < tol * 5
