@@ -72,8 +72,8 @@ def test_plus_surface_without_gpu(plus_setup, monkeypatch):
         build_model(dict(type="PatchRefinerPlus", config=cfg))
     with pytest.raises(RuntimeError):                             # no CPU path
         m(mode="infer", image_lr=lr, image_hr=hr, cai_mode="m1", process_num=2)
-    bad = dict(cfg); bad["refiner"] = dict(cfg["refiner"]); bad["refiner"]["fusion_model"] = dict(cfg["refiner"]["fusion_model"], coarse2fine_type="only-gate")
-    with pytest.raises(NotImplementedError):
+    bad = dict(cfg); bad["refiner"] = dict(cfg["refiner"]); bad["refiner"]["fusion_model"] = dict(cfg["refiner"]["fusion_model"], coarse2fine_type="no-such-type")
+    with pytest.raises(NotImplementedError):                      # unknown fusion variants fail loudly
         build_model(dict(type="PatchRefinerPlus", config=bad, fine_encoder=O.ToyFineEncoder(4)))
 
 

@@ -183,7 +183,8 @@ def test_reference_configs_construct_or_fail_loudly():
             ok[m["type"]] += 1
         except (NotImplementedError, KeyError) as e:
             msg = str(e)
-            key = ("ZoeDepth coarse branch" if "ZoeDepth" in msg else "pretrain_stage" if "pretrain_stage" in msg else
+            key = ("other model family" if isinstance(e, KeyError) else
+                   "ZoeDepth coarse branch" if "ZoeDepth" in msg else "pretrain_stage" if "pretrain_stage" in msg else
                    "convnext encoder" if "convnext" in msg else "other model family")
             why[key] += 1
     assert ok == {"PatchRefiner": 3, "PatchRefinerPlus": 4}
