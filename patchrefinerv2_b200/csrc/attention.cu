@@ -1,6 +1,6 @@
 // Fused multi-head attention for the DINOv2 blocks (attention.py:49-62): softmax(q k^T / 8) v with head_dim 64, on tcgen05:
 // S = Q K^T and O = P V on the tensor cores (S, P and O live in tensor memory), online softmax with one thread per query row.
-// The design notes are at the kernel (attention_v5_kernel).  X3 = (hi, lo) operand splitting for the fp32-class precision mode
+// The design notes are at the kernel (attention_v6_kernel).  X3 = (hi, lo) operand splitting for the fp32-class precision mode
 // (3 MMAs per product).
 #include "common.cuh"
 #include <cuda.h>
@@ -112,31 +112,38 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
 }
 
 // ---------------------------------------------------------------------------------------------
-// v5: one softmax THREAD per query row, P stays in tensor memory, scores double-buffered.
+// v6: one softmax THREAD per query row, ONE score slot per tile with P written over the scores, several independent CTAs per SM.
 //   warps 0..3    softmax warpgroup of query tile 0 (thread = TMEM lane = query row: no shuffles, no shared-memory exchange)
-//   warps 4..7    softmax warpgroup of query tile 1
-//   warp 8        MMA issuer (one elected lane): S_w = Q_w K^T (operands in shared memory), O_w += P_w V (A = P_w from TMEM)
-//   warp 9        TMA producer: Q tiles once, then a ring of K / V chunks          (warps 10, 11: idle, they only give registers back)
-// Keys are processed in 64-wide chunks and every query tile owns TWO score slots in tensor memory: S_w(j+1) is computed while the
-// softmax of S_w(j) runs, so a softmax warpgroup never waits for the tensor pipe (round 1's kernel, and the first version of this
-// one, spent a third of the softmax warps' time waiting for S: ncu, profiles/).  A softmax thread reads its 64 scores from TMEM
-// ONCE, takes the maximum, forms p = 2^(s*c - m*c), packs bf16 pairs and writes them back OVER the scores with tcgen05.st: P
-// aliases S, so the P V product takes its A operand straight from tensor memory (no shared-memory staging of P, no
-// generic->async proxy fence).  The tensor pipe executes in issue order, so S_w(j+2) -- issued after P_w(j) V(j) -- may
-// overwrite P_w(j) safely.  The row owner rescales O_w in place, lazily (only when the running maximum grew by more than 2^8),
-// after waiting for P_w(j-1) V(j-1) to retire.  With two tiles and two slots per tile in flight the MUFU pipe always has
-// exponentials to run; that pipe (16 ex2 / clock / SM) is the bound of this kernel at head_dim 64.
-// X3 = fp32-class mode: Q, K, V arrive as (hi, lo) 16-bit planes, S = Qh Kh + Qh Kl + Ql Kh, P is split into (hi, lo) planes that
-// together fill the score slot, O = Ph Vh + Ph Vl + Pl Vh; the output is written as (hi, lo) planes.
-// The last key chunk is 16..80 wide: 1025 tokens = 15 x 64 + 65.  Leftover query rows (T mod 128 <= 16) go to the SIMT tail kernel.
-// TMEM (512 columns): S slots [tile][buffer] at 96-column pitch | O0 | O1 (64 columns each).
+//   warps 4..7    softmax warpgroup of query tile 1 ((hi, lo) mode only)
+//   next warp     MMA issuer (one elected lane): S_w = Q_w K^T (operands in shared memory), O_w += P_w V (A = P_w from TMEM)
+//   next warp     TMA producer: Q tiles once, then a ring of K / V chunks      ((hi, lo) mode: two more idle warps complete the warpgroup)
+// What round 2's clock64 traces showed (gpurun_out/att_trace_*.log):
+//   * a softmax warp cannot overlap its own MUFU, FMA and ALU work: the 64 exponentials of a 64-key chunk take ~960 clocks when the
+//     warp has its scheduler to itself (512 clocks of MUFU), and ~600 more clocks per chunk go to synchronisation (barrier wait, TMEM
+//     load / store round trips, arrive).  Pipes only overlap ACROSS warps;
+//   * the chain softmax(j) -> P V(j), S(j+1) -> softmax(j+1) of one query tile is serial whatever the buffering (the MMA warp needs
+//     ~700 clocks to wake up, issue eight MMAs and see them commit), so with two tiles per SM every pipe idled half the time; wider
+//     chunks (128 keys), two score slots, or two threads per row all landed on the same ~290 us per 27-patch call.
+// Hence the one-pass configuration: 64-key chunks, S 64 + O 64 = 128 TMEM columns and 50 KB of shared memory per CTA, FOUR CTAs per
+// SM: four independent chains keep four softmax warps on every scheduler (222 us, 1.31x; MUFU pipe ~70 % busy).  The scores are read
+// from tensor memory twice in 32-column pieces (pass 1: row maximum; pass 2: exponentials), so a thread holds 32 score registers (80
+// registers per thread); P (16-bit pairs) overwrites the score columns pass 2 has already consumed, and the tensor pipe executes in
+// issue order, so S_w(j+1) -- issued right after P_w(j) V(j) -- may overwrite P_w(j) safely.  POLY of every 8 exponentials are
+// evaluated on the FMA pipe (Cody-Waite reduction x = n + f, |f| <= 1/2, cubic minimax polynomial for 2^f with relative error
+// 7.5e-5 -- far below the 2^-9 of the bf16 P -- and the exponent inserted with an integer add: the FlashAttention-4 trick; a sweep
+// of 0 / 2 / 4 / 6 of 8 gave 226 / 222 / 229 / 244 us: the kernel is no longer MUFU-bound alone, issue slots are as scarce).
+// The row owner rescales O_w in place, lazily (only when the running maximum grew by more than 2^8), after P_w(j-1) V(j-1) retired.
+// X3 = fp32-class mode: Q, K, V arrive as (hi, lo) FP16 planes, S = Qh Kl + Ql Kh + Qh Kh, P is split into (hi, lo) planes (P_lo in
+// its own 64 columns), O = Ph Vl + Pl Vh + Ph Vh; 128-key chunks, two tiles per CTA, one CTA per SM (tensor-bound: 3 MMAs per
+// product), piece loads software-pipelined, all exponentials on the MUFU pipe; the output is written as (hi, lo) planes.
+// The last key chunk holds the remaining 1..CH keys; its MMAs run 16-key slices up to the next multiple of 16 (TMA zero-fills rows
+// past T), so the 1025th DINOv2 token costs one 16-wide slice.  Leftover query rows (T mod 128 <= 16) go to the SIMT tail kernel.
+// TMEM per tile: S [0, CH) (P_hi over its first half) | X3: P_lo [128, 192) | O (64 columns).
 // ---------------------------------------------------------------------------------------------
-constexpr int CH = 64;                              // keys per chunk
-constexpr int CHW = 80;                             // widest (last) chunk
-constexpr int KVB = CHW * 128;                      // bytes of one K or V chunk buffer (10 KB, 1024-aligned)
-constexpr int SLOT = 96;                            // TMEM column pitch of a score slot
-constexpr int P_LO_COL = CHW / 2;                   // X3: P_lo plane starts 40 columns into the slot (P_hi of an 80-wide chunk ends there)
 constexpr float TRUNC_BIAS_LOG2 = 0.0028150156f;    // log2(1 + 2^-9)
+#ifndef PRV2_ATTN_POLY
+#define PRV2_ATTN_POLY 2                            // exponentials per 8 evaluated on the FMA pipe (one-pass mode), 0..8, even
+#endif
 
 __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(tmem_d), "r"(tmem_a),
@@ -150,37 +157,45 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
       "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
-               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-// two independent fp32 FMAs per instruction (FFMA2 on sm_100)
-__device__ __forceinline__ void fma2(float& x0, float& x1, float a0, float a1, float b, float c) {
-  uint64_t d, av, bv, cv;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(av) : "f"(a0), "f"(a1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(cv) : "f"(c));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(av), "l"(bv), "l"(cv));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
+// two independent fp32 operations per instruction (FFMA2 / FADD2 on sm_100)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  return v;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2v(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2v(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
-struct alignas(64) AttnParamsV5 {
-  CUtensorMap tmq_hi, tmq_lo, tm64_hi, tm64_lo, tm80_hi, tm80_lo;    // boxes {64 ch, 128 | 64 | 80 tokens, 1 image} over the qkv planes
+struct alignas(64) AttnParamsV6 {
+  CUtensorMap tm_hi, tm_lo;       // box {64 ch, 128 tokens, 1 image} over the qkv planes: Q tiles
+  CUtensorMap tmkv_hi, tmkv_lo;   // box {64 ch, CH tokens, 1 image}: K / V chunks
   bf16* out_hi; bf16* out_lo;
-  const bf16* qkv_hi; const bf16* qkv_lo;        // plain pointers for the leftover-row CTA (qkv_lo == nullptr in one-pass mode)
-  int B, T, heads, D, n_chunks, last_width, tq_main;
+  int B, T, heads, D, n_chunks, last_valid, tq_main;
   unsigned long long* trace;      // diagnostics (PRV2_ATTN_TRACE=1): clock64 stamps of CTA (0,0,0), [role 0..2][chunk][5]
 };
+// (compiled in only with -DPRV2_ATTN_TRACE_BUILD: the stamps cost ~10 instructions each in the MMA and softmax loops)
+#ifdef PRV2_ATTN_TRACE_BUILD
 #define TRACE(role, j, k)                                                                                             \
   do {                                                                                                                \
     if (p.trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 32) p.trace[((role) * 32 + (j)) * 5 + (k)] = clock64(); \
   } while (0)
+#else
+#define TRACE(role, j, k) do { } while (0)
+#endif
 
 // Leftover query rows [tq_main, T) (1 row for the 1025-token DINOv2 sequence) are computed in plain SIMT code by a small second
 // kernel, one 256-thread CTA per (row, head, image): a 128-row tensor-core tile for one row would cost an eighth of the whole
@@ -299,25 +314,30 @@ __global__ void __launch_bounds__(256) attention_tail_kernel(const bf16* __restr
   attention_tail_row<256>(smem, qkv, qkv_lo, out, out_lo, T, heads, blockIdx.z, blockIdx.y, tq_main + blockIdx.x);
 }
 
-// NT = query tiles per CTA.  One-pass mode: NT = 1 with TWO CTAs per SM (256 TMEM columns, 97 KB of shared memory each) -- two
-// tiles owned by one CTA fall into lockstep (both wait / load / hand over at the same time and then contend for the MUFU pipe),
-// two independent CTAs do not, and one CTA's prologue / epilogue hides under the other's main loop.  (hi, lo) mode: NT = 2, one
-// CTA per SM (its shared-memory ring is twice as large and it is bound by the tensor pipe, 3 MMAs per product).
-template <bool X3> struct V5Cfg {
+
+// NT = query tiles per CTA, CTAS = CTAs per SM.  One-pass mode: NT = 1, four CTAs per SM (128 TMEM columns, 50 KB of shared memory,
+// 192 threads x 80 registers each).  (hi, lo) mode: NT = 2, one CTA per SM (512 TMEM columns, 193 KB, setmaxnreg 192 / 112).
+template <bool X3> struct V6Cfg {
   static constexpr int NT = X3 ? 2 : 1;
+  static constexpr int CTAS = X3 ? 1 : 4;                          // CTAs per SM
+  static constexpr int CH = X3 ? 128 : 64;                         // keys per chunk
+  static constexpr int KVB = CH * 128;                             // bytes of one K or V chunk buffer
   static constexpr int PLANES = X3 ? 2 : 1;
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = 2;
   static constexpr int STAGE_BYTES = 2 * PLANES * KVB;             // K_hi | V_hi [| K_lo | V_lo]
   static constexpr int SMEM = NT * PLANES * TILE_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int THREADS = 128 * NT + 128;                   // softmax warpgroup(s) + one warpgroup holding the MMA and TMA warps
-  static constexpr int TMEM_COLS = NT == 2 ? 512 : 256;            // 2 score slots per tile at 96-column pitch + 64 columns of O per tile
-  static constexpr int O_COL = 2 * NT * SLOT;
+  static constexpr int THREADS = X3 ? 128 * NT + 128 : 192;        // softmax warpgroup(s) + the MMA and TMA warps (X3: a whole warpgroup, for setmaxnreg)
+  static constexpr int TILE_COLS = X3 ? 256 : 128;                 // S CH (P_hi over its first half) | X3: P_lo 64 | O 64
+  static constexpr int P_LO_COL = 128;
+  static constexpr int O_COL = X3 ? 192 : 64;
+  static constexpr int TMEM_COLS = X3 ? 512 : 128;
 };
 
-template <bool X3>
-__global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attention_v5_kernel(const __grid_constant__ AttnParamsV5 p) {
-  constexpr int PLANES = V5Cfg<X3>::PLANES, STAGES = V5Cfg<X3>::STAGES, STAGE_BYTES = V5Cfg<X3>::STAGE_BYTES, NT = V5Cfg<X3>::NT;
-  constexpr int O_COL = V5Cfg<X3>::O_COL, MMA_WARP = 4 * NT, TMA_WARP = 4 * NT + 1;
+template <bool X3, int POLY_T>
+__global__ void __launch_bounds__(V6Cfg<X3>::THREADS, V6Cfg<X3>::CTAS) attention_v6_kernel(const __grid_constant__ AttnParamsV6 p) {
+  constexpr int PLANES = V6Cfg<X3>::PLANES, STAGES = V6Cfg<X3>::STAGES, STAGE_BYTES = V6Cfg<X3>::STAGE_BYTES, NT = V6Cfg<X3>::NT;
+  constexpr int CH = V6Cfg<X3>::CH, KVB = V6Cfg<X3>::KVB, P_LO_COL = V6Cfg<X3>::P_LO_COL;
+  constexpr int O_COL = V6Cfg<X3>::O_COL, TILE_COLS = V6Cfg<X3>::TILE_COLS, MMA_WARP = 4 * NT, TMA_WARP = MMA_WARP + 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -327,17 +347,18 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
   const uint32_t bar_q = bars;
   auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bars + 8u * (1 + STAGES + s); };
-  auto s_full = [&](int w, int sl) { return bars + 8u * (1 + 2 * STAGES + 2 * w + sl); };
-  auto p_full = [&](int w, int sl) { return bars + 8u * (5 + 2 * STAGES + 2 * w + sl); };
-  auto o_done = [&](int w) { return bars + 8u * (9 + 2 * STAGES + w); };
-  auto o_final = [&](int w) { return bars + 8u * (11 + 2 * STAGES + w); };
-  const uint32_t tmem_slot = bars + 8u * (13 + 2 * STAGES);
+  auto s_full = [&](int w) { return bars + 8u * (1 + 2 * STAGES + w); };
+  auto p_full = [&](int w) { return bars + 8u * (3 + 2 * STAGES + w); };
+  auto o_done = [&](int w) { return bars + 8u * (5 + 2 * STAGES + w); };
+  auto o_final = [&](int w) { return bars + 8u * (7 + 2 * STAGES + w); };
+  const uint32_t tmem_slot = bars + 8u * (9 + 2 * STAGES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * (128 * NT), head = blockIdx.y, b = blockIdx.z;
   const int D = p.D, T = p.T;
   const int n_chunks = p.n_chunks;
   const int n_wg = (NT == 2 && q0 + 128 < p.tq_main) ? 2 : 1;
+  const int last_width = (p.last_valid + 15) & ~15;                 // columns the MMAs of the last chunk write / read
 
   const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const long long cta_clk0 = clock64();
@@ -346,14 +367,15 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
     mbar_init(bar_q, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     for (int w = 0; w < NT; ++w) {
-      for (int sl = 0; sl < 2; ++sl) { mbar_init(s_full(w, sl), 1); mbar_init(p_full(w, sl), 4); }
+      mbar_init(s_full(w), 1);
+      mbar_init(p_full(w), 4);
       mbar_init(o_done(w), 1);
       mbar_init(o_final(w), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)V5Cfg<X3>::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)V6Cfg<X3>::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -361,20 +383,17 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  auto width_of = [&](int j) { return j == n_chunks - 1 ? p.last_width : CH; };
-  const bool last_wide = p.last_width > CH;
 
   if (warp >= MMA_WARP) {
   // (the register split must dominate each role's code, or ptxas applies the minimum to all of it)
-  if (NT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  if (X3) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
   if (warp == TMA_WARP) {
     // ------------------------------------------------ TMA producer (converged warp, elected lane issues)
     if (elect_one()) {
       mbar_expect_tx(bar_q, n_wg * PLANES * TILE_BYTES);
       for (int w = 0; w < n_wg; ++w) {
-        tma_load_3d(sQ + w * TILE_BYTES, &p.tmq_hi, bar_q, head * 64, q0 + w * 128, b);
-        if (X3) tma_load_3d(sQ + (NT + w) * TILE_BYTES, &p.tmq_lo, bar_q, head * 64, q0 + w * 128, b);
+        tma_load_3d(sQ + w * TILE_BYTES, &p.tm_hi, bar_q, head * 64, q0 + w * 128, b);
+        if (X3) tma_load_3d(sQ + (NT + w) * TILE_BYTES, &p.tm_lo, bar_q, head * 64, q0 + w * 128, b);
       }
     }
     __syncwarp();
@@ -383,16 +402,13 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
     for (int j = 0; j < n_chunks; ++j) {
       mbar_wait(kv_empty(stage), phase ^ 1);
       if (elect_one()) {
-        const bool wide = last_wide && j == n_chunks - 1;
-        const CUtensorMap* mh = wide ? &p.tm80_hi : &p.tm64_hi;
-        const CUtensorMap* ml = wide ? &p.tm80_lo : &p.tm64_lo;
         const uint32_t dst = sRing + stage * STAGE_BYTES;
-        mbar_expect_tx(kv_full(stage), 2 * PLANES * (wide ? CHW : CH) * 128);
-        tma_load_3d(dst, mh, kv_full(stage), D + head * 64, j * CH, b);
-        tma_load_3d(dst + KVB, mh, kv_full(stage), 2 * D + head * 64, j * CH, b);
+        mbar_expect_tx(kv_full(stage), 2 * PLANES * KVB);          // rows past T are zero-filled by TMA and count like the others
+        tma_load_3d(dst, &p.tmkv_hi, kv_full(stage), D + head * 64, j * CH, b);
+        tma_load_3d(dst + KVB, &p.tmkv_hi, kv_full(stage), 2 * D + head * 64, j * CH, b);
         if (X3) {
-          tma_load_3d(dst + 2 * KVB, ml, kv_full(stage), D + head * 64, j * CH, b);
-          tma_load_3d(dst + 3 * KVB, ml, kv_full(stage), 2 * D + head * 64, j * CH, b);
+          tma_load_3d(dst + 2 * KVB, &p.tmkv_lo, kv_full(stage), D + head * 64, j * CH, b);
+          tma_load_3d(dst + 3 * KVB, &p.tmkv_lo, kv_full(stage), 2 * D + head * 64, j * CH, b);
         }
       }
       __syncwarp();
@@ -401,10 +417,10 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------ MMA issuer
     // Everything the elected lane needs is warp-uniform and computed by the converged warp; the issue blocks are straight-line
-    // (descriptor + constant) so the operands stay in uniform registers -- a loop with per-iteration descriptor arithmetic cost
-    // ~75 clocks per MMA in R2UR round trips and made this warp, not the MUFU pipe, the bound of the first version.
+    // (descriptor + constant) so the operands stay in uniform registers.
     constexpr uint32_t FMT = X3 ? 0u : 1u;              // operand format: F16 for the (hi, lo) pair planes, BF16 in one-pass mode
-    const uint32_t idesc_s64 = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(CH >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_s = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(CH >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_s_last = (idesc_s & ~(0x3fu << 17)) | ((uint32_t)(last_width >> 3) << 17);
     const uint32_t idesc_o = (1u << 4) | (FMT << 7) | (FMT << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
     // The tensor core adds every MMA into the fp32 accumulator with round-toward-zero (a bias of ~2^-24 of the running sum per
     // MMA, scripts/diag_accum.py), so in (hi, lo) mode the two small cross terms go FIRST and the main term last.
@@ -439,104 +455,174 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
     auto kv_desc = [&](int stage, int buf) { return ring_d + (uint64_t)((stage * STAGE_BYTES + buf * KVB) >> 4); };
     const bool leader = elect_one();
     mbar_wait(bar_q, 0);
-    // the ring position of chunk j is (j % STAGES, parity (j / STAGES) & 1)
-    for (int j = 0; j < 2 && j < n_chunks; ++j) {
-      mbar_wait(kv_full(j), 0);
-      tc_fence_after();
-      const int width = width_of(j);
-      const uint32_t idesc = (idesc_s64 & ~(0x3fu << 17)) | ((uint32_t)(width >> 3) << 17);
-      for (int w = 0; w < n_wg; ++w)
-        if (leader) issue_s(tmem_base + (2 * w + j) * SLOT, qd_h[w], qd_l[w], kv_desc(j, 0), kv_desc(j, 2), idesc, s_full(w, j));
-      __syncwarp();
-    }
-    int stage = 0, stage2 = 2 % STAGES;
-    uint32_t phase2 = (2 / STAGES) & 1;
+    mbar_wait(kv_full(0), 0);
+    tc_fence_after();
+    for (int w = 0; w < n_wg; ++w)
+      if (leader) issue_s(tmem_base + w * TILE_COLS, qd_h[w], qd_l[w], kv_desc(0, 0), kv_desc(0, 2), n_chunks == 1 ? idesc_s_last : idesc_s, s_full(w));
+    __syncwarp();
+    int stage = 0, stage1 = 1 % STAGES;
+    uint32_t phase1 = (1 / STAGES) & 1;
     for (int j = 0; j < n_chunks; ++j) {
-      const int sl = j & 1;
-      const bool more = j + 2 < n_chunks;
-      const bool fast = j < n_chunks - 1 || p.last_width == CH;          // 64-wide chunk: four straight-line slices
-      const bool fast2 = j + 2 < n_chunks - 1 || p.last_width == CH;
-      const uint64_t vh = kv_desc(stage, 1), vl = kv_desc(stage, 3), kh2 = kv_desc(stage2, 0), kl2 = kv_desc(stage2, 2);
-      const uint32_t idesc2 = fast2 ? idesc_s64 : ((idesc_s64 & ~(0x3fu << 17)) | ((uint32_t)(p.last_width >> 3) << 17));
+      const bool more = j + 1 < n_chunks;
+      const bool full = j < n_chunks - 1 || last_width == CH;           // 128-wide chunk: eight straight-line slices
+      const uint64_t vh = kv_desc(stage, 1), vl = kv_desc(stage, 3), kh1 = kv_desc(stage1, 0), kl1 = kv_desc(stage1, 2);
+      const uint32_t idesc1 = (j + 1 == n_chunks - 1) ? idesc_s_last : idesc_s;
       const uint32_t accum = j > 0 ? 1u : 0u;
       for (int w = 0; w < n_wg; ++w) {
-        const uint32_t tP = tmem_base + (2 * w + sl) * SLOT, tO = tmem_base + O_COL + w * 64;
+        const uint32_t tS = tmem_base + w * TILE_COLS, tP = tS, tO = tS + O_COL;
         if (lane == 0 && w == 0) TRACE(2, j, 0);
-        mbar_wait(p_full(w, sl), (j >> 1) & 1);          // P_w(j) is in TMEM over S_w(j), O_w rescaled if it had to be
-        if (more && w == 0) mbar_wait(kv_full(stage2), phase2);
+        mbar_wait(p_full(w), j & 1);                     // P_w(j) is in TMEM over S_w(j), O_w rescaled if it had to be
         tc_fence_after();
         if (lane == 0) TRACE(2, j, w == 0 ? 1 : 3);
         if (leader) {
-          if (fast) {
-            issue_o_slice(tO, tP, vh, vl, 0, accum);
-            issue_o_slice(tO, tP, vh, vl, 1, 1u);
-            issue_o_slice(tO, tP, vh, vl, 2, 1u);
-            issue_o_slice(tO, tP, vh, vl, 3, 1u);
+          if (full) {
+#pragma unroll
+            for (int k = 0; k < CH / 16; ++k) issue_o_slice(tO, tP, vh, vl, k, k > 0 ? 1u : accum);
           } else {
-            for (int k = 0; k < (p.last_width >> 4); ++k) issue_o_slice(tO, tP, vh, vl, k, k > 0 ? 1u : accum);
+            for (int k = 0; k < (last_width >> 4); ++k) issue_o_slice(tO, tP, vh, vl, k, k > 0 ? 1u : accum);
           }
           tc_commit(o_done(w));
-          if (j == n_chunks - 1) tc_commit(o_final(w));
-          if (more) issue_s(tP, qd_h[w], qd_l[w], kh2, kl2, idesc2, s_full(w, sl));
+          if (!more) tc_commit(o_final(w));
         }
         __syncwarp();
+        if (more) {
+          mbar_wait(kv_full(stage1), phase1);            // K(j+1) has landed (returns at once for the second tile)
+          tc_fence_after();
+          if (leader) issue_s(tS, qd_h[w], qd_l[w], kh1, kl1, idesc1, s_full(w));
+          __syncwarp();
+        }
         if (lane == 0) TRACE(2, j, w == 0 ? 2 : 4);
       }
       if (leader) tc_commit(kv_empty(stage));   // K_j / V_j are free once everything issued so far has retired
       __syncwarp();
       if (++stage == STAGES) stage = 0;
-      if (++stage2 == STAGES) { stage2 = 0; phase2 ^= 1; }
+      if (++stage1 == STAGES) { stage1 = 0; phase1 ^= 1; }
     }
   }
   } else {
     // ------------------------------------------------ softmax warpgroups: thread = query row
-    if (NT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
-    const int w = warp >> 2;
+    if (X3) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    const int w = warp >> 2;                                 // query tile of this warpgroup
     if (w < n_wg) {
       const int row = (warp & 3) * 32 + lane;               // TMEM lane == query row of this tile
       const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t tSw = tmem_base + 2 * w * SLOT + lane_off, tO = tmem_base + O_COL + w * 64 + lane_off;
+      const uint32_t tS = tmem_base + w * TILE_COLS + lane_off, tO = tS + O_COL;
       const float c_log2 = 0.125f * 1.4426950408889634f;    // head_dim^-0.5 * log2(e)   (attention.py:41)
       const float tau = RESCALE_LOG2 / c_log2;
       float m_run = -INFINITY, l_run = 0.f;
-      constexpr int PIECE = X3 ? 16 : 64;                    // scores packed per tcgen05.st (x8 / x32 registers per plane)
+      constexpr int POLY = X3 ? 0 : POLY_T;
 
-      const bool last_general = p.last_width != CH || T - (n_chunks - 1) * CH < CH;
-      // scores of chunk j: wait for S_w(j), issue the TMEM loads into `s` (+ `sx` for columns 64..79 of a wide last chunk); no wait
-      auto load_scores = [&](const int j, uint32_t (&s)[CH]) {
-        const int sl = j & 1;
-        const uint32_t tS = tSw + sl * SLOT;
-        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 0);
-        mbar_wait(s_full(w, sl), (j >> 1) & 1);
-        tc_fence_after();
-        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 1);
-        tc_ld32_issue(tS, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-        tc_ld32_issue(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-      };
-      // softmax of chunk j from registers: maximum, p = 2^(s*c - m*c) packed to 16 bits and written back over the scores, row sum
-      auto chunk_math = [&](auto general_tag, const int j, uint32_t (&s)[CH], uint32_t (&sx)[16]) {
+      // ---- pass 1 over one 32-column piece: running maxima (four independent chains of 3-input maxima)
+      auto piece_max = [&](auto general_tag, const uint32_t (&s)[32], const int nv, float (&mx4)[4]) {
         constexpr bool GENERAL = decltype(general_tag)::value;
-        constexpr int NS = GENERAL ? CHW : CH;
-        const int n_valid = GENERAL ? T - j * CH : CH;         // keys of this chunk that exist
-        const int width = GENERAL ? p.last_width : CH;          // columns the MMA wrote / will read
-        const int sl = j & 1;
-        const uint32_t tS = tSw + sl * SLOT;
-        // scores by compile-time index: the 64 columns, then columns 64..79 of the wide last chunk
-        auto sc = [&](int i) { return __uint_as_float(i < CH ? s[i & (CH - 1)] : sx[i & 15]); };
-        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 2);
-        // ---- row maximum (four independent chains of 3-input maxima)
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (!GENERAL) {
 #pragma unroll
-          for (int i = 0; i < NS; i += 8) {
+          for (int i = 0; i < 32; i += 8) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) mx4[u] = max3(mx4[u], sc(i + 2 * u), sc(i + 2 * u + 1));
+            for (int u = 0; u < 4; ++u) mx4[u] = max3(mx4[u], __uint_as_float(s[i + 2 * u]), __uint_as_float(s[i + 2 * u + 1]));
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < NS; ++i) if (i < n_valid) mx4[i & 3] = fmaxf(mx4[i & 3], sc(i));
+          for (int i = 0; i < 32; ++i) if (i < nv) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[i]));
         }
+      };
+      // ---- pass 2 over one piece: p = 2^(s*c - m*c) for 32 scores, row-sum partials, 16-bit packing, store over the scores.
+      // One-pass mode packs bf16 by TRUNCATION with one byte-permute per pair; the exponent carries +log2(1 + 2^-9), which
+      // centres the truncation error (|rel| <= 2^-8, mean 0); the row sum is taken from the same values and corrected once at
+      // the end.  (hi, lo) mode: FP16 pair, hi = rn(p), lo = rn(p - hi): ~22 bits of p.
+      auto piece_exp = [&](auto general_tag, const int q, const uint32_t (&s)[32], const int nv, const float nmc, uint64_t (&l2)[2]) {
+        constexpr bool GENERAL = decltype(general_tag)::value;
+        const uint64_t c2 = pack2(c_log2, c_log2), n2 = pack2(nmc, nmc);
+        float e[32];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          const uint64_t x2 = fma2v(pack2(__uint_as_float(s[t]), __uint_as_float(s[t + 1])), c2, n2);
+          if ((t & 7) < POLY) {
+            // FMA-pipe 2^x: x = n + f with n = round(x) (magic-number add), |f| <= 1/2, cubic in f, n into the exponent field.
+            // x is clamped to >= -125 so the exponent field stays positive (2^-125 is zero for every purpose here).
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            const uint64_t xc = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+            const uint64_t magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f), m1 = pack2(-1.f, -1.f);
+            const uint64_t xf = add2v(xc, magic);                          // low mantissa bits = n (two's complement)
+            const uint64_t fr = fma2v(add2v(xf, nmagic), m1, xc);          // f = x - n
+            uint64_t pl = fma2v(pack2(0.05517164617776871f, 0.05517164617776871f), fr, pack2(0.2426111251115799f, 0.2426111251115799f));
+            pl = fma2v(pl, fr, pack2(0.6932609677314758f, 0.6932609677314758f));
+            pl = fma2v(pl, fr, pack2(0.9999280571937561f, 0.9999280571937561f));
+            float p0, p1, f0, f1;
+            unpack2(pl, p0, p1);
+            unpack2(xf, f0, f1);
+            e[t] = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(f0) << 23));
+            e[t + 1] = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(f1) << 23));
+          } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            e[t] = ex2_ftz(x0);
+            e[t + 1] = ex2_ftz(x1);
+          }
+          if (GENERAL) {
+            if (t >= nv) e[t] = 0.f;
+            if (t + 1 >= nv) e[t + 1] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 32; t += 4) { l2[0] = add2v(l2[0], pack2(e[t], e[t + 1])); l2[1] = add2v(l2[1], pack2(e[t + 2], e[t + 3])); }
+        uint32_t hi[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          if constexpr (X3) {
+            const __half2 h = __floats2half2_rn(e[2 * t], e[2 * t + 1]);
+            hi[t] = *reinterpret_cast<const uint32_t*>(&h);
+            const float2 f = __half22float2(h);
+            e[2 * t] -= f.x;
+            e[2 * t + 1] -= f.y;
+          } else {
+            hi[t] = __byte_perm(__float_as_uint(e[2 * t]), __float_as_uint(e[2 * t + 1]), 0x7632);
+          }
+        }
+        tc_st16(tS + 16 * q, hi);
+        if constexpr (X3) {
+          uint32_t lo[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const __half2 h = __floats2half2_rn(e[2 * t], e[2 * t + 1]);
+            lo[t] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          tc_st16(tS + P_LO_COL + 16 * q, lo);
+        }
+      };
+
+      auto chunk_pipelined = [&](auto general_tag, const int j) {
+        constexpr bool GENERAL = decltype(general_tag)::value;
+        const int n_valid = GENERAL ? p.last_valid : CH;        // keys of this chunk that exist
+        const int n_pieces = GENERAL ? (last_width + 31) >> 5 : CH / 32;
+        uint32_t sa[32], sb[32];
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 0);
+        mbar_wait(s_full(w), j & 1);
+        tc_fence_after();
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 1);
+        // ---- pass 1: row maximum; the load of piece q + 1 is in flight while piece q is reduced
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        tc_ld32_issue(tS, sa);
+        tc_ld_wait();
+        if (n_pieces > 1) tc_ld32_issue(tS + 32, sb);
+        piece_max(general_tag, sa, n_valid, mx4);
+        if (n_pieces > 1) {
+          tc_ld_wait();
+          if (n_pieces > 2) tc_ld32_issue(tS + 64, sa);
+          piece_max(general_tag, sb, n_valid - 32, mx4);
+          if (n_pieces > 2) {
+            tc_ld_wait();
+            if (n_pieces > 3) tc_ld32_issue(tS + 96, sb);
+            piece_max(general_tag, sa, n_valid - 64, mx4);
+            if (n_pieces > 3) {
+              tc_ld_wait();
+              tc_ld32_issue(tS, sa);                              // piece 0 again, for pass 2
+              piece_max(general_tag, sb, n_valid - 96, mx4);
+            }
+          }
+        }
+        if (n_pieces <= 3) tc_ld32_issue(tS, sa);
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // ---- lazy rescale decision: keep the stale maximum unless the new one is > 2^8 larger
         const bool need = mx > m_run + tau;
@@ -547,105 +633,139 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
           l_run *= alpha;
         }
         const float nmc = fmaf(-m_run, c_log2, X3 ? 0.f : TRUNC_BIAS_LOG2);
-        constexpr int PC = (GENERAL || X3) ? 16 : 32;           // scores per tcgen05.st piece (the ragged chunk is 16..80 wide)
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int q = 0; q < NS / PC; ++q) {
-          if (GENERAL && q * PC >= width) break;
-          float e[PC];
-#pragma unroll
-          for (int t = 0; t < PC; t += 2) {
-            float x0, x1;
-            fma2(x0, x1, sc(q * PC + t), sc(q * PC + t + 1), c_log2, nmc);
-            e[t] = ex2_ftz(x0);
-            e[t + 1] = ex2_ftz(x1);
-            if (GENERAL) {
-              if (q * PC + t >= n_valid) e[t] = 0.f;
-              if (q * PC + t + 1 >= n_valid) e[t + 1] = 0.f;
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 2);
+        // ---- pass 2: exponentials; P piece q (16 columns) lands on score columns that pass 2 has already consumed
+        uint64_t l2[2] = {0ull, 0ull};
+        tc_ld_wait();
+        if (n_pieces > 1) tc_ld32_issue(tS + 32, sb);
+        piece_exp(general_tag, 0, sa, n_valid, nmc, l2);
+        if (n_pieces > 1) {
+          tc_ld_wait();
+          if (n_pieces > 2) tc_ld32_issue(tS + 64, sa);
+          piece_exp(general_tag, 1, sb, n_valid - 32, nmc, l2);
+          if (n_pieces > 2) {
+            tc_ld_wait();
+            if (n_pieces > 3) tc_ld32_issue(tS + 96, sb);
+            piece_exp(general_tag, 2, sa, n_valid - 64, nmc, l2);
+            if (n_pieces > 3) {
+              tc_ld_wait();
+              piece_exp(general_tag, 3, sb, n_valid - 96, nmc, l2);
             }
-          }
-#pragma unroll
-          for (int t = 0; t < PC; t += 4) { l4[0] += e[t]; l4[1] += e[t + 1]; l4[2] += e[t + 2]; l4[3] += e[t + 3]; }
-          // One-pass mode: bf16 packing by TRUNCATION with one byte-permute per pair (ALU pipe) -- the exponent carries
-          // +log2(1 + 2^-9), which centres the truncation error (|rel| <= 2^-8, mean 0); the row sum is taken from the same
-          // values and corrected once at the end.  (hi, lo) mode: FP16 pair, hi = rn(p), lo = rn(p - hi): ~22 bits of p.
-          uint32_t hi[PC / 2];
-#pragma unroll
-          for (int t = 0; t < PC / 2; ++t) {
-            if constexpr (X3) {
-              const __half2 h = __floats2half2_rn(e[2 * t], e[2 * t + 1]);
-              hi[t] = *reinterpret_cast<const uint32_t*>(&h);
-              const float2 f = __half22float2(h);
-              e[2 * t] -= f.x;
-              e[2 * t + 1] -= f.y;
-            } else {
-              hi[t] = __byte_perm(__float_as_uint(e[2 * t]), __float_as_uint(e[2 * t + 1]), 0x7632);
-            }
-          }
-          if constexpr (X3) {
-            uint32_t lo[PC / 2];
-#pragma unroll
-            for (int t = 0; t < PC / 2; ++t) {
-              const __half2 h = __floats2half2_rn(e[2 * t], e[2 * t + 1]);
-              lo[t] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            tc_st8(tS + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[8]>(&hi[0]));
-            tc_st8(tS + P_LO_COL + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[8]>(&lo[0]));
-          } else if constexpr (PC == 16) {
-            tc_st8(tS + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[8]>(&hi[0]));
-          } else {
-            tc_st16(tS + (PC / 2) * q, *reinterpret_cast<uint32_t(*)[16]>(&hi[0]));
           }
         }
-        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        // ---- O_w rescale by the row owner (rare): P_w(j-1) V(j-1) must have retired.  S_w(j) was issued after P_w(j-2) V(j-2), so
-        // o_done has completed j-1 or j phases by now and the parity wait is unambiguous.
+        {
+          float a0, a1, a2, a3;
+          unpack2(l2[0], a0, a1);
+          unpack2(l2[1], a2, a3);
+          l_run += (a0 + a1) + (a2 + a3);
+        }
+        // ---- O_w rescale by the row owner (rare): P_w(j-1) V(j-1) must have retired.  S_w(j) was issued after P_w(j-1) V(j-1), so
+        // o_done has completed exactly j phases by now and the parity wait is unambiguous.
         if (j > 0 && __any_sync(0xffffffffu, need)) {
           mbar_wait(o_done(w), (j - 1) & 1);
           tc_fence_after();
-          uint32_t ro[32];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            tc_ld32_issue(tO + 32 * h, ro);
-            tc_ld_wait();                                       // (also drains the prefetched scores of the next chunk)
+            tc_ld32_issue(tO + 32 * h, sa);
+            tc_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-            tc_st32(tO + 32 * h, ro);
+            for (int i = 0; i < 32; ++i) sa[i] = __float_as_uint(__uint_as_float(sa[i]) * alpha);
+            tc_st32(tO + 32 * h, sa);
           }
         }
         if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 3);
         tc_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_local(p_full(w, sl));
+        if (lane == 0) mbar_arrive_local(p_full(w));
         if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 4);
       };
-      // (Fetching the scores of chunk j+1 into a second register set during the last exponentials of chunk j -- software
-      // pipelining inside the thread -- was measured 25 % SLOWER: 128 live score registers push the loop over the 184 registers a
-      // softmax thread can have with two CTAs per SM, and the spills land in the MUFU-bound section.)
-      uint32_t sA[CH], sx[16];
+      // One-pass mode (four CTAs per SM, 80 registers per thread): one 32-column piece in registers at a time; the TMEM round
+      // trips hide behind the other three softmax warps of the scheduler.
+      auto chunk_simple = [&](auto general_tag, const int j) {
+        constexpr bool GENERAL = decltype(general_tag)::value;
+        const int n_valid = GENERAL ? p.last_valid : CH;
+        const int n_pieces = GENERAL ? (last_width + 31) >> 5 : CH / 32;
+        uint32_t sa[32];
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 0);
+        mbar_wait(s_full(w), j & 1);
+        tc_fence_after();
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 1);
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int q = 0; q < CH / 32; ++q) {
+          if (q < n_pieces) { tc_ld32_issue(tS + 32 * q, sa); tc_ld_wait(); piece_max(general_tag, sa, n_valid - 32 * q, mx4); }
+        }
+        tc_ld32_issue(tS, sa);                                  // piece 0 again, in flight across the rescale decision
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        const bool need = mx > m_run + tau;
+        float alpha = 1.f;
+        if (need) {
+          alpha = ex2_ftz((m_run - mx) * c_log2);
+          m_run = mx;
+          l_run *= alpha;
+        }
+        const float nmc = fmaf(-m_run, c_log2, X3 ? 0.f : TRUNC_BIAS_LOG2);
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 2);
+        uint64_t l2[2] = {0ull, 0ull};
+#pragma unroll
+        for (int q = 0; q < CH / 32; ++q) {
+          if (q < n_pieces) {
+            if (q > 0) tc_ld32_issue(tS + 32 * q, sa);
+            tc_ld_wait();
+            piece_exp(general_tag, q, sa, n_valid - 32 * q, nmc, l2);
+          }
+        }
+        {
+          float a0, a1, a2, a3;
+          unpack2(l2[0], a0, a1);
+          unpack2(l2[1], a2, a3);
+          l_run += (a0 + a1) + (a2 + a3);
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          mbar_wait(o_done(w), (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tc_ld32_issue(tO + 32 * h, sa);
+            tc_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sa[i] = __float_as_uint(__uint_as_float(sa[i]) * alpha);
+            tc_st32(tO + 32 * h, sa);
+          }
+        }
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 3);
+        tc_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(p_full(w));
+        if (lane == 0 && (warp & 3) == 0) TRACE(w, j, 4);
+      };
+      auto chunk = [&](auto general_tag, const int j) {
+        if constexpr (X3) chunk_pipelined(general_tag, j);
+        else chunk_simple(general_tag, j);
+      };
+      const bool last_general = p.last_valid != CH;
       for (int j = 0; j < n_chunks; ++j) {
-        const bool general = last_general && j == n_chunks - 1;
-        load_scores(j, sA);
-        if (general) tc_ld16_issue(tSw + (j & 1) * SLOT + 64, sx);
-        tc_ld_wait();
-        if (general) chunk_math(std::true_type{}, j, sA, sx);
-        else chunk_math(std::false_type{}, j, sA, sx);
+        if (last_general && j == n_chunks - 1) chunk(std::true_type{}, j);
+        else chunk(std::false_type{}, j);
       }
-      // ---- epilogue: O / l -> 16-bit (hi[, lo]) -> staged row -> one bulk copy per plane.  The rows are staged in this tile's own Q
-      // buffers (every S_w has retired).  o_final completes once, after the last P V (o_done's parity would be ambiguous here).
+      // ---- epilogue: O / l -> 16-bit (hi[, lo]) -> staged row -> one bulk copy per plane (SPLIT: per half row).  The rows are
+      // staged in this tile's own Q buffers (every S_w has retired).  o_final completes once, after the last P V (o_done's parity
+      // would be ambiguous here).
       mbar_wait(o_final(w), 0);
       tc_fence_after();
       const float inv = (X3 ? 1.0f : 1.0f + 0x1p-9f) / l_run;    // one-pass mode: l was summed from values carrying the +2^-9 bias
+      constexpr int NCOL = 64;
       uint8_t* const srow = base_ptr + w * TILE_BYTES + row * 128;
       uint8_t* const srow_lo = srow + NT * TILE_BYTES;
-      uint32_t ro[64];
+      uint32_t ro[NCOL];
       tc_ld32_issue(tO, *reinterpret_cast<uint32_t(*)[32]>(&ro[0]));
       tc_ld32_issue(tO + 32, *reinterpret_cast<uint32_t(*)[32]>(&ro[32]));
       tc_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint32_t h2[4], l2[4];
+      for (int g = 0; g < NCOL / 8; ++g) {
+        uint32_t h2[4], l2w[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float a = __uint_as_float(ro[g * 8 + 2 * t]) * inv, c = __uint_as_float(ro[g * 8 + 2 * t + 1]) * inv;
@@ -654,21 +774,21 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
             const float2 f = __half22float2(h);
             const __half2 l = __floats2half2_rn(a - f.x, c - f.y);
             h2[t] = *reinterpret_cast<const uint32_t*>(&h);
-            l2[t] = *reinterpret_cast<const uint32_t*>(&l);
+            l2w[t] = *reinterpret_cast<const uint32_t*>(&l);
           } else {
             const __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
             h2[t] = *reinterpret_cast<const uint32_t*>(&h);
           }
         }
         *reinterpret_cast<uint4*>(srow + g * 16) = *reinterpret_cast<const uint4*>(h2);
-        if (X3) *reinterpret_cast<uint4*>(srow_lo + g * 16) = *reinterpret_cast<const uint4*>(l2);
+        if (X3) *reinterpret_cast<uint4*>(srow_lo + g * 16) = *reinterpret_cast<const uint4*>(l2w);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       const int q = q0 + w * 128 + row;
       if (q < p.tq_main) {
         const size_t go = ((size_t)b * T + q) * D + head * 64;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(p.out_hi + go), "r"(smem_u32(srow)) : "memory");
-        if (X3) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(p.out_lo + go), "r"(smem_u32(srow_lo)) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out_hi + go), "r"(smem_u32(srow)), "n"(NCOL * 2) : "memory");
+        if (X3) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out_lo + go), "r"(smem_u32(srow_lo)), "n"(NCOL * 2) : "memory");
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -682,7 +802,7 @@ __global__ void __launch_bounds__(V5Cfg<X3>::THREADS, 3 - V5Cfg<X3>::NT) attenti
   }
   if (warp == MMA_WARP) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)V5Cfg<X3>::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)V6Cfg<X3>::TMEM_COLS) : "memory");
   }
 }
 
@@ -719,27 +839,27 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
   if (!enc) { set_error("prv2_attention: cuTensorMapEncodeTiled unavailable"); return PRV2_ECUDA; }
   const int D = heads * 64;
   const bool x3 = qkv_lo != nullptr;
-  AttnParamsV5 p;
+  AttnParamsV6 p;
   memset(&p, 0, sizeof(p));
-  CUresult r = encode_qkv_map(enc, &p.tmq_hi, qkv_hi, B, T, D, 128);
-  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tm64_hi, qkv_hi, B, T, D, CH);
-  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tm80_hi, qkv_hi, B, T, D, CHW);
-  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tmq_lo, x3 ? qkv_lo : qkv_hi, B, T, D, 128);
-  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tm64_lo, x3 ? qkv_lo : qkv_hi, B, T, D, CH);
-  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tm80_lo, x3 ? qkv_lo : qkv_hi, B, T, D, CHW);
+  CUresult r = encode_qkv_map(enc, &p.tm_hi, qkv_hi, B, T, D, 128);
+  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tm_lo, x3 ? qkv_lo : qkv_hi, B, T, D, 128);
+  const int CH = x3 ? V6Cfg<true>::CH : V6Cfg<false>::CH;
+  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tmkv_hi, qkv_hi, B, T, D, CH);
+  if (r == CUDA_SUCCESS) r = encode_qkv_map(enc, &p.tmkv_lo, x3 ? qkv_lo : qkv_hi, B, T, D, CH);
   if (r != CUDA_SUCCESS) { set_error("prv2_attention: cuTensorMapEncodeTiled failed (%d)", (int)r); return PRV2_ECUDA; }
   p.out_hi = (bf16*)out_hi; p.out_lo = (bf16*)out_lo;
   p.B = B; p.T = T; p.heads = heads; p.D = D;
-  // key chunks: 64 wide, the last one 16..80 (multiple of 16) so that T mod 64 <= 16 does not cost a whole chunk
-  p.n_chunks = T <= CHW ? 1 : cdiv(T - TAIL_MAX, CH);
-  p.last_width = ((T - CH * (p.n_chunks - 1)) + 15) / 16 * 16;
+  // key chunks: CH wide; the last one holds the remaining 1..CH keys (its MMAs run in 16-key slices)
+  p.n_chunks = cdiv(T, CH);
+  p.last_valid = T - CH * (p.n_chunks - 1);
   // query rows: leftover rows (<= 16) go to the SIMT tail kernel instead of a mostly empty 128-row tile
   const int rem = T % 128;
   p.tq_main = (rem != 0 && rem <= TAIL_MAX && T > 128 && T <= TAIL_MAX_T) ? T - rem : T;
-  const int smem_bf = V5Cfg<false>::SMEM, smem_x3 = V5Cfg<true>::SMEM;
+  static const bool one_cta = getenv("PRV2_ATTN_ONE_CTA") != nullptr;     // diagnostics: pad the request so only one CTA fits an SM
+  const int smem_bf = one_cta ? 120 * 1024 : V6Cfg<false>::SMEM, smem_x3 = V6Cfg<true>::SMEM;
   if (!g_attr_set) {
-    PRV2_CUDA(cudaFuncSetAttribute(attention_v5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bf));
-    PRV2_CUDA(cudaFuncSetAttribute(attention_v5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x3));
+    PRV2_CUDA(cudaFuncSetAttribute(attention_v6_kernel<false, PRV2_ATTN_POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bf));
+    PRV2_CUDA(cudaFuncSetAttribute(attention_v6_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x3));
     g_attr_set = true;
   }
   static const bool want_trace = getenv("PRV2_ATTN_TRACE") != nullptr;
@@ -749,9 +869,9 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
     PRV2_CUDA(cudaMemsetAsync(d_trace, 0, (480 + 3 * 8192) * 8, (cudaStream_t)stream));
     p.trace = d_trace;
   }
-  p.qkv_hi = (const bf16*)qkv_hi; p.qkv_lo = (const bf16*)qkv_lo;
-  if (x3) attention_v5_kernel<true><<<dim3(cdiv(p.tq_main, 128 * V5Cfg<true>::NT), heads, B), V5Cfg<true>::THREADS, smem_x3, (cudaStream_t)stream>>>(p);
-  else attention_v5_kernel<false><<<dim3(cdiv(p.tq_main, 128 * V5Cfg<false>::NT), heads, B), V5Cfg<false>::THREADS, smem_bf, (cudaStream_t)stream>>>(p);
+  const dim3 grid_bf(cdiv(p.tq_main, 128 * V6Cfg<false>::NT), heads, B);
+  if (x3) attention_v6_kernel<true, 0><<<dim3(cdiv(p.tq_main, 128 * V6Cfg<true>::NT), heads, B), V6Cfg<true>::THREADS, smem_x3, (cudaStream_t)stream>>>(p);
+  else attention_v6_kernel<false, PRV2_ATTN_POLY><<<grid_bf, V6Cfg<false>::THREADS, smem_bf, (cudaStream_t)stream>>>(p);
   PRV2_LAUNCH_CHECK();
   if (want_trace) {
     static unsigned long long h[3 * 32 * 5];
