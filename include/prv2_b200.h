@@ -30,7 +30,7 @@ typedef uint16_t prv2_bf16;            /* raw bfloat16 bits */
 #define PRV2_EUNSUPPORTED (-3)         /* shape outside what the kernels implement */
 
 /* ABI version: bumped whenever a signature or the GemmDesc layout changes; the Python binding refuses any other value. */
-#define PRV2_ABI_VERSION 204
+#define PRV2_ABI_VERSION 205
 int prv2_version(void);
 /* sha256 of the CUDA sources + flags this library was compiled from (stamped by build.py with -DPRV2_BUILD_DIGEST);
  * the binding compares it with the digest of the sources it sits next to, so a stale .so is an error, not a silent mismatch. */
@@ -268,6 +268,18 @@ int prv2_zoe_attractor(const float* a_raw, int a_ld, int n_attractors, const flo
  * sum_k softmax((log C(K-1,k) + k log p + (K-1-k) log(1-p)) / T)_k * bilinear_ac(centers)_k. */
 int prv2_zoe_logbinomial_depth(const float* pt_raw, int pt_ld, const float* centers, int hb, int wb, float* depth,
                                int B, int H, int W, int n_bins, float min_temp, float max_temp, prv2_stream_t stream);
+
+/* Depthwise k x k convolution (k in {3, 5}, stride in {1, 2}, zero padding k/2) on channels-last acts with BatchNorm folded into
+ * w [k*k, C] fp32 (tap-major) and bias [C] (may be NULL); relu != 0 applies ReLU.  Output [N, (H-1)/stride+1, (W-1)/stride+1, C].
+ * The dw_start / dw_mid stages of timm's UniversalInvertedResidual (MobileNetV4), the encoder that
+ * estimator/models/blocks/lightweight_refiner.py:259-262 creates through timm.create_model(features_only=True). */
+int prv2_dwconv(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int H, int W, int C, int in_cs, const float* w, const float* bias,
+                int k, int stride, int relu, prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
+
+/* lightweight_refiner.py:293-298: out[n,y,x,0..2] = (crops[n,c,y,x] - mean[c]) / std[c], out[..,3] = depth[n,0,y,x] (depth may be NULL:
+ * coarse_condition=False), channels 4.. zero; mean3 / std3 are HOST arrays of three floats. */
+int prv2_encoder_input(const float* crops, const float* depth, int N, int H, int W, const float* mean3, const float* std3,
+                       prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
 
 /* act <-> fp32 helpers (layout changes at the API edge and for tests). */
 int prv2_nchw_f32_to_act(const float* in, int N, int C, int H, int W,

@@ -401,6 +401,72 @@ __global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict_
     act_store(hi, lo, (size_t)i, in[i]);
 }
 
+// Depthwise k x k convolution (k = 3 or 5, stride 1 or 2, symmetric zero padding k / 2) on channels-last acts, BatchNorm already
+// folded into (w, bias) by the host, optional ReLU: the dw_start / dw_mid stages of MobileNetV4's UniversalInvertedResidual blocks
+// (the V2 family's light-weight refiner encoder, lightweight_refiner.py:259-262).  Thread = one output pixel x 8 channels: k*k
+// 16-byte activation vectors (consecutive threads walk the channel groups of a pixel, so a warp reads whole 128-byte lines) and
+// k*k*8 fp32 weights from the [k*k, C] table (L1-resident), fp32 accumulation in tap order (ky outer, kx inner).  HBM-bound.
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_kernel(const bf16* __restrict__ ih, const bf16* __restrict__ il, int N, int H, int W, int C, int in_cs,
+                                                     const float* __restrict__ w, const float* __restrict__ bias, int stride, int relu,
+                                                     bf16* __restrict__ oh, bf16* __restrict__ ol, int OH, int OW, int out_cs, long long total) {
+  const int cv = C / 8;
+  constexpr int P = K / 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cv) * 8;
+    long long pix = idx / cv;
+    const int ox = (int)(pix % OW);
+    pix /= OW;
+    const int oy = (int)(pix % OH);
+    const int n = (int)(pix / OH);
+    float acc[8];
+    {
+      const float4 b0 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b1 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c8 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int y = oy * stride + ky - P;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int x = ox * stride + kx - P;
+        if (x < 0 || x >= W) continue;
+        float v[8];
+        act_load8(ih, il, (((size_t)n * H + y) * W + x) * in_cs + c8, v);
+        const float* wk = w + (size_t)(ky * K + kx) * C + c8;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wk)), w1 = __ldg(reinterpret_cast<const float4*>(wk + 4));
+        acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]); acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+        acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]); acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    act_store8(oh, ol, (((size_t)n * OH + oy) * OW + ox) * out_cs + c8, acc);
+  }
+}
+
+// Encoder input of the light-weight refiner (lightweight_refiner.py:293-298): (crop - mean) / std for the three colour channels,
+// the coarse depth as a fourth channel (coarse_condition), channels 4..7 zero -> one 16-byte channels-last vector per pixel.
+__global__ void __launch_bounds__(256) encoder_input_kernel(const float* __restrict__ crops, const float* __restrict__ depth, int N, int H, int W,
+                                                            float m0, float m1, float m2, float s0, float s1, float s2, bf16* __restrict__ oh,
+                                                            bf16* __restrict__ ol, int out_cs, long long total) {
+  const size_t hw = (size_t)H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const size_t n = (size_t)(idx / hw), px = (size_t)(idx % hw);
+    const float* c = crops + n * 3 * hw + px;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    v[0] = __fdiv_rn(__fsub_rn(c[0], m0), s0);
+    v[1] = __fdiv_rn(__fsub_rn(c[hw], m1), s1);
+    v[2] = __fdiv_rn(__fsub_rn(c[2 * hw], m2), s2);
+    if (depth) v[3] = depth[n * hw + px];
+    act_store8(oh, ol, (size_t)idx * out_cs, v);
+  }
+}
+
 int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -549,6 +615,37 @@ extern "C" int prv2_split_f32(const float* in, int64_t n, prv2_bf16* hi, prv2_bf
   PRV2_CHECK_ARG(in && hi && n >= 0, "prv2_split_f32: bad arguments");
   if (n == 0) return PRV2_OK;
   split_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, n, (bf16*)hi, (bf16*)lo);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_dwconv(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int H, int W, int C, int in_cs, const float* w, const float* bias,
+                           int k, int stride, int relu, prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(in_hi && out_hi && w, "prv2_dwconv: null pointer");
+  PRV2_CHECK_ARG((k == 3 || k == 5) && (stride == 1 || stride == 2), "prv2_dwconv: k must be 3 or 5 and stride 1 or 2 (got k=%d stride=%d)", k, stride);
+  PRV2_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && in_cs % 8 == 0 && out_cs % 8 == 0 && in_cs >= C && out_cs >= C,
+                 "prv2_dwconv: C and the pitches must be multiples of 8");
+  PRV2_CHECK_ARG((in_lo == nullptr) == (out_lo == nullptr), "prv2_dwconv: lo planes must both be present or absent");
+  PRV2_CHECK_ARG(((uintptr_t)w & 15) == 0 && ((uintptr_t)bias & 15) == 0, "prv2_dwconv: weights / bias must be 16-byte aligned");
+  const int OH = (H + 2 * (k / 2) - k) / stride + 1, OW = (W + 2 * (k / 2) - k) / stride + 1;
+  const long long total = (long long)N * OH * OW * (C / 8);
+  if (k == 3)
+    dwconv_kernel<3><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, N, H, W, C, in_cs, w, bias, stride,
+                                                                            relu, (bf16*)out_hi, (bf16*)out_lo, OH, OW, out_cs, total);
+  else
+    dwconv_kernel<5><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in_hi, (const bf16*)in_lo, N, H, W, C, in_cs, w, bias, stride,
+                                                                            relu, (bf16*)out_hi, (bf16*)out_lo, OH, OW, out_cs, total);
+  PRV2_LAUNCH_CHECK();
+  return PRV2_OK;
+}
+
+extern "C" int prv2_encoder_input(const float* crops, const float* depth, int N, int H, int W, const float* mean3, const float* std3,
+                                  prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(crops && out_hi && mean3 && std3, "prv2_encoder_input: null pointer");
+  PRV2_CHECK_ARG(N > 0 && H > 0 && W > 0 && out_cs >= 8 && out_cs % 8 == 0, "prv2_encoder_input: bad shape");
+  const long long total = (long long)N * H * W;
+  encoder_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(crops, depth, N, H, W, mean3[0], mean3[1], mean3[2], std3[0], std3[1],
+                                                                              std3[2], (bf16*)out_hi, (bf16*)out_lo, out_cs, total);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }

@@ -532,12 +532,24 @@ class PatchRefinerPlus(PatchRefiner):
         self.precision, self.patch_batch, self.output_device = precision, int(patch_batch), output_device
         if "convnext" in str(_get(fb, "encoder_name", "")):
             raise NotImplementedError("convnext encoders add an upsample_convx stage (lightweight_refiner.py:276-283,307-314): not implemented")
-        self.refiner_fine_encoder = fine_encoder if fine_encoder is not None else _default_fine_encoder(_get(fb, "encoder_name"), 4 if self.coarse_condition else 3)
-        self.refiner_fine_encoder.eval()
-        cfgd = getattr(self.refiner_fine_encoder, "default_cfg", None) or {}
-        self._enc_mean = tuple(cfgd.get("mean", (0.485, 0.456, 0.406)))
-        self._enc_std = tuple(cfgd.get("std", (0.229, 0.224, 0.225)))
+        enc_name, in_chans = str(_get(fb, "encoder_name", "")), 4 if self.coarse_condition else 3
+        # mobilenetv4_conv_small (configs/patchrefinerv2_dav2/plus_mobile_*): this package's own kernels (mnv4.py).  Any other
+        # encoder: a PyTorch module the caller supplies, or timm where it is installed (library code, parity unpinned either way).
+        self._native_enc = fine_encoder is None and enc_name.startswith("mobilenetv4_conv_small")
+        self._enc_in_chans = in_chans
         self._weights = OrderedDict()
+        if self._native_enc:
+            from .mnv4 import DEFAULT_MEAN, DEFAULT_STD, mnv4_conv_small_spec
+            self.refiner_fine_encoder = None
+            self._enc_mean, self._enc_std = DEFAULT_MEAN, DEFAULT_STD
+            for k, shp in mnv4_conv_small_spec(in_chans).items():           # a fresh BatchNorm: weight 1, running_var 1, the rest 0
+                self._weights[self.ENC_PREFIX + k] = torch.ones(shp) if k.endswith(("bn.weight", "bn1.weight", "running_var")) else torch.zeros(shp)
+        else:
+            self.refiner_fine_encoder = fine_encoder if fine_encoder is not None else _default_fine_encoder(enc_name, in_chans)
+            self.refiner_fine_encoder.eval()
+            cfgd = getattr(self.refiner_fine_encoder, "default_cfg", None) or {}
+            self._enc_mean = tuple(cfgd.get("mean", (0.485, 0.456, 0.406)))
+            self._enc_std = tuple(cfgd.get("std", (0.229, 0.224, 0.225)))
         for k, shp in dav2_weight_spec(self._cb_cfg["encoder"], self._cb_cfg["features"], self._cb_cfg["out_channels"]).items():
             self._weights["coarse_branch." + k] = torch.zeros(shp)
         keys = ("coarse_chl", "fine_chl", "fine_chl_after_coarse2fine", "temp_chl", "dec_chl")
@@ -558,6 +570,8 @@ class PatchRefinerPlus(PatchRefiner):
     ENC_PREFIX = "refiner_fine_branch.refiner_encoder."
 
     def _load(self, sd, strict):
+        if self._native_enc:
+            return super()._load(sd, strict)
         enc = {k[len(self.ENC_PREFIX):]: v for k, v in sd.items() if k.startswith(self.ENC_PREFIX)}
         rest = {k: v for k, v in sd.items() if not k.startswith(self.ENC_PREFIX)}
         res = super()._load(rest, strict)
@@ -570,8 +584,9 @@ class PatchRefinerPlus(PatchRefiner):
 
     def state_dict(self, *args, **kwargs):
         sd = OrderedDict((k, v.clone()) for k, v in self._weights.items())
-        for k, v in self.refiner_fine_encoder.state_dict().items():
-            sd[self.ENC_PREFIX + k] = v.detach().cpu().clone()
+        if not self._native_enc:
+            for k, v in self.refiner_fine_encoder.state_dict().items():
+                sd[self.ENC_PREFIX + k] = v.detach().cpu().clone()
         return sd
 
     def get_save_dict(self):                        # patchrefinerplus.py:215-216 (keeps the coarse branch)
@@ -585,8 +600,14 @@ class PatchRefinerPlus(PatchRefiner):
         x3 = self.precision == "fp32"
         sd, fu = self._weights, self._fu_cfg
         keys = ("coarse_chl", "fine_chl", "fine_chl_after_coarse2fine", "temp_chl", "dec_chl")
-        self.refiner_fine_encoder.to(device)
+        enc = None
+        if self._native_enc:
+            from .mnv4 import MobileNetV4ConvSmallB200
+            enc = MobileNetV4ConvSmallB200(sd, self.ENC_PREFIX, self._enc_in_chans, x3, device, self._enc_mean, self._enc_std)
+        else:
+            self.refiner_fine_encoder.to(device)
         return dict(
+            encoder=enc,
             coarse=DepthAnythingV2B200(sd, "coarse_branch.", self._cb_cfg["encoder"], self._cb_cfg["features"], self._cb_cfg["out_channels"], self.max_depth, x3, device),
             fusion=BiDirectionalFusionB200(sd, "refiner_fusion_model.", *[_get(fu, k) for k in keys], coarse2fine_type=_get(fu, "coarse2fine_type"),
                                            x3=x3, device=device, heavy=self._fu_heavy),
@@ -605,9 +626,12 @@ class PatchRefinerPlus(PatchRefiner):
             pb = len(idx)
             crops, c_roi, d_roi = self._gather_batch(eng, image_hr, bboxs_np, rois_np, coarse_feats, coarse_depth, idx, P)
             # LightWeightRefiner.forward (lightweight_refiner.py:285-322): normalise, condition on the coarse depth, encode
-            x = (crops - eng["enc_mean"]) / eng["enc_std"]
-            feats = list(self.refiner_fine_encoder(torch.cat([x, d_roi], dim=1) if self.coarse_condition else x))
-            f_acts = [Act.from_nchw(f, x3) for f in feats]
+            if eng["encoder"] is not None:
+                f_acts = eng["encoder"].forward(crops, d_roi if self.coarse_condition else None, ws)
+            else:
+                x = (crops - eng["enc_mean"]) / eng["enc_std"]
+                feats = list(self.refiner_fine_encoder(torch.cat([x, d_roi], dim=1) if self.coarse_condition else x))
+                f_acts = [Act.from_nchw(f, x3) for f in feats]
             top = f_acts[0]
             up = ops.resize_bilinear(top, ws.act("enc_up", pb, top.H * 2, top.W * 2, top.C))       # :316-318
             r_feats = ([up] + f_acts)[::-1]                                                        # :320, coarsest first

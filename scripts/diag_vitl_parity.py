@@ -24,7 +24,7 @@ def stats(name, got, want):
     rel = err / want.abs().clamp_min(1e-3)
     k = rel.flatten().argmax().item()
     print(f"  {name:14s} max_abs {err.max():.3e}  rel_to_max {rel_max(got, want):.3e}  px_rel max {rel.max():.3e} (want {want.flatten()[k]:.4f} got {got.flatten()[k]:.4f})  "
-          f"p99.99 {rel.flatten().kthvalue(int(rel.numel() * 0.9999)).values:.3e}  mean {rel.mean():.3e}  n(rel>1e-3) {(rel > 1e-3).sum().item()}/{rel.numel()}")
+          f"p99 {rel.flatten().kthvalue(int(rel.numel() * 0.99)).values:.3e}  p99.99 {rel.flatten().kthvalue(int(rel.numel() * 0.9999)).values:.3e}  mean {rel.mean():.3e}  n(rel>1e-3) {(rel > 1e-3).sum().item()}/{rel.numel()}")
 
 
 # (1) the oracle itself on the GPU (eager fp32)

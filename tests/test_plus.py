@@ -68,8 +68,9 @@ def test_plus_surface_without_gpu(plus_setup, monkeypatch):
     res = m.load_dict(sd)
     assert not res.missing_keys and not res.unexpected_keys
     assert m.tile_cfg == O.prepare_tile_cfg(cfg["patch_process_shape"], cfg["image_raw_shape"], cfg["patch_split_num"])
-    with pytest.raises(NotImplementedError):                      # timm is not installed here: loud, with the way out
-        build_model(dict(type="PatchRefinerPlus", config=cfg))
+    eff = dict(cfg, refiner=dict(cfg["refiner"], fine_branch=dict(cfg["refiner"]["fine_branch"], encoder_name="tf_efficientnet_b5_ap")))
+    with pytest.raises(NotImplementedError):                      # a timm-only encoder and no timm here: loud, with the way out
+        build_model(dict(type="PatchRefinerPlus", config=eff))
     with pytest.raises(RuntimeError):                             # no CPU path
         m(mode="infer", image_lr=lr, image_hr=hr, cai_mode="m1", process_num=2)
     bad = dict(cfg); bad["refiner"] = dict(cfg["refiner"]); bad["refiner"]["fusion_model"] = dict(cfg["refiner"]["fusion_model"], coarse2fine_type="no-such-type")
