@@ -30,7 +30,7 @@ typedef uint16_t prv2_bf16;            /* raw bfloat16 bits */
 #define PRV2_EUNSUPPORTED (-3)         /* shape outside what the kernels implement */
 
 /* ABI version: bumped whenever a signature or the GemmDesc layout changes; the Python binding refuses any other value. */
-#define PRV2_ABI_VERSION 205
+#define PRV2_ABI_VERSION 206
 int prv2_version(void);
 /* sha256 of the CUDA sources + flags this library was compiled from (stamped by build.py with -DPRV2_BUILD_DIGEST);
  * the binding compares it with the digest of the sources it sits next to, so a stale .so is an error, not a silent mismatch. */
@@ -280,6 +280,12 @@ int prv2_dwconv(const prv2_bf16* in_hi, const prv2_bf16* in_lo, int N, int H, in
  * coarse_condition=False), channels 4.. zero; mean3 / std3 are HOST arrays of three floats. */
 int prv2_encoder_input(const float* crops, const float* depth, int N, int H, int W, const float* mean3, const float* std3,
                        prv2_bf16* out_hi, prv2_bf16* out_lo, int out_cs, prv2_stream_t stream);
+
+/* Multi-GPU exchange (the reference has no multi-GPU inference: tester.py:62-69 runs one frame per process): in-place
+ * ncclAllReduce(sum, float32) of the packed partial buffer [num_canvas (Hc*Wc) | m1_canvas (Hc*Wc) | num_raw (H*W)] written by
+ * prv2_blend_partial_*, on the caller's ncclComm_t and stream.  NCCL is resolved from the process at run time (dlopen of
+ * libnccl.so.2): no link-time dependency.  PRV2_ECUDA when NCCL is absent or the collective fails. */
+int prv2_reduce_canvas(void* nccl_comm /*ncclComm_t*/, float* packed, int64_t count, prv2_stream_t stream);
 
 /* act <-> fp32 helpers (layout changes at the API edge and for tests). */
 int prv2_nchw_f32_to_act(const float* in, int N, int C, int H, int W,

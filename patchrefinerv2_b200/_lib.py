@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 205          # == PRV2_ABI_VERSION in include/prv2_b200.h
+ABI_VERSION = 206          # == PRV2_ABI_VERSION in include/prv2_b200.h
 MAX_SRC = 12
 MAX_SEG = 128
 
@@ -88,6 +88,7 @@ SIGNATURES = {
     "prv2_act_to_nchw_f32": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
     "prv2_phase_split": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p],
     "prv2_split_f32": [_p, _i64, _p, _p, _p],
+    "prv2_reduce_canvas": [_p, _p, _i64, _p],
     "prv2_dwconv": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p, _i, _p],
     "prv2_encoder_input": [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p],
     "prv2_zoe_attractor": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _i, _i, _i, _f, _i, _p],

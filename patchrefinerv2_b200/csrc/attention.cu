@@ -8,6 +8,7 @@
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 #include <type_traits>
+#include <mutex>
 
 using namespace prv2;
 
@@ -819,6 +820,26 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 bool g_attr_set = false;
 
+// one side stream + fork / join events per device, created on first use (the library's only stream; see prv2_attention)
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; bool ok; };
+SideStream g_side[64];
+std::mutex g_side_mu;
+SideStream* side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_side_mu);
+  SideStream& s = g_side[dev];
+  if (!s.ok) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    s.ok = true;
+  }
+  return &s;
+}
+
 }  // namespace
 
 static CUresult encode_qkv_map(PFN_cuTensorMapEncodeTiled_v12000 enc, CUtensorMap* tm, const void* ptr, int B, int T, int D, int box_rows) {
@@ -869,6 +890,28 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
     PRV2_CUDA(cudaMemsetAsync(d_trace, 0, (480 + 3 * 8192) * 8, (cudaStream_t)stream));
     p.trace = d_trace;
   }
+  // The leftover-row kernel (memory-bound: it re-reads K and V of every head for one query row, 31 us per 27-patch call under
+  // ncu = 3 ms per frame) is independent of the tile kernel, so it runs on a side stream of the library, forked from and joined
+  // back into the caller's stream with events (capturable in a CUDA graph like any fork / join); it is launched FIRST so that
+  // its small CTAs find room before the tile kernel fills every SM.  PRV2_ATTN_TAIL_SERIAL=1 keeps it on the caller's stream.
+  static const bool tail_serial = getenv("PRV2_ATTN_TAIL_SERIAL") != nullptr;
+  const bool has_tail = p.tq_main < T;
+  // (Measured, scripts/bench_attention.py: 40 -> 27 us for a one-image call and 120 -> 117 us at 12 patches, but 223 -> 233 us at
+  // 27 patches, where the tail's CTAs delay the first wave of tiles: the fork is used for grids of up to ~7 waves only.)
+  const long long tile_ctas = (long long)cdiv(p.tq_main, 128 * (x3 ? V6Cfg<true>::NT : V6Cfg<false>::NT)) * heads * B;
+  SideStream* side = (has_tail && !tail_serial && tile_ctas <= 2048) ? side_stream() : nullptr;
+  if (has_tail) {
+    cudaStream_t ts = (cudaStream_t)stream;
+    if (side) {
+      std::lock_guard<std::mutex> lock(g_side_mu);          // record + wait as one step: callers on other host threads share the events
+      PRV2_CUDA(cudaEventRecord(side->fork, (cudaStream_t)stream));
+      PRV2_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      ts = side->stream;
+    }
+    attention_tail_kernel<<<dim3(T - p.tq_main, heads, B), 256, 0, ts>>>((const bf16*)qkv_hi, (const bf16*)qkv_lo, (bf16*)out_hi, (bf16*)out_lo, T, heads, p.tq_main);
+    PRV2_LAUNCH_CHECK();
+    if (side) PRV2_CUDA(cudaEventRecord(side->join, side->stream));
+  }
   const dim3 grid_bf(cdiv(p.tq_main, 128 * V6Cfg<false>::NT), heads, B);
   if (x3) attention_v6_kernel<true, 0><<<dim3(cdiv(p.tq_main, 128 * V6Cfg<true>::NT), heads, B), V6Cfg<true>::THREADS, smem_x3, (cudaStream_t)stream>>>(p);
   else attention_v6_kernel<false, PRV2_ATTN_POLY><<<grid_bf, V6Cfg<false>::THREADS, smem_bf, (cudaStream_t)stream>>>(p);
@@ -907,10 +950,6 @@ extern "C" int prv2_attention(const prv2_bf16* qkv_hi, const prv2_bf16* qkv_lo, 
         fprintf(stderr, "  cta %4d start %8.2f us dur %6.2f us (%llu clocks)\n", i, (hc[3 * i] - first) / 1e3, (hc[3 * i + 1] - hc[3 * i]) / 1e3, hc[3 * i + 2]);
     }
   }
-  if (p.tq_main < T) {
-    attention_tail_kernel<<<dim3(T - p.tq_main, heads, B), 256, 0, (cudaStream_t)stream>>>((const bf16*)qkv_hi, (const bf16*)qkv_lo, (bf16*)out_hi, (bf16*)out_lo, T,
-                                                                                       heads, p.tq_main);
-    PRV2_LAUNCH_CHECK();
-  }
+  if (side) PRV2_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, side->join, 0));
   return PRV2_OK;
 }

@@ -41,6 +41,38 @@ extern "C" int prv2_device_info(int32_t* out4) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The one real exchange of the sharded path: sum the packed partial buffer [num_canvas | m1_canvas | num_raw]
+// over the ranks, in place, with NCCL on the caller's communicator and stream.  NCCL is resolved at run time from the process
+// (PyTorch ships and loads libnccl.so.2), so the library has no link-time dependency on it and loads on a box without NCCL.
+// ---------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+namespace {
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/, void* /*ncclComm_t*/, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+nccl_allreduce_fn g_nccl_allreduce = nullptr;
+nccl_errstr_fn g_nccl_errstr = nullptr;
+bool nccl_resolve() {
+  if (g_nccl_allreduce) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);          // already mapped by the host framework?
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return false;
+  g_nccl_allreduce = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
+  g_nccl_errstr = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
+  return g_nccl_allreduce != nullptr;
+}
+}  // namespace
+
+extern "C" int prv2_reduce_canvas(void* nccl_comm, float* packed, int64_t count, prv2_stream_t stream) {
+  PRV2_CHECK_ARG(nccl_comm && packed && count >= 0, "prv2_reduce_canvas: null communicator / buffer");
+  if (count == 0) return PRV2_OK;
+  if (!nccl_resolve()) { set_error("prv2_reduce_canvas: libnccl.so.2 (ncclAllReduce) could not be resolved in this process"); return PRV2_ECUDA; }
+  const int rc = g_nccl_allreduce(packed, packed, (size_t)count, 7 /*ncclFloat32*/, 0 /*ncclSum*/, nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) { set_error("prv2_reduce_canvas: ncclAllReduce failed (%d: %s)", rc, g_nccl_errstr ? g_nccl_errstr(rc) : "?"); return PRV2_ECUDA; }
+  return PRV2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // crop + bilinear(align_corners=True) resize            baseline_pretrain.py:272-280
 // ---------------------------------------------------------------------------------------------
 // grid: (ceil(pw/4/128), ph, P*3); each thread writes 4 consecutive x (one float4).

@@ -13,6 +13,7 @@ Changed by design: patches are cropped, gathered, refined and blended on the dev
 """
 from __future__ import annotations
 
+import os
 import random as _random
 from collections import OrderedDict
 from typing import Dict, List, Optional
@@ -24,7 +25,7 @@ import torch.nn as nn
 from . import _lib, masks, ops, tiling
 from .dav2 import VIT_CFG, DepthAnythingV2B200, PATCH
 from .fusion import FusionUnetB200
-from .nn import Act, Workspace
+from .nn import Act, Workspace, ptr, stream_ptr
 from .registry import MODELS
 
 
@@ -203,6 +204,15 @@ class PatchRefiner(nn.Module):
     def state_dict(self, *args, **kwargs):
         return OrderedDict((k, v.clone()) for k, v in self._weights.items())
 
+    _native_comm = None
+
+    def use_native_reduce(self):
+        """Route the sharded path's sum-reduce through ``prv2_reduce_canvas`` on a communicator of this model's own (comm.py)."""
+        from .comm import NcclComm
+        if self._native_comm is None:
+            self._native_comm = NcclComm(self._device if self._device.type == "cuda" else torch.device("cuda", torch.cuda.current_device()))
+        return self
+
     def load_dict(self, dict):                      # patchrefiner.py:155-156
         return self.load_state_dict(dict, strict=False)
 
@@ -272,6 +282,7 @@ class PatchRefiner(nn.Module):
         crops = ws.f32(f"crops{pb}", pb, 3, ph, pw)
         d_roi = ws.f32(f"droi{pb}", pb, 1, ph, pw)
         c_roi = [ws.act(f"roi{li}", pb, f.H, f.W, f.C) for li, f in enumerate(coarse_feats)]
+        tiling.check_roi_regime(rois_np[idx], [(f.H, f.W, f.H / ph) for f in coarse_feats] + [(ph, pw, 1.0)])
         bb = torch.from_numpy(np.ascontiguousarray(bboxs_np[idx])).to(dev, non_blocking=True)
         rois = torch.from_numpy(np.ascontiguousarray(rois_np[idx])).to(dev, non_blocking=True)
         frames = idx // P
@@ -437,8 +448,13 @@ class PatchRefiner(nn.Module):
                 ops.blend_partial_canvas(pf[:n_regular], of[:n_regular].contiguous(), mask, grid_stages, Hc, Wc, pk[:n_c].view(Hc, Wc), pk[n_c:2 * n_c].view(Hc, Wc))
                 if is_r and n_random:
                     ops.blend_partial_raw(pf[n_regular:], of[n_regular:].contiguous(), starts_all[f], rmask, ph, pw, H, W, pk[2 * n_c:].view(H, W), prep=rprep)
-            if world > 1:
-                torch.distributed.all_reduce(packed)                                         # ONE sum-reduce of the packed partial canvases of the whole batch
+            if world > 1:                                                                    # ONE sum-reduce of the packed partial canvases of the whole batch
+                if self._native_comm is None and os.environ.get("PRV2_NATIVE_REDUCE") == "1":
+                    self.use_native_reduce()
+                if self._native_comm is not None:                                            # issued by the library on its own ncclComm_t (prv2_reduce_canvas)
+                    _lib.call("prv2_reduce_canvas", self._native_comm.handle, ptr(packed), packed.numel(), stream_ptr())
+                else:
+                    torch.distributed.all_reduce(packed)
         depths, cnts = [], []
         for f in range(F_):
             pf = preds[f * P:(f + 1) * P]

@@ -57,6 +57,22 @@ def bboxs_to_feat(bboxs: np.ndarray, image_raw_shape, patch_process_shape) -> np
     return np.concatenate([inds, bf.astype(np.float32)], axis=1)
 
 
+def check_roi_regime(rois: np.ndarray, levels) -> None:
+    """The gather kernels implement torchvision's roi_align (aligned=True, sampling_ratio=-1) in its ONE-sample-per-bin regime:
+    adaptive grid ceil(roi_size / pooled_size) == 1, evaluated in float32 exactly as torchvision does.  ``levels`` =
+    [(pooled_h, pooled_w, spatial_scale)].  A ROI as large as the whole map (patch_split_num [1, 1]) can round to a grid of 2;
+    that regime is not implemented, so it is refused here instead of silently differing from the reference."""
+    r = np.asarray(rois, dtype=np.float32).reshape(-1, 4)
+    for ph, pw, scale in levels:
+        sc = np.float32(scale)
+        rw = (r[:, 2] * sc - np.float32(0.5)) - (r[:, 0] * sc - np.float32(0.5))
+        rh = (r[:, 3] * sc - np.float32(0.5)) - (r[:, 1] * sc - np.float32(0.5))
+        gw, gh = np.ceil(rw / np.float32(pw)), np.ceil(rh / np.float32(ph))
+        if r.shape[0] and (gw.max() > 1 or gh.max() > 1):
+            raise NotImplementedError(f"roi_align sampling grid {int(gh.max())}x{int(gw.max())} at a {ph}x{pw} level: only the one-sample-per-bin "
+                                      "regime (ROI no larger than the pooled map, i.e. patch_split_num >= [1, 1] without float32 overshoot) is implemented")
+
+
 @dataclasses.dataclass
 class Stage:
     """One ``regular_tile`` / ``random_tile`` call: its patches in reference order."""

@@ -11,7 +11,7 @@ from patchrefinerv2_b200.nn import Act, GemmLayer, conv_segments
 
 DEV = "cuda:0"
 torch.manual_seed(0)
-B, T, D = 12, 1025, 1024
+B, T, D = int(os.environ.get("PRV2_PROF_B", "12")), 1025, 1024
 M = B * T
 which = sys.argv[1:]
 results = []
@@ -61,7 +61,7 @@ def conv(name, Bc, H, W, splits, pitches, Cout, **kw):
     timed(name, lambda: lay(srcs, out=out), 2.0 * Bc * H * W * 9 * sum(splits) * Cout, iters=3)
 
 
-for kk in (512, 1024, 2048, 4096, 8192):        # K sweep at the qkv shape: separates per-tile overhead from per-chunk cost
+for kk in (64, 128, 256, 512, 1024, 2048, 4096, 8192):        # K sweep at the qkv shape: separates per-tile overhead from per-chunk cost
     linear(f"k{kk}", kk, 3 * D)
 linear("qkv", D, 3 * D)
 linear("fc1", D, 4 * D, act=_lib.ACT_GELU)

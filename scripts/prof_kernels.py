@@ -1,4 +1,4 @@
-"""Single launches of the hot kernels at ViT-L / 12-patch shapes, for ncu captures."""
+"""Single launches of the hot kernels at ViT-L shapes (PRV2_PROF_B patches per launch, default 27 = the batch bench.py runs), for ncu captures."""
 import math
 import os
 import sys
@@ -10,7 +10,7 @@ from patchrefinerv2_b200.nn import Act, GemmLayer, conv_segments
 DEV = "cuda:0"
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 torch.manual_seed(0)
-B, T, D, heads = 12, 1025, 1024, 16
+B, T, D, heads = int(os.environ.get("PRV2_PROF_B", "27")), 1025, 1024, 16      # 27 = bench.py's patch batch (round 1 profiled 12)
 M = B * T
 reps = 3
 

@@ -200,3 +200,19 @@ def test_integration_doc_lists_every_c_abi_symbol():
         grouped.update(stem + a for a in alts.split(","))
     missing = [s for s in syms if s not in doc and s not in grouped]
     assert not missing, missing
+
+
+def test_roi_regime_check_accepts_baseline_geometries_and_refuses_a_two_sample_grid():
+    """roi_align's adaptive sampling grid must be 1x1 (the regime the gather kernels implement): true for every BASELINE geometry,
+    refused loudly otherwise."""
+    import random
+    import numpy as np
+    import pytest
+    from patchrefinerv2_b200 import tiling
+    for raw, split, mode in (((1080, 1920), (2, 2), "r8"), ((2160, 3840), (4, 4), "r8"), ((4320, 7680), (8, 8), "r8"), ((432, 768), (1, 1), "m1")):
+        tc = tiling.prepare_tile_cfg((448, 448), raw, split)
+        bb = np.concatenate([s.bboxs for s in tiling.schedule(tc, (448, 448), mode, 4, random.Random(0))])
+        rois = tiling.bboxs_to_feat(bb, raw, (448, 448))[:, 1:]
+        tiling.check_roi_regime(rois, [(32, 32, 32 / 448), (256, 256, 256 / 448), (448, 448, 1.0)])
+    with pytest.raises(NotImplementedError):
+        tiling.check_roi_regime(np.array([[0, 0, 449, 448]], np.float32), [(448, 448, 1.0)])
