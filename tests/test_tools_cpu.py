@@ -177,8 +177,10 @@ def test_reference_configs_construct_or_fail_loudly():
                 if c.get(k):
                     c[k] = None
             kw = dict(type=m["type"], config=c)
-            if m["type"] == "PatchRefinerPlus":
-                kw["fine_encoder"] = O.ToyFineEncoder(4)                      # timm stand-in (the encoder is caller-supplied)
+            enc_name = str(((c.get("refiner") or {}).get("fine_branch") or {}).get("encoder_name", ""))
+            if m["type"] == "PatchRefinerPlus" and not enc_name.startswith("mobilenetv4_conv_small"):
+                kw["fine_encoder"] = O.ToyFineEncoder(4)                      # timm stand-in (EfficientNet / ConvNeXt encoders are caller-supplied);
+                                                                              # the plus_mobile configs build the package's own MobileNetV4 encoder
             build_model(kw)
             ok[m["type"]] += 1
         except (NotImplementedError, KeyError) as e:
