@@ -20,7 +20,7 @@ HEADERS = ["common.cuh", os.path.join("..", "..", "include", "prv2_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("PRV2_EXTRA_NVCC_FLAGS", "").split()        # diagnostics builds, e.g. -DPRV2_GEMM_TRACE_BUILD -DPRV2_ATTN_TRACE_BUILD
 
 
 def _nvcc() -> str:

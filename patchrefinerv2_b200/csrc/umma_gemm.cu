@@ -57,6 +57,7 @@ constexpr long long SPIN_LIMIT_CLK = 8000000000ll;     // ~4 s of SM clocks: a d
 struct alignas(64) KParams {
   CUtensorMap tmA[PRV2_MAX_SRC];
   CUtensorMap tmB;
+  CUtensorMap tmOut;                          // row epilogue in TMA-store mode: the output tensor, box = one warp's 32 rows x 128 bytes
   int16_t seg_src[PRV2_MAX_SEG];
   int16_t seg_dh[PRV2_MAX_SEG];
   int16_t seg_dw[PRV2_MAX_SEG];
@@ -84,9 +85,22 @@ struct alignas(64) KParams {
   float acc_scale;          // accumulators are multiplied by this on their way out of TMEM (weights pre-scaled by its inverse, see the header)
   int32_t f16;              // operand planes are FP16 (the (hi, lo) pair format) instead of bf16
   int32_t stg_warp_bytes;   // epilogue staging per warp (row epilogue of the fp32 residual stream double-buffers its row)
+  int32_t tma_store;        // row epilogue (bf16 outputs): 1 = ship each warp's 32 x 128-byte panels with TMA tensor stores, 0 = one bulk copy per lane
   int32_t debug;      // diagnostics (PRV2_GEMM_DEBUG): bit0 = no TMA after the first ring pass, bit1 = epilogue drains TMEM only
 };
 static_assert(sizeof(KParams) <= 4096, "kernel parameter block too large");
+
+// Diagnostics (compiled in only with -DPRV2_GEMM_TRACE_BUILD): clock64 stamps of CTA 0's roles per tile, [role][tile][point], read
+// back with prv2_debug_gemm_trace.  role 0 = epilogue warp 2, role 1 = MMA warp, role 2 = TMA producer.
+#ifdef PRV2_GEMM_TRACE_BUILD
+__device__ unsigned long long g_gemm_trace[3 * 64 * 8];
+#define GTRACE(role, it, k)                                                                                  \
+  do {                                                                                                       \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it) < 64) g_gemm_trace[((role) * 64 + (it)) * 8 + (k)] = clock64(); \
+  } while (0)
+#else
+#define GTRACE(role, it, k) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -162,8 +176,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) { 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Accumulator hand-back of the epilogue warps.  RELAXED: what has to be ordered before the MMA warp overwrites the accumulator are this
+// warp's TMEM loads, and those are complete (tcgen05.wait::ld) and fenced (tcgen05.fence::before_thread_sync) -- no memory of the
+// generic proxy is published through this barrier.  The .release.cluster form waited for the warp's outstanding global / async
+// writes every tile: ~3000 clocks per tile in the per-tile traces (scripts/gemm_trace.py), a third of the epilogue loop.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -265,6 +283,13 @@ __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t b
 __device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }
+// TMA tensor store of one staged panel (32 rows x 128 bytes, 128-byte swizzle): out-of-range rows / channels are clipped by the
+// tensor map, so ragged edges need no predicates
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t ssrc, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(ssrc), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -321,7 +346,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
-  uint8_t* const stage_area = smem_raw + (bar_base - smem_u32(smem_raw)) + 256;     // epilogue transpose tiles
+  // epilogue staging behind the barriers (TMA-store mode: 1024-byte aligned for the swizzled panels; bar_base is 1024-aligned there)
+  uint8_t* const stage_area = smem_raw + (bar_base - smem_u32(smem_raw)) + (p.tma_store ? 1024 : 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -440,8 +466,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       for (int tile = worker; tile < p.total_tiles; tile += n_workers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        GTRACE(1, it, 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
+        GTRACE(1, it, 1);
         const uint32_t tmem_d = tmem_base + acc * p.block_n;
         uint32_t accumulate = 0;
         for (int s = 0; s < p.n_seg; ++s) {
@@ -504,6 +532,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         }
         if (elect_one()) { if (CG == 2) tc_commit_pair(tfull_bar(acc)); else tc_commit(tfull_bar(acc)); }
         __syncwarp();
+        GTRACE(1, it, 2);
       }
     }
   } else if (FAST) {
@@ -518,6 +547,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
     // RESID: two 128-byte rows per lane (pitch ROW_PITCH, second buffer at +32*ROW_PITCH); bf16 outputs: one 256-byte row (pitch ROW_PITCH2)
     uint8_t* const srow = stage_area + ew * p.stg_warp_bytes + lane * (EPI == PRV2_EPI_RESID_F32 ? ROW_PITCH : ROW_PITCH2);
     const uint32_t srow_s = smem_u32(srow);
+    // TMA-store mode (layers whose epilogue, not their MMAs, paces the tile: per-tile clock64 traces, scripts/gemm_trace.py, show
+    // ~2300-3000 clocks per tile for the 32 serialised per-lane bulk copies of a warp, doubled by the second warp of the scheduler):
+    // per warp two 4 KB panels (32 rows x 128 B) in the tensor map's 128-byte-swizzled box layout, ONE tensor store per panel
+    // issued by one lane.  (For the MMA-bound ViT linears the tensor stores compete with the operand loads for the TMA unit:
+    // measured 137 -> 147 us at qkv, so those keep the per-lane copies.)
+    const bool tma = p.tma_store != 0;
+    uint8_t* const wstage = stage_area + ew * p.stg_warp_bytes;
+    const uint32_t wstage_s = smem_u32(wstage);
+    uint8_t* const lrow = wstage + lane * 128;
+    const uint32_t lsw = (uint32_t)(lane & 7);
+    const int bq_w = (quad * 32) & tile_w_mask, bq_h = (quad * 32) >> tile_w_log2;      // this warp's box origin inside the tile
     float* const s_par = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * p.stg_warp_bytes);
     float* const s_ln = reinterpret_cast<float*>(stage_area + NUM_EPI_WARPS * p.stg_warp_bytes + PAR_BYTES);
     int n_sub_done = 0;
@@ -539,6 +579,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       const bool valid = (h < pH) && (w < pW) && (img < p.N);
       bf16* const grow = out_hi + (((size_t)img * pH + h) * pW + w) * out_cs + n0;
       float* const par = s_par + acc * 768;
+      if (ew == 0) GTRACE(0, it, 0);
       if (te < block_n) {
         const int n = min(n0 + te, Cout - 1);
         par[te] = p.bias ? __ldg(p.bias + n) : 0.f;
@@ -546,30 +587,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         if (EPI == PRV2_EPI_RESID_F32) par[256 + te] = __ldg(p.gamma + n);
       }
       asm volatile("bar.sync 5, 256;" ::: "memory");          // parameters visible to all epilogue warps
+      if (ew == 0) GTRACE(0, it, 1);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (ew == 0) GTRACE(0, it, 2);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * block_n;
       float mean = 0.f, rstd = 1.f;
       if (is_ln) {
-        // channels-first LayerNorm statistics of this lane's pixel (convs.py:24-27): each warp of the quadrant reduces
-        // its own panels two-pass (mean, then centred squares); the halves merge with Chan's parallel update.
-        float v[16];
-        float sum = 0.f;
+        // channels-first LayerNorm statistics of this lane's pixel (convs.py:24-27): each warp of the quadrant reduces its own
+        // panels in ONE pass over tensor memory -- sums of (x - shift) and (x - shift)^2 with shift = the first channel of the
+        // warp's range, which keeps the cancellation in s2 - s1^2 / n at the (shift - mean)^2 / var level (< 1e-5 relative on the
+        // variance for a shift within 10 sigma) -- the load of chunk q + 1 in flight while chunk q is reduced; the halves merge
+        // with Chan's parallel update.  (Round 1 read the accumulator three times with a blocking wait per chunk; at K = 1152 +
+        // depth taps the epilogue, not the MMAs, paced FusionUnet's encoder_layers_2[0]: 701 TFLOP/s in-step.)
+        float s1 = 0.f, s2 = 0.f, shift = 0.f;
         int cnt = 0;
-        for (int q = q_start; q < q_start + q_cnt; ++q) {
-          const int c0 = q * 16;
-          tc_ld16(taddr + c0, v, p.acc_scale);
+        uint32_t ra[16], rb[16];
+        if (q_cnt > 0) { tc_ld16_issue(taddr + q_start * 16, ra); tc_ld_wait(); }
+        for (int q = 0; q < q_cnt; ++q) {
+          if (q + 1 < q_cnt) tc_ld16_issue(taddr + (q_start + q + 1) * 16, rb);
+          const int c0 = (q_start + q) * 16;
+          if (q == 0) shift = fmaf(__uint_as_float(ra[0]), p.acc_scale, par[c0]);
+          if (n0 + c0 + 16 <= Cout) {                          // whole chunk valid: four independent accumulation chains, no predicates
+            float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { sum += v[j] + par[c0 + j]; ++cnt; }
-        }
-        const float mean_a = cnt ? sum / (float)cnt : 0.f;
-        float m2 = 0.f;
-        for (int q = q_start; q < q_start + q_cnt; ++q) {
-          const int c0 = q * 16;
-          tc_ld16(taddr + c0, v, p.acc_scale);
+            for (int g = 0; g < 4; ++g) {
+              const float4 b4 = *reinterpret_cast<const float4*>(par + c0 + g * 4);
+              const float d0 = fmaf(__uint_as_float(ra[g * 4 + 0]), p.acc_scale, b4.x) - shift, d1 = fmaf(__uint_as_float(ra[g * 4 + 1]), p.acc_scale, b4.y) - shift;
+              const float d2 = fmaf(__uint_as_float(ra[g * 4 + 2]), p.acc_scale, b4.z) - shift, d3 = fmaf(__uint_as_float(ra[g * 4 + 3]), p.acc_scale, b4.w) - shift;
+              a1[0] += d0; a1[1] += d1; a1[2] += d2; a1[3] += d3;
+              a2[0] = fmaf(d0, d0, a2[0]); a2[1] = fmaf(d1, d1, a2[1]); a2[2] = fmaf(d2, d2, a2[2]); a2[3] = fmaf(d3, d3, a2[3]);
+            }
+            s1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
+            s2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
+            cnt += 16;
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (n0 + c0 + j < Cout) { const float d = v[j] + par[c0 + j] - mean_a; m2 += d * d; }
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < Cout) { const float d = fmaf(__uint_as_float(ra[j]), p.acc_scale, par[c0 + j]) - shift; s1 += d; s2 = fmaf(d, d, s2); ++cnt; }
+          }
+          if (q + 1 < q_cnt) {
+            tc_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ra[j] = rb[j];
+          }
         }
+        const float inv_cnt = cnt ? 1.0f / (float)cnt : 0.f;
+        const float mean_a = cnt ? fmaf(s1, inv_cnt, shift) : 0.f;
+        const float m2 = fmaxf(s2 - s1 * s1 * inv_cnt, 0.f);
         float* const mine = s_ln + (ew * 2 + acc) * 64;
         const float* const theirs = s_ln + ((ew ^ 4) * 2 + acc) * 64;
         mine[lane] = mean_a;
@@ -616,7 +681,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
       } else
       if (q_cnt > 0) {
         const int c_first = q_start * 16;
-        bulk_wait_read0();                                    // this lane's copy of the previous tile has left its staging row
+        if (tma) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }   // the stores of the previous tile have read the panels
+        else bulk_wait_read0();                               // this lane's copy of the previous tile has left its staging row
+        if (ew == 0) GTRACE(0, it, 3);
         uint32_t rr[16], rn[16];
         tc_ld16_issue(taddr + c_first, rr);
         tc_ld_wait();
@@ -640,8 +707,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
           __nv_bfloat162 h2[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) h2[j] = __floats2bfloat162_rn(act_fn<ACT>(t[2 * j]), act_fn<ACT>(t[2 * j + 1]));
-          *reinterpret_cast<uint4*>(srow + q * 32) = *reinterpret_cast<const uint4*>(&h2[0]);
-          *reinterpret_cast<uint4*>(srow + q * 32 + 16) = *reinterpret_cast<const uint4*>(&h2[4]);
+          if (tma) {                                          // chunk q = 32 bytes of panel q / 4, swizzled 16-byte pieces
+            uint8_t* const pb = lrow + (q >> 2) * 4096;
+            const uint32_t j0 = (uint32_t)(q & 3) * 2;
+            *reinterpret_cast<uint4*>(pb + ((j0 ^ lsw) << 4)) = *reinterpret_cast<const uint4*>(&h2[0]);
+            *reinterpret_cast<uint4*>(pb + (((j0 + 1) ^ lsw) << 4)) = *reinterpret_cast<const uint4*>(&h2[4]);
+          } else {
+            *reinterpret_cast<uint4*>(srow + q * 32) = *reinterpret_cast<const uint4*>(&h2[0]);
+            *reinterpret_cast<uint4*>(srow + q * 32 + 16) = *reinterpret_cast<const uint4*>(&h2[4]);
+          }
           if (q + 1 < q_cnt) {
             tc_ld_wait();
 #pragma unroll
@@ -650,15 +724,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gemm_kernel(const __grid_
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // staged row -> visible to the bulk copy engine
         const int nvalid = min(q_cnt * 16, Cout - (n0 + c_first));
-        if (valid && nvalid > 0 && !(p.debug & 4)) bulk_store(grow + c_first, srow_s, (uint32_t)nvalid * 2u);
-        bulk_commit();
+        if (ew == 0) GTRACE(0, it, 4);
+        if (tma) {
+          __syncwarp();                                        // all 32 rows of the panels are staged
+          if (lane == 0) {
+            for (int pn = 0; pn * 64 < q_cnt * 16; ++pn)
+              if (n0 + c_first + pn * 64 < Cout && !(p.debug & 4))
+                tma_store_4d(&p.tmOut, wstage_s + pn * 4096, n0 + c_first + pn * 64, w0 + bq_w, h0 + bq_h, img);
+            bulk_commit();
+          }
+        } else {
+          if (valid && nvalid > 0 && !(p.debug & 4)) bulk_store(grow + c_first, srow_s, (uint32_t)nvalid * 2u);
+          bulk_commit();
+        }
       }
+      if (ew == 0) GTRACE(0, it, 5);
       tc_fence_before();
       __syncwarp();                                          // every lane's TMEM reads of this accumulator have completed
+      if (ew == 0) GTRACE(0, it, 6);
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc);
         else mbar_arrive(tempty_bar(acc));
       }
+      if (ew == 0) GTRACE(0, it, 7);
     }
     bulk_wait_all();
   } else {
@@ -979,6 +1067,14 @@ cudaError_t launch(const cudaLaunchConfig_t& cfg, const KParams& p) {
 
 }  // namespace
 
+#ifdef PRV2_GEMM_TRACE_BUILD
+extern "C" int prv2_debug_gemm_trace(unsigned long long* out /*host, 3*64*8*/) {
+  PRV2_CUDA(cudaDeviceSynchronize());
+  PRV2_CUDA(cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(unsigned long long) * 3 * 64 * 8));
+  return PRV2_OK;
+}
+#endif
+
 extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   PRV2_CHECK_ARG(d != nullptr, "prv2_umma_gemm: null desc");
   PRV2_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->Cout > 0, "prv2_umma_gemm: bad output shape");
@@ -1142,6 +1238,25 @@ extern "C" int prv2_umma_gemm(const prv2_gemm_desc* d, prv2_stream_t stream) {
   if (use_fast_resid || fast) {
     p.stg_warp_bytes = STG_BYTES_PER_WARP_RESID;
     if (resid_stages < p.stages) p.stages = resid_stages;
+    // TMA-store mode of the bf16 row epilogue where the epilogue paces the tile: narrow N tile (the MMAs of a tile are short) with
+    // the LayerNorm epilogue, or a short K loop.  Every warp's column share must be whole 128-byte panels.
+    static const char* ts_env = getenv("PRV2_GEMM_TMA_STORE");      // diagnostics: 0 = never, 1 = wherever possible
+    const long long mma_clk = (long long)(d->Ktot / BK) * (d->block_n > 128 ? 512 : 256);     // tensor-pipe clocks of one tile's K loop
+    bool want = fast && d->block_n % 128 == 0 && mma_clk < (d->epi == PRV2_EPI_LN_GELU ? 12000 : 6000);
+    if (ts_env && ts_env[0] == '0') want = false;
+    if (ts_env && ts_env[0] == '1') want = fast && d->block_n % 128 == 0;
+    if (want) {
+      p.tma_store = 1;
+      p.stg_warp_bytes = 8192;                                      // two 4 KB panels per warp
+      const int box_w = d->tile_w >= 32 ? 32 : d->tile_w, box_h = 32 / box_w;
+      cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+      cuuint64_t strides[3] = {(cuuint64_t)d->out_cs * 2, (cuuint64_t)d->W * d->out_cs * 2, (cuuint64_t)d->H * d->W * d->out_cs * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&p.tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)d->out_hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("prv2_umma_gemm: cuTensorMapEncodeTiled(out) failed (%d) Cout=%d cs=%d", (int)r, d->Cout, d->out_cs); return PRV2_ECUDA; }
+    }
   }
   // always request the full budget: guarantees one CTA per SM, so a 512-column TMEM allocation can never deadlock
   int grid = p.total_tiles * cg < g_num_sms ? p.total_tiles * cg : g_num_sms;

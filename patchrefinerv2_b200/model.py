@@ -131,7 +131,7 @@ class _Resizer:
 class PatchRefiner(nn.Module):
     """B200-native PatchRefiner (DA2 coarse + DA2 refiner + FusionUnet family)."""
 
-    def __init__(self, config, precision: str = "bf16", patch_batch: int = 8, output_device: str = "cpu"):
+    def __init__(self, config, precision: str = "fp32", patch_batch: int = 8, output_device: str = "cpu"):
         super().__init__()
         if hasattr(config, "to_dict"):
             config = config.to_dict()
@@ -513,7 +513,7 @@ class PatchRefinerPlus(PatchRefiner):
     caller supplies or timm builds -- library code, not one of this package's kernels) and hands its features to
     ``BiDirectionalFusionB200``, where 99 % of the V2 refiner's FLOPs are."""
 
-    def __init__(self, config, precision: str = "bf16", patch_batch: int = 8, output_device: str = "cpu", fine_encoder: Optional[nn.Module] = None):
+    def __init__(self, config, precision: str = "fp32", patch_batch: int = 8, output_device: str = "cpu", fine_encoder: Optional[nn.Module] = None):
         nn.Module.__init__(self)
         from .bifusion import C2F_TYPES, bifusion_weight_spec
         if hasattr(config, "to_dict"):
