@@ -188,11 +188,14 @@ class PatchRefiner(nn.Module):
     def _load(self, sd, strict):
         missing = [k for k in self._weights if k not in sd]
         unexpected = [k for k in sd if k not in self._weights]
+        if not hasattr(self, "_loaded_keys"):
+            self._loaded_keys = set()
         for k, v in sd.items():
             if k in self._weights:
                 if tuple(v.shape) != tuple(self._weights[k].shape):
                     raise RuntimeError(f"size mismatch for {k}: {tuple(v.shape)} vs {tuple(self._weights[k].shape)}")
                 self._weights[k] = v.detach().float().cpu().clone()
+                self._loaded_keys.add(k)
         if strict and (missing or unexpected):
             raise RuntimeError(f"missing keys {missing[:4]}..., unexpected keys {unexpected[:4]}...")
         self._engine = None
@@ -227,9 +230,19 @@ class PatchRefiner(nn.Module):
         return super()._apply(fn, recurse)
 
     # -- device engine -------------------------------------------------------------------------
+    def _warn_unloaded(self):
+        """load_dict / the checkpoint keys of the config are strict=False like the reference's (patchrefiner.py:155-156): a wrong-keyed or
+        absent checkpoint must not run silently on the zero weights this class starts from."""
+        never = [k for k in self._weights if k not in getattr(self, "_loaded_keys", ()) and not k.endswith(("mask_token", "num_batches_tracked"))]
+        if never:
+            import warnings
+            warnings.warn(f"{type(self).__name__}: {len(never)} of {len(self._weights)} weight tensors were never loaded and are still at their "
+                          f"initial values (first: {never[0]}); check the checkpoint's key names", RuntimeWarning, stacklevel=3)
+
     def _build_engine(self, device):
         if device.type != "cuda":
             raise RuntimeError("patchrefinerv2_b200 runs on CUDA (sm_100a) only; there is no CPU path. Call .cuda() first.")
+        self._warn_unloaded()
         _lib.load()
         x3 = self.precision == "fp32"
         sd = self._weights
@@ -612,6 +625,7 @@ class PatchRefinerPlus(PatchRefiner):
         if device.type != "cuda":
             raise RuntimeError("patchrefinerv2_b200 runs on CUDA (sm_100a) only; there is no CPU path. Call .cuda() first.")
         from .bifusion import BiDirectionalFusionB200
+        self._warn_unloaded()
         _lib.load()
         x3 = self.precision == "fp32"
         sd, fu = self._weights, self._fu_cfg

@@ -216,3 +216,27 @@ def test_roi_regime_check_accepts_baseline_geometries_and_refuses_a_two_sample_g
         tiling.check_roi_regime(rois, [(32, 32, 32 / 448), (256, 256, 256 / 448), (448, 448, 1.0)])
     with pytest.raises(NotImplementedError):
         tiling.check_roi_regime(np.array([[0, 0, 449, 448]], np.float32), [(448, 448, 1.0)])
+
+
+def test_unloaded_weights_are_reported_loudly():
+    """A model whose checkpoint never populated some tensors must say so when its engine is built (strict=False loading)."""
+    import warnings
+    from oracle import pr_oracle as O
+    from patchrefinerv2_b200 import build_model
+    cfg = O.make_config("vits", (224, 224), (432, 768), (2, 2))
+    m = build_model(dict(type="PatchRefiner", config=cfg))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m._warn_unloaded()
+    assert len(w) == 1 and "never loaded" in str(w[0].message)
+    sd = O.init_patchrefiner_state_dict(cfg, 0)
+    m.load_dict({k: v for k, v in sd.items() if not k.startswith("refiner_fusion_model.")})     # a checkpoint without the fusion model
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m._warn_unloaded()
+    assert len(w) == 1 and "refiner_fusion_model." in str(w[0].message)
+    m.load_dict(sd)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m._warn_unloaded()
+    assert not w
