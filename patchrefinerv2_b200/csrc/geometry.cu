@@ -484,7 +484,8 @@ static bool blend_generic_forced() {
   if (g_blend_generic < 0) { const char* e = getenv("PRV2_BLEND_GENERIC"); g_blend_generic = (e && e[0] == '1') ? 1 : 0; }
   return g_blend_generic == 1;
 }
-extern "C" int prv2_debug_blend_generic(int on) { g_blend_generic = on ? 1 : 0; return PRV2_OK; }
+static void seg_knobs(int on);
+extern "C" int prv2_debug_blend_generic(int on) { g_blend_generic = (on & 1) ? 1 : 0; seg_knobs(on); return PRV2_OK; }
 
 static bool canvas_aligned(const StageTable& t, int pw, int Wc) {
   if (blend_generic_forced() || (pw & 3) || (Wc & 3) || t.n > 4) return false;
@@ -940,12 +941,246 @@ extern "C" int prv2_blend_raw_prepare(const float* rmask, int rh, int rw, int pw
   return PRV2_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Segment kernel of the rN stage (MODE 0: sequential-exact, MODE 2: finalize from reduced sums).  Same arithmetic on pixel values,
+// in the same order, as blend_raw_kernel / blend_raw_tab_kernel -> same bits; what changes is how the operands arrive:
+//  * CTA = R consecutive raw rows x one x segment of 128*w pixels (w warps, thread = 4 consecutive pixels).  Everything that
+//    depends on the column only (table reads, unpacking, shared-memory tap addresses, 1 - l1) is done once per thread and
+//    reused for the R rows.
+//  * The canvas rows a raw row needs (nearest row of the average map, the two bilinear rows of the count map), restricted to the
+//    segment's column span, are staged in shared memory by three bulk copies (cp.async.bulk + mbarrier) issued by one thread:
+//    the 20 per-group canvas reads become LDS with immediate offsets -- no 64-bit address arithmetic, no tap sharing selects.
+//  * The covering-patch list of a row is filtered to the segment and stored as ready-made operands: with c = x0 & 3 the group
+//    at absolute column xb finds its four weights at mask4 + moff + xb (copy c of the prepared weight map) and its four source
+//    columns at srcx4 + soff + xb, for EVERY group of the row (c does not depend on the group because xb is a multiple of 4).
+// ---------------------------------------------------------------------------------------------
+#define PRV2_SEG_SPAN 512          // canvas columns staged per row and segment (floats)
+#define PRV2_SEG_LIST 128          // covering patches per row and segment
+struct RawSegs { int nseg, segw, lo[12]; };                      // lo: first staged canvas column of each segment (multiple of 4)
+
+__device__ __forceinline__ uint32_t seg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void seg_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(seg_smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int MODE, int R>
+__global__ void __launch_bounds__(320) blend_raw_seg_kernel(const float* __restrict__ avg_c, const float* __restrict__ cnt_c, int Hc, int Wc,
+                                                            const float* __restrict__ preds, const int32_t* __restrict__ starts, int n,
+                                                            int ph, int pw, int rh, int rw, int H, int W, float* __restrict__ out,
+                                                            float* __restrict__ out_cnt, const float* __restrict__ num_in, RawScales sc,
+                                                            RawTables tb, RawPrep prep, RawSegs sg) {
+  __shared__ __align__(16) float s_rows[R][3][PRV2_SEG_SPAN + 4];
+  __shared__ __align__(16) int4 s_ent[R][PRV2_SEG_LIST];         // {x0a, rw + c, moff, soff}
+  __shared__ int s_poff[R][PRV2_SEG_LIST];
+  __shared__ int s_m[R];
+  __shared__ float2 s_ly[R];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int seg = blockIdx.x, y0 = blockIdx.y * R;
+  int lo = 0;
+#pragma unroll
+  for (int s = 0; s < 12; ++s) if (s == seg) lo = sg.lo[s];     // (no dynamic indexing of the parameter struct: that would copy it to local memory)
+  const int xs = seg * sg.segw, xe = min(xs + sg.segw, W);
+  const int nrows = min(R, H - y0);
+  const uint32_t bar = seg_smem_u32(&s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)min(PRV2_SEG_SPAN, Wc - lo) * 4u;               // Wc and lo are multiples of 4 -> of 16 bytes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * 3u * (uint32_t)nrows) : "memory");
+    for (int r = 0; r < nrows; ++r) {
+      const int y = y0 + r;
+      const BilinearTap ty = ac_tap(sc.bs_y, y, Hc);                                  // utils.py:42-43, row part
+      s_ly[r] = make_float2(ty.l0, ty.l1);
+      seg_bulk_g2s(&s_rows[r][0][0], avg_c + (size_t)nearest_src(y, sc.ns_y, Hc) * Wc + lo, bytes, bar);
+      seg_bulk_g2s(&s_rows[r][1][0], cnt_c + (size_t)ty.i0 * Wc + lo, bytes, bar);
+      seg_bulk_g2s(&s_rows[r][2][0], cnt_c + (size_t)ty.i1 * Wc + lo, bytes, bar);
+    }
+  }
+  if (warp < R) {                                                 // warp r lists the patches covering (row y0 + r) x [xs, xe), draw order kept
+    const int y = y0 + warp;
+    int m = 0;
+    if (y < H) {
+      for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
+        int py0 = 0, px0 = 0;
+        bool hit = false;
+        if (k < n) {
+          py0 = starts[k * 2 + 0]; px0 = starts[k * 2 + 1];
+          hit = y >= py0 && y < py0 + rh && px0 < xe && px0 + rw > xs;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+          const int pos = m + __popc(b & ((1u << lane) - 1));
+          const int ly = y - py0, c = px0 & 3, x0a = px0 - c;
+          s_ent[warp][pos] = make_int4(x0a, rw + c, (c * rh + ly) * prep.pitch - x0a, c * prep.pitch - x0a);
+          s_poff[warp][pos] = (MODE == 2) ? 0 : (k * ph + nearest_src(ly, sc.ps_y, ph)) * pw;    // baseline_pretrain.py:210 (nearest), row part
+        }
+        m += __popc(b);
+      }
+    }
+    if (lane == 0) s_m[warp] = m;
+  }
+  // column-only state of this thread's four pixels
+  const int xb = xs + tid * 4;
+  const bool active = tid * 4 < sg.segw && xb < W;                // W % 4 == 0: an active group is a full group
+  int sa[4], si[4];
+  float l0[4], l1[4];
+  if (active) {
+    const uint2 ta = __ldg(reinterpret_cast<const uint2*>(tb.a_ix + xb));
+    const uint2 ti = __ldg(reinterpret_cast<const uint2*>(tb.c_i0 + xb));
+    const float4 tl = __ldg(reinterpret_cast<const float4*>(tb.c_l1 + xb));
+    sa[0] = (int)(ta.x & 0xffffu) - lo; sa[1] = (int)(ta.x >> 16) - lo; sa[2] = (int)(ta.y & 0xffffu) - lo; sa[3] = (int)(ta.y >> 16) - lo;
+    si[0] = (int)(ti.x & 0xffffu) - lo; si[1] = (int)(ti.x >> 16) - lo; si[2] = (int)(ti.y & 0xffffu) - lo; si[3] = (int)(ti.y >> 16) - lo;
+    l1[0] = tl.x; l1[1] = tl.y; l1[2] = tl.z; l1[3] = tl.w;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) l0[q] = __fsub_rn(1.0f, l1[q]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { sa[q] = si[q] = 0; l0[q] = l1[q] = 0.f; }
+  }
+  __syncthreads();                                                // lists written, barrier initialised
+  {
+    uint32_t ok = 0;
+    while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(0) : "memory");
+  }
+  if (lo + PRV2_SEG_SPAN >= Wc) {
+    // the segment reaches the last canvas column: tap i1 == i0 there (ac_tap), i.e. column Wc repeats column Wc - 1
+    if (tid < 3 * R) s_rows[tid / 3][tid % 3][Wc - lo] = s_rows[tid / 3][tid % 3][Wc - 1 - lo];
+    __syncthreads();
+  }
+  if (!active) return;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int y = y0 + r;
+    if (y >= H) break;
+    const float2 ly = s_ly[r];
+    const size_t o = (size_t)y * W + xb;
+    float avg[4], cnt[4], c0[4], num[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      avg[q] = s_rows[r][0][sa[q]];
+      const float r0 = __fmaf_rn(l0[q], s_rows[r][1][si[q]], __fmul_rn(l1[q], s_rows[r][1][si[q] + 1]));     // ac_blend, ATen order
+      const float r1 = __fmaf_rn(l0[q], s_rows[r][2][si[q]], __fmul_rn(l1[q], s_rows[r][2][si[q] + 1]));
+      cnt[q] = __fmaf_rn(ly.x, r0, __fmul_rn(ly.y, r1));
+      c0[q] = cnt[q];
+    }
+    if (MODE == 2) {
+      const float4 nin = __ldcs(reinterpret_cast<const float4*>(num_in + o));
+      num[0] = nin.x; num[1] = nin.y; num[2] = nin.z; num[3] = nin.w;
+    }
+    const int m = s_m[r];
+    for (int i = 0; i < m; ++i) {
+      const int4 e = s_ent[r][i];
+      if ((unsigned)(xb - e.x) >= (unsigned)e.y) continue;        // group entirely outside this patch
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(prep.mask4 + (e.z + xb)));
+      const float ct[4] = {c4.x, c4.y, c4.z, c4.w};
+      if (MODE == 2) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (ct[q] > 0.f) cnt[q] = __fadd_rn(cnt[q], ct[q]);
+      } else {
+        const uint2 s2 = __ldg(reinterpret_cast<const uint2*>(prep.srcx4 + (e.w + xb)));
+        const int po = s_poff[r][i];                               // 32-bit element offsets: one IMAD.WIDE per gather
+        const float p[4] = {__ldg(preds + (po + (int)(s2.x & 0xffffu))), __ldg(preds + (po + (int)(s2.x >> 16))),
+                            __ldg(preds + (po + (int)(s2.y & 0xffffu))), __ldg(preds + (po + (int)(s2.y >> 16)))};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // utils.py:31-36 as a select, not a branch: a zero weight (the padding of an edge group) leaves the pixel untouched
+          const float den = __fadd_rn(cnt[q], ct[q]);
+          const float qv = __fdiv_rn(__fadd_rn(__fmul_rn(p[q], ct[q]), __fmul_rn(cnt[q], avg[q])), den);
+          const bool pos = ct[q] > 0.f;
+          avg[q] = pos ? qv : avg[q];
+          cnt[q] = pos ? den : cnt[q];
+        }
+      }
+    }
+    if (MODE == 2) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) avg[q] = (cnt[q] > c0[q]) ? __fdiv_rn(__fadd_rn(__fmul_rn(avg[q], c0[q]), num[q]), cnt[q]) : avg[q];
+    }
+    __stcs(reinterpret_cast<float4*>(out + o), make_float4(avg[0], avg[1], avg[2], avg[3]));
+    if (out_cnt) __stcs(reinterpret_cast<float4*>(out_cnt + o), make_float4(cnt[0], cnt[1], cnt[2], cnt[3]));
+  }
+}
+
+// host replay of the column index math (plain IEEE fp32, same operations as nearest_src / ac_tap on the device)
+static int h_nearest_src(int dst, float scale, int n_in) { const int v = (int)floorf((float)dst * scale); return v < n_in - 1 ? v : n_in - 1; }
+static int h_ac_i0(float scale, int dst, int n_in) { const int v = (int)(scale * (float)dst); return v < n_in - 1 ? v : n_in - 1; }
+
+static int g_seg_R = -1, g_seg_w = 0, g_seg_off = -1;            // A/B knobs (prv2_debug_blend_generic / PRV2_BLEND_SEG=0)
+// bit 1: segment kernel off; bits 4-7: rows per CTA (1, 2, 4; 0 = default); bits 8-15: warps per CTA (0 = automatic)
+static void seg_knobs(int on) { g_seg_off = (on & 2) ? 1 : 0; g_seg_R = (on >> 4) & 15; g_seg_w = (on >> 8) & 255; if (!g_seg_R) g_seg_R = -1; }
+static bool seg_disabled() {
+  if (g_seg_off < 0) { const char* e = getenv("PRV2_BLEND_SEG"); g_seg_off = (e && e[0] == '0') ? 1 : 0; }
+  return g_seg_off == 1;
+}
+
+// Chooses the segmentation (w warps per CTA, 128*w pixels per segment) and fills the per-segment canvas origins.
+static bool seg_plan(int Wc, int W, int pw, int rh, int rw, int n, int ph, const RawScales& sc, const void* prep, const void* a, const void* b,
+                     const void* c, const void* d, const void* e, RawSegs* sg, int* warps) {
+  if (seg_disabled() || (W & 3) || (Wc & 3) || n > PRV2_SEG_LIST || (n > 0 && !prep)) return false;
+  if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e) & 15) != 0) return false;
+  if ((long long)4 * rh * raw_prep_pitch(rw) >= (1ll << 31) || (long long)n * ph * pw >= (1ll << 31) || (long long)W + 4ll * rh * raw_prep_pitch(rw) >= (1ll << 31)) return false;
+  static const int order[] = {8, 6, 10, 5, 7, 9, 4, 3, 2};
+  int best_w = 0; long long best_waste = -1;
+  for (int k = 0; k < (int)(sizeof(order) / sizeof(order[0])); ++k) {
+    const int w = g_seg_w > 0 ? g_seg_w : order[k];
+    const int segw = 128 * w, nseg = cdiv(W, segw);
+    if (nseg > 12) continue;
+    bool fits = true;
+    for (int s = 0; s < nseg && fits; ++s) {
+      const int xs = s * segw, xl = (xs + segw < W ? xs + segw : W) - 1;
+      const int a0 = h_nearest_src(xs, sc.ns_x, Wc), i0 = h_ac_i0(sc.bs_x, xs, Wc);
+      const int a1 = h_nearest_src(xl, sc.ns_x, Wc), i1 = h_ac_i0(sc.bs_x, xl, Wc) + 1;
+      const int lo = (a0 < i0 ? a0 : i0) & ~3, hi = (a1 > i1 ? a1 : i1);              // hi <= Wc (column Wc = the repeated last column)
+      if (hi - lo >= PRV2_SEG_SPAN) fits = false;
+    }
+    if (!fits) { if (g_seg_w > 0) return false; continue; }
+    const long long waste = (long long)nseg * segw - W;
+    if (best_waste < 0 || waste < best_waste) { best_waste = waste; best_w = w; }
+    if (g_seg_w > 0 || waste == 0) break;
+  }
+  if (!best_w) return false;
+  const int segw = 128 * best_w;
+  sg->nseg = cdiv(W, segw); sg->segw = segw;
+  for (int s = 0; s < sg->nseg; ++s) {
+    const int xs = s * segw;
+    const int a0 = h_nearest_src(xs, sc.ns_x, Wc), i0 = h_ac_i0(sc.bs_x, xs, Wc);
+    sg->lo[s] = (a0 < i0 ? a0 : i0) & ~3;
+  }
+  *warps = best_w;
+  return true;
+}
+
+template <int MODE, int R>
+static void launch_seg(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* preds, const int32_t* starts, int n, int ph, int pw, int rh,
+                       int rw, int H, int W, float* out, float* out_cnt, const float* num_in, const RawScales& sc, const RawTables& tb, const RawPrep& pv,
+                       const RawSegs& sg, int warps, cudaStream_t stream) {
+  blend_raw_seg_kernel<MODE, R><<<dim3(sg.nseg, cdiv(H, R)), warps * 32, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out,
+                                                                                      out_cnt, num_in, sc, tb, pv, sg);
+}
+
 template <int MODE>
 static void launch_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* preds, const uint8_t* own, const int32_t* starts,
                        int n, int ph, int pw, const float* rmask, int rh, int rw, int H, int W, float* out, float* out_cnt,
                        const float* num_in, const RawScales& sc, const void* prep, cudaStream_t stream) {
   dim3 grid(1, H);
   RawTables tb;
+  RawSegs sg;
+  int warps = 0;
+  if (MODE != 1 && !blend_generic_forced() && seg_plan(Wc, W, pw, rh, rw, n, ph, sc, prep, avg_c, cnt_c, out, out_cnt, num_in, &sg, &warps) &&
+      raw_tables_get(Wc, W, pw, rw, sc, stream, &tb)) {
+    constexpr int M = MODE == 1 ? 0 : MODE;                       // (MODE 1 never gets here; keeps the instantiation list to modes 0 and 2)
+    const RawPrep pv = raw_prep_view(prep, rh, rw);
+    const int R = g_seg_R > 0 ? g_seg_R : 1;
+    if (R == 1) launch_seg<M, 1>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out, out_cnt, num_in, sc, tb, pv, sg, warps, stream);
+    else if (R == 4) launch_seg<M, 4>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out, out_cnt, num_in, sc, tb, pv, sg, warps, stream);
+    else launch_seg<M, 2>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out, out_cnt, num_in, sc, tb, pv, sg, warps, stream);
+    return;
+  }
   if (!blend_generic_forced() && raw_tables_get(Wc, W, pw, rw, sc, stream, &tb)) {
     blend_raw_tab_kernel<MODE><<<grid, 256, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W, out, out_cnt,
                                                          num_in, sc, tb, raw_prep_view(prep, rh, rw));

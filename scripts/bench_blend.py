@@ -70,6 +70,21 @@ def main():
             r["GBps"] = bytes_raw / r["median_us"] / 1e3
             out[f"{label}_{fl_label}"] = {"canvas": c, "raw": r}
             print(label, fl_label, "canvas", c, "raw", r, flush=True)
+    # rN-stage variants (prv2_debug_blend_generic knobs: bit 1 = segment kernel off, bits 4-7 rows per CTA, bits 8-15 warps per CTA)
+    rprep = ops.blend_raw_prepare(rmask, pw)
+    ref = None
+    for label, knob in (("tab", 2), ("seg_R1", 1 << 4), ("seg_R2", 2 << 4), ("seg_R4", 4 << 4), ("seg_R1_w5", (1 << 4) | (5 << 8)), ("seg_R2_w5", (2 << 4) | (5 << 8)),
+                        ("seg_R2_w10", (2 << 4) | (10 << 8)), ("seg_R1_w10", (1 << 4) | (10 << 8)), ("seg_R4_w5", (4 << 4) | (5 << 8))):
+        _lib.call("prv2_debug_blend_generic", knob)
+        got = ops.blend_raw(avg_c, cnt_c, preds[first:], starts, rmask, ph, pw, rh, rw, H, W, prep=rprep)
+        if ref is None:
+            ref = got
+        same = bool(torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]))
+        r = time_launches(lambda: ops.blend_raw(avg_c, cnt_c, preds[first:], starts, rmask, ph, pw, rh, rw, H, W, prep=rprep), flush=flush)
+        r["GBps"] = bytes_raw / r["median_us"] / 1e3
+        r["bit_identical_to_tab"] = same
+        out["raw_" + label] = r
+        print("raw", label, r, flush=True)
     _lib.call("prv2_debug_blend_generic", 0)
     print(json.dumps(out))
 
