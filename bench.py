@@ -626,11 +626,11 @@ def main():
             time.sleep(2.0)                      # let the power-capped clocks of the frame loop recover: these two kernels are timed alone
             bt = blend_launch_times(pshape, raw, split, cai_mode, process_num, dev)
             b_bytes, b_s = sum(v["bytes"] for v in bt.values()), sum(v["s"] for v in bt.values())
-            roofline["blend"] = {"kernel": "blend_canvas_fast_kernel + blend_raw_tab_kernel", "bound": "hbm", "achieved": b_bytes / b_s / 1e9, "peak": peaks["hbm"],
+            roofline["blend"] = {"kernel": "blend_canvas_fast_kernel + blend_raw_seg_kernel", "bound": "hbm", "achieved": b_bytes / b_s / 1e9, "peak": peaks["hbm"],
                                  "unit": "GB/s", "frac": b_bytes / b_s / 1e9 / peaks["hbm"], "us_per_frame": b_s * 1e6,
                                  "stages": {k: {"algorithmic_bytes": v["bytes"], "us": v["s"] * 1e6, "GBps": v["bytes"] / v["s"] / 1e9,
                                                 "frac": v["bytes"] / v["s"] / 1e9 / peaks["hbm"]} for k, v in bt.items()},
-                                 "traffic": {k: traffic.get(k, {}).get("dram_bytes_per_launch") for k in ("blend_canvas_fast_kernel", "blend_raw_tab_kernel")},
+                                 "traffic": {k: traffic.get(k, {}).get("dram_bytes_per_launch") for k in ("blend_canvas_fast_kernel", "blend_raw_seg_kernel", "blend_raw_tab_kernel")},
                                  "note": "median of 20 launches each, 256 MB L2 flush before every launch, own event pair per launch, timed alone (burst HBM peak applies)"}
         except Exception as e:
             roofline["blend"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}

@@ -665,22 +665,24 @@ static RawScales raw_scales(int Hc, int Wc, int H, int W, int ph, int pw, int rh
 // the count canvas, nearest column of a prediction for every in-patch x -- is read from small device tables that
 // prv2_blend_raw_* builds once per geometry (raw_tables_kernel), instead of being recomputed with int<->float conversions for
 // each of the H rows.  The arithmetic on pixel values is unchanged (same ops, same order) -> same bits as blend_raw_kernel.
-struct RawTables { const unsigned short* a_ix; const unsigned short* c_i0; const float* c_l1; const unsigned short* src_x; };
+struct RawTables { const unsigned short* a_ix; const unsigned short* c_i0; const float* c_l1; const unsigned short* src_x; const int* a_b; const int* c_b; };
 // Prepared patch mask (prv2_blend_raw_prepare): four copies of the [rh, rw] weight map, copy c shifted right by c columns and
 // zero-padded to `pitch` (a multiple of 4, >= rw + 8), and four equally shifted copies of the nearest-source-column table.  For
 // an output group starting l0 columns into a patch, copy c = (-l0) & 3 holds the group's four weights / source columns in ONE
 // aligned 16-byte / 8-byte vector -- also where the group straddles a patch edge (the padding weighs 0).
-struct RawPrep { const float* mask4; const unsigned short* srcx4; int pitch; };
+struct RawPrep { const float* mask4; const unsigned short* srcx4; const int* srci4; int pitch; };
 
-__global__ void raw_tables_kernel(unsigned short* a_ix, unsigned short* c_i0, float* c_l1, unsigned short* src_x, int Wc, int W, int Wpad,
-                                  int pw, int rw, RawScales sc) {
+__global__ void raw_tables_kernel(unsigned short* a_ix, unsigned short* c_i0, float* c_l1, unsigned short* src_x, int* a_b, int* c_b, int Wc, int W,
+                                  int Wpad, int pw, int rw, RawScales sc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Wpad) {
     const int x = min(i, W - 1);
-    a_ix[i] = (unsigned short)nearest_src(x, sc.ns_x, Wc);
+    const int a = nearest_src(x, sc.ns_x, Wc);
+    a_ix[i] = (unsigned short)a;
     const BilinearTap tx = ac_tap(sc.bs_x, x, Wc);
     c_i0[i] = (unsigned short)tx.i0;
     c_l1[i] = tx.l1;
+    a_b[i] = a * 4; c_b[i] = tx.i0 * 4;                           // the same columns as byte offsets (segment kernel)
   }
   if (i < rw) src_x[i] = (unsigned short)nearest_src(i, sc.ps_x, pw);
 }
@@ -883,46 +885,56 @@ static bool raw_tables_get(int Wc, int W, int pw, int rw, const RawScales& sc, c
   }
   if (!slot) return false;                                      // cache full: the caller falls back to the generic kernel
   const int Wpad = (W + 3) & ~3, rwpad = (rw + 7) & ~7;
-  const size_t bytes = (size_t)Wpad * (2 + 2 + 4) + (size_t)rwpad * 2 + 64;
+  const size_t bytes = (size_t)Wpad * (2 + 2 + 4 + 4 + 4) + (size_t)rwpad * 2 + 64;
   void* mem = nullptr;
   if (cudaMalloc(&mem, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
   char* base = (char*)mem;
   float* c_l1 = (float*)base;                                   // 16-byte aligned first
-  unsigned short* a_ix = (unsigned short*)(base + (size_t)Wpad * 4);
+  int* a_b = (int*)(base + (size_t)Wpad * 4);
+  int* c_b = a_b + Wpad;
+  unsigned short* a_ix = (unsigned short*)(c_b + Wpad);
   unsigned short* c_i0 = a_ix + Wpad;
   unsigned short* src_x = c_i0 + Wpad;
   const int nthr = Wpad > rw ? Wpad : rw;
-  raw_tables_kernel<<<cdiv(nthr, 256), 256, 0, stream>>>(a_ix, c_i0, c_l1, src_x, Wc, W, Wpad, pw, rw, sc);
+  raw_tables_kernel<<<cdiv(nthr, 256), 256, 0, stream>>>(a_ix, c_i0, c_l1, src_x, a_b, c_b, Wc, W, Wpad, pw, rw, sc);
   cudaEvent_t ev;
   if (cudaGetLastError() != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaFree(mem); return false; }
   cudaEventRecord(ev, stream);
   slot->dev = dev; slot->Wc = Wc; slot->W = W; slot->pw = pw; slot->rw = rw; slot->mem = mem; slot->ready = ev;
-  slot->tb.a_ix = a_ix; slot->tb.c_i0 = c_i0; slot->tb.c_l1 = c_l1; slot->tb.src_x = src_x;
+  slot->tb.a_ix = a_ix; slot->tb.c_i0 = c_i0; slot->tb.c_l1 = c_l1; slot->tb.src_x = src_x; slot->tb.a_b = a_b; slot->tb.c_b = c_b;
   slot->used = 1;
   *tb = slot->tb;
   return true;
 }
 
 static int raw_prep_pitch(int rw) { return ((rw + 3) & ~3) + 8; }
-static size_t raw_prep_bytes(int rh, int rw) { return (size_t)4 * rh * raw_prep_pitch(rw) * sizeof(float) + (size_t)4 * raw_prep_pitch(rw) * sizeof(unsigned short); }
+static size_t raw_prep_bytes(int rh, int rw) {                   // four shifted weight maps | source columns (u16) | the same as i32
+  return (size_t)4 * rh * raw_prep_pitch(rw) * sizeof(float) + (size_t)4 * raw_prep_pitch(rw) * (sizeof(unsigned short) + sizeof(int));
+}
 
 __global__ void raw_prepare_kernel(const float* __restrict__ rmask, int rh, int rw, int pw, int pitch, float ps_x, float* __restrict__ mask4,
-                                   unsigned short* __restrict__ srcx4) {
+                                   unsigned short* __restrict__ srcx4, int* __restrict__ srci4) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y, c = blockIdx.z;
   if (j >= pitch) return;
   const int src = j - c;                                         // copy c is shifted right by c columns, zero elsewhere
   const bool in = src >= 0 && src < rw;
   mask4[((size_t)c * rh + row) * pitch + j] = in ? rmask[(size_t)row * rw + src] : 0.f;
-  if (row == 0) srcx4[(size_t)c * pitch + j] = in ? (unsigned short)nearest_src(src, ps_x, pw) : (unsigned short)0;
+  if (row == 0) {
+    // the padding weighs 0; its source column is the nearest real one, so that a padded pixel still reads inside the run
+    const int sx = nearest_src(min(max(src, 0), rw - 1), ps_x, pw);
+    srcx4[(size_t)c * pitch + j] = (unsigned short)sx;
+    srci4[(size_t)c * pitch + j] = sx;
+  }
 }
 
 static RawPrep raw_prep_view(const void* prep, int rh, int rw) {
   RawPrep v;
-  v.mask4 = nullptr; v.srcx4 = nullptr; v.pitch = 0;
+  v.mask4 = nullptr; v.srcx4 = nullptr; v.srci4 = nullptr; v.pitch = 0;
   if (prep) {
     v.pitch = raw_prep_pitch(rw);
     v.mask4 = (const float*)prep;
     v.srcx4 = (const unsigned short*)((const char*)prep + (size_t)4 * rh * v.pitch * sizeof(float));
+    v.srci4 = (const int*)(v.srcx4 + (size_t)4 * v.pitch);                            // 8 * pitch bytes further: 16-byte aligned (pitch % 4 == 0)
   }
   return v;
 }
@@ -936,7 +948,7 @@ extern "C" int prv2_blend_raw_prepare(const float* rmask, int rh, int rw, int pw
   const int pitch = raw_prep_pitch(rw);
   const RawPrep v = raw_prep_view(prep, rh, rw);
   raw_prepare_kernel<<<dim3(cdiv(pitch, 256), rh, 4), 256, 0, (cudaStream_t)stream>>>(rmask, rh, rw, pw, pitch, (float)pw / (float)rw, (float*)v.mask4,
-                                                                                      (unsigned short*)v.srcx4);
+                                                                                      (unsigned short*)v.srcx4, (int*)v.srci4);
   PRV2_LAUNCH_CHECK();
   return PRV2_OK;
 }
@@ -945,192 +957,186 @@ extern "C" int prv2_blend_raw_prepare(const float* rmask, int rh, int rw, int pw
 // ---------------------------------------------------------------------------------------------
 // Segment kernel of the rN stage (MODE 0: sequential-exact, MODE 2: finalize from reduced sums).  Same arithmetic on pixel values,
 // in the same order, as blend_raw_kernel / blend_raw_tab_kernel -> same bits; what changes is how the operands arrive:
-//  * CTA = R consecutive raw rows x one x segment of 128*w pixels (w warps, thread = 4 consecutive pixels).  Everything that
-//    depends on the column only (table reads, unpacking, shared-memory tap addresses, 1 - l1) is done once per thread and
-//    reused for the R rows.
-//  * The canvas rows a raw row needs (nearest row of the average map, the two bilinear rows of the count map), restricted to the
-//    segment's column span, are staged in shared memory by three bulk copies (cp.async.bulk + mbarrier) issued by one thread:
-//    the 20 per-group canvas reads become LDS with immediate offsets -- no 64-bit address arithmetic, no tap sharing selects.
-//  * The covering-patch list of a row is filtered to the segment and stored as ready-made operands: with c = x0 & 3 the group
-//    at absolute column xb finds its four weights at mask4 + moff + xb (copy c of the prepared weight map) and its four source
-//    columns at srcx4 + soff + xb, for EVERY group of the row (c does not depend on the group because xb is a multiple of 4).
+//  * CTA = one raw row x one x segment of 128*w pixels (w warps, thread = 4 consecutive pixels): many small CTAs, ~2000 threads
+//    per SM, so that the two dependent L2 reads per covering patch (weights, then the up-sampled prediction) are hidden.
+//  * The canvas rows the raw row needs (nearest row of the average map, the two bilinear rows of the count map), restricted to
+//    the segment's column span, are staged in shared memory by three bulk copies (cp.async.bulk + mbarrier) issued by one thread:
+//    the 20 canvas reads per group become LDS with immediate offsets from per-column byte offsets read as vectors from tables.
+//  * Warp 0 lists the patches covering (row, segment) in draw order as ready-made operands: with c = x0 & 3 the group at absolute
+//    column xb finds its four weights at mask4 + moff + xb (copy c of the prepared weight map) and its four source columns at
+//    srci4 + soff + xb, for EVERY group of the row (c does not depend on the group because xb is a multiple of 4).
+// (A persistent variant that also staged weights and predictions through a ring of shared-memory stages fed by a producer warp
+//  was measured at 55-61 us against this kernel's time: shared memory caps it at ~30 pixel warps per SM and the per-warp
+//  dependency chains then set the pace -- profiles/r02/blend_pipeline_experiment.patch.)
 // ---------------------------------------------------------------------------------------------
 #define PRV2_SEG_SPAN 512          // canvas columns staged per row and segment (floats)
 #define PRV2_SEG_LIST 128          // covering patches per row and segment
-struct RawSegs { int nseg, segw, lo[12]; };                      // lo: first staged canvas column of each segment (multiple of 4)
+#define PRV2_SEG_ROWB ((PRV2_SEG_SPAN + 4) * 4)
 
-__device__ __forceinline__ uint32_t seg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void seg_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(seg_smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(bar)
+__device__ __forceinline__ void seg_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+template <int OFF>
+__device__ __forceinline__ float seg_lds(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
 
-template <int MODE, int R>
-__global__ void __launch_bounds__(320) blend_raw_seg_kernel(const float* __restrict__ avg_c, const float* __restrict__ cnt_c, int Hc, int Wc,
+struct SegTables { const int* a_b; const int* c_b; const float* c_l1; };     // byte offsets 4*a_ix, 4*c_i0 per raw column; l1 per raw column
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 8) blend_raw_seg_kernel(const float* __restrict__ avg_c, const float* __restrict__ cnt_c, int Hc, int Wc,
                                                             const float* __restrict__ preds, const int32_t* __restrict__ starts, int n,
                                                             int ph, int pw, int rh, int rw, int H, int W, float* __restrict__ out,
                                                             float* __restrict__ out_cnt, const float* __restrict__ num_in, RawScales sc,
-                                                            RawTables tb, RawPrep prep, RawSegs sg) {
-  __shared__ __align__(16) float s_rows[R][3][PRV2_SEG_SPAN + 4];
-  __shared__ __align__(16) int4 s_ent[R][PRV2_SEG_LIST];         // {x0a, rw + c, moff, soff}
-  __shared__ int s_poff[R][PRV2_SEG_LIST];
-  __shared__ int s_m[R];
-  __shared__ float2 s_ly[R];
+                                                            SegTables tb, RawPrep prep, int segw) {
+  __shared__ __align__(16) float s_rows[3][PRV2_SEG_SPAN + 4];
+  __shared__ __align__(16) int4 s_ent[PRV2_SEG_LIST];             // {x0a, rw + c, moff, soff}
+  __shared__ int s_poff[PRV2_SEG_LIST];
+  __shared__ int s_m;
+  __shared__ float s_ly1;
   __shared__ __align__(8) unsigned long long s_bar;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int seg = blockIdx.x, y0 = blockIdx.y * R;
-  int lo = 0;
-#pragma unroll
-  for (int s = 0; s < 12; ++s) if (s == seg) lo = sg.lo[s];     // (no dynamic indexing of the parameter struct: that would copy it to local memory)
-  const int xs = seg * sg.segw, xe = min(xs + sg.segw, W);
-  const int nrows = min(R, H - y0);
-  const uint32_t bar = seg_smem_u32(&s_bar);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int y = blockIdx.y;
+  const int xs = blockIdx.x * segw, xe = min(xs + segw, W);
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar), rows0 = (uint32_t)__cvta_generic_to_shared(&s_rows[0][0]);
+  // first staged canvas column (multiple of 4 floats), in bytes: both resamplings are monotonic in x
+  const int lo4 = min(__ldg(tb.a_b + xs), __ldg(tb.c_b + xs)) & ~15;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t bytes = (uint32_t)min(PRV2_SEG_SPAN, Wc - lo) * 4u;               // Wc and lo are multiples of 4 -> of 16 bytes
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * 3u * (uint32_t)nrows) : "memory");
-    for (int r = 0; r < nrows; ++r) {
-      const int y = y0 + r;
-      const BilinearTap ty = ac_tap(sc.bs_y, y, Hc);                                  // utils.py:42-43, row part
-      s_ly[r] = make_float2(ty.l0, ty.l1);
-      seg_bulk_g2s(&s_rows[r][0][0], avg_c + (size_t)nearest_src(y, sc.ns_y, Hc) * Wc + lo, bytes, bar);
-      seg_bulk_g2s(&s_rows[r][1][0], cnt_c + (size_t)ty.i0 * Wc + lo, bytes, bar);
-      seg_bulk_g2s(&s_rows[r][2][0], cnt_c + (size_t)ty.i1 * Wc + lo, bytes, bar);
-    }
-  }
-  if (warp < R) {                                                 // warp r lists the patches covering (row y0 + r) x [xs, xe), draw order kept
-    const int y = y0 + warp;
+    const uint32_t bytes = (uint32_t)min(PRV2_SEG_SPAN * 4, Wc * 4 - lo4);            // Wc and lo are multiples of 4 floats
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * 3u) : "memory");
+    const BilinearTap ty = ac_tap(sc.bs_y, y, Hc);                                    // utils.py:42-43, row part
+    s_ly1 = ty.l1;
+    seg_bulk_g2s(rows0, reinterpret_cast<const char*>(avg_c + (size_t)nearest_src(y, sc.ns_y, Hc) * Wc) + lo4, bytes, bar);
+    seg_bulk_g2s(rows0 + PRV2_SEG_ROWB, reinterpret_cast<const char*>(cnt_c + (size_t)ty.i0 * Wc) + lo4, bytes, bar);
+    seg_bulk_g2s(rows0 + 2 * PRV2_SEG_ROWB, reinterpret_cast<const char*>(cnt_c + (size_t)ty.i1 * Wc) + lo4, bytes, bar);
+  } else if (tid >= 32 && tid < 64) {                             // warp 1 lists the patches covering row y x [xs, xe), draw order kept
     int m = 0;
-    if (y < H) {
-      for (int base = 0; base < n; base += 32) {
-        const int k = base + lane;
-        int py0 = 0, px0 = 0;
-        bool hit = false;
-        if (k < n) {
-          py0 = starts[k * 2 + 0]; px0 = starts[k * 2 + 1];
-          hit = y >= py0 && y < py0 + rh && px0 < xe && px0 + rw > xs;
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-          const int pos = m + __popc(b & ((1u << lane) - 1));
-          const int ly = y - py0, c = px0 & 3, x0a = px0 - c;
-          s_ent[warp][pos] = make_int4(x0a, rw + c, (c * rh + ly) * prep.pitch - x0a, c * prep.pitch - x0a);
-          s_poff[warp][pos] = (MODE == 2) ? 0 : (k * ph + nearest_src(ly, sc.ps_y, ph)) * pw;    // baseline_pretrain.py:210 (nearest), row part
-        }
-        m += __popc(b);
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      int py0 = 0, px0 = 0;
+      bool hit = false;
+      if (k < n) {
+        py0 = starts[k * 2 + 0]; px0 = starts[k * 2 + 1];
+        hit = y >= py0 && y < py0 + rh && px0 < xe && px0 + rw > xs;
       }
+      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = m + __popc(b & ((1u << lane) - 1));
+        const int ly = y - py0, c = px0 & 3, x0a = px0 - c;
+        s_ent[pos] = make_int4(x0a, rw + c, (c * rh + ly) * prep.pitch - x0a, c * prep.pitch - x0a);
+        s_poff[pos] = (MODE == 2) ? 0 : (k * ph + nearest_src(ly, sc.ps_y, ph)) * pw;    // baseline_pretrain.py:210 (nearest), row part
+      }
+      m += __popc(b);
     }
-    if (lane == 0) s_m[warp] = m;
+    if (lane == 0) s_m = m;
   }
-  // column-only state of this thread's four pixels
+  // column-only part: shared-memory addresses of the canvas taps, 1 - l1
   const int xb = xs + tid * 4;
-  const bool active = tid * 4 < sg.segw && xb < W;                // W % 4 == 0: an active group is a full group
-  int sa[4], si[4];
+  const bool active = xb < xe;                                    // W % 4 == 0: an active group is a full group
+  uint32_t sa[4], si[4];
   float l0[4], l1[4];
-  if (active) {
-    const uint2 ta = __ldg(reinterpret_cast<const uint2*>(tb.a_ix + xb));
-    const uint2 ti = __ldg(reinterpret_cast<const uint2*>(tb.c_i0 + xb));
-    const float4 tl = __ldg(reinterpret_cast<const float4*>(tb.c_l1 + xb));
-    sa[0] = (int)(ta.x & 0xffffu) - lo; sa[1] = (int)(ta.x >> 16) - lo; sa[2] = (int)(ta.y & 0xffffu) - lo; sa[3] = (int)(ta.y >> 16) - lo;
-    si[0] = (int)(ti.x & 0xffffu) - lo; si[1] = (int)(ti.x >> 16) - lo; si[2] = (int)(ti.y & 0xffffu) - lo; si[3] = (int)(ti.y >> 16) - lo;
+  {
+    const int xl = active ? xb : xs;
+    const int4 ta = __ldg(reinterpret_cast<const int4*>(tb.a_b + xl));
+    const int4 ti = __ldg(reinterpret_cast<const int4*>(tb.c_b + xl));
+    const float4 tl = __ldg(reinterpret_cast<const float4*>(tb.c_l1 + xl));
+    const uint32_t r0 = rows0 - (uint32_t)lo4;
+    sa[0] = r0 + ta.x; sa[1] = r0 + ta.y; sa[2] = r0 + ta.z; sa[3] = r0 + ta.w;
+    si[0] = r0 + ti.x; si[1] = r0 + ti.y; si[2] = r0 + ti.z; si[3] = r0 + ti.w;
     l1[0] = tl.x; l1[1] = tl.y; l1[2] = tl.z; l1[3] = tl.w;
 #pragma unroll
     for (int q = 0; q < 4; ++q) l0[q] = __fsub_rn(1.0f, l1[q]);
-  } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { sa[q] = si[q] = 0; l0[q] = l1[q] = 0.f; }
   }
-  __syncthreads();                                                // lists written, barrier initialised
+  __syncthreads();                                                // list written, barrier initialised
   {
     uint32_t ok = 0;
     while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(0) : "memory");
   }
-  if (lo + PRV2_SEG_SPAN >= Wc) {
+  if (lo4 + PRV2_SEG_SPAN * 4 >= Wc * 4) {
     // the segment reaches the last canvas column: tap i1 == i0 there (ac_tap), i.e. column Wc repeats column Wc - 1
-    if (tid < 3 * R) s_rows[tid / 3][tid % 3][Wc - lo] = s_rows[tid / 3][tid % 3][Wc - 1 - lo];
+    if (tid < 3) s_rows[tid][Wc - lo4 / 4] = s_rows[tid][Wc - 1 - lo4 / 4];
     __syncthreads();
   }
   if (!active) return;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int y = y0 + r;
-    if (y >= H) break;
-    const float2 ly = s_ly[r];
-    const size_t o = (size_t)y * W + xb;
-    float avg[4], cnt[4], c0[4], num[4] = {0.f, 0.f, 0.f, 0.f};
+  float avg[4], cnt[4], c0[4];
+  {
+    const float ly1 = s_ly1, ly0 = __fsub_rn(1.0f, ly1);          // (ac_tap's row weights)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      avg[q] = s_rows[r][0][sa[q]];
-      const float r0 = __fmaf_rn(l0[q], s_rows[r][1][si[q]], __fmul_rn(l1[q], s_rows[r][1][si[q] + 1]));     // ac_blend, ATen order
-      const float r1 = __fmaf_rn(l0[q], s_rows[r][2][si[q]], __fmul_rn(l1[q], s_rows[r][2][si[q] + 1]));
-      cnt[q] = __fmaf_rn(ly.x, r0, __fmul_rn(ly.y, r1));
+      avg[q] = seg_lds<0>(sa[q]);
+      const float v00 = seg_lds<PRV2_SEG_ROWB>(si[q]), v01 = seg_lds<PRV2_SEG_ROWB + 4>(si[q]);
+      const float v10 = seg_lds<2 * PRV2_SEG_ROWB>(si[q]), v11 = seg_lds<2 * PRV2_SEG_ROWB + 4>(si[q]);
+      const float r0 = __fmaf_rn(l0[q], v00, __fmul_rn(l1[q], v01));                  // ac_blend, ATen order
+      const float r1 = __fmaf_rn(l0[q], v10, __fmul_rn(l1[q], v11));
+      cnt[q] = __fmaf_rn(ly0, r0, __fmul_rn(ly1, r1));
       c0[q] = cnt[q];
     }
+  }
+  const int m = s_m;
+  for (int i = 0; i < m; ++i) {
+    const int4 e = s_ent[i];
+    if ((unsigned)(xb - e.x) >= (unsigned)e.y) continue;          // group entirely outside this patch
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(prep.mask4 + (e.z + xb)));
+    const float ct[4] = {c4.x, c4.y, c4.z, c4.w};
     if (MODE == 2) {
-      const float4 nin = __ldcs(reinterpret_cast<const float4*>(num_in + o));
-      num[0] = nin.x; num[1] = nin.y; num[2] = nin.z; num[3] = nin.w;
-    }
-    const int m = s_m[r];
-    for (int i = 0; i < m; ++i) {
-      const int4 e = s_ent[r][i];
-      if ((unsigned)(xb - e.x) >= (unsigned)e.y) continue;        // group entirely outside this patch
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(prep.mask4 + (e.z + xb)));
-      const float ct[4] = {c4.x, c4.y, c4.z, c4.w};
-      if (MODE == 2) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) if (ct[q] > 0.f) cnt[q] = __fadd_rn(cnt[q], ct[q]);
-      } else {
-        const uint2 s2 = __ldg(reinterpret_cast<const uint2*>(prep.srcx4 + (e.w + xb)));
-        const int po = s_poff[r][i];                               // 32-bit element offsets: one IMAD.WIDE per gather
-        const float p[4] = {__ldg(preds + (po + (int)(s2.x & 0xffffu))), __ldg(preds + (po + (int)(s2.x >> 16))),
-                            __ldg(preds + (po + (int)(s2.y & 0xffffu))), __ldg(preds + (po + (int)(s2.y >> 16)))};
+      for (int q = 0; q < 4; ++q) if (ct[q] > 0.f) cnt[q] = __fadd_rn(cnt[q], ct[q]);
+    } else {
+      const int4 sx = __ldg(reinterpret_cast<const int4*>(prep.srci4 + (e.w + xb)));
+      const int po = s_poff[i];                                   // 32-bit element offsets: one add + one IMAD.WIDE per gather
+      const float p[4] = {__ldg(preds + (po + sx.x)), __ldg(preds + (po + sx.y)), __ldg(preds + (po + sx.z)), __ldg(preds + (po + sx.w))};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          // utils.py:31-36 as a select, not a branch: a zero weight (the padding of an edge group) leaves the pixel untouched
-          const float den = __fadd_rn(cnt[q], ct[q]);
-          const float qv = __fdiv_rn(__fadd_rn(__fmul_rn(p[q], ct[q]), __fmul_rn(cnt[q], avg[q])), den);
-          const bool pos = ct[q] > 0.f;
-          avg[q] = pos ? qv : avg[q];
-          cnt[q] = pos ? den : cnt[q];
-        }
+      for (int q = 0; q < 4; ++q) {
+        // utils.py:31-36 as a select, not a branch: a zero weight (the padding of an edge group) leaves the pixel untouched
+        const float den = __fadd_rn(cnt[q], ct[q]);
+        const float qv = __fdiv_rn(__fadd_rn(__fmul_rn(p[q], ct[q]), __fmul_rn(cnt[q], avg[q])), den);
+        const bool pos = ct[q] > 0.f;
+        avg[q] = pos ? qv : avg[q];
+        cnt[q] = pos ? den : cnt[q];
       }
     }
-    if (MODE == 2) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) avg[q] = (cnt[q] > c0[q]) ? __fdiv_rn(__fadd_rn(__fmul_rn(avg[q], c0[q]), num[q]), cnt[q]) : avg[q];
-    }
-    __stcs(reinterpret_cast<float4*>(out + o), make_float4(avg[0], avg[1], avg[2], avg[3]));
-    if (out_cnt) __stcs(reinterpret_cast<float4*>(out_cnt + o), make_float4(cnt[0], cnt[1], cnt[2], cnt[3]));
   }
+  const size_t o = (size_t)y * W + xb;
+  if (MODE == 2) {
+    const float4 nin = __ldcs(reinterpret_cast<const float4*>(num_in + o));
+    const float num[4] = {nin.x, nin.y, nin.z, nin.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) avg[q] = (cnt[q] > c0[q]) ? __fdiv_rn(__fadd_rn(__fmul_rn(avg[q], c0[q]), num[q]), cnt[q]) : avg[q];
+  }
+  __stcs(reinterpret_cast<float4*>(out + o), make_float4(avg[0], avg[1], avg[2], avg[3]));
+  if (out_cnt) __stcs(reinterpret_cast<float4*>(out_cnt + o), make_float4(cnt[0], cnt[1], cnt[2], cnt[3]));
 }
 
 // host replay of the column index math (plain IEEE fp32, same operations as nearest_src / ac_tap on the device)
 static int h_nearest_src(int dst, float scale, int n_in) { const int v = (int)floorf((float)dst * scale); return v < n_in - 1 ? v : n_in - 1; }
 static int h_ac_i0(float scale, int dst, int n_in) { const int v = (int)(scale * (float)dst); return v < n_in - 1 ? v : n_in - 1; }
 
-static int g_seg_R = -1, g_seg_w = 0, g_seg_off = -1;            // A/B knobs (prv2_debug_blend_generic / PRV2_BLEND_SEG=0)
-// bit 1: segment kernel off; bits 4-7: rows per CTA (1, 2, 4; 0 = default); bits 8-15: warps per CTA (0 = automatic)
-static void seg_knobs(int on) { g_seg_off = (on & 2) ? 1 : 0; g_seg_R = (on >> 4) & 15; g_seg_w = (on >> 8) & 255; if (!g_seg_R) g_seg_R = -1; }
+static int g_seg_w = 0, g_seg_off = -1;            // A/B knobs (prv2_debug_blend_generic / PRV2_BLEND_SEG=0)
+// bit 1: segment kernel off; bits 8-15: warps per CTA (0 = automatic)
+static void seg_knobs(int on) { g_seg_off = (on & 2) ? 1 : 0; g_seg_w = (on >> 8) & 255; }
 static bool seg_disabled() {
   if (g_seg_off < 0) { const char* e = getenv("PRV2_BLEND_SEG"); g_seg_off = (e && e[0] == '0') ? 1 : 0; }
   return g_seg_off == 1;
 }
 
-// Chooses the segmentation (w warps per CTA, 128*w pixels per segment) and fills the per-segment canvas origins.
+// Can the segment kernel take this call, and with how many warps per CTA (128*w pixels per segment)?
 static bool seg_plan(int Wc, int W, int pw, int rh, int rw, int n, int ph, const RawScales& sc, const void* prep, const void* a, const void* b,
-                     const void* c, const void* d, const void* e, RawSegs* sg, int* warps) {
+                     const void* c, const void* d, const void* e, const void* preds, int* warps) {
   if (seg_disabled() || (W & 3) || (Wc & 3) || n > PRV2_SEG_LIST || (n > 0 && !prep)) return false;
-  if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e) & 15) != 0) return false;
-  if ((long long)4 * rh * raw_prep_pitch(rw) >= (1ll << 31) || (long long)n * ph * pw >= (1ll << 31) || (long long)W + 4ll * rh * raw_prep_pitch(rw) >= (1ll << 31)) return false;
-  static const int order[] = {8, 6, 10, 5, 7, 9, 4, 3, 2};
+  if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e | (uintptr_t)preds) & 15) != 0) return false;
+  const long long pitch = raw_prep_pitch(rw);
+  if (4ll * rh * pitch + W >= (1ll << 29) || (long long)n * ph * pw + pw >= (1ll << 29) || (long long)Wc * 4 >= (1ll << 29)) return false;   // 32-bit byte offsets
+  static const int order[] = {6, 8, 5, 7, 4, 3, 2};
   int best_w = 0; long long best_waste = -1;
   for (int k = 0; k < (int)(sizeof(order) / sizeof(order[0])); ++k) {
     const int w = g_seg_w > 0 ? g_seg_w : order[k];
     const int segw = 128 * w, nseg = cdiv(W, segw);
-    if (nseg > 12) continue;
-    bool fits = true;
+    bool fits = w >= 2 && w <= 8;                                 // (__launch_bounds__ of the kernel; warp 1 builds the list)
     for (int s = 0; s < nseg && fits; ++s) {
       const int xs = s * segw, xl = (xs + segw < W ? xs + segw : W) - 1;
       const int a0 = h_nearest_src(xs, sc.ns_x, Wc), i0 = h_ac_i0(sc.bs_x, xs, Wc);
@@ -1144,23 +1150,18 @@ static bool seg_plan(int Wc, int W, int pw, int rh, int rw, int n, int ph, const
     if (g_seg_w > 0 || waste == 0) break;
   }
   if (!best_w) return false;
-  const int segw = 128 * best_w;
-  sg->nseg = cdiv(W, segw); sg->segw = segw;
-  for (int s = 0; s < sg->nseg; ++s) {
-    const int xs = s * segw;
-    const int a0 = h_nearest_src(xs, sc.ns_x, Wc), i0 = h_ac_i0(sc.bs_x, xs, Wc);
-    sg->lo[s] = (a0 < i0 ? a0 : i0) & ~3;
-  }
   *warps = best_w;
   return true;
 }
 
-template <int MODE, int R>
-static void launch_seg(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* preds, const int32_t* starts, int n, int ph, int pw, int rh,
-                       int rw, int H, int W, float* out, float* out_cnt, const float* num_in, const RawScales& sc, const RawTables& tb, const RawPrep& pv,
-                       const RawSegs& sg, int warps, cudaStream_t stream) {
-  blend_raw_seg_kernel<MODE, R><<<dim3(sg.nseg, cdiv(H, R)), warps * 32, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out,
-                                                                                      out_cnt, num_in, sc, tb, pv, sg);
+template <int MODE>
+static bool launch_seg(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* preds, const int32_t* starts, int n, int ph, int pw, int rh,
+                       int rw, int H, int W, float* out, float* out_cnt, const float* num_in, const RawScales& sc, const SegTables& tb, const RawPrep& pv,
+                       int warps, cudaStream_t stream) {
+  const int segw = warps * 128;
+  blend_raw_seg_kernel<MODE><<<dim3(cdiv(W, segw), H), warps * 32, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out, out_cnt,
+                                                                                num_in, sc, tb, pv, segw);
+  return true;
 }
 
 template <int MODE>
@@ -1169,17 +1170,15 @@ static void launch_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, c
                        const float* num_in, const RawScales& sc, const void* prep, cudaStream_t stream) {
   dim3 grid(1, H);
   RawTables tb;
-  RawSegs sg;
   int warps = 0;
-  if (MODE != 1 && !blend_generic_forced() && seg_plan(Wc, W, pw, rh, rw, n, ph, sc, prep, avg_c, cnt_c, out, out_cnt, num_in, &sg, &warps) &&
+  if (MODE != 1 && !blend_generic_forced() && seg_plan(Wc, W, pw, rh, rw, n, ph, sc, prep, avg_c, cnt_c, out, out_cnt, num_in, preds, &warps) &&
       raw_tables_get(Wc, W, pw, rw, sc, stream, &tb)) {
     constexpr int M = MODE == 1 ? 0 : MODE;                       // (MODE 1 never gets here; keeps the instantiation list to modes 0 and 2)
     const RawPrep pv = raw_prep_view(prep, rh, rw);
-    const int R = g_seg_R > 0 ? g_seg_R : 1;
-    if (R == 1) launch_seg<M, 1>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out, out_cnt, num_in, sc, tb, pv, sg, warps, stream);
-    else if (R == 4) launch_seg<M, 4>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out, out_cnt, num_in, sc, tb, pv, sg, warps, stream);
-    else launch_seg<M, 2>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out, out_cnt, num_in, sc, tb, pv, sg, warps, stream);
-    return;
+    SegTables st;
+    st.a_b = tb.a_b; st.c_b = tb.c_b; st.c_l1 = tb.c_l1;
+    if (launch_seg<M>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out, out_cnt, num_in, sc, st, pv, warps, stream))
+      return;
   }
   if (!blend_generic_forced() && raw_tables_get(Wc, W, pw, rw, sc, stream, &tb)) {
     blend_raw_tab_kernel<MODE><<<grid, 256, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, own, starts, n, ph, pw, rmask, rh, rw, H, W, out, out_cnt,

@@ -73,8 +73,7 @@ def main():
     # rN-stage variants (prv2_debug_blend_generic knobs: bit 1 = segment kernel off, bits 4-7 rows per CTA, bits 8-15 warps per CTA)
     rprep = ops.blend_raw_prepare(rmask, pw)
     ref = None
-    for label, knob in (("tab", 2), ("seg_R1", 1 << 4), ("seg_R2", 2 << 4), ("seg_R4", 4 << 4), ("seg_R1_w5", (1 << 4) | (5 << 8)), ("seg_R2_w5", (2 << 4) | (5 << 8)),
-                        ("seg_R2_w10", (2 << 4) | (10 << 8)), ("seg_R1_w10", (1 << 4) | (10 << 8)), ("seg_R4_w5", (4 << 4) | (5 << 8))):
+    for label, knob in (("tab", 2), ("seg", 0), ("seg_w8", 8 << 8), ("seg_w5", 5 << 8), ("seg_w4", 4 << 8), ("seg_w3", 3 << 8), ("seg_w2", 2 << 8)):
         _lib.call("prv2_debug_blend_generic", knob)
         got = ops.blend_raw(avg_c, cnt_c, preds[first:], starts, rmask, ph, pw, rh, rw, H, W, prep=rprep)
         if ref is None:

@@ -80,11 +80,12 @@ if which in ("all", "blend"):
     rmask = torch.from_numpy(masks.random_patch_mask((540, 960), 0.15).copy()).to(DEV)
     starts = torch.from_numpy(np.ascontiguousarray(bb[first:, [1, 0]])).to(DEV)
     flush = torch.empty(64 * 1024 * 1024, device=DEV)
+    rprep = ops.blend_raw_prepare(rmask, 448)                 # once per geometry, as the model does
 
     def f():
         flush.fill_(1.0)                                      # cold L2, as in the frame loop
         avg, cnt = ops.blend_canvas(preds[:first], mask, stages, 1792, 1792)
-        ops.blend_raw(avg, cnt, preds[first:], starts, rmask, 448, 448, 540, 960, 2160, 3840)
+        ops.blend_raw(avg, cnt, preds[first:], starts, rmask, 448, 448, 540, 960, 2160, 3840, prep=rprep)
     run(f)
 if which in ("all", "resize"):
     a = Act.empty(12, 256, 256, 256, False, DEV); a.hi.normal_()
