@@ -94,11 +94,13 @@ int prv2_blend_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc,
                    const float* rmask, int rh, int rw, int H, int W,
                    float* out, float* out_cnt, const void* prep /*NULL or prv2_blend_raw_prepare output*/, prv2_stream_t stream);
 
-/* Optional one-time preparation of the random-patch weight map for the three *_raw entry points (same results, ~40 % fewer load
- * instructions): `prep` (device, 16-byte aligned, prv2_blend_raw_prep_bytes(rh, rw) bytes) receives four column-shifted,
- * zero-padded copies of rmask [rh, rw] and of the nearest-source-column table of a [*, pw] prediction (baseline_pretrain.py:210),
- * so that the four weights / source columns of any aligned group of four output pixels are ONE 16-byte / 8-byte vector.  The
- * weight map depends only on (rh, rw): prepare it once per geometry and pass it to every frame's calls. */
+/* Optional one-time preparation of the random-patch weight map for the three *_raw entry points (same results; with it, and with
+ * W, Wc multiples of 4 and 16-byte aligned canvases, prv2_blend_raw / prv2_blend_finalize_raw run the segment kernel, which
+ * stages the canvas rows in shared memory by bulk copies: 41 instead of 60 us for the r32 stage of a 2160x3840 frame):
+ * `prep` (device, 16-byte aligned, prv2_blend_raw_prep_bytes(rh, rw) bytes) receives four column-shifted,
+ * zero-padded copies of rmask [rh, rw] and of the nearest-source-column table of a [*, pw] prediction (baseline_pretrain.py:210;
+ * as u16 and as i32), so that the four weights / source columns of any aligned group of four output pixels are ONE 16-byte
+ * vector.  The weight map depends only on (rh, rw): prepare it once per geometry and pass it to every frame's calls. */
 int64_t prv2_blend_raw_prep_bytes(int rh, int rw);
 int prv2_blend_raw_prepare(const float* rmask, int rh, int rw, int pw, void* prep, prv2_stream_t stream);
 
@@ -120,8 +122,9 @@ int prv2_blend_finalize_canvas(const float* num_c, const float* m1, const float*
 int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, int Hc, int Wc, const float* num_r,
                             const int32_t* starts, int n, const float* rmask, int rh, int rw, int H, int W,
                             float* out, float* out_cnt, const void* prep, prv2_stream_t stream);
-/* Test / A-B hook: on != 0 routes every blend entry point through the any-alignment generic kernels instead of the
- * aligned fast paths (both produce the same bits; tests assert it). */
+/* Test / A-B hook: bit 0 routes every blend entry point through the any-alignment generic kernels instead of the
+ * aligned fast paths; bit 1 switches the rN stage's segment kernel off (the table kernel runs); bits 8-15 force the segment
+ * kernel's warps per CTA (0 = automatic).  Every path produces the same bits; tests assert it. */
 int prv2_debug_blend_generic(int on);
 
 /* ------------------------------------------------------------------------------------------

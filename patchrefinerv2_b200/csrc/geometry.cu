@@ -447,27 +447,46 @@ __global__ void __launch_bounds__(256) blend_canvas_fast_kernel(const float* __r
   if (MODE == 1) { acc_a = *reinterpret_cast<const float4*>(avg_out + o); acc_c = *reinterpret_cast<const float4*>(cnt_out + o); }
   if (MODE == 2) { acc_a = __ldcs(reinterpret_cast<const float4*>(num_in + o)); acc_c = __ldcs(reinterpret_cast<const float4*>(m1_in + o)); }
   float r_a[4], r_c[4];
+  if (MODE == 0) {
+    // stage-major: ONE branch per stage for the whole group (a group is inside one patch of a stage or outside all of them), the
+    // weight test as a select -- utils.py:31-36 leaves a pixel untouched where the weight is not positive
+    float avg[4], cnt[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    float avg = 0.f, cnt = 0.f, num = (MODE == 2) ? (&acc_a.x)[k] : 0.f, m1 = (MODE == 2) ? (&acc_c.x)[k] : 0.f, cnt0 = 0.f;
+    for (int k = 0; k < 4; ++k) { avg[k] = ok[0] ? (&pv[0].x)[k] : 0.f; cnt[k] = ok[0] ? (&ct[0].x)[k] : 0.f; }
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const float c = (&ct[s].x)[k], p = (&pv[s].x)[k];
+    for (int s = 1; s < NS; ++s) {
       if (!ok[s]) continue;
-      if (MODE == 0) {
-        if (s == 0) { avg = p; cnt = c; }
-        else if (c > 0.f) ram_update(avg, cnt, p, c);
-      } else if (MODE == 1) {
-        if (s == 0) m1 = p;
-        else if (c > 0.f) num = __fadd_rn(num, __fmul_rn(p, c));
-      } else {
-        if (s == 0) { cnt = c; cnt0 = c; }
-        else if (c > 0.f) cnt = __fadd_rn(cnt, c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float c = (&ct[s].x)[k], p = (&pv[s].x)[k];
+        const float den = __fadd_rn(cnt[k], c);
+        const float qv = __fdiv_rn(__fadd_rn(__fmul_rn(p, c), __fmul_rn(cnt[k], avg[k])), den);
+        const bool pos = c > 0.f;
+        avg[k] = pos ? qv : avg[k];
+        cnt[k] = pos ? den : cnt[k];
       }
     }
-    if (MODE == 0) { r_a[k] = avg; r_c[k] = cnt; }
-    else if (MODE == 1) { r_a[k] = (&acc_a.x)[k] + num; r_c[k] = (&acc_c.x)[k] + m1; }
-    else { r_a[k] = (cnt > cnt0) ? __fdiv_rn(__fadd_rn(__fmul_rn(m1, cnt0), num), cnt) : m1; r_c[k] = cnt; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { r_a[k] = avg[k]; r_c[k] = cnt[k]; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float cnt = 0.f, num = (MODE == 2) ? (&acc_a.x)[k] : 0.f, m1 = (MODE == 2) ? (&acc_c.x)[k] : 0.f, cnt0 = 0.f;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float c = (&ct[s].x)[k], p = (&pv[s].x)[k];
+        if (!ok[s]) continue;
+        if (MODE == 1) {
+          if (s == 0) m1 = p;
+          else if (c > 0.f) num = __fadd_rn(num, __fmul_rn(p, c));
+        } else {
+          if (s == 0) { cnt = c; cnt0 = c; }
+          else if (c > 0.f) cnt = __fadd_rn(cnt, c);
+        }
+      }
+      if (MODE == 1) { r_a[k] = (&acc_a.x)[k] + num; r_c[k] = (&acc_c.x)[k] + m1; }
+      else { r_a[k] = (cnt > cnt0) ? __fdiv_rn(__fadd_rn(__fmul_rn(m1, cnt0), num), cnt) : m1; r_c[k] = cnt; }
+    }
   }
   if (MODE == 1) {
     *reinterpret_cast<float4*>(avg_out + o) = make_float4(r_a[0], r_a[1], r_a[2], r_a[3]);

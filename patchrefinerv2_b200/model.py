@@ -377,7 +377,8 @@ class PatchRefiner(nn.Module):
         if self._engine is None or self._engine["device"] != dev:
             self._engine = self._build_engine(dev)
         eng = self._engine
-        hr_ready = None
+        hr_ready = hr_host = None
+        hr_shape = tuple(image_hr.shape)
         if not image_hr.is_cuda:
             # frame ingest: host frames are uploaded by the model -- image_lr first on the compute stream,
             # the 100 MB image_hr on a copy stream UNDER the coarse pass (only the crop kernel needs it); pinned memory makes
@@ -385,20 +386,15 @@ class PatchRefiner(nn.Module):
             if "copy_stream" not in eng:
                 eng["copy_stream"] = torch.cuda.Stream(device=dev)
             image_lr = image_lr.to(dev, non_blocking=True)
-            cs = eng["copy_stream"]
-            cs.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(cs):
-                image_hr = image_hr.to(dev, non_blocking=True)
-                hr_ready = torch.cuda.Event()
-                hr_ready.record(cs)
+            hr_host, image_hr = image_hr, None                     # uploaded below, once this rank's share of the work list is known
         elif not image_lr.is_cuda:
             image_lr = image_lr.to(dev, non_blocking=True)
         ph, pw = self.patch_process_shape
         rh, rw = tile_cfg["patch_raw_shape"]
         H, W = tile_cfg["image_raw_shape"]
         Hc, Wc = tile_cfg["patch_reensemble_shape"]
-        if tuple(image_hr.shape[-2:]) != (H, W):
-            raise ValueError(f"image_hr is {tuple(image_hr.shape[-2:])} but tile_cfg.image_raw_shape is {(H, W)}")
+        if hr_shape[-2:] != (H, W):
+            raise ValueError(f"image_hr is {hr_shape[-2:]} but tile_cfg.image_raw_shape is {(H, W)}")
         if image_lr.shape[0] != F_:
             raise ValueError(f"image_lr holds {image_lr.shape[0]} frames, image_hr {F_}")
 
@@ -418,6 +414,20 @@ class PatchRefiner(nn.Module):
             bboxs_np = _broadcast_bboxs(bboxs_np, dev)
         rois_np = tiling.bboxs_to_feat(bboxs_np, (H, W), (ph, pw))[:, 1:]
 
+        own_np = tiling.shard_patches(F_ * P, rank, world, frames=F_)
+        sel = np.nonzero(own_np)[0]
+        if hr_host is not None:
+            # the frames this rank's patches are cut from -- all of them on one GPU, this rank's own frame when a batch holds one
+            # frame per rank -- go up on a copy stream UNDER the coarse pass (only the crop kernel needs them)
+            cs = eng["copy_stream"]
+            cs.wait_stream(torch.cuda.current_stream(dev))
+            image_hr = eng["ws"].f32("hr_in", *hr_shape) if hr_host.dtype == torch.float32 else torch.empty(hr_shape, dtype=hr_host.dtype, device=dev)
+            with torch.cuda.stream(cs):
+                for f in np.unique(sel // P):
+                    image_hr[int(f)].copy_(hr_host[int(f)], non_blocking=True)
+                hr_ready = torch.cuda.Event()
+                hr_ready.record(cs)
+
         if world > 1 and F_ % world == 0:
             # the coarse passes of a batch are sharded too (a contiguous block of frames per rank) and all-gathered: ~100 MB of
             # features per frame over NVLink instead of F replicated 0.94-TFLOP passes on every rank
@@ -429,9 +439,6 @@ class PatchRefiner(nn.Module):
             image_hr.record_stream(torch.cuda.current_stream(dev))
         hr = image_hr.float().contiguous()
         preds = eng["ws"].f32("preds", F_ * P, ph, pw)
-
-        own_np = tiling.shard_patches(F_ * P, rank, world)
-        sel = np.nonzero(own_np)[0]
         self.refine_patches(eng, hr, bboxs_np, rois_np, coarse_feats, coarse_depth, sel, preds, P, trace)
 
         grid_stages, first = [], 0

@@ -142,9 +142,14 @@ def schedule(tile_cfg: dict, patch_process_shape, cai_mode: str, process_num: in
     return stages
 
 
-def shard_patches(n_patches: int, rank: int, world_size: int) -> np.ndarray:
-    """Round-robin ownership mask over the flattened patch list: patch i belongs
-    to rank i % world_size.  Every rank computes the same full schedule first."""
+def shard_patches(n_patches: int, rank: int, world_size: int, frames: int = 1) -> np.ndarray:
+    """Ownership mask over the flattened patch list; every rank computes the same full schedule first.
+    One frame: round-robin, patch i belongs to rank i % world_size.  A batch of frames (``frames`` > 1, frame-major list):
+    contiguous blocks of the same sizes (+-1 patch), so that a rank touches the fewest frames -- exactly its own frame when
+    there are as many frames as ranks -- and only those frames need to be uploaded to it."""
     own = np.zeros(n_patches, dtype=np.uint8)
-    own[rank::world_size] = 1
+    if frames > 1:
+        own[(n_patches * rank) // world_size:(n_patches * (rank + 1)) // world_size] = 1
+    else:
+        own[rank::world_size] = 1
     return own

@@ -71,6 +71,22 @@ def test_shard_partition():
         assert max(int(o.sum()) for o in owns) - min(int(o.sum()) for o in owns) <= 1
 
 
+def test_shard_partition_batch_of_frames():
+    """A batch of frames is split into contiguous blocks: same balance, and a rank touches the fewest frames (its own frame when
+    the batch holds one frame per rank), so only those frames have to be uploaded to it."""
+    for F, P, G in [(8, 81, 8), (16, 353, 8), (2, 9, 2), (3, 49, 4), (2, 5, 8)]:
+        owns = [tiling.shard_patches(F * P, r, G, frames=F) for r in range(G)]
+        assert np.array_equal(np.sum(owns, axis=0), np.ones(F * P, np.uint8))
+        assert max(int(o.sum()) for o in owns) - min(int(o.sum()) for o in owns) <= 1
+        for r, o in enumerate(owns):
+            idx = np.nonzero(o)[0]
+            if len(idx):
+                assert np.array_equal(idx, np.arange(idx[0], idx[-1] + 1))              # contiguous
+                assert len(np.unique(idx // P)) <= -(-len(idx) // P) + 1
+            if F == G:
+                assert np.array_equal(np.unique(idx // P), [r])
+
+
 @pytest.mark.parametrize("size,border", [((448, 448), 0.15), ((224, 224), 0.15), ((540, 960), 0.15), ((384, 512), 0.1)])
 def test_masks_bit_identical_to_oracle(size, border):
     assert np.array_equal(masks.generatemask(size, border), O.generatemask(size, border))

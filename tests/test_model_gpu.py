@@ -155,6 +155,26 @@ def test_batch_of_frames_equals_frame_by_frame(models, tiny_setup, mode, pn):
     assert ((sharded - both).abs() / both.abs().clamp_min(1e-3)).max().item() < 1e-3
 
 
+def test_host_frames_in_equal_device_frames_in(models, tiny_setup):
+    """Frame ingest: pinned host frames -- uploaded by the model on its copy stream, only the frames this rank's
+    patches are cut from -- give the bits the device-resident call gives, for one frame and for a batch, plain and sharded."""
+    cfg, sd, lr, hr = tiny_setup
+    m = models["bf16"]
+    lr2, hr2 = O.synthetic_frame(cfg, 11)
+    lrs, hrs = torch.cat([lr, lr2]), torch.cat([hr, hr2])
+    for shard in (False, True):
+        random.seed(5)
+        dev_in, _ = m(mode="infer", image_lr=lrs.to(DEV), image_hr=hrs.to(DEV), cai_mode="r4", process_num=2, shard=shard)
+        random.seed(5)
+        host_in, _ = m(mode="infer", image_lr=lrs.pin_memory(), image_hr=hrs.pin_memory(), cai_mode="r4", process_num=2, shard=shard)
+        assert torch.equal(dev_in, host_in), shard
+    random.seed(5)
+    one_dev, _ = m(mode="infer", image_lr=lr.to(DEV), image_hr=hr.to(DEV), cai_mode="m2", process_num=2)
+    random.seed(5)
+    one_host, _ = m(mode="infer", image_lr=lr.pin_memory(), image_hr=hr.pin_memory(), cai_mode="m2", process_num=2)
+    assert torch.equal(one_dev, one_host)
+
+
 @pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("bf16", 5e-2)])
 @pytest.mark.parametrize("hw", [(98, 126), (112, 154)])
 def test_dav2_non_square_and_odd_token_grids(prec, tol, hw):
