@@ -499,14 +499,14 @@ def main():
             dist.all_reduce(torch.zeros(1, device=dev))
             torch.cuda.synchronize()
     # A step = ONE model call on a batch of F frames (default F = number of GPUs): the F x 81 patches form one work list that is
-    # sharded round-robin over the ranks, every frame keeps its own canvases, ONE sum-reduce combines the batch.  Per-GPU work
+    # split into contiguous blocks over the ranks (round-robin for a single frame), every frame keeps its own canvases, ONE sum-reduce combines the batch.  Per-GPU work
     # is one frame's worth at every N (weak scaling); at N = 1 this is the single-frame call of BASELINE config 4.
     F_ = args.frames_per_step or world
     n_local = -(-(n_patches * F_) // world)
     pb = args.patch_batch or -(-n_local // (-(-n_local // 27)))
     config["patch_batch"] = pb
     config["frames_per_step"] = F_
-    config["parallelism"] = (f"batch of {F_} frames = {F_ * n_patches} patches sharded round-robin over {world} ranks + 1 NCCL sum-reduce per batch"
+    config["parallelism"] = (f"batch of {F_} frames = {F_ * n_patches} patches split into {world} contiguous blocks (one per rank; host frames are uploaded only to the ranks that cut patches from them) + 1 NCCL sum-reduce per batch"
                              if world > 1 else "single GPU")
     import torch as _t
     hr = _t.cat([synthetic_frame(raw, 1 + f) for f in range(F_)])
@@ -571,7 +571,7 @@ def main():
             ms_e, _, _ = timed(step_e2e, steps, 2)
             res["e2e"] = {"value": F_ * steps / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": lr_pin.numel() * 4 + hr_pin.numel() * 4,
                           "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e / steps,
-                          "note": "pinned host frame in, pinned host depth out; image_hr upload overlaps the coarse pass on a copy stream; D2H on rank 0"}
+                          "note": "pinned host frames in, pinned host depth out; each rank uploads only the frames its patches are cut from (bytes = the whole job's), under the coarse pass on a copy stream; D2H on rank 0"}
         psteps = min(steps, 3)
         ms_p, _, plog = timed(step_resident, psteps, 1, profile=True)
         res["kernels"], res["gemm_layers"] = kernel_tables(plog, psteps, ms_p, peaks)
@@ -606,7 +606,7 @@ def main():
         random.seed(1)
         d_one, _ = model(mode="infer", image_lr=lr_dev, image_hr=hr_dev, cai_mode=cai_mode, process_num=process_num, shard=False)
         shard_check = {"max_rel_diff_vs_unsharded": float(((d_sh - d_one).abs() / d_one.abs().clamp_min(1e-3)).max().item()),
-                       "what": f"all {F_} frames of the sharded batch (sharded + all-gathered coarse passes, round-robin patches, one sum-reduce) against "
+                       "what": f"all {F_} frames of the sharded batch (sharded + all-gathered coarse passes, one block of patches per rank, one sum-reduce) against "
                                "the same batch refined by this rank alone"}
         torch.distributed.barrier()
 

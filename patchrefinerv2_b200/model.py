@@ -370,8 +370,9 @@ class PatchRefiner(nn.Module):
         # The reference asserts batch 1 (patchrefiner.py:348) and its Tester feeds frames one by one (tester.py:62-69).  Here a
         # batch of F frames is ONE work list of F x P patches (BASELINE config 5): the schedules are drawn frame by
         # frame in order (so the global `random` stream is consumed exactly as F successive reference calls would), the coarse
-        # pass runs once on the whole batch, the flattened patches are refined in mixed-frame batches (and sharded round-robin
-        # over the ranks), every frame keeps its own canvases and one sum-reduce combines the whole batch.
+        # pass runs once on the whole batch, the flattened patches are refined in mixed-frame batches (and split over the ranks:
+        # round-robin for one frame, contiguous blocks for a batch), every frame keeps its own canvases and one sum-reduce
+        # combines the whole batch.
         F_ = int(image_hr.shape[0])
         dev = image_hr.device if image_hr.is_cuda else self._device
         if self._engine is None or self._engine["device"] != dev:
