@@ -240,9 +240,32 @@ def plus():
         print("plus", mode, tuple(depth.shape), float(depth.mean()))
 
 
+def plus_convx():
+    """plus_convx_r2.npz: the same with a convnext-named encoder (oracle.ToyConvNeXtEncoder: four maps) -- the reference then runs its
+    4-channel ``stem_0`` surgery (patchrefinerplus.py:194-200) and LightWeightRefiner's ``upsample_convx`` stage (:276-283, 307-314)."""
+    cfg = O.make_plus_config(convnext=True)
+    sd = O.init_patchrefinerplus_state_dict(cfg, 0)
+    d = tempfile.mkdtemp()
+    cp = os.path.join(d, "c.pth")
+    torch.save({k[len("coarse_branch."):]: v for k, v in sd.items() if k.startswith("coarse_branch.")}, cp)
+    ref = ref_shim.build_reference_patchrefinerplus(cfg, cp, lambda: O.ToyConvNeXtEncoder(3))
+    res = ref.load_state_dict(sd, strict=False)
+    assert not res.missing_keys and not res.unexpected_keys, res
+    lr, hr = O.synthetic_frame(cfg, 1)
+    random.seed(1)
+    with torch.no_grad():
+        depth, log = ref(mode="infer", image_lr=lr, image_hr=hr, cai_mode="r2", process_num=2, tile_cfg=None)
+    np.savez_compressed(os.path.join(OUT, "plus_convx_r2.npz"), mode="r2", process_num=2, depth=depth.numpy(), coarse=log["coarse_prediction"].numpy(),
+                        sd_sha=sd_digest(sd), frame_sha=O.sha256_f32(hr.numpy()), keys=np.array(sorted(ref.state_dict().keys())))
+    print("plus_convx r2", tuple(depth.shape), float(depth.mean()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if "--plus-convx-only" in sys.argv:
+        plus_convx()
+        sys.exit(0)
     if "--bifusion-only" in sys.argv:
         bifusion()
         sys.exit(0)
@@ -253,6 +276,7 @@ if __name__ == "__main__":
         plus()
         sys.exit(0)
     plus()
+    plus_convx()
     zoe_head()
     bifusion()
     tiny()

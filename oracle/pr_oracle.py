@@ -1011,6 +1011,46 @@ class ToyFineEncoder(torch.nn.Module):
         return feats
 
 
+TOY_CONVX_NAME = "convnext_large"                               # the name whose 4-channel ``stem_0`` surgery the reference knows (patchrefinerplus.py:194-200)
+TOY_CONVX_CHL = (32, 192, 32, 48, 64)                           # encoder_channels: [up-sampled level, stem (192 is hard-coded by the surgery), 3 stages]
+
+
+class ToyConvNeXtEncoder(torch.nn.Module):
+    """Stand-in for timm's ``convnext_large`` ``features_only`` model inside ``LightWeightRefiner``: FOUR maps at strides
+    4 / 8 / 16 / 32 (the reference adds the stride-2 and stride-1 levels itself with ``upsample_convx`` and a bilinear resize,
+    lightweight_refiner.py:276-283, 307-314).  ``stem_0`` (4x4 stride-4 conv with a bias) and ``default_cfg`` are the attributes
+    the reference touches.  The arithmetic of the real encoder is UNPINNED (timm absent); the stage around it is pinned."""
+
+    default_cfg = {"mean": (0.485, 0.456, 0.406), "std": (0.229, 0.224, 0.225)}
+
+    def __init__(self, in_chans: int = 3):
+        super().__init__()
+        nn = torch.nn
+        c = TOY_CONVX_CHL
+        self.stem_0 = nn.Conv2d(in_chans, c[1], 4, stride=4)
+        self.stages = nn.ModuleList([nn.Conv2d(c[i], c[i + 1], 3, stride=2, padding=1, bias=True) for i in range(1, 4)])
+
+    def forward(self, x):
+        feats = [F.relu(self.stem_0(x))]
+        for st in self.stages:
+            feats.append(F.relu(st(feats[-1])))
+        return feats
+
+
+def init_toy_convx_state_dict(seed: int, in_chans: int = 4) -> Dict[str, Tensor]:
+    """Encoder weights plus the reference's own ``upsample_convx`` (ConvTranspose2d(192 -> 32, k = s = 2), keys relative to
+    ``refiner_fine_branch.``)."""
+    g = torch.Generator().manual_seed(seed)
+    c = TOY_CONVX_CHL
+    sd = {"refiner_encoder.stem_0.weight": _conv_w(g, c[1], in_chans, 4, gain=1.7), "refiner_encoder.stem_0.bias": _vec(g, c[1], 0.05)}
+    for i in range(3):
+        sd[f"refiner_encoder.stages.{i}.weight"] = _conv_w(g, c[i + 2], c[i + 1], 3, gain=1.7)
+        sd[f"refiner_encoder.stages.{i}.bias"] = _vec(g, c[i + 2], 0.05)
+    sd["upsample_convx.0.weight"] = _conv_w(g, c[1], c[0], 2, gain=1.7)              # ConvTranspose2d weight: [in, out, 2, 2]
+    sd["upsample_convx.0.bias"] = _vec(g, c[0], 0.05)
+    return sd
+
+
 def init_toy_encoder_state_dict(seed: int, in_chans: int = 4) -> Dict[str, Tensor]:
     g = torch.Generator().manual_seed(seed)
     c = TOY_ENCODER_CHL
@@ -1022,9 +1062,15 @@ def init_toy_encoder_state_dict(seed: int, in_chans: int = 4) -> Dict[str, Tenso
 
 
 def make_plus_config(encoder="vits", features=256, out_channels=(48, 96, 192, 384), patch_process_shape=(224, 224), image_raw_shape=(432, 768),
-                     patch_split_num=(2, 2), coarse2fine_type="coarse-gated", max_depth=80.0) -> dict:
+                     patch_split_num=(2, 2), coarse2fine_type="coarse-gated", max_depth=80.0, convnext=False) -> dict:
     """A config dict shaped like configs/patchrefinerv2_dav2/plus_mobile_u4k_base_coarse_e2e_c2f_pretrain.py (DA2 coarse branch
-    with 256 decoder features, LightWeightRefiner fine branch, BiDirectionalFusion)."""
+    with 256 decoder features, LightWeightRefiner fine branch, BiDirectionalFusion); ``convnext=True``: like plus_convx_u4k_* (four
+    encoder maps + the ``upsample_convx`` stage)."""
+    if convnext:
+        cfg = make_plus_config(encoder, features, out_channels, patch_process_shape, image_raw_shape, patch_split_num, coarse2fine_type, max_depth)
+        cfg["refiner"]["fine_branch"].update(encoder_name=TOY_CONVX_NAME, encoder_channels=list(TOY_CONVX_CHL))
+        cfg["refiner"]["fusion_model"].update(encoder_name=TOY_CONVX_NAME, fine_chl=list(TOY_CONVX_CHL))
+        return cfg
     return dict(
         image_raw_shape=list(image_raw_shape), patch_process_shape=list(patch_process_shape), patch_split_num=list(patch_split_num),
         fusion_feat_level=6, min_depth=1e-3, max_depth=max_depth, strategy_refiner_target="offset_coarse",
@@ -1048,8 +1094,12 @@ def init_patchrefinerplus_state_dict(cfg: dict, seed: int = 0) -> Dict[str, Tens
     sd: Dict[str, Tensor] = {}
     for k, v in init_dav2_state_dict(cb["encoder"], cb["features"], cb["out_channels"], seed * 3 + 21).items():
         sd["coarse_branch." + k] = v
-    for k, v in init_toy_encoder_state_dict(seed * 3 + 22).items():
-        sd["refiner_fine_branch.refiner_encoder." + k] = v
+    if "convnext" in cfg["refiner"]["fine_branch"]["encoder_name"]:
+        for k, v in init_toy_convx_state_dict(seed * 3 + 22).items():
+            sd["refiner_fine_branch." + k] = v
+    else:
+        for k, v in init_toy_encoder_state_dict(seed * 3 + 22).items():
+            sd["refiner_fine_branch.refiner_encoder." + k] = v
     for k, v in init_bidirectional_fusion_state_dict(fu["coarse_chl"], fu["fine_chl"], fu["fine_chl_after_coarse2fine"], fu["temp_chl"], fu["dec_chl"],
                                                      seed * 3 + 23, fu["coarse2fine_type"]).items():
         sd["refiner_fusion_model." + k] = v
@@ -1081,7 +1131,10 @@ class PatchRefinerPlusOracle(PatchRefinerOracle):
         std = torch.tensor(self.encoder.default_cfg["std"], device=imgs_crop.device).view(-1, 1, 1)
         x = (imgs_crop - mean) / std                                                      # lightweight_refiner.py:293
         feats = list(self.encoder(torch.cat([x, coarse_depth_roi], dim=1)))                # :296 (coarse_condition)
-        feats.insert(0, F.interpolate(feats[0], scale_factor=2, mode="bilinear", align_corners=True))   # :316-318
+        if "convnext" in self.cfg["refiner"]["fine_branch"]["encoder_name"]:              # :307-314: ConvTranspose2d(k = s = 2) + ReLU, then bilinear x2
+            q = "refiner_fine_branch.upsample_convx.0."
+            feats.insert(0, F.relu(F.conv_transpose2d(feats[0], self.sd[q + "weight"], self.sd[q + "bias"], stride=2)))
+        feats.insert(0, F.interpolate(feats[0], scale_factor=2, mode="bilinear", align_corners=True))   # :316-318 / :312-313
         r_feats = feats[::-1]                                                             # :320
         r_depth = torch.zeros_like(x[:, :1])                                              # :321
         if trace is not None:

@@ -150,8 +150,6 @@ class PatchRefiner(nn.Module):
         self._cb_cfg, self._fb_cfg, self._fu_cfg = dict(_get(cb, "model_cfg")), dict(_get(fb, "model_cfg")), fu
         self.fusion_feat_level = int(_get(config, "fusion_feat_level"))
         self.strategy_refiner_target = _get(config, "strategy_refiner_target")
-        if self.strategy_refiner_target == "direct":
-            raise NotImplementedError("strategy_refiner_target='direct' is not implemented")
         self.pre_norm_bbox = _get(config, "pre_norm_bbox", True)
         self.resizer = _Resizer(self.patch_process_shape)
         if tuple(self.resizer.size) != tuple(self.patch_process_shape):
@@ -331,6 +329,8 @@ class PatchRefiner(nn.Module):
             c_list = c_roi[-level:][::-1]                                                   # patchrefiner.py:245-251
             f_list = r_feats[-level:][::-1]
             pred = eng["fusion"].forward(c_list, f_list, d_roi, r_depth, base, trace)        # fusion_model.py:84-122
+            if self.strategy_refiner_target == "direct":                                    # patchrefiner.py:280-281 (no shipped config; base is None above)
+                pred = torch.sigmoid(pred) * self.max_depth
             preds[torch.from_numpy(idx).to(dev, non_blocking=True)] = pred.reshape(pb, ph, pw)
             if trace is not None:
                 trace.setdefault("crops", crops.clone()); trace.setdefault("roi_depth", d_roi.clone())
@@ -559,17 +559,17 @@ class PatchRefinerPlus(PatchRefiner):
         self.coarse_condition = bool(_get(fb, "coarse_condition", True))
         self.fusion_feat_level = int(_get(config, "fusion_feat_level"))
         self.strategy_refiner_target = _get(config, "strategy_refiner_target")
-        if self.strategy_refiner_target == "direct":
-            raise NotImplementedError("strategy_refiner_target='direct' is not implemented")
         self.pre_norm_bbox = _get(config, "pre_norm_bbox", True)
         self.resizer = _Resizer(self.patch_process_shape)
         if tuple(self.resizer.size) != tuple(self.patch_process_shape):
             raise NotImplementedError("patch_process_shape must be a multiple of 14 for the DA2 coarse branch")
         assert precision in ("bf16", "fp32")
         self.precision, self.patch_batch, self.output_device = precision, int(patch_batch), output_device
-        if "convnext" in str(_get(fb, "encoder_name", "")):
-            raise NotImplementedError("convnext encoders add an upsample_convx stage (lightweight_refiner.py:276-283,307-314): not implemented")
         enc_name, in_chans = str(_get(fb, "encoder_name", "")), 4 if self.coarse_condition else 3
+        # convnext encoders return four maps (strides 4..32); LightWeightRefiner adds the stride-2 level with its own
+        # ``upsample_convx`` = ConvTranspose2d(encoder_channels[1] -> encoder_channels[0], k = s = 2) + ReLU (lightweight_refiner.py:276-283, 307-314)
+        self._convx = "convnext" in enc_name
+        self._enc_chl = list(_get(fb, "encoder_channels", None) or [16, 24, 40, 112, 960])
         # mobilenetv4_conv_small (configs/patchrefinerv2_dav2/plus_mobile_*): this package's own kernels (mnv4.py).  Any other
         # encoder: a PyTorch module the caller supplies, or timm where it is installed (library code, parity unpinned either way).
         self._native_enc = fine_encoder is None and enc_name.startswith("mobilenetv4_conv_small")
@@ -587,6 +587,9 @@ class PatchRefinerPlus(PatchRefiner):
             cfgd = getattr(self.refiner_fine_encoder, "default_cfg", None) or {}
             self._enc_mean = tuple(cfgd.get("mean", (0.485, 0.456, 0.406)))
             self._enc_std = tuple(cfgd.get("std", (0.229, 0.224, 0.225)))
+        if self._convx:
+            self._weights["refiner_fine_branch.upsample_convx.0.weight"] = torch.zeros(self._enc_chl[1], self._enc_chl[0], 2, 2)
+            self._weights["refiner_fine_branch.upsample_convx.0.bias"] = torch.zeros(self._enc_chl[0])
         for k, shp in dav2_weight_spec(self._cb_cfg["encoder"], self._cb_cfg["features"], self._cb_cfg["out_channels"]).items():
             self._weights["coarse_branch." + k] = torch.zeros(shp)
         keys = ("coarse_chl", "fine_chl", "fine_chl_after_coarse2fine", "temp_chl", "dec_chl")
@@ -644,8 +647,15 @@ class PatchRefinerPlus(PatchRefiner):
             enc = MobileNetV4ConvSmallB200(sd, self.ENC_PREFIX, self._enc_in_chans, x3, device, self._enc_mean, self._enc_std)
         else:
             self.refiner_fine_encoder.to(device)
+        up_convx = None
+        if self._convx:
+            from .nn import GemmLayer
+            wt, c0 = sd["refiner_fine_branch.upsample_convx.0.weight"].detach().float(), self._enc_chl[0]          # [Cin, C0, 2, 2]
+            up_convx = GemmLayer([(0, 0, 0, wt.permute(2, 3, 1, 0).reshape(4 * c0, wt.shape[0]))], 1, 4 * c0, x3, device, epi=_lib.EPI_SHUFFLE,
+                                 act=_lib.ACT_RELU, bias=sd["refiner_fine_branch.upsample_convx.0.bias"].detach().float(), shuffle_k=2,
+                                 name="lwr.upsample_convx")
         return dict(
-            encoder=enc,
+            encoder=enc, up_convx=up_convx,
             coarse=DepthAnythingV2B200(sd, "coarse_branch.", self._cb_cfg["encoder"], self._cb_cfg["features"], self._cb_cfg["out_channels"], self.max_depth, x3, device),
             fusion=BiDirectionalFusionB200(sd, "refiner_fusion_model.", *[_get(fu, k) for k in keys], coarse2fine_type=_get(fu, "coarse2fine_type"),
                                            x3=x3, device=device, heavy=self._fu_heavy),
@@ -670,8 +680,12 @@ class PatchRefinerPlus(PatchRefiner):
                 x = (crops - eng["enc_mean"]) / eng["enc_std"]
                 feats = list(self.refiner_fine_encoder(torch.cat([x, d_roi], dim=1) if self.coarse_condition else x))
                 f_acts = [Act.from_nchw(f, x3) for f in feats]
+            if self._convx:                                                                        # :307-314
+                top = ws.act("enc_up_convx", pb, f_acts[0].H * 2, f_acts[0].W * 2, self._enc_chl[0])
+                eng["up_convx"]([f_acts[0]], out=top)                                              # ConvTranspose2d(k = s = 2) + bias -> ReLU
+                f_acts = [top] + f_acts
             top = f_acts[0]
-            up = ops.resize_bilinear(top, ws.act("enc_up", pb, top.H * 2, top.W * 2, top.C))       # :316-318
+            up = ops.resize_bilinear(top, ws.act("enc_up", pb, top.H * 2, top.W * 2, top.C))       # :316-318 / :312-313
             r_feats = ([up] + f_acts)[::-1]                                                        # :320, coarsest first
             if self.strategy_refiner_target == "offset_fine":
                 base = torch.zeros_like(d_roi)                                                     # :321: the refiner depth is zeros
@@ -682,6 +696,8 @@ class PatchRefinerPlus(PatchRefiner):
             c_list = c_roi[-level:][::-1]
             f_list = r_feats[-level:][::-1]
             pred = eng["fusion"].forward(c_list, f_list, d_roi, None, base, trace)
+            if self.strategy_refiner_target == "direct":                                           # patchrefinerplus.py:362-363
+                pred = torch.sigmoid(pred) * self.max_depth
             preds[torch.from_numpy(idx).to(dev, non_blocking=True)] = pred.reshape(pb, ph, pw)
             if trace is not None:
                 trace.setdefault("crops", crops.clone()); trace.setdefault("roi_depth", d_roi.clone())

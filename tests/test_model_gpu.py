@@ -155,6 +155,24 @@ def test_batch_of_frames_equals_frame_by_frame(models, tiny_setup, mode, pn):
     assert ((sharded - both).abs() / both.abs().clamp_min(1e-3)).max().item() < 1e-3
 
 
+@pytest.mark.parametrize("target", ["offset_fine", "direct"])
+def test_strategy_refiner_targets(tiny_setup, target):
+    """strategy_refiner_target 'offset_fine' (the refiner's own depth is the update base) and 'direct' (no base, sigmoid * max_depth;
+    patchrefiner.py:270-283) against the oracle (pinned bit-identical to the reference for both, tests/test_oracle_vs_reference.py)."""
+    from patchrefinerv2_b200 import build_model
+    cfg, sd, lr, hr = tiny_setup
+    cfg2 = dict(cfg, strategy_refiner_target=target)
+    random.seed(1)
+    want, _, _ = O.PatchRefinerOracle(cfg2, sd).infer(lr, hr, None, "m1", 2)
+    m = build_model(dict(type="PatchRefiner", config=cfg2, precision="fp32", patch_batch=4))
+    m.load_dict(sd)
+    m = m.cuda().eval()
+    random.seed(1)
+    got, _ = m(mode="infer", image_lr=lr.to(DEV), image_hr=hr.to(DEV), cai_mode="m1", process_num=2)
+    rel = ((got - want).abs() / want.abs().clamp_min(1e-2)).max().item()
+    assert rel < 1e-3, rel
+
+
 def test_host_frames_in_equal_device_frames_in(models, tiny_setup):
     """Frame ingest: pinned host frames -- uploaded by the model on its copy stream, only the frames this rank's
     patches are cut from -- give the bits the device-resident call gives, for one frame and for a batch, plain and sharded."""

@@ -43,6 +43,25 @@ def test_oracle_is_bit_identical_to_reference(pair, mode):
     assert torch.equal(log["coarse_prediction"], coarse)
 
 
+@pytest.mark.parametrize("target", ["offset_fine", "direct"])
+def test_oracle_strategy_refiner_targets_bit_identical_to_reference(pair, target):
+    """strategy_refiner_target other than the shipped 'offset_coarse' (patchrefiner.py:270-283): the refiner depth as update base,
+    and 'direct' (no base, sigmoid * max_depth)."""
+    cfg, sd, ref = pair
+    lr, hr = O.synthetic_frame(cfg, 1)
+    old = ref.strategy_refiner_target
+    try:
+        ref.strategy_refiner_target = target
+        random.seed(1)
+        with torch.no_grad():
+            dref, _ = ref(mode="infer", image_lr=lr, image_hr=hr, cai_mode="m1", process_num=2, tile_cfg=None)
+    finally:
+        ref.strategy_refiner_target = old
+    random.seed(1)
+    dor, _, _ = O.PatchRefinerOracle(dict(cfg, strategy_refiner_target=target), sd).infer(lr, hr, None, "m1", 2)
+    assert torch.equal(dref, dor)
+
+
 def test_state_dict_keys_match_reference(pair):
     cfg, sd, ref = pair
     assert set(ref.state_dict().keys()) == set(sd.keys())

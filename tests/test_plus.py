@@ -100,3 +100,68 @@ def test_b200_plus_matches_reference_golden(golden_dir, plus_setup, mode, pn, pr
     else:
         assert ((depth - want).abs().max() / want.abs().max()).item() < tol
     assert ((log["coarse_prediction"].cpu() - torch.from_numpy(g["coarse"])).abs().max() / float(g["coarse"].max())) < tol
+
+
+# ---- convnext-named encoders: four encoder maps + LightWeightRefiner's own upsample_convx stage (lightweight_refiner.py:276-283, 307-314) ----
+@pytest.fixture(scope="module")
+def convx_setup():
+    cfg = O.make_plus_config(convnext=True)
+    sd = O.init_patchrefinerplus_state_dict(cfg, 0)
+    lr, hr = O.synthetic_frame(cfg, 1)
+    return cfg, sd, lr, hr
+
+
+def test_plus_convx_oracle_matches_reference_golden(golden_dir, convx_setup):
+    cfg, sd, lr, hr = convx_setup
+    g = np.load(os.path.join(golden_dir, "plus_convx_r2.npz"))
+    assert str(g["sd_sha"]) == sd_digest(sd) and str(g["frame_sha"]) == O.sha256_f32(hr.numpy()), "generators drifted from the golden run"
+    assert sorted(sd.keys()) == list(g["keys"])
+    random.seed(1)
+    depth, coarse, _ = O.PatchRefinerPlusOracle(cfg, sd, O.ToyConvNeXtEncoder(4)).infer(lr, hr, None, "r2", 2)
+    np.testing.assert_allclose(depth.numpy(), g["depth"], rtol=1e-3, atol=1e-3)
+    from patchrefinerv2_b200 import build_model
+    mine = build_model(dict(type="PatchRefinerPlus", config=cfg, fine_encoder=O.ToyConvNeXtEncoder(4)))
+    assert sorted(mine.state_dict().keys()) == list(g["keys"])                       # incl. refiner_fine_branch.upsample_convx.0.{weight,bias}
+    res = mine.load_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
+def test_plus_convx_oracle_is_bit_identical_to_reference(convx_setup):
+    cfg, sd, lr, hr = convx_setup
+    d = tempfile.mkdtemp()
+    cp = os.path.join(d, "c.pth")
+    torch.save({k[len("coarse_branch."):]: v for k, v in sd.items() if k.startswith("coarse_branch.")}, cp)
+    cwd = os.getcwd()
+    try:
+        ref = ref_shim.build_reference_patchrefinerplus(cfg, cp, lambda: O.ToyConvNeXtEncoder(3))
+        res = ref.load_state_dict(sd, strict=False)
+        assert not res.missing_keys and not res.unexpected_keys
+        random.seed(1)
+        with torch.no_grad():
+            dref, log = ref(mode="infer", image_lr=lr, image_hr=hr, cai_mode="m1", process_num=2, tile_cfg=None)
+        random.seed(1)
+        dor, coarse, _ = O.PatchRefinerPlusOracle(cfg, sd, O.ToyConvNeXtEncoder(4)).infer(lr, hr, None, "m1", 2)
+        assert torch.equal(dref, dor) and torch.equal(log["coarse_prediction"], coarse)
+    finally:
+        os.chdir(cwd)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("bf16", 5e-2)])
+def test_b200_plus_convx_matches_reference_golden(golden_dir, convx_setup, prec, tol):
+    from patchrefinerv2_b200 import build_model
+    cfg, sd, lr, hr = convx_setup
+    g = np.load(os.path.join(golden_dir, "plus_convx_r2.npz"))
+    m = build_model(dict(type="PatchRefinerPlus", config=cfg, precision=prec, patch_batch=3, fine_encoder=O.ToyConvNeXtEncoder(4)))
+    m.load_dict(sd)
+    m = m.cuda().eval()
+    random.seed(1)
+    depth, log = m(mode="infer", image_lr=lr.cuda(), image_hr=hr.cuda(), cai_mode="r2", process_num=2)
+    want = torch.from_numpy(g["depth"])
+    assert depth.shape == want.shape
+    if prec == "fp32":
+        rel = ((depth - want).abs() / want.abs().clamp_min(1e-2)).max().item()
+        assert rel < tol, rel
+    else:
+        assert ((depth - want).abs().max() / want.abs().max()).item() < tol

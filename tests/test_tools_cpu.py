@@ -179,7 +179,7 @@ def test_reference_configs_construct_or_fail_loudly():
             kw = dict(type=m["type"], config=c)
             enc_name = str(((c.get("refiner") or {}).get("fine_branch") or {}).get("encoder_name", ""))
             if m["type"] == "PatchRefinerPlus" and not enc_name.startswith("mobilenetv4_conv_small"):
-                kw["fine_encoder"] = O.ToyFineEncoder(4)                      # timm stand-in (EfficientNet / ConvNeXt encoders are caller-supplied);
+                kw["fine_encoder"] = O.ToyConvNeXtEncoder(4) if "convnext" in enc_name else O.ToyFineEncoder(4)   # timm stand-in (EfficientNet / ConvNeXt encoders are caller-supplied);
                                                                               # the plus_mobile configs build the package's own MobileNetV4 encoder
             build_model(kw)
             ok[m["type"]] += 1
@@ -189,8 +189,8 @@ def test_reference_configs_construct_or_fail_loudly():
                    "ZoeDepth coarse branch" if "ZoeDepth" in msg else "pretrain_stage" if "pretrain_stage" in msg else
                    "convnext encoder" if "convnext" in msg else "other model family")
             why[key] += 1
-    assert ok == {"PatchRefiner": 3, "PatchRefinerPlus": 4}
-    assert why == {"ZoeDepth coarse branch": 46, "pretrain_stage": 14, "convnext encoder": 1, "other model family": 31}
+    assert ok == {"PatchRefiner": 3, "PatchRefinerPlus": 5}                  # incl. plus_convx_* (upsample_convx stage on the kernels, encoder caller-supplied)
+    assert why == {"ZoeDepth coarse branch": 46, "pretrain_stage": 14, "other model family": 31}
 
 
 def test_compute_metrics_matches_reference_and_hand_values():
