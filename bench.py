@@ -653,11 +653,11 @@ def main():
             r2 = measure(m2, lr_dev, lr_pin, hr_pin, o_steps, 3, not args.no_e2e)
             models[other] = m2
             if rank == 0:
-                other_line = {"precision": other, "dtype": "bf16x3 (hi/lo split, fp32 accumulate)" if other == "fp32" else "bf16", "value": r2["fps"], "unit": "frames/s",
+                other_line = {"precision": other, "dtype": "f16x3 ((hi, lo) FP16 planes, three tensor-core passes per product, fp32 accumulate)" if other == "fp32" else "bf16", "value": r2["fps"], "unit": "frames/s",
                               "ms_per_step": r2["ms"] / r2["steps"], "steps": r2["steps"], "warmup": 3, "e2e": r2.get("e2e"), "gpu_launches": r2["launches"],
                               "patches_per_sec": r2["fps"] * n_patches, "roofline": roofline_of(r2, traffic),
                               "kernels": {k: {kk: v[kk] for kk in ("achieved", "unit", "frac", "ms_per_step", "launches_per_step")} for k, v in r2["kernels"].items()},
-                              "note": "roofline.achieved counts ALGORITHMIC FLOPs (one product per multiply); the tensor pipe executes 3 bf16 passes per product in this mode"}
+                              "note": "roofline.achieved counts ALGORITHMIC FLOPs (one product per multiply); the tensor pipe executes 3 FP16 passes per product in this mode"}
         except Exception as e:
             other_line = {"precision": other, "unavailable": f"{type(e).__name__}: {e}"[:300]}
 
@@ -708,7 +708,7 @@ def main():
 
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if F_ == world else "strong", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-class split)", "data": "synthetic", "config": config,
+            "dtype": "bf16" if args.precision == "bf16" else "f16x3 ((hi, lo) FP16 planes, fp32-class)", "data": "synthetic", "config": config,
             "patches_per_sec": fps * n_patches, "frames_per_step": F_, "algorithmic_tflop_per_frame": flops_frame / 1e12,
             "model_tflops_per_gpu": flops_frame * fps / 1e12 / world,
             "l2_policy": "working set per step (activations, several GB) far exceeds the 126 MB L2; no explicit flush",
