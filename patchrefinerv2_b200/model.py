@@ -164,17 +164,23 @@ class PatchRefiner(nn.Module):
                           ("refiner_fusion_model.", fusion_weight_spec(_get(fu, "input_chl"), _get(fu, "temp_chl"), _get(fu, "dec_chl")))):
             for k, shp in spec.items():
                 self._weights[pre + k] = torch.zeros(shp)
+        # checkpoints named by the config, in the reference's order and strictness (patchrefiner.py:94-98, 118-121, 129-147): the branch
+        # files are loaded strict=True over their branch (a wrong-keyed file raises, as DepthAnythingV2.load_state_dict would),
+        # `pretrained` is strict=False and skips coarse_branch.* unless `load_whole`
         for pre, br in (("coarse_branch.", cb), ("refiner_fine_branch.", fb)):
             path = _get(br, "pretrained")
             if path:
-                sd = torch.load(path, map_location="cpu")            # patchrefiner.py:94,118
-                self._load({pre + k: v for k, v in sd.items()}, strict=False)
+                self._load_branch(pre, torch.load(path, map_location="cpu"))
         for key in ("pretrain_coarse_model", "pretrain_fine_model"):
             path = _get(config, key)
             if path:
-                pre = "coarse_branch." if "coarse" in key else "refiner_fine_branch."
-                sd = torch.load(path, map_location="cpu")["model_state_dict"]
-                self._load({pre + k: v for k, v in sd.items()}, strict=False)
+                self._load_branch("coarse_branch." if "coarse" in key else "refiner_fine_branch.", torch.load(path, map_location="cpu")["model_state_dict"])
+        path = _get(config, "pretrained")
+        if path:
+            sd = torch.load(path, map_location="cpu")["model_state_dict"]
+            if not _get(config, "load_whole", False):
+                sd = {k: v for k, v in sd.items() if "coarse_branch" not in k}
+            self._load(sd, strict=False)
         self._engine = None
         self._device = torch.device("cpu")
         self.last_stats: dict = {}
@@ -199,11 +205,23 @@ class PatchRefiner(nn.Module):
         self._engine = None
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
+    def _load_branch(self, pre: str, sd):
+        """``self.<branch>.load_state_dict(sd)`` of the reference (strict=True): every tensor of the branch, nothing else."""
+        want = {k[len(pre):] for k in self._weights if k.startswith(pre)}
+        missing, unexpected = sorted(want - set(sd)), sorted(set(sd) - want)
+        if missing or unexpected:
+            raise RuntimeError(f"Error(s) in loading state_dict for {pre[:-1]}: missing keys {missing[:4]}{'...' if len(missing) > 4 else ''}, "
+                               f"unexpected keys {unexpected[:4]}{'...' if len(unexpected) > 4 else ''}")
+        return self._load({pre + k: v for k, v in sd.items()}, strict=False)
+
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         return self._load(state_dict, strict)
 
-    def state_dict(self, *args, **kwargs):
-        return OrderedDict((k, v.clone()) for k, v in self._weights.items())
+    def state_dict(self, *args, destination=None, prefix: str = "", keep_vars: bool = False):
+        out = OrderedDict() if destination is None else destination
+        for k, v in self._weights.items():
+            out[prefix + k] = v.clone()
+        return out
 
     _native_comm = None
 
@@ -595,14 +613,18 @@ class PatchRefinerPlus(PatchRefiner):
         keys = ("coarse_chl", "fine_chl", "fine_chl_after_coarse2fine", "temp_chl", "dec_chl")
         for k, shp in bifusion_weight_spec(*[_get(fu, x) for x in keys], coarse2fine_type=_get(fu, "coarse2fine_type"), heavy=self._fu_heavy).items():
             self._weights["refiner_fusion_model." + k] = torch.zeros(shp)
+        # checkpoints named by the config, in the reference's order and strictness (patchrefinerplus.py:121-126, 138-141, 202-205):
+        # the coarse-branch files strict=True over the branch, `pretrained` / `whole_pretrained` strict=False
         path = _get(cb, "pretrained")
         if path:
-            self._load({"coarse_branch." + k: v for k, v in torch.load(path, map_location="cpu").items()}, strict=False)
-        for key in ("pretrain_coarse_model", "pretrained", "whole_pretrained"):
+            self._load_branch("coarse_branch.", torch.load(path, map_location="cpu"))
+        path = _get(config, "pretrain_coarse_model")
+        if path:
+            self._load_branch("coarse_branch.", torch.load(path, map_location="cpu")["model_state_dict"])
+        for key in ("pretrained", "whole_pretrained"):
             path = _get(config, key)
             if path:
-                sd = torch.load(path, map_location="cpu")["model_state_dict"]
-                self._load({("coarse_branch." + k if key == "pretrain_coarse_model" else k): v for k, v in sd.items()}, strict=False)
+                self._load(torch.load(path, map_location="cpu")["model_state_dict"], strict=False)
         self._engine = None
         self._device = torch.device("cpu")
         self.last_stats = {}

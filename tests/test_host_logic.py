@@ -256,3 +256,38 @@ def test_unloaded_weights_are_reported_loudly():
         warnings.simplefilter("always")
         m._warn_unloaded()
     assert not w
+
+
+def test_checkpoint_keys_of_the_config_follow_the_reference(tmp_path):
+    """patchrefiner.py:94-98, 118-121, 129-147: branch files are strict over their branch (a wrong-keyed file raises), `pretrained` is
+    strict=False and skips coarse_branch.* unless `load_whole`; state_dict() honours prefix / destination like nn.Module's."""
+    import torch
+    from patchrefinerv2_b200.model import PatchRefiner
+    cfg = O.make_config("vits", (224, 224), (432, 768), (2, 2))
+    sd = O.init_patchrefiner_state_dict(cfg, 0)
+    coarse = {k[len("coarse_branch."):]: v for k, v in sd.items() if k.startswith("coarse_branch.")}
+    fine = {k[len("refiner_fine_branch."):]: v for k, v in sd.items() if k.startswith("refiner_fine_branch.")}
+    cp, fp, wp = str(tmp_path / "c.pth"), str(tmp_path / "f.pth"), str(tmp_path / "w.pth")
+    torch.save(coarse, cp); torch.save(fine, fp)
+    whole = {k: v + 1.0 for k, v in sd.items()}
+    torch.save({"model_state_dict": whole}, wp)
+    c2 = dict(cfg, coarse_branch=dict(cfg["coarse_branch"], pretrained=cp), refiner=dict(cfg["refiner"], fine_branch=dict(cfg["refiner"]["fine_branch"], pretrained=fp)))
+    m = PatchRefiner(c2)
+    got = m.state_dict()
+    k_c, k_f, k_u = "coarse_branch.pretrained.cls_token", "refiner_fine_branch.pretrained.cls_token", "refiner_fusion_model.final_conv.weight"
+    assert torch.equal(got[k_c], sd[k_c]) and torch.equal(got[k_f], sd[k_f]) and not got[k_u].any()
+    # `pretrained` without load_whole: everything but the coarse branch
+    m = PatchRefiner(dict(c2, pretrained=wp, load_whole=False))
+    got = m.state_dict()
+    assert torch.equal(got[k_c], sd[k_c]) and torch.equal(got[k_f], whole[k_f]) and torch.equal(got[k_u], whole[k_u])
+    m = PatchRefiner(dict(c2, pretrained=wp, load_whole=True))
+    assert torch.equal(m.state_dict()[k_c], whole[k_c])
+    # a wrong-keyed branch file raises instead of leaving the branch at its initial values
+    bad = str(tmp_path / "bad.pth")
+    torch.save({"module." + k: v for k, v in coarse.items()}, bad)
+    with pytest.raises(RuntimeError, match="coarse_branch"):
+        PatchRefiner(dict(c2, coarse_branch=dict(cfg["coarse_branch"], pretrained=bad)))
+    # nn.Module.state_dict signature
+    dest = {}
+    out = m.state_dict(destination=dest, prefix="module.")
+    assert out is dest and set(dest) == {"module." + k for k in sd}
