@@ -1,7 +1,8 @@
 """Diagnostic only (never on the product path): cuBLAS bf16 GEMM rate at the ViT-L linear shapes, to know what the
 library reaches on the same problem sizes under the same power cap."""
 import torch
-M = 12 * 1025
+import os
+M = int(os.environ.get("PRV2_PROF_B", "12")) * 1025
 for name, K, N in (("qkv", 1024, 3072), ("fc1", 1024, 4096), ("fc2", 4096, 1024), ("proj", 1024, 1024), ("big", 8192, 8192)):
     m = 8192 if name == "big" else M
     a = torch.randn(m, K, device="cuda", dtype=torch.bfloat16)
