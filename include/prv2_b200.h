@@ -124,7 +124,8 @@ int prv2_blend_finalize_raw(const float* avg_c, const float* cnt_c, int Hc, int 
                             float* out, float* out_cnt, const void* prep, prv2_stream_t stream);
 /* Test / A-B hook: bit 0 routes every blend entry point through the any-alignment generic kernels instead of the
  * aligned fast paths; bit 1 switches the rN stage's segment kernel off (the table kernel runs); bits 8-15 force the segment
- * kernel's warps per CTA (0 = automatic).  Every path produces the same bits; tests assert it. */
+ * kernel's warps per CTA (0 = automatic).  Every path produces the same bits; tests assert it.  The value 0x10000 changes nothing
+ * and returns how many *_raw calls the segment kernel has taken so far (tests use it to know which path they exercised). */
 int prv2_debug_blend_generic(int on);
 
 /* ------------------------------------------------------------------------------------------

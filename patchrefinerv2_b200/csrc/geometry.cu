@@ -504,7 +504,13 @@ static bool blend_generic_forced() {
   return g_blend_generic == 1;
 }
 static void seg_knobs(int on);
-extern "C" int prv2_debug_blend_generic(int on) { g_blend_generic = (on & 1) ? 1 : 0; seg_knobs(on); return PRV2_OK; }
+static int g_seg_launches = 0;                                   // (test hook: how often the segment kernel took a *_raw call)
+extern "C" int prv2_debug_blend_generic(int on) {
+  if (on == 0x10000) return g_seg_launches;                      // query only
+  g_blend_generic = (on & 1) ? 1 : 0;
+  seg_knobs(on);
+  return PRV2_OK;
+}
 
 static bool canvas_aligned(const StageTable& t, int pw, int Wc) {
   if (blend_generic_forced() || (pw & 3) || (Wc & 3) || t.n > 4) return false;
@@ -1180,6 +1186,7 @@ static bool launch_seg(const float* avg_c, const float* cnt_c, int Hc, int Wc, c
   const int segw = warps * 128;
   blend_raw_seg_kernel<MODE><<<dim3(cdiv(W, segw), H), warps * 32, 0, stream>>>(avg_c, cnt_c, Hc, Wc, preds, starts, n, ph, pw, rh, rw, H, W, out, out_cnt,
                                                                                 num_in, sc, tb, pv, segw);
+  ++g_seg_launches;
   return true;
 }
 

@@ -290,3 +290,105 @@ def test_blend_ragged_geometries_bit_exact_vs_oracle(dev, case):
     depth, _, avg = go.infer(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, H, W), None, mode, pn)
     assert torch.equal(res[1][1], avg.count_map)
     assert torch.equal(res[1][0], depth[0, 0])
+
+
+SEGMENT_TOOK = []
+
+
+def _cpu_raw_stage(avg_c, cnt_c, preds, starts, rmask, H, W):
+    """The rN stage restated with ATen CPU ops exactly as the reference runs it (utils.py:31-43, baseline_pretrain.py:204-229):
+    resize the canvases (average nearest, count bilinear align_corners=True), then the sequential per-patch update."""
+    import torch.nn.functional as F
+    avg = F.interpolate(avg_c[None, None], (H, W), mode="nearest")[0, 0].clone()
+    cnt = F.interpolate(cnt_c[None, None], (H, W), mode="bilinear", align_corners=True)[0, 0].clone()
+    rh, rw = rmask.shape
+    for k in range(preds.shape[0]):
+        y0, x0 = int(starts[k, 0]), int(starts[k, 1])
+        p = F.interpolate(preds[k][None, None], (rh, rw), mode="nearest")[0, 0]
+        a, c = avg[y0:y0 + rh, x0:x0 + rw], cnt[y0:y0 + rh, x0:x0 + rw]
+        m = rmask > 0
+        a[m] = (p[m] * rmask[m] + c[m] * a[m]) / (c[m] + rmask[m])
+        c[m] = c[m] + rmask[m]
+    return avg, cnt
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_blend_segment_kernel_random_geometries(dev, seed):
+    """The rN stage's segment kernel (prepared weight map, widths that are multiples of 4: the path the model takes) on geometries
+    no tiling produces: arbitrary canvas / frame ratios incl. down-sampling, patches flush with the frame edges and stacked on one
+    another, up to 128 random patches, weight maps with zeros and negative entries (utils.py:31 skips them), zero counts.  Bit-identical
+    to the table kernel, to the generic kernel and to the reference's own sequence of ATen CPU ops; the finalize form agrees too."""
+    from patchrefinerv2_b200 import _lib, ops
+    g = torch.Generator().manual_seed(100 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    H, W = ri(40, 260), 4 * ri(30, 500)
+    Hc, Wc = ri(17, 300), 4 * ri(8, 300 if seed % 2 else 90)       # even seeds: strong up-sampling of the canvas, odd: also down-sampling
+    ph, pw = ri(9, 70), ri(9, 90)
+    rh, rw = ri(5, min(H - 2, 120)), ri(7, min(W - 2, 400))
+    n = [1, 7, 33, 128, 64, 100][seed]
+    ys = torch.randint(0, H - rh + 1, (n,), generator=g)
+    xs = torch.randint(0, W - rw + 1, (n,), generator=g)
+    ys[0], xs[0] = 0, 0
+    if n > 1:
+        ys[1], xs[1] = H - rh, W - rw                               # flush with the bottom-right corner
+    if n > 2:
+        ys[2], xs[2] = ys[1], xs[1]                                 # the same place twice
+    starts = torch.stack([ys, xs], 1).to(torch.int32)
+    avg_c = torch.rand(Hc, Wc, generator=g) * 20
+    cnt_c = torch.rand(Hc, Wc, generator=g) * 3
+    cnt_c[torch.rand(Hc, Wc, generator=g) < 0.1] = 0.0
+    rmask = torch.rand(rh, rw, generator=g) + 1e-3
+    rmask[torch.rand(rh, rw, generator=g) < 0.05] = 0.0
+    rmask[torch.rand(rh, rw, generator=g) < 0.02] = -0.5
+    preds = torch.rand(n, ph, pw, generator=g) * 30
+    want_a, want_c = _cpu_raw_stage(avg_c, cnt_c, preds, starts, rmask, H, W)
+    d = lambda t: t.to(dev).contiguous()
+    a_c, c_c, pr, st, rm = d(avg_c), d(cnt_c), d(preds), d(starts), d(rmask)
+    prep = ops.blend_raw_prepare(rm, pw)
+    outs = {}
+    seg_before = _lib.load().prv2_debug_blend_generic(0x10000)
+    try:
+        for name, knob in (("segment", 0), ("table", 2), ("generic", 1)):
+            _lib.call("prv2_debug_blend_generic", knob)
+            outs[name] = ops.blend_raw(a_c, c_c, pr, st, rm, ph, pw, rh, rw, H, W, prep=prep)
+            if name == "segment":
+                took = _lib.load().prv2_debug_blend_generic(0x10000) - seg_before
+                # the segment kernel stages <= 512 canvas columns per 256-pixel (or wider) segment: it declines strong down-sampling
+                assert took == (1 if 256.0 * Wc / W + 8 < 512 else took), (took, Wc, W)
+                SEGMENT_TOOK.append(took)
+        # finalize form: count map recomputed locally, depth from the reduced sums -- segment vs generic kernel
+        num_r = torch.zeros(H, W, device=dev)
+        ops.blend_partial_raw(pr, torch.ones(n, dtype=torch.uint8, device=dev), st, rm, ph, pw, H, W, num_r, prep=prep)
+        fin = {}
+        for name, knob in (("segment", 0), ("generic", 1)):
+            _lib.call("prv2_debug_blend_generic", knob)
+            fin[name] = ops.blend_finalize_raw(a_c, c_c, num_r, st, rm, rh, rw, H, W, prep=prep)
+    finally:
+        _lib.call("prv2_debug_blend_generic", 0)
+    finite = torch.isfinite(want_a)                                  # (0 / 0 where a zero count meets a zero-weight... never: such pixels are skipped)
+    assert bool(finite.all())
+    for name in ("segment", "table", "generic"):
+        assert torch.equal(outs[name][1].cpu(), want_c), name
+        assert torch.equal(outs[name][0].cpu(), want_a), name
+    assert torch.equal(fin["segment"][0], fin["generic"][0]) and torch.equal(fin["segment"][1], fin["generic"][1])
+    assert torch.equal(fin["segment"][1].cpu(), want_c)
+
+
+def test_blend_config5_size_prepared_segment_kernel(dev):
+    """BASELINE config 5 geometry through the path the model takes (prepared weight map -> segment kernel): bit-exact vs the oracle."""
+    from patchrefinerv2_b200 import ops
+    shape, raw, split, mode, pn = (448, 448), (4320, 7680), (8, 8), "r128", 4
+    tc, preds, grid, n_reg, mask, rmask, starts = _blend_inputs(dev, shape, mode, pn, raw, split)
+    Hc, Wc = tc["patch_reensemble_shape"]
+    H, W = tc["image_raw_shape"]
+    rh, rw = tc["patch_raw_shape"]
+    a, c = ops.blend_canvas(preds[:n_reg], mask, grid, Hc, Wc)
+    from patchrefinerv2_b200 import _lib
+    before = _lib.load().prv2_debug_blend_generic(0x10000)
+    got = ops.blend_raw(a, c, preds[n_reg:], starts, rmask, shape[0], shape[1], rh, rw, H, W, prep=ops.blend_raw_prepare(rmask, shape[1]))
+    assert _lib.load().prv2_debug_blend_generic(0x10000) == before + 1        # the segment kernel took it
+    assert sum(SEGMENT_TOOK) >= 3 or not SEGMENT_TOOK                          # ... and most of the random geometries above
+    go = O.GeometryOracle(shape, raw, split)
+    random.seed(1)
+    depth, _, avg = go.infer(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, H, W), None, mode, pn)
+    assert torch.equal(got[1].cpu(), avg.count_map) and torch.equal(got[0].cpu(), depth[0, 0])
