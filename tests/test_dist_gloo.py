@@ -36,14 +36,22 @@ def _schedule():
     return tc, stages
 
 
-def _partials(rank, world):
-    tc, stages = _schedule()
+def _schedule_batch(frames):
+    """Schedules of a batch of frames, drawn frame by frame from ONE `random` stream (as `frames` successive reference calls do)."""
+    tc = tiling.prepare_tile_cfg(SHAPE, RAW, SPLIT)
+    random.seed(1)
+    return tc, [tiling.schedule(tc, SHAPE, MODE, PN) for _ in range(frames)]
+
+
+def _partials(rank, world, stages=None, own=None):
+    tc, st1 = _schedule()
+    stages = st1 if stages is None else stages
     ph, pw = SHAPE
     rh, rw = tc["patch_raw_shape"]
     H, W = tc["image_raw_shape"]
     Hc, Wc = tc["patch_reensemble_shape"]
     bb = np.concatenate([s.bboxs for s in stages])
-    own = tiling.shard_patches(bb.shape[0], rank, world)
+    own = tiling.shard_patches(bb.shape[0], rank, world) if own is None else own
     mask = torch.from_numpy(masks.generatemask(SHAPE, 0.15).copy())
     rmask = torch.from_numpy(masks.random_patch_mask((rh, rw), 0.15).copy())
     num_c, m1, num_r = torch.zeros(Hc, Wc), torch.zeros(Hc, Wc), torch.zeros(H, W)
@@ -131,6 +139,52 @@ def test_two_rank_sharded_blend_matches_sequential_reference():
     assert np.array_equal(cnt, avg.count_map.numpy())                       # bit-exact count map regardless of world size
     rel = np.abs(out - want[0, 0].numpy()) / np.maximum(np.abs(want[0, 0].numpy()), 1e-6)
     assert rel.max() < 1e-3, rel.max()
+
+
+def _batch_worker(rank, world, port, q, frames):
+    """A batch of frames: the flattened F x P work list is split into one contiguous block per rank (model.py / tiling.shard_patches
+    with frames > 1), every frame keeps its own packed canvases, ONE all_reduce combines the whole batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tc, sched = _schedule_batch(frames)
+    P = sum(s.bboxs.shape[0] for s in sched[0])
+    own = tiling.shard_patches(frames * P, rank, world, frames=frames)
+    parts, ctxs = [], []
+    for f in range(frames):
+        packed, ctx = _partials(rank, world, stages=sched[f], own=own[f * P:(f + 1) * P])
+        parts.append(packed)
+        ctxs.append((ctx[0], sched[f], ctx[2], ctx[3]))
+    batch = torch.stack(parts)
+    dist.all_reduce(batch)                                      # the single sum-reduce of the batch
+    outs = [_finalize(batch[f], ctxs[f]) for f in range(frames)]
+    if rank == 0:
+        q.put(([o[0].numpy() for o in outs], [o[1].numpy() for o in outs], [int(x) for x in np.unique(np.nonzero(own)[0] // P)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_batch_of_frames_block_split():
+    world, frames = 2, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, q, frames)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs, cnts, frames_rank0 = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert frames_rank0 == [0]                                   # one frame per rank: rank 0 only ever touches (and uploads) frame 0
+    go = O.GeometryOracle(SHAPE, RAW, SPLIT)
+    cfg = O.make_config("vits", SHAPE, RAW, SPLIT)
+    _, hr = O.synthetic_frame(cfg, 1)
+    random.seed(1)                                               # ... against two successive single-frame reference runs on one `random` stream
+    for f in range(frames):
+        want, _, avg = go.infer(torch.zeros(1, 3, *SHAPE), hr, None, MODE, PN)
+        assert np.array_equal(cnts[f], avg.count_map.numpy()), f
+        rel = np.abs(outs[f] - want[0, 0].numpy()) / np.maximum(np.abs(want[0, 0].numpy()), 1e-6)
+        assert rel.max() < 1e-3, (f, rel.max())
 
 
 def test_every_rank_draws_the_same_schedule():
