@@ -404,10 +404,12 @@ __global__ void __launch_bounds__(256) blend_canvas_kernel(const float* __restri
   }
 }
 
-// threads per CTA so that a canvas row splits into CTAs without a mostly idle last one (1792 / 4 = 448 = 2 x 224)
+// threads per CTA so that a canvas row splits into CTAs without a mostly idle last one (1792 / 4 = 448 = 4 x 112 -> 128 threads)
 static int blend_threads(int Wc) {
   const int groups = cdiv(Wc, 4);
-  const int ctas = cdiv(groups, 256);
+  static const char* cap_env = getenv("PRV2_BLEND_CANVAS_THREADS");        // A/B knob: threads per CTA cap
+  const int cap = cap_env ? atoi(cap_env) : 128;                            // 128: 19.5 against 20.5 us by events at 256 (2160x3840, m2 canvas, cold L2); 14.9 us either way under ncu
+  const int ctas = cdiv(groups, cap > 0 ? cap : 128);
   return cdiv(cdiv(groups, ctas), 32) * 32;
 }
 
