@@ -55,3 +55,27 @@ def test_cli_general_mode_writes_reference_format_predictions(tmp_path, tiny_set
         assert got.dtype == np.uint16 and got.shape == (432, 768)
         w16 = want[0, 0].numpy() * 256
         assert np.all(np.abs(got.astype(np.float64) - w16) <= 1e-3 * np.abs(w16) + 1.0)
+
+
+def test_cli_frames_per_call_gives_the_same_files(tmp_path, tiny_setup):
+    """--frames-per-call F: F frames are one work list (the form that scales under torchrun).  The depth maps must be the very files
+    the frame-by-frame run writes -- same schedule draws (one `random` stream consumed frame by frame), same per-patch results."""
+    cfg, sd, lr, hr = tiny_setup
+    (tmp_path / "cfg").mkdir(); (tmp_path / "imgs").mkdir()
+    (tmp_path / "cfg" / "base_dataset.py").write_text(BASE)
+    (tmp_path / "cfg" / "tiny.py").write_text(CFG % (cfg,))
+    torch.save({"model_state_dict": sd}, tmp_path / "ckpt.pth")
+    rng = np.random.default_rng(5)
+    for name in ("f0.png", "f1.png", "f2.png"):
+        cv2.imwrite(str(tmp_path / "imgs" / name), rng.integers(0, 256, (216, 384, 3), dtype=np.uint8))
+    t = _tools()
+    base = [str(tmp_path / "cfg" / "tiny.py"), "--ckp-path", str(tmp_path / "ckpt.pth"), "--cai-mode", "r2", "--process-num", "2",
+            "--cfg-option", f"general_dataloader.dataset.rgb_image_dir={tmp_path / 'imgs'}", "--save", "--test-type", "general",
+            "--image-raw-shape", "432", "768", "--patch-split-num", "2", "2", "--precision", "bf16", "--patch-batch", "4", "--seed", "7"]
+    t.main(base + ["--work-dir", str(tmp_path / "one"), "--frames-per-call", "1"])
+    t.main(base + ["--work-dir", str(tmp_path / "two"), "--frames-per-call", "2"])          # 3 frames: a batch of 2 and a batch of 1
+    assert sorted(os.listdir(tmp_path / "one")) == sorted(os.listdir(tmp_path / "two")) and len(os.listdir(tmp_path / "one")) == 9
+    for name in ("f0", "f1", "f2"):
+        a = cv2.imread(str(tmp_path / "one" / f"{name}_uint16.png"), cv2.IMREAD_UNCHANGED)
+        b = cv2.imread(str(tmp_path / "two" / f"{name}_uint16.png"), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(a, b), name

@@ -43,6 +43,9 @@ def parse_args(argv=None):
     ap.add_argument("--precision", default="fp32", choices=["bf16", "fp32"],
                     help="fp32 (default): the fp32-class mode that meets the reference within 1e-3 relative; bf16: the one-pass mode, ~2.7x faster, its own tolerance (5e-2)")
     ap.add_argument("--patch-batch", type=int, default=27)
+    ap.add_argument("--frames-per-call", type=int, default=0,
+                    help="frames handed to one model call (0 = one per GPU under torchrun, else 1).  A batch of F frames is ONE work list of F x P patches "
+                         "(split over the ranks, one NCCL sum-reduce per batch); the depth maps are the ones F successive single-frame calls give")
     return ap.parse_args(argv)
 
 
@@ -105,15 +108,27 @@ def main(argv=None):
             print(res)
         return
     n, t0 = 0, time.perf_counter()
-    for name, image_hr in frames.iter_frames(img_dir, args.image_raw_shape):
-        hr = image_hr.cuda().unsqueeze(0)
+    per_call = args.frames_per_call if args.frames_per_call > 0 else (world if shard else 1)
+    tile_cfg = {"image_raw_shape": list(args.image_raw_shape), "patch_split_num": list(args.patch_split_num)}
+
+    def run_batch(names, hrs):
+        hr = torch.stack(hrs).cuda()
         lr = model.resizer(hr)                                           # general_dataset.py:218 (on the device)
-        tile_cfg = {"image_raw_shape": list(args.image_raw_shape), "patch_split_num": list(args.patch_split_num)}
         result, log = model(mode="infer", cai_mode=args.cai_mode, process_num=args.process_num, tile_cfg=tile_cfg, image_lr=lr, image_hr=hr, shard=shard)
         if args.save and rank == 0:
-            print(torch.max(result))                                     # tester.py:73
-            frames.save_prediction(result, args.work_dir, name, args.gray_scale, log["coarse_prediction"], args.image_raw_shape)
+            for f, name in enumerate(names):                             # frame by frame, as Tester.run writes them (tester.py:73-122)
+                print(torch.max(result[f:f + 1]))
+                frames.save_prediction(result[f:f + 1], args.work_dir, name, args.gray_scale, log["coarse_prediction"][f:f + 1], args.image_raw_shape)
+
+    names, hrs = [], []
+    for name, image_hr in frames.iter_frames(img_dir, args.image_raw_shape):
+        names.append(name); hrs.append(image_hr)
         n += 1
+        if len(names) == per_call:
+            run_batch(names, hrs)
+            names, hrs = [], []
+    if names:
+        run_batch(names, hrs)
     dt = time.perf_counter() - t0
     if shard:
         torch.distributed.destroy_process_group()
